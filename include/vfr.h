@@ -1,0 +1,130 @@
+/* libvfr - C ABI of the B200-native moment-scoring hot path (sm_100a).
+ *
+ * This header is the drop-in boundary.  The reference (mariyashcheg/video-fragments-retrieval) is
+ * pure Python with no FFI of its own, so each entry point below names the reference lines whose
+ * work it replaces; the Python shim in video-fragments-retrieval_b200/ binds them with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only.  Unless a parameter is marked HOST every pointer is a DEVICE
+ *    pointer owned by the caller; the library never allocates or frees caller-visible memory and
+ *    takes caller-supplied workspaces (sizes from the vfr_*_bytes queries).
+ *  - every call takes the CUDA stream to enqueue on (cudaStream_t passed as void*, NULL = legacy
+ *    default stream) and is asynchronous with respect to the host unless stated otherwise.
+ *  - return value: 0 = ok, negative = error (VFR_ERR_*); vfr_last_error() gives the text for the
+ *    calling thread.  Nothing throws or aborts.
+ *  - moments of an n-clip video are indexed as the reference enumerates them
+ *    (model/utils.py:71-75): the n single clips, then all (s<e) pairs in lexicographic order.
+ *  - a "bank" is the set of clip embeddings of V videos: fp32 [C, D] row-major, with CSR clip
+ *    offsets vid_off int32 [V+1] and moment offsets mom_off int64 [V+1]
+ *    (mom_off[v+1]-mom_off[v] = n_v (n_v+1)/2, n_v <= 32).
+ */
+#ifndef VFR_H_
+#define VFR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFR_OK 0
+#define VFR_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, misalignment) */
+#define VFR_ERR_UNSUPPORTED (-2) /* shape outside what the kernels handle */
+#define VFR_ERR_CUDA (-3)        /* a CUDA runtime call / launch failed */
+
+#define VFR_TILE_Q 128    /* queries per scoring tile */
+#define VFR_TILE_C 96     /* clip columns per scoring tile */
+#define VFR_TOPK_MAX 128  /* largest k of the fused top-k */
+#define VFR_TOPK_CAP 256  /* candidate slots per (query, part) list in the top-k workspace */
+#define VFR_MAX_TAU 16    /* thresholds per query in count mode */
+
+typedef void* vfr_stream_t;
+
+const char* vfr_last_error(void);
+int vfr_version(void);
+/* number of SMs of the current device (grid sizing), or negative error */
+int vfr_device_sms(void);
+
+/* ---- K4 : query x clip distance -> moment means -> full / count / top-k --------------------
+ * replaces model/evaluate.py:49-58 (and evaluate_single.py:48-53, main.py:148-157):
+ *   d[q,c] = || v_c - q + 1e-6 ||_2 ;  score[q,(v,s,e)] = mean(d[q, v, s..e])  (fp32)
+ * Exact-fp32 CUDA-core path (direct-difference form, k-sequential FFMA chain, IEEE sqrt/div);
+ * every mode evaluates the SAME arithmetic, so thresholds taken from one mode compare exactly
+ * against scores of another.
+ */
+
+/* Packed operand layouts (k-major tiles streamed by cp.async.bulk).
+ * videos per tile VT = VFR_TILE_C / n_max ; tiles = ceil(V / VT). */
+size_t vfr_bank_pack_bytes(int64_t n_videos, int n_max, int dim);
+int vfr_bank_pack(const float* bank, const int32_t* vid_off, int64_t n_videos, int n_max, int dim,
+                  float* packed, vfr_stream_t stream);
+size_t vfr_query_pack_bytes(int64_t n_queries, int dim);
+int vfr_query_pack(const float* queries, int64_t n_queries, int dim, float* packed, vfr_stream_t stream);
+
+/* all scores, reference order (video-major, then moment index): out fp32 [Q, M_total] */
+int vfr_score_full(const float* bank_packed, const int32_t* vid_off, const int64_t* mom_off,
+                   int64_t n_videos, int n_max, int dim, const float* query_packed, int64_t n_queries,
+                   float* out, int64_t m_total, vfr_stream_t stream);
+
+/* scores of each query against ONE video (its own): out fp32 [Q, m_stride], +inf padded.
+ * bank is the UNPACKED fp32 [C, D] array, queries the unpacked [Q, D]. (evaluate_single.py:48-53) */
+int vfr_score_own(const float* bank, const int32_t* vid_off, int dim, const float* queries,
+                  int64_t n_queries, const int32_t* q_video, float* out, int m_stride, vfr_stream_t stream);
+
+/* rank counting (replaces the argsort of model/evaluate.py:71,77 - only the position of the
+ * first positive is consumed): for each query q and threshold t<n_tau,
+ *   cnt_lt[q,t]  += #{ moments : score <  tau[q,t] }
+ *   cnt_eqb[q,t] += #{ moments : score == tau[q,t] and video < q_video[q] }   (deterministic ties)
+ * counters are uint32 [Q, n_tau] and must be zeroed by the caller. */
+int vfr_score_count(const float* bank_packed, const int32_t* vid_off, int64_t n_videos, int n_max, int dim,
+                    const float* query_packed, int64_t n_queries, const float* tau, int n_tau,
+                    const int32_t* q_video, uint32_t* cnt_lt, uint32_t* cnt_eqb, int n_split,
+                    vfr_stream_t stream);
+
+/* fused top-k (k <= VFR_TOPK_MAX) by ascending (score, moment id):
+ * out_scores fp32 [Q, k], out_ids int64 [Q, k] = id_base + local moment id; unused slots
+ * (+inf, -1).  workspace: vfr_score_topk_bytes(Q, n_split). */
+size_t vfr_score_topk_bytes(int64_t n_queries, int n_split);
+int vfr_score_topk(const float* bank_packed, const int32_t* vid_off, const int64_t* mom_off,
+                   int64_t n_videos, int n_max, int dim, const float* query_packed, int64_t n_queries,
+                   int k, int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace,
+                   int n_split, vfr_stream_t stream);
+
+/* K7 : merge P per-shard top-k lists (after the NCCL all-gather): in_scores fp32 [P, Q, k],
+ * in_ids int64 [P, Q, k] -> out [Q, k] by ascending (score, id).  P * k <= 4096. */
+int vfr_topk_merge(const float* in_scores, const int64_t* in_ids, int n_parts, int64_t n_queries, int k,
+                   float* out_scores, int64_t* out_ids, vfr_stream_t stream);
+
+/* ---- K5 : integer-exact temporal IoU, ground truth, rank statistics -------------------------
+ * times int32 [Q, n_annot, 2] inclusive (start, end), absent annotators = (-1, -1);
+ * q_nseg int32 [Q] = clips of the query's own video; own_scores fp32 [Q, m_stride] (vfr_score_own);
+ * tables uint8 [n_thr, 65, 65]: tables[t][inter][union] = (inter/union > thr_t) built on the host
+ * in float64 (vfr_b200.utils.threshold_table) - replaces model/utils.py:78-82. */
+
+/* ground-truth rule of model/evaluate.py:59-65: gt uint8 [Q, n_thr, m_stride]; per (q, t) the
+ * smallest positive score tau (+inf if none), its moment index pos (-1 if none, lowest index on
+ * ties), the number of positives npos, and eq_before = #{m < pos : own_scores[m] == tau}. */
+int vfr_gt_select(const float* own_scores, int m_stride, const int32_t* q_nseg, const int32_t* times,
+                  int n_annot, const uint8_t* tables, int n_thr, int64_t n_queries, uint8_t* gt,
+                  float* tau, int32_t* pos, int32_t* npos, int32_t* eq_before, vfr_stream_t stream);
+
+/* ranking of one video's moments (model/evaluate_single.py:52-54): order int32 [Q, m_stride] =
+ * moment indices sorted by ascending (score, index); descending != 0 reverses that list, which
+ * is what the reference's "[::-1]" does.  -1 padded.  m_stride <= 1024. */
+int vfr_rank_order(const float* own_scores, int m_stride, const int32_t* q_nseg, int64_t n_queries,
+                   int descending, int32_t* order, vfr_stream_t stream);
+
+/* rank statistics of model/evaluate_single.py:58-73 for a ranked list: ranks int32 [Q, n_annot]
+ * (1-based position of each annotated time; 0 = absent annotator, -1 = not a candidate moment),
+ * integer IoU (top1_inter / top1_union [Q, n_annot]) between the top-1 moment and each annotation,
+ * first_pos int32 [Q, n_thr] = position of the first positive moment in the list (m_stride if none). */
+int vfr_single_metrics(const int32_t* order, int m_stride, const int32_t* q_nseg, const int32_t* times,
+                       int n_annot, const uint8_t* tables, int n_thr, int64_t n_queries, int32_t* ranks,
+                       int32_t* top1_inter, int32_t* top1_union, int32_t* first_pos, vfr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFR_H_ */

@@ -1,0 +1,77 @@
+"""ctypes binding of the C-ABI library ``csrc/libvfr.so`` (declared in ``include/vfr.h``).
+
+There is no fallback of any kind: if the shared library is missing or a call returns a non-zero
+status this module raises.  Build the library with ``python -c "import __graft_entry__ as g;
+g.build()"`` or ``make -C video-fragments-retrieval_b200/csrc``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libvfr.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vfr.h")
+
+VFR_TILE_Q = 128
+VFR_TILE_C = 96
+VFR_TOPK_MAX = 128
+VFR_MAX_TAU = 16
+
+
+class VfrError(RuntimeError):
+    pass
+
+
+_p = C.c_void_p
+_i = C.c_int
+_l = C.c_int64
+_z = C.c_size_t
+
+# name -> (restype, argtypes); kept in the order of include/vfr.h
+PROTOTYPES = {
+    "vfr_last_error": (C.c_char_p, []),
+    "vfr_version": (_i, []),
+    "vfr_device_sms": (_i, []),
+    "vfr_bank_pack_bytes": (_z, [_l, _i, _i]),
+    "vfr_bank_pack": (_i, [_p, _p, _l, _i, _i, _p, _p]),
+    "vfr_query_pack_bytes": (_z, [_l, _i]),
+    "vfr_query_pack": (_i, [_p, _l, _i, _p, _p]),
+    "vfr_score_full": (_i, [_p, _p, _p, _l, _i, _i, _p, _l, _p, _l, _p]),
+    "vfr_score_own": (_i, [_p, _p, _i, _p, _l, _p, _p, _i, _p]),
+    "vfr_score_count": (_i, [_p, _p, _l, _i, _i, _p, _l, _p, _i, _p, _p, _p, _i, _p]),
+    "vfr_score_topk_bytes": (_z, [_l, _i]),
+    "vfr_score_topk": (_i, [_p, _p, _p, _l, _i, _i, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
+    "vfr_topk_merge": (_i, [_p, _p, _i, _l, _i, _p, _p, _p]),
+    "vfr_gt_select": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p, _p]),
+    "vfr_rank_order": (_i, [_p, _i, _p, _l, _i, _p, _p]),
+    "vfr_single_metrics": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libvfr.so once; raises ``VfrError`` if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VfrError(f"{LIB_PATH} not found: the CUDA library has not been built "
+                       f"(run __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().vfr_last_error().decode(errors="replace")
+        raise VfrError(f"{what} failed with status {status}: {msg}")
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on a non-zero status."""
+    check(getattr(load(), name)(*args), name)
