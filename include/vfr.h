@@ -124,6 +124,59 @@ int vfr_single_metrics(const int32_t* order, int m_stride, const int32_t* q_nseg
                        int n_annot, const uint8_t* tables, int n_thr, int64_t n_queries, int32_t* ranks,
                        int32_t* top1_inter, int32_t* top1_union, int32_t* first_pos, vfr_stream_t stream);
 
+/* ---- K2 : visual embedding ------------------------------------------------------------------
+ * replaces model/models.py:21-27,55-56 in eval mode: out = relu(x W1^T + b1) W2^T + b2, fp32.
+ * x [n_rows, in_dim] is the reference's [segment | context | tef] row (model/data.py:204-213);
+ * hidden is a caller workspace fp32 [n_rows, hid]. */
+int vfr_linear(const float* x, int64_t n_rows, int in_dim, int ldx, const float* w, const float* bias,
+               int out_dim, int relu, float* out, int ldo, vfr_stream_t stream);
+int vfr_visual_embed(const float* x, int64_t n_rows, int in_dim, const float* w1, const float* b1, int hid,
+                     const float* w2, const float* b2, int dim, float* hidden, float* out,
+                     vfr_stream_t stream);
+
+/* ---- K3 : query embedding (GloVe gather -> BiLSTM -> Linear) -----------------------------------
+ * replaces model/models.py:33-48,61-66.  Weights of one direction are re-laid-out once per weight
+ * update by vfr_lstm_pack ([W_hh | W_ih] rows interleaved by gate, bias = b_ih + b_hh;
+ * vfr_lstm_pack_bytes bytes).  tokens int64 [B, L]; table fp32 [vocab, emb] (row 0 = pad);
+ * length_table fp32 [vocab] or NULL (the normalize_lang variant, models.py:62-64);
+ * fc_w fp32 [dim, 2*hidden]; out fp32 [B, dim]; workspace vfr_text_embed_bytes bytes whose LAST
+ * int32 is set to 1 if a token id was outside [0, vocab) (the reference raises IndexError). */
+size_t vfr_lstm_pack_bytes(int hidden, int emb);
+int vfr_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int hidden,
+                  int emb, float* packed, vfr_stream_t stream);
+size_t vfr_text_embed_bytes(int64_t n_queries, int seq_len, int hidden, int emb);
+int vfr_text_embed(const int64_t* tokens, int64_t n_queries, int seq_len, const float* table, int64_t vocab,
+                   const float* length_table, int emb, const float* packed_fwd, const float* packed_bwd,
+                   int hidden, const float* fc_w, const float* fc_b, int dim, void* workspace, float* out,
+                   vfr_stream_t stream);
+
+/* ---- K1 : frame -> segment pooling --------------------------------------------------------------
+ * replaces model/data.py:142-188.  frames fp32 [sum_v F_v, dim] (the get_rgb_features.py .npy rows
+ * of all videos back to back), frame_off int64 [V+1].  mode 0 = avg, 1 = max (.npy branch,
+ * data.py:163-181), 2 = the preprocessed-.h5 branch (data.py:144-161).  Outputs, L2-normalised
+ * x/(|x|+1e-5): seg fp32 [V, seg_stride, dim] (rows >= n_seg[v] zeroed), ctx fp32 [V, dim],
+ * n_seg int32 [V].  dim % 4 == 0.  workspace: vfr_segment_pool_bytes. */
+size_t vfr_segment_pool_bytes(int64_t n_videos, int dim, int seg_stride);
+int vfr_segment_pool(const float* frames, const int64_t* frame_off, int64_t n_videos, int dim, int window,
+                     int mode, float* seg, int seg_stride, float* ctx, int32_t* n_seg, void* workspace,
+                     vfr_stream_t stream);
+
+/* ---- K6 : ranking loss (forward + backward) -------------------------------------------------------
+ * replaces model/main.py:214-232 and its autograd graph.  posit/inter fp32 [rows_posit, dim] with
+ * sample ids maskp int64 [rows_posit]; intra fp32 [rows_intra, dim] with maskn; lang fp32
+ * [n_samples, dim].  loss_out: device scalar (a SUM over samples).  The same workspace
+ * (vfr_ranking_loss_bytes) must be passed to bwd after fwd.  grad_out: device scalar or NULL (=1). */
+size_t vfr_ranking_loss_bytes(int rows_posit, int rows_intra, int rows_inter, int n_samples);
+int vfr_ranking_loss_fwd(const float* posit, const float* intra, const float* inter, const float* lang,
+                         const int64_t* maskp, const int64_t* maskn, int rows_posit, int rows_intra,
+                         int rows_inter, int n_samples, int dim, int normalize, float b, float lamb,
+                         void* workspace, float* loss_out, vfr_stream_t stream);
+int vfr_ranking_loss_bwd(const float* posit, const float* intra, const float* inter, const float* lang,
+                         const int64_t* maskp, const int64_t* maskn, int rows_posit, int rows_intra,
+                         int rows_inter, int n_samples, int dim, int normalize, float b, float lamb,
+                         void* workspace, const float* grad_out, float* grad_posit, float* grad_intra,
+                         float* grad_inter, float* grad_lang, vfr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,251 @@
+"""GPU parity tests of K1 (pooling), K2 (visual embedding), K3 (query embedding), K6 (ranking loss)
+and of the end-to-end drop-in entry points, against golden outputs of the unmodified reference."""
+import random
+
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import DataLoader
+
+import vfr_b200  # noqa: F401
+from vfr_b200 import data as vdata
+from vfr_b200 import evaluate as vev
+from vfr_b200 import evaluate_single as vsingle
+from vfr_b200 import main as vmain
+from vfr_b200 import models, ops, synth
+from oracle import cal_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _inputs(meta):
+    videos = synth.make_videos(meta["seed"], meta["n_videos"], meta["feat_dim"],
+                               tuple(meta["seg_choices"]), tuple(meta["seg_probs"]))
+    queries = synth.make_queries(meta["seed"], videos, meta["n_queries"], meta["vocab"])
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], spread=meta["spread"])
+    return videos, queries, sd
+
+
+def _model(sd, feat_dim, normalize_lang=False):
+    m = models.CALModel(visual_input_dim=2 * feat_dim + 2, pretrained_emb=torch.from_numpy(sd["word_embedding.weight"]),
+                        normalize_lang=normalize_lang)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return m.to(DEV).eval()
+
+
+def _close(got, want, tol):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= tol * scale, (np.abs(got - want).max(), scale)
+
+
+@pytest.mark.parametrize("case", ["tiny_eval", "long_eval", "val_eval"])
+def test_visual_and_text_embeddings_match_reference(golden, case):
+    z, meta = golden(case)
+    videos, queries, sd = _inputs(meta)
+    model = _model(sd, meta["feat_dim"])
+    feats = torch.from_numpy(np.concatenate([synth.clip_features(v) for v in videos])).to(DEV)
+    with torch.no_grad():
+        vemb = model(feats)
+        qemb = model(torch.from_numpy(queries["tokens"]).to(DEV), False, DEV)
+    _close(vemb.cpu().numpy(), z["video_emb"], 1e-5)
+    _close(qemb.cpu().numpy(), z["query_emb"], 1e-5)
+    # and the scores computed from OUR embeddings stay within the north-star tolerance
+    n_keep = z["scores"].shape[0]
+    got = ops.score_full(ops.Bank(vemb, z["vid_off"]), qemb[:n_keep]).cpu().numpy()
+    assert (np.abs(got - z["scores"]) / z["scores"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("nl", [0, 1])
+def test_text_embed_normalize_lang_variants(golden, nl):
+    z, meta = golden(f"text_nl{nl}")
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], normalize_lang=bool(nl))
+    q = synth.make_queries(meta["seed"], synth.make_videos(meta["seed"], 4, meta["feat_dim"]), meta["n_queries"], meta["vocab"])
+    model = _model(sd, meta["feat_dim"], bool(nl))
+    with torch.no_grad():
+        emb = model(torch.from_numpy(q["tokens"]).to(DEV), False, DEV)
+        one = model(torch.from_numpy(q["tokens"][:1]).to(DEV), False, DEV)   # the reference's batch-1 call
+    _close(emb.cpu().numpy(), z["emb_batch1"], 1e-5)
+    _close(one.cpu().numpy(), z["emb_batch1"][:1], 1e-5)
+    with pytest.raises(IndexError):
+        bad = torch.from_numpy(q["tokens"]).clone()
+        bad[0, 0] = meta["vocab"] + 5
+        model(bad.to(DEV), False, DEV)
+
+
+def test_segment_pooling_matches_reference(golden):
+    z, meta = golden("pool")
+    frames = [synth.make_frames(s, nf, meta["feat_dim"]) for s, nf in zip(meta["frame_seeds"], meta["n_frames"])]
+    for pooling in ("avg", "max"):
+        pooled = vdata.pool_videos(frames, pooling, device=DEV)
+        for i, feats in enumerate(pooled):
+            want_seg, want_ctx = z[f"{pooling}_v{i}_seg"], z[f"{pooling}_v{i}_ctx"]
+            assert feats["num_segments"] == want_seg.shape[0]
+            assert feats["segment_features"].dtype == np.float64 and feats["context_features"].dtype == np.float32
+            np.testing.assert_allclose(feats["segment_features"], want_seg, rtol=2e-6, atol=1e-9)
+            np.testing.assert_allclose(feats["context_features"], want_ctx, rtol=2e-6, atol=1e-9)
+    h5 = [synth.make_frames(s, nf, meta["feat_dim"]) for s, nf in zip(meta["h5_seeds"], meta["h5_n_frames"])]
+    pooled = vdata.pool_videos(h5, "avg", preprocessed=True, device=DEV)
+    for i, feats in enumerate(pooled):
+        np.testing.assert_allclose(feats["segment_features"], z[f"h5_h{i}_seg"], rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(feats["context_features"], z[f"h5_h{i}_ctx"], rtol=2e-6, atol=1e-9)
+
+
+def test_segment_pooling_full_size_vs_oracle():
+    # DiDeMo-sized video: 150 frames x 4096 fc7 features, plus a ragged one and a 5-segment h5 clip
+    frames = [synth.make_frames(1, 150, 4096), synth.make_frames(2, 137, 4096), synth.make_frames(3, 120, 4096)]
+    for pooling in ("avg", "max"):
+        for feats, fr in zip(vdata.pool_videos(frames, pooling, device=DEV), frames):
+            seg, ctx, n = orc.segment_pool(fr, pooling)
+            assert feats["num_segments"] == n
+            np.testing.assert_allclose(feats["segment_features"], seg, rtol=2e-6, atol=1e-9)
+            np.testing.assert_allclose(feats["context_features"], ctx, rtol=2e-6, atol=1e-9)
+    for feats, fr in zip(vdata.pool_videos(frames, preprocessed=True, device=DEV), frames):
+        seg, ctx, n = orc.segment_pool_h5(fr)
+        assert feats["num_segments"] == n == (5 if len(fr) <= 125 else 6)
+        np.testing.assert_allclose(feats["segment_features"], seg, rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(feats["context_features"], ctx, rtol=2e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("norm", [0, 1])
+def test_ranking_loss_forward_backward_match_reference(golden, norm):
+    z, meta = golden("train_step")
+    embs = [torch.from_numpy(z[f"emb_{k}"]).to(DEV).requires_grad_(True) for k in ("posit", "intra", "inter", "lang")]
+    tr = vmain.Trainer(device=DEV, normalize_loss=bool(norm), b=meta["b"], lamb=meta["lamb"])
+    loss, n = tr.ranking_loss(*embs, torch.from_numpy(z["maskp"]).to(DEV), torch.from_numpy(z["maskn"]).to(DEV))
+    assert n == int(z[f"norm{norm}_n"])
+    np.testing.assert_allclose(loss.item(), float(z[f"norm{norm}_loss"]), rtol=2e-6)
+    (2.0 * loss).backward()
+    for k, t in zip(("posit", "intra", "inter", "lang"), embs):
+        want = 2.0 * z[f"norm{norm}_grad_{k}"]
+        _close(t.grad.cpu().numpy(), want, 2e-5)
+
+
+def _dataset(videos, queries, validate=True):
+    ds = vdata.CustomDataset.__new__(vdata.CustomDataset)
+    ds.validate = validate
+    ds.video_features = {v["name"]: v for v in videos}
+    ds.num_segments_info = {v["name"]: v["num_segments"] for v in videos}
+    ds.lang_features = {a: torch.from_numpy(queries["tokens"][i:i + 1]) for i, a in enumerate(queries["annot_id"])}
+    annotations = {a: dict(video=videos[int(queries["video_idx"][i])]["name"], description="", times=queries["times"][i])
+                   for i, a in enumerate(queries["annot_id"])}
+    return ds, annotations
+
+
+def _iters(ds, videos, annotations, max_seg=6):
+    vit = DataLoader(ds, collate_fn=vdata.validate_collate,
+                     batch_sampler=vdata.VideoBatchSampler([v["name"] for v in videos], ds.num_segments_info))
+    lit = DataLoader(ds, collate_fn=vdata.validate_collate,
+                     batch_sampler=vdata.LanguageBatchSampler(annotations, ds.num_segments_info, max_seg))
+    return vit, lit
+
+
+def test_evaluate_drop_in_end_to_end(golden, capsys):
+    """evaluate.evaluate / evaluate_single.evaluate with the reference's signatures, iterators in,
+    metric dicts out - identical to what the unmodified reference returned on the same inputs."""
+    z, meta = golden("tiny_eval")
+    videos, queries, sd = _inputs(meta)
+    model = _model(sd, meta["feat_dim"])
+    ds, annotations = _dataset(videos, queries)
+    vit, lit = _iters(ds, videos, annotations)
+    torch.random.manual_seed(123); random.seed(123); np.random.seed(123)
+    m = vev.evaluate(model, vit, lit, annotations, DEV, preliminary=10, model_types=["model", "chance"])
+    assert {k: {kk: float(vv) for kk, vv in v.items()} for k, v in m.items()} == meta["metrics_corpus"]
+    assert "model, IoU=0.5:" in capsys.readouterr().out
+    prior = synth.make_prior(sorted(set(v["num_segments"] for v in videos)))
+    random.seed(123)
+    m = vsingle.evaluate(model, vit, lit, annotations, DEV, ["model", "chance", "prior"], prior)
+    assert {k: {kk: float(vv) for kk, vv in v.items()} for k, v in m.items()} == meta["metrics_single"]
+    with pytest.raises(IndexError):   # reference quirk: prior[] is indexed unconditionally
+        vsingle.evaluate(model, vit, lit, annotations, DEV)
+
+
+def test_long_video_drop_in(golden):
+    z, meta = golden("long_eval")
+    videos, queries, sd = _inputs(meta)
+    model = _model(sd, meta["feat_dim"])
+    ds, annotations = _dataset(videos, queries)
+    vit, lit = _iters(ds, videos, annotations, max_seg=30)
+    m = vev.evaluate(model, vit, lit, annotations, DEV, preliminary=0)
+    want = {k: v for k, v in meta["metrics_corpus"].items() if k.startswith("model")}
+    got = {k: {kk: float(vv) for kk, vv in v.items()} for k, v in m.items()}
+    for k in want:   # 465 overlapping moments per video: allow the tie range on MR only
+        for kk in ("R@1", "R@10", "R@100"):
+            assert abs(got[k][kk] - want[k][kk]) <= 100.0 / meta["n_queries"] + 1e-9
+        assert abs(got[k]["MR"] - want[k]["MR"]) <= 2
+
+
+def test_training_step_gradients_match_torch_reference(golden):
+    z, meta = golden("train_step")
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], spread=meta["spread"])
+    model = _model(sd, meta["feat_dim"])            # eval(): dropout off, as the golden was produced
+    for p in model.parameters():
+        p.grad = None
+    tr = vmain.Trainer(device=DEV)
+    batch = {k: torch.from_numpy(z[k]) for k in ("posit", "intra", "inter", "lang", "maskp", "maskn")}
+    loss, n = tr.ranking_loss(*tr._embed_batch(model, batch))
+    np.testing.assert_allclose(loss.item(), float(z["norm0_loss"]), rtol=1e-5)
+    loss.backward()
+    # oracle: the same step in plain torch fp32 on the CPU
+    cpu = {k: torch.from_numpy(v.copy()).requires_grad_(k != "word_embedding.weight") for k, v in sd.items()}
+    embs = [orc.visual_embed(cpu, batch[k]) for k in ("posit", "intra", "inter")]
+    lang = orc.text_embed(cpu, batch["lang"])
+    ref_loss, _ = orc.ranking_loss(*embs, lang, batch["maskp"], batch["maskn"])
+    ref_loss.backward()
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        assert p.grad is not None, name
+        _close(p.grad.cpu().numpy(), cpu[name].grad.numpy(), 2e-4)
+
+
+def test_train_and_test_epoch_run(golden):
+    z, meta = golden("train_step")
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], spread=meta["spread"])
+    model = _model(sd, meta["feat_dim"])
+    batch = {k: torch.from_numpy(z[k]) for k in ("posit", "intra", "inter", "lang", "maskp", "maskn")}
+    tr = vmain.Trainer(device=DEV, compute_grads=True)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-3)
+    before = tr.test_epoch(model, [batch])
+    np.testing.assert_allclose(before, float(z["norm0_loss"]) / int(z["norm0_n"]), rtol=1e-5)
+    torch.manual_seed(0)
+    for _ in range(3):
+        tr.train_epoch(model, [batch], opt)
+    after = tr.test_epoch(model, [batch])
+    assert after < before and tr.global_step == 3
+
+
+def test_validate_epoch_matches_oracle(golden):
+    z, meta = golden("tiny_eval")
+    videos, queries, sd = _inputs(meta)
+    model = _model(sd, meta["feat_dim"])
+    ds, annotations = _dataset(videos, queries)
+    vit, lit = _iters(ds, videos, annotations)
+    tr = vmain.Trainer(device=DEV)
+    pr = tr.validate_epoch(model, vit, lit, annotations, size=-1)
+    # oracle: full scores + argsort with the '>=' rule (model/main.py:148-183)
+    off = z["vid_off"]
+    full = orc.score_matrix(z["video_emb"], off, z["query_emb"]).numpy()
+    mom_off = np.concatenate([[0], np.cumsum([len(orc.generate_moments(off[i + 1] - off[i])) for i in range(len(off) - 1)])])
+    thr_range = [i / 10 for i in range(11)]
+    tp = {t: {k: 0 for k in (1, 10, 100)} for t in thr_range}
+    rel = {t: 0 for t in thr_range}
+    ranks = {0.5: [], 0.7: []}
+    for q in range(meta["n_queries"]):
+        v = int(queries["video_idx"][q])
+        order = np.argsort(full[q], kind="stable")
+        for t in thr_range:
+            gt = np.zeros(full.shape[1], dtype=int)
+            gt[mom_off[v]:mom_off[v + 1]] = orc.gt_bits(queries["times"][q], orc.generate_moments(off[v + 1] - off[v]), t, True)
+            pred = gt[order]
+            rel[t] += pred.sum()
+            if t in ranks:
+                ranks[t].append(int(np.where(pred == 1)[0][0]) + 1)
+            for k in tp[t]:
+                tp[t][k] += pred[:k].sum()
+    for k in (1, 10, 100):
+        np.testing.assert_allclose(pr["precision"][k], [tp[t][k] / (k * meta["n_queries"]) for t in thr_range])
+        np.testing.assert_allclose(pr["recall"][k], [tp[t][k] / rel[t] for t in thr_range])
+    assert tr.last_validation["median_rank"][0.5] == ranks[0.5]
+    assert tr.last_validation["median_rank"][0.7] == ranks[0.7]

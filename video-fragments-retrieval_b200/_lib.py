@@ -25,6 +25,7 @@ _p = C.c_void_p
 _i = C.c_int
 _l = C.c_int64
 _z = C.c_size_t
+_f = C.c_float
 
 # name -> (restype, argtypes); kept in the order of include/vfr.h
 PROTOTYPES = {
@@ -44,6 +45,17 @@ PROTOTYPES = {
     "vfr_gt_select": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p, _p]),
     "vfr_rank_order": (_i, [_p, _i, _p, _l, _i, _p, _p]),
     "vfr_single_metrics": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p]),
+    "vfr_linear": (_i, [_p, _l, _i, _i, _p, _p, _i, _i, _p, _i, _p]),
+    "vfr_visual_embed": (_i, [_p, _l, _i, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
+    "vfr_lstm_pack_bytes": (_z, [_i, _i]),
+    "vfr_lstm_pack": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
+    "vfr_text_embed_bytes": (_z, [_l, _i, _i, _i]),
+    "vfr_text_embed": (_i, [_p, _l, _i, _p, _l, _p, _i, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
+    "vfr_segment_pool_bytes": (_z, [_l, _i, _i]),
+    "vfr_segment_pool": (_i, [_p, _p, _l, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "vfr_ranking_loss_bytes": (_z, [_i, _i, _i, _i]),
+    "vfr_ranking_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p]),
+    "vfr_ranking_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

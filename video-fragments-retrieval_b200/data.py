@@ -1,0 +1,184 @@
+"""Feature assembly - drop-in for the hot-path members of the reference's ``model/data.py``.
+
+* ``CustomDataset.load_video_features`` (data.py:142-188)  -> K1 ``vfr_segment_pool`` (one batched
+  device pass over all videos instead of a per-video NumPy loop);
+* ``CustomDataset.make_visual_features`` (data.py:204-213), ``__getitem__`` (data.py:215-246);
+* ``custom_collate`` (data.py:340-356, defines the ``maskp``/``maskn`` layout K6 consumes),
+  ``validate_collate`` (data.py:412-418);
+* ``VideoBatchSampler`` / ``LanguageBatchSampler`` (data.py:359-409) - one video / one query per
+  batch, ``.moments`` table read by ``evaluate``.
+
+Host-side string work is out of scope: the GloVe text-file parser
+``WordIndexer`` (data.py:33-118) and the random negative sampler ``CustomBatchSampler``
+(data.py:249-337) are meant to be reused from the reference unchanged; ``CustomDataset`` here
+accepts any object with the reference's ``items2tensor(list_of_token_lists, max_len)`` method.
+"""
+import re
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch.utils.data.dataset import Dataset
+from torch.utils.data.sampler import BatchSampler
+
+from . import ops
+from .utils import generate_moments
+
+SELECT_FPS = 25
+FRAMES_PER_SEC = 5
+SEC_PER_SEGMENT = 5
+FEATURE_DIM = dict(vgg19=4096, resnet152=2048)
+EMBEDDING_DIM = 100
+_WINDOW = FRAMES_PER_SEC * SEC_PER_SEGMENT
+
+_TOKEN_RE = re.compile(r"('\w )|([\w\d]+)")
+
+
+def tokenize(description):
+    """Query tokeniser of data.py:190-193 (lower-case, alphanumeric runs)."""
+    query = description.rstrip("\n ").lower()
+    return [m[1] for m in _TOKEN_RE.findall(query) if m[1] != ""]
+
+
+def pool_videos(frame_arrays, pooling="avg", preprocessed=False, device="cuda", max_frames_per_call=1 << 16):
+    """K1 over a list of per-video frame arrays ``[F_v, dim]`` -> list of dicts in the reference's
+    ``video_features`` format: ``segment_features`` float64 [n, dim] (fp32 values),
+    ``context_features`` fp32 [dim], ``num_segments``."""
+    mode = "h5" if preprocessed else pooling
+    if mode not in ops.POOL_MODES:
+        raise KeyError(pooling)
+    out = []
+    i = 0
+    while i < len(frame_arrays):
+        j, tot = i, 0
+        while j < len(frame_arrays) and (j == i or tot + len(frame_arrays[j]) <= max_frames_per_call):
+            tot += len(frame_arrays[j])
+            j += 1
+        chunk = [np.ascontiguousarray(a, dtype=np.float32).reshape(len(a), -1) for a in frame_arrays[i:j]]
+        off = np.concatenate([[0], np.cumsum([len(a) for a in chunk])])
+        frames = torch.from_numpy(np.concatenate(chunk)).to(device, non_blocking=True)
+        seg, ctx, n_seg = ops.segment_pool(frames, off, mode, _WINDOW)
+        seg, ctx, n_seg = seg.cpu().numpy(), ctx.cpu().numpy(), n_seg.cpu().numpy()
+        for k in range(j - i):
+            n = int(n_seg[k])
+            out.append(dict(segment_features=seg[k, :n].astype(np.float64), context_features=ctx[k].copy(),
+                            num_segments=n))
+        i = j
+    return out
+
+
+class CustomDataset(Dataset):
+    """Same constructor and item format as the reference's ``CustomDataset`` (data.py:121-246)."""
+
+    def __init__(self, videos, annotations, ft_directory, ft_type, word_indexer=None, bert_tokenizer=None,
+                 bert_model=None, validate=False, max_query_len=20, pooling="avg", prep=False, device="cuda"):
+        self.word_indexer = word_indexer
+        self.bert_tokenizer = bert_tokenizer
+        self.bert_model = bert_model
+        self.max_query_len = max_query_len
+        self.ft_directory = ft_directory
+        self.ft_type = ft_type
+        self.validate = validate
+        self.pooling = pooling
+        self.preprocessed = prep
+        self.device = device
+        self.num_segments_info = {}
+        self.video_features = {}
+        self.load_video_features(videos)
+        self.lang_features = {}
+        self.load_lang_features(annotations)
+
+    def _read_frames(self, video):
+        if self.preprocessed:
+            import h5py  # only needed for MCN's released .h5 features (data.py:144-148)
+            with h5py.File(Path(self.ft_directory).joinpath(f"fc7_subsample5_fps25_{video}.h5")) as f:
+                return np.array(f["features"])
+        arr = np.load(Path(self.ft_directory).joinpath(f"features_{self.ft_type}/{self.ft_type}_ft_{video}.npy"))
+        return arr.reshape((arr.shape[0], FEATURE_DIM[self.ft_type]))
+
+    def load_video_features(self, videos):
+        videos = list(videos)
+        pooled = pool_videos([self._read_frames(v) for v in videos], self.pooling, self.preprocessed, self.device)
+        for video, feats in zip(videos, pooled):
+            self.video_features[video] = feats
+            self.num_segments_info[video] = feats["num_segments"]
+
+    def load_lang_features(self, annotations):
+        for annot_id, info in annotations.items():
+            words = tokenize(info["description"])
+            if self.word_indexer is not None:
+                self.lang_features[annot_id] = self.word_indexer.items2tensor([words], self.max_query_len)
+            elif self.bert_tokenizer is not None:
+                with torch.no_grad():
+                    tokens = self.bert_tokenizer.encode_plus(" ".join(words), return_tensors="pt")
+                    self.lang_features[annot_id] = self.bert_model(**tokens)[1]
+
+    def make_visual_features(self, video, start_t, end_t):
+        """``[segment | context | (i/n, (i+1)/n)]`` rows for clips start_t..end_t (data.py:204-213)."""
+        info = self.video_features[video]
+        n = info["num_segments"]
+        seg = torch.from_numpy(info["segment_features"][start_t:end_t + 1]).float()
+        ctx = torch.from_numpy(np.asarray(info["context_features"]).reshape(1, -1)).float().expand(seg.size(0), -1)
+        left = torch.arange(start_t, end_t + 1).view(-1, 1)
+        tef = torch.cat([left, left + 1], dim=1).float() / n
+        return torch.cat([seg, ctx, tef], dim=1)
+
+    def __getitem__(self, sample):
+        if self.validate:
+            if "annotation_id" in sample:
+                return dict(features=self.lang_features[sample["annotation_id"]], video=sample["video_pos"],
+                            annot_id=sample["annotation_id"])
+            return dict(features=self.make_visual_features(sample["video_pos"], sample["start_t"], sample["end_t"]),
+                        video=sample["video_pos"])
+        return dict(
+            posit=self.make_visual_features(sample["video_pos"], sample["start_t"], sample["end_t"]),
+            intra=self.make_visual_features(sample["video_pos"], sample["start_tn"], sample["end_tn"]),
+            inter=self.make_visual_features(sample["video_neg"], sample["start_t"], sample["end_t"]),
+            lang=self.lang_features[sample["annotation_id"]])
+
+
+def custom_collate(batch):
+    """Training collate (data.py:340-356): rows of ``posit``/``inter`` belong to sample
+    ``maskp[r]``, rows of ``intra`` to ``maskn[r]``; runs are contiguous and ascending."""
+    keys = ("posit", "intra", "inter", "lang")
+    cat = {k: torch.cat([s[k] for s in batch], dim=0) for k in keys}
+    cat["maskp"] = torch.LongTensor([i for i, s in enumerate(batch) for _ in range(s["posit"].size(0))])
+    cat["maskn"] = torch.LongTensor([i for i, s in enumerate(batch) for _ in range(s["intra"].size(0))])
+    return cat
+
+
+def validate_collate(batch):
+    """Evaluation collate (data.py:412-418): batches hold exactly one video or one query."""
+    item = batch[0]
+    return dict(feature=item["features"], video=item["video"], annot_id=item.get("annot_id", []))
+
+
+class VideoBatchSampler(BatchSampler):
+    """One whole video per batch (data.py:359-379)."""
+
+    def __init__(self, videos, num_segments_info):
+        self.videos = videos
+        self.num_segments_info = num_segments_info
+
+    def __iter__(self):
+        for video in self.videos:
+            yield [dict(video_pos=video, start_t=0, end_t=self.num_segments_info[video] - 1)]
+
+    def __len__(self):
+        return len(self.videos)
+
+
+class LanguageBatchSampler(BatchSampler):
+    """One query per batch; ``moments[n]`` is the candidate table (data.py:382-409)."""
+
+    def __init__(self, annotations, num_segments_info, max_segments=6):
+        self.annotations = annotations
+        self.num_segments_info = num_segments_info
+        self.moments = {n: generate_moments(n) for n in range(max_segments + 1)}
+
+    def __iter__(self):
+        for annot_id, info in self.annotations.items():
+            yield [dict(annotation_id=annot_id, video_pos=info["video"])]
+
+    def __len__(self):
+        return len(self.annotations)

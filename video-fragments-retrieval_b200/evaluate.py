@@ -63,7 +63,7 @@ def collect_embeddings(model, video_iterator, lang_iterator, device, rows_per_ca
     return bank, names, q_emb.float().contiguous(), q_names, q_annots
 
 
-def rank_first_positive(bank, q_emb, q_video, times_list, iou_thresholds, inclusive=False):
+def rank_first_positive(bank, q_emb, q_video, times_list, iou_thresholds, inclusive=False, want_topk=0):
     """The scoring core shared by ``evaluate`` and ``Trainer.validate_epoch``.
 
     Returns dict with host arrays: ``rank`` int64 [Q, T] (0-based position of the first positive in
@@ -78,7 +78,18 @@ def rank_first_positive(bank, q_emb, q_video, times_list, iou_thresholds, inclus
     gt, tau, pos, npos, own_eqb = ops.gt_select(own, q_nseg, times, tables)
     lt, eqb = ops.score_count(bank, q_emb, tau, q_video_t)
     rank = lt + eqb + own_eqb.to(torch.int64)
-    return dict(rank=rank.cpu().numpy(), rank_lo=lt.cpu().numpy(), npos=npos.cpu().numpy(),
+    extra = {}
+    if want_topk:
+        # which of the global top-k moments are positives (validate_epoch's precision/recall counts,
+        # main.py:179-183): positives only exist inside the query's own video
+        _, ids = ops.score_topk(bank, q_emb, int(want_topk))
+        base = torch.as_tensor(bank.mom_off_host[np.asarray(q_video)], device=dev).view(-1, 1)
+        rel = ids - base
+        m_own = (q_nseg.to(torch.int64) * (q_nseg.to(torch.int64) + 1) // 2).view(-1, 1)
+        inside = (ids >= 0) & (rel >= 0) & (rel < m_own)
+        idx = rel.clamp(0, gt.shape[2] - 1).unsqueeze(1).expand(-1, gt.shape[1], -1)
+        extra["topk_hits"] = (torch.gather(gt, 2, idx).bool() & inside.unsqueeze(1)).cpu().numpy()
+    return dict(**extra, rank=rank.cpu().numpy(), rank_lo=lt.cpu().numpy(), npos=npos.cpu().numpy(),
                 gt=gt.cpu().numpy(), own=own.cpu().numpy(), pos=pos.cpu().numpy(), tau=tau.cpu().numpy())
 
 

@@ -1,0 +1,143 @@
+"""``CALModel`` - drop-in for the reference's ``model/models.py:12-68``.
+
+Same constructor signature, same sub-module names (so the reference's ``state_dict`` /
+``last.pth`` checkpoints load unchanged: ``visual_fc.0.weight [500, 2F+2]``, ``visual_fc.2.weight``,
+``word_embedding.weight``, ``lstm.weight_ih_l0`` ... ``lstm.bias_hh_l0_reverse``, ``lang_fc.weight``,
+``learnable_length.weight``), same ``forward(batch, visual=True, device=None, bert=False)``.
+The ``nn`` modules are parameter containers only: the forward pass runs the hand-written kernels
+(K2 ``vfr_visual_embed``, K3 ``vfr_text_embed``) on CUDA tensors and raises on CPU tensors.
+
+Backward (training, SURVEY.md 8(f) item 2 - "next"): gradients of the two embedding branches are
+obtained by re-running the branch with stock torch CUDA ops inside ``backward`` (activation
+recompute); the ranking loss itself has hand-written forward AND backward kernels (K6).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+EMBEDDING_DIM = 100   # reference model/data.py:30 (GloVe dim and joint-space dim)
+
+
+def init_weights(m):
+    """U(-0.08, 0.08) weights and zero bias for Linear layers (reference model/models.py:7-10)."""
+    if isinstance(m, nn.Linear):
+        nn.init.uniform_(m.weight, -0.08, 0.08)
+        nn.init.constant_(m.bias, 0)
+
+
+class _VisualEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        ctx.save_for_backward(x, w1, b1, w2, b2)
+        return ops.visual_embed(x, w1, b1, w2, b2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, w1, b1, w2, b2 = ctx.saved_tensors
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(t.requires_grad) for t in (x, w1, b1, w2, b2)]
+            out = F.linear(torch.relu(F.linear(leaves[0].float(), leaves[1], leaves[2])), leaves[3], leaves[4])
+            need = [t for t in leaves if t.requires_grad]
+            grads = iter(torch.autograd.grad(out, need, grad))
+        return tuple(next(grads) if t.requires_grad else None for t in leaves)
+
+
+class _TextEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, tokens, *params):
+        ctx.model = model
+        ctx.tokens = tokens
+        return model._text_forward_kernels(tokens)
+
+    @staticmethod
+    def backward(ctx, grad):
+        model = ctx.model
+        with torch.enable_grad():
+            out = model._text_forward_torch(ctx.tokens)
+            params = [p for p in model._text_params()]
+            need = [p for p in params if p.requires_grad]
+            grads = iter(torch.autograd.grad(out, need, grad, allow_unused=True))
+        return (None, None) + tuple(next(grads) if p.requires_grad else None for p in params)
+
+
+class CALModel(nn.Module):
+
+    def __init__(self, visual_input_dim, pretrained_emb=None, emb_dim=EMBEDDING_DIM, hidden_size=1000, bert_emb=768,
+                 dropout_rate=0.3, normalize_lang=False):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.normalize_lang = normalize_lang
+        # creation order == the reference's, so a fixed torch seed gives the same initial weights
+        self.visual_fc = nn.Sequential(
+            nn.Linear(visual_input_dim, 500), nn.ReLU(), nn.Linear(500, emb_dim), nn.Dropout(p=dropout_rate))
+        self.visual_fc.apply(init_weights)
+        if pretrained_emb is None:      # BERT-pooled queries: a single projection (models.py:30-31)
+            self.lang_fc = nn.Linear(bert_emb, emb_dim)
+        else:                           # GloVe + BiLSTM (models.py:33-48)
+            self.word_embedding = nn.Embedding.from_pretrained(pretrained_emb, freeze=True, padding_idx=0)
+            if normalize_lang:
+                self.learnable_length = nn.Embedding.from_pretrained(
+                    torch.ones(pretrained_emb.size(0), 1), freeze=False, padding_idx=0)
+            self.lstm = nn.LSTM(input_size=pretrained_emb.size(1), hidden_size=hidden_size, num_layers=1,
+                                batch_first=True, bidirectional=True)
+            self.lang_fc = nn.Linear(hidden_size * 2, emb_dim)
+            self.lang_fc.apply(init_weights)
+        self._packed = None   # (version key, packed fwd, packed bwd)
+
+    def init_hidden(self, batch_size, device):
+        """Zero (h0, c0) of the BiLSTM (models.py:50-52); the kernels start from zeros implicitly."""
+        shape = (2, batch_size, self.hidden_size)
+        return [torch.zeros(shape, device=device), torch.zeros(shape, device=device)]
+
+    # -- text branch -------------------------------------------------------------------------
+    def _text_params(self):
+        ps = [self.lstm.weight_ih_l0, self.lstm.weight_hh_l0, self.lstm.bias_ih_l0, self.lstm.bias_hh_l0,
+              self.lstm.weight_ih_l0_reverse, self.lstm.weight_hh_l0_reverse, self.lstm.bias_ih_l0_reverse,
+              self.lstm.bias_hh_l0_reverse, self.lang_fc.weight, self.lang_fc.bias]
+        if self.normalize_lang:
+            ps.append(self.learnable_length.weight)
+        return ps
+
+    def _packed_lstm(self):
+        ps = self._text_params()[:8]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key, ops.lstm_pack(*[p.detach() for p in ps[:4]]), ops.lstm_pack(*[p.detach() for p in ps[4:]]))
+        return self._packed[1], self._packed[2]
+
+    def _text_forward_kernels(self, tokens):
+        fwd, bwd = self._packed_lstm()
+        length = self.learnable_length.weight.detach() if self.normalize_lang else None
+        return ops.text_embed(tokens, self.word_embedding.weight.detach(), length, fwd, bwd, self.hidden_size,
+                              self.lang_fc.weight.detach(), self.lang_fc.bias.detach())
+
+    def _text_forward_torch(self, tokens):
+        # stock-torch re-execution used only inside backward (activation recompute)
+        embedded = self.word_embedding(tokens)
+        if self.normalize_lang:
+            embedded = embedded.div(embedded.norm(dim=-1, keepdim=True) + 1e-5) * self.learnable_length(tokens)
+        _, hidden = self.lstm(embedded)
+        return self.lang_fc(hidden[0].transpose(0, 1).reshape(tokens.size(0), 2 * self.hidden_size))
+
+    # -- forward -----------------------------------------------------------------------------
+    def forward(self, batch, visual=True, device=None, bert=False):
+        if not batch.is_cuda:
+            raise RuntimeError("vfr_b200.CALModel runs on CUDA tensors only (no CPU fallback): move the model "
+                               "and the batch to a B200 device")
+        if visual:
+            lin1, lin2, drop = self.visual_fc[0], self.visual_fc[2], self.visual_fc[3]
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.visual_fc.parameters()):
+                out = _VisualEmbed.apply(batch, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+            else:
+                out = ops.visual_embed(batch, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+            return drop(out)            # identity in eval mode; torch RNG mask in train mode (models.py:25)
+        if bert:
+            if torch.is_grad_enabled() and self.lang_fc.weight.requires_grad:
+                return F.linear(batch, self.lang_fc.weight, self.lang_fc.bias)
+            return ops.linear(batch, self.lang_fc.weight, self.lang_fc.bias)
+        params = self._text_params()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _TextEmbed.apply(self, batch, *params)
+        return self._text_forward_kernels(batch)

@@ -190,3 +190,142 @@ def single_metrics(order, q_nseg, times, tables):
     _lib.call("vfr_single_metrics", _ptr(order.contiguous()), ms, _ptr(q_nseg), _ptr(times), A, _ptr(tables), T, Q,
               _ptr(ranks), _ptr(ti), _ptr(tu), _ptr(fp), _stream())
     return ranks, ti, tu, fp
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 / K3 : embeddings
+# ---------------------------------------------------------------------------------------------
+def linear(x, weight, bias=None, relu=False):
+    """fp32 ``x @ weight.T + bias`` (optionally ReLU) through vfr_linear."""
+    _need_cuda(x, weight, bias)
+    x = _f32c(x)
+    w = _f32c(weight)
+    b = None if bias is None else _f32c(bias)
+    out = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+    _lib.call("vfr_linear", _ptr(x), x.shape[0], x.shape[1], x.shape[1], _ptr(w), _ptr(b), w.shape[0],
+              int(bool(relu)), _ptr(out), w.shape[0], _stream())
+    return out
+
+
+def visual_embed(x, w1, b1, w2, b2, return_hidden=False):
+    """K2: relu(x W1^T + b1) W2^T + b2 (reference model/models.py:21-26,56, eval mode)."""
+    _need_cuda(x, w1, b1, w2, b2)
+    x = _f32c(x)
+    if x.dim() != 2 or x.shape[1] != w1.shape[1]:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x.shape)} and {tuple(w1.t().shape)})")
+    w1, b1, w2, b2 = (_f32c(t) for t in (w1, b1, w2, b2))
+    n = x.shape[0]
+    hidden = torch.empty((n, w1.shape[0]), dtype=torch.float32, device=x.device)
+    out = torch.empty((n, w2.shape[0]), dtype=torch.float32, device=x.device)
+    if n:
+        _lib.call("vfr_visual_embed", _ptr(x), n, x.shape[1], _ptr(w1), _ptr(b1), w1.shape[0], _ptr(w2), _ptr(b2),
+                  w2.shape[0], _ptr(hidden), _ptr(out), _stream())
+    return (out, hidden) if return_hidden else out
+
+
+def lstm_pack(w_ih, w_hh, b_ih, b_hh):
+    """Re-layout of one LSTM direction for vfr_text_embed (once per weight update)."""
+    _need_cuda(w_ih, w_hh, b_ih, b_hh)
+    H, E = w_hh.shape[1], w_ih.shape[1]
+    nbytes = _lib.load().vfr_lstm_pack_bytes(H, E)
+    packed = torch.empty(nbytes // 4, dtype=torch.float32, device=w_ih.device)
+    _lib.call("vfr_lstm_pack", _ptr(_f32c(w_ih)), _ptr(_f32c(w_hh)), _ptr(_f32c(b_ih)), _ptr(_f32c(b_hh)), H, E,
+              _ptr(packed), _stream())
+    return packed
+
+
+def text_embed(tokens, table, length_table, packed_fwd, packed_bwd, hidden, fc_w, fc_b, check_tokens=True,
+               max_batch=8192):
+    """K3: tokens int64 [B, L] -> fp32 [B, D] (reference model/models.py:61-66)."""
+    _need_cuda(tokens, table, packed_fwd, packed_bwd, fc_w, fc_b)
+    tokens = tokens.to(torch.int64).contiguous()
+    B, L = tokens.shape
+    table = _f32c(table)
+    E = table.shape[1]
+    lt = None if length_table is None else _f32c(length_table).reshape(-1)
+    fc_w, fc_b = _f32c(fc_w), _f32c(fc_b)
+    D = fc_w.shape[0]
+    out = torch.empty((B, D), dtype=torch.float32, device=tokens.device)
+    for b0 in range(0, B, max_batch):
+        nb = min(max_batch, B - b0)
+        nbytes = _lib.load().vfr_text_embed_bytes(nb, L, hidden, E)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=tokens.device)
+        _lib.call("vfr_text_embed", _ptr(tokens[b0:b0 + nb]), nb, L, _ptr(table), table.shape[0], _ptr(lt), E,
+                  _ptr(packed_fwd), _ptr(packed_bwd), hidden, _ptr(fc_w), _ptr(fc_b), D, _ptr(ws),
+                  _ptr(out[b0:b0 + nb]), _stream())
+        if check_tokens and int(ws[-4:].view(torch.int32)[0].item()) != 0:
+            raise IndexError("index out of range in self")   # what nn.Embedding raises in the reference
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 : frame -> segment pooling
+# ---------------------------------------------------------------------------------------------
+POOL_MODES = {"avg": 0, "max": 1, "h5": 2}
+
+
+def segment_pool(frames, frame_off, mode="avg", window=25, seg_stride=None):
+    """K1: frames fp32 [sum F, dim] + int64 offsets [V+1] -> (seg [V, S, dim], ctx [V, dim], n_seg [V])."""
+    _need_cuda(frames)
+    frames = _f32c(frames)
+    fo = np.asarray(frame_off, dtype=np.int64)
+    V = len(fo) - 1
+    dim = frames.shape[1]
+    counts = np.diff(fo)
+    if (counts < 1).any() or fo[-1] != frames.shape[0]:
+        raise ValueError("frame_off must be increasing offsets covering all frames")
+    if seg_stride is None:
+        seg_stride = 6 if mode == "h5" else int(-(-counts.max() // window))
+    if seg_stride > MAX_SEGMENTS:
+        raise _lib.VfrError(f"videos with more than {MAX_SEGMENTS} segments are not supported")
+    dev = frames.device
+    fo_d = torch.from_numpy(fo).to(dev)
+    seg = torch.empty((V, seg_stride, dim), dtype=torch.float32, device=dev)
+    ctx = torch.empty((V, dim), dtype=torch.float32, device=dev)
+    n_seg = torch.empty(V, dtype=torch.int32, device=dev)
+    ws = torch.empty(_lib.load().vfr_segment_pool_bytes(V, dim, seg_stride) // 4, dtype=torch.float32, device=dev)
+    _lib.call("vfr_segment_pool", _ptr(frames), _ptr(fo_d), V, dim, window, POOL_MODES[mode], _ptr(seg), seg_stride,
+              _ptr(ctx), _ptr(n_seg), _ptr(ws), _stream())
+    return seg, ctx, n_seg
+
+
+# ---------------------------------------------------------------------------------------------
+# K6 : ranking loss
+# ---------------------------------------------------------------------------------------------
+class _RankingLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, posit, intra, inter, lang, maskp, maskn, n_samples, normalize, b, lamb):
+        _need_cuda(posit, intra, inter, lang, maskp, maskn)
+        posit, intra, inter, lang = (_f32c(t) for t in (posit, intra, inter, lang))
+        maskp = maskp.to(torch.int64).contiguous()
+        maskn = maskn.to(torch.int64).contiguous()
+        if lang.shape[0] < n_samples:
+            raise IndexError(f"index {lang.shape[0]} is out of bounds for dimension 0 with size {lang.shape[0]}")
+        dim = posit.shape[1]
+        nbytes = _lib.load().vfr_ranking_loss_bytes(posit.shape[0], intra.shape[0], inter.shape[0], n_samples)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=posit.device)
+        loss = torch.empty((), dtype=torch.float32, device=posit.device)
+        _lib.call("vfr_ranking_loss_fwd", _ptr(posit), _ptr(intra), _ptr(inter), _ptr(lang), _ptr(maskp), _ptr(maskn),
+                  posit.shape[0], intra.shape[0], inter.shape[0], n_samples, dim, int(bool(normalize)), float(b),
+                  float(lamb), _ptr(ws), _ptr(loss), _stream())
+        ctx.save_for_backward(posit, intra, inter, lang, maskp, maskn, ws)
+        ctx.cfg = (n_samples, int(bool(normalize)), float(b), float(lamb), lang.shape[0])
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        posit, intra, inter, lang, maskp, maskn, ws = ctx.saved_tensors
+        n_samples, normalize, b, lamb, n_lang = ctx.cfg
+        dim = posit.shape[1]
+        go = _f32c(grad_out).reshape(1)
+        gp, gn, gi = torch.empty_like(posit), torch.empty_like(intra), torch.empty_like(inter)
+        gl = torch.zeros_like(lang)
+        _lib.call("vfr_ranking_loss_bwd", _ptr(posit), _ptr(intra), _ptr(inter), _ptr(lang), _ptr(maskp), _ptr(maskn),
+                  posit.shape[0], intra.shape[0], inter.shape[0], n_samples, dim, normalize, b, lamb, _ptr(ws),
+                  _ptr(go), _ptr(gp), _ptr(gn), _ptr(gi), _ptr(gl), _stream())
+        return gp, gn, gi, gl, None, None, None, None, None, None
+
+
+def ranking_loss(posit, intra, inter, lang, maskp, maskn, n_samples, normalize=False, b=0.1, lamb=0.4):
+    """K6 (reference model/main.py:214-232): differentiable scalar loss (a sum over samples)."""
+    return _RankingLoss.apply(posit, intra, inter, lang, maskp, maskn, int(n_samples), normalize, b, lamb)
