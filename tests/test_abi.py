@@ -35,7 +35,7 @@ def test_argument_errors_are_reported_not_thrown():
     lib = _lib.load()
     assert lib.vfr_version() >= 100
     assert lib.vfr_bank_pack_bytes(10, 64, 100) == 0          # n_max > 32: unsupported
-    assert lib.vfr_bank_pack_bytes(16, 6, 100) == 5 * 20 * 96 * 4
+    assert lib.vfr_bank_pack_bytes(16, 6, 100) == (5 * 20 * 96 + 96) * 4
     rc = lib.vfr_bank_pack(None, None, 10, 6, 100, None, None)
     assert rc == -1 and b"null" in lib.vfr_last_error()
     with pytest.raises(_lib.VfrError):

@@ -5,12 +5,15 @@
 //
 // Layout (B200-first): both operands are pre-packed k-major in HBM so that one pipeline stage =
 // one contiguous block moved by a single cp.async.bulk (UBLKCP) onto an mbarrier:
-//   bank  packed [tile][kchunk][KC][96]   (value = v + 1e-6, the pairwise_distance eps folded in)
-//   query packed [qtile][kchunk][KC][128]
+//   bank  packed [tile][kchunk][KC][96]   then [tile][96]  row sums  (sum_k v_k)
+//   query packed [qtile][kchunk][KC][128] then [qtile][128] row sums (sum_k q_k)
 // A CTA owns one 128-query tile and walks a contiguous range of bank tiles; 256 threads each keep
-// an 8-query x 6-clip block of squared distances in registers (direct-difference form
-// (v+eps-q)^2, one FADD + one FFMA per element, k strictly sequential so every mode and
-// vfr_score_own produce bit-identical values).  After the last k-chunk the distances go through
+// an 8-query x 6-clip block of squared distances in registers.  Direct-difference form: with
+// delta = v - q (exact for near-duplicates, unlike the GEMM expansion),
+//   sum_k (delta_k + eps)^2 = sum_k delta_k^2 + 2 eps (sum_k v_k - sum_k q_k) + D eps^2,
+// so the inner loop is one FADD + one FFMA per element and the pairwise_distance eps enters as a
+// per-pair correction from the pre-computed row sums.  k is strictly sequential, so every mode and
+// vfr_score_own produce bit-identical values.  After the last k-chunk the distances go through
 // shared memory to the moment phase, where a thread owns ONE query (so count / top-k state is
 // thread-private: no atomics in the loop) and walks the tile's videos.
 #include "vfr_common.cuh"
@@ -36,6 +39,9 @@ enum Mode { MODE_FULL = 0, MODE_COUNT = 1, MODE_TOPK = 2 };
 struct ScoreParams {
   const float* bank_packed;
   const float* query_packed;
+  const float* bank_rowsum;   // [n_tiles][96]
+  const float* query_rowsum;  // [q_tiles][128]
+  float deps2;                // D * eps^2
   const int32_t* vid_off;
   const int64_t* mom_off;
   int64_t n_videos;
@@ -65,8 +71,22 @@ static inline int nkc_of(int dim) { return (dim + KC - 1) / KC; }
 // ---------------------------------------------------------------------------------------------
 // packing
 // ---------------------------------------------------------------------------------------------
+// sequential fp32 row sum: the same loop in the pack kernels and in score_own (bit-identical)
+__device__ __forceinline__ float row_sum(const float* __restrict__ r, int dim) {
+  float s = 0.f;
+  for (int k = 0; k < dim; ++k) s = __fadd_rn(s, r[k]);
+  return s;
+}
+
+// d^2 from sum delta^2 and the row sums (see the header comment)
+__device__ __forceinline__ float dist_from(float s2, float sv, float sq, float deps2) {
+  const float corr = __fmaf_rn(2.f * VFR_PAIRWISE_EPS, __fsub_rn(sv, sq), deps2);
+  return __fsqrt_rn(fmaxf(__fadd_rn(s2, corr), 0.f));
+}
+
 __global__ void pack_bank_kernel(const float* __restrict__ bank, const int32_t* __restrict__ vid_off,
-                                 int64_t n_videos, int vt, int dim, int nkc, float* __restrict__ packed) {
+                                 int64_t n_videos, int vt, int dim, int nkc, float* __restrict__ packed,
+                                 float* __restrict__ rowsum) {
   const int64_t tile = blockIdx.x;
   const int64_t v0 = tile * vt;
   const int64_t v1 = min(v0 + (int64_t)vt, n_videos);
@@ -78,13 +98,17 @@ __global__ void pack_bank_kernel(const float* __restrict__ bank, const int32_t* 
     const int col = i % TC;
     const int k = i / TC;
     float val = 0.f;
-    if (col < ncols && k < dim) val = __fadd_rn(__ldg(bank + (c0 + col) * dim + k), VFR_PAIRWISE_EPS);
+    if (col < ncols && k < dim) val = __ldg(bank + (c0 + col) * dim + k);
     dst[i] = val;  // [k][col] with k = chunk*KC + kk : chunks are contiguous
+  }
+  if (threadIdx.x < TC) {
+    const int col = threadIdx.x;
+    rowsum[tile * TC + col] = (col < ncols) ? row_sum(bank + (c0 + col) * dim, dim) : 0.f;
   }
 }
 
 __global__ void pack_query_kernel(const float* __restrict__ q, int64_t n_queries, int dim, int nkc,
-                                  float* __restrict__ packed) {
+                                  float* __restrict__ packed, float* __restrict__ rowsum) {
   const int64_t tile = blockIdx.x;
   float* dst = packed + tile * (int64_t)nkc * Q_STAGE;
   const int total = nkc * KC * TQ;
@@ -93,6 +117,10 @@ __global__ void pack_query_kernel(const float* __restrict__ q, int64_t n_queries
     const int k = i / TQ;
     const int64_t qi = tile * TQ + row;
     dst[i] = (qi < n_queries && k < dim) ? __ldg(q + qi * dim + k) : 0.f;
+  }
+  if (threadIdx.x < TQ) {
+    const int64_t qi = tile * TQ + threadIdx.x;
+    rowsum[tile * TQ + threadIdx.x] = (qi < n_queries) ? row_sum(q + qi * dim, dim) : 0.f;
   }
 }
 
@@ -288,11 +316,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) score_kernel(const ScoreParams p)
     }
 
     // ---- distances of this tile -> shared ----
+    {
+      const int tile_e = tile_begin + it / p.nkc;
+      float sv[6];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int ql = (i < 4) ? (4 * tq + i) : (64 + 4 * tq + (i - 4));
+      for (int j = 0; j < 6; ++j) sv[j] = __ldg(p.bank_rowsum + (int64_t)tile_e * TC + 6 * tc + j);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) ds[ql * DS_LD + 6 * tc + j] = __fsqrt_rn(acc[i][j]);
+      for (int i = 0; i < 8; ++i) {
+        const int ql = (i < 4) ? (4 * tq + i) : (64 + 4 * tq + (i - 4));
+        const float sq = __ldg(p.query_rowsum + (int64_t)qtile * TQ + ql);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ds[ql * DS_LD + 6 * tc + j] = dist_from(acc[i][j], sv[j], sq, p.deps2);
+      }
     }
     __syncthreads();  // ds complete; also releases stage s
 
@@ -372,10 +407,10 @@ __global__ void score_own_kernel(const float* __restrict__ bank, const int32_t* 
       const float* qr = queries + q * dim;
       float acc = 0.f;
       for (int k = 0; k < dim; ++k) {
-        const float diff = __fsub_rn(__fadd_rn(vr[k], VFR_PAIRWISE_EPS), qr[k]);
+        const float diff = __fsub_rn(vr[k], qr[k]);
         acc = __fmaf_rn(diff, diff, acc);
       }
-      d[ql][c] = __fsqrt_rn(acc);
+      d[ql][c] = dist_from(acc, row_sum(vr, dim), row_sum(qr, dim), (float)dim * VFR_PAIRWISE_EPS * VFR_PAIRWISE_EPS);
     }
   }
   __syncthreads();
@@ -538,7 +573,7 @@ using namespace vfr;
 extern "C" size_t vfr_bank_pack_bytes(int64_t n_videos, int n_max, int dim) {
   int vt, nt, nkc;
   if (plan(n_videos, n_max, dim, vt, nt, nkc) != VFR_OK) return 0;
-  return (size_t)nt * nkc * V_STAGE * sizeof(float);
+  return ((size_t)nt * nkc * V_STAGE + (size_t)nt * TC) * sizeof(float);
 }
 
 extern "C" int vfr_bank_pack(const float* bank, const int32_t* vid_off, int64_t n_videos, int n_max, int dim,
@@ -547,13 +582,15 @@ extern "C" int vfr_bank_pack(const float* bank, const int32_t* vid_off, int64_t 
   int vt, nt, nkc;
   int rc = plan(n_videos, n_max, dim, vt, nt, nkc);
   if (rc) return rc;
-  pack_bank_kernel<<<nt, 256, 0, (cudaStream_t)stream>>>(bank, vid_off, n_videos, vt, dim, nkc, packed);
+  pack_bank_kernel<<<nt, 256, 0, (cudaStream_t)stream>>>(bank, vid_off, n_videos, vt, dim, nkc, packed,
+                                                         packed + (size_t)nt * nkc * V_STAGE);
   return check_launch("pack_bank_kernel");
 }
 
 extern "C" size_t vfr_query_pack_bytes(int64_t n_queries, int dim) {
   if (n_queries <= 0 || dim <= 0) return 0;
-  return (size_t)((n_queries + TQ - 1) / TQ) * nkc_of(dim) * Q_STAGE * sizeof(float);
+  const size_t qt = (size_t)((n_queries + TQ - 1) / TQ);
+  return (qt * nkc_of(dim) * Q_STAGE + qt * TQ) * sizeof(float);
 }
 
 extern "C" int vfr_query_pack(const float* queries, int64_t n_queries, int dim, float* packed, vfr_stream_t stream) {
@@ -561,7 +598,8 @@ extern "C" int vfr_query_pack(const float* queries, int64_t n_queries, int dim, 
   VFR_REQUIRE(n_queries > 0 && dim > 0 && dim <= 8192, VFR_ERR_INVALID, "vfr_query_pack: bad shape");
   const int64_t qt = (n_queries + TQ - 1) / TQ;
   VFR_REQUIRE(qt < (int64_t(1) << 31), VFR_ERR_UNSUPPORTED, "too many query tiles");
-  pack_query_kernel<<<(int)qt, 256, 0, (cudaStream_t)stream>>>(queries, n_queries, dim, nkc_of(dim), packed);
+  pack_query_kernel<<<(int)qt, 256, 0, (cudaStream_t)stream>>>(queries, n_queries, dim, nkc_of(dim), packed,
+                                                               packed + (size_t)qt * nkc_of(dim) * Q_STAGE);
   return check_launch("pack_query_kernel");
 }
 
@@ -583,6 +621,9 @@ static int fill_common(ScoreParams& p, const float* bank_packed, const int32_t* 
   p.vt = vt;
   p.n_tiles = nt;
   p.nkc = nkc;
+  p.bank_rowsum = bank_packed + (size_t)nt * nkc * V_STAGE;
+  p.query_rowsum = query_packed + (size_t)((n_queries + TQ - 1) / TQ) * nkc * Q_STAGE;
+  p.deps2 = (float)dim * VFR_PAIRWISE_EPS * VFR_PAIRWISE_EPS;
   return VFR_OK;
 }
 

@@ -118,7 +118,8 @@ class CALModel(nn.Module):
         embedded = self.word_embedding(tokens)
         if self.normalize_lang:
             embedded = embedded.div(embedded.norm(dim=-1, keepdim=True) + 1e-5) * self.learnable_length(tokens)
-        _, hidden = self.lstm(embedded)
+        with torch.backends.cudnn.flags(enabled=self.lstm.training):   # cuDNN RNN backward needs train mode
+            _, hidden = self.lstm(embedded)
         return self.lang_fc(hidden[0].transpose(0, 1).reshape(tokens.size(0), 2 * self.hidden_size))
 
     # -- forward -----------------------------------------------------------------------------
