@@ -1,0 +1,374 @@
+"""Contract benchmark: query-moment pairs scored per second on the corpus-retrieval workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4]): a bank of 1,000,000 six-clip videos
+(6 M clip embeddings, D = 100, 21 M candidate moments) resident in HBM; the 100,000 queries arrive in
+batches of --batch queries.  One STEP = one batch of tokenised queries through the retrieval hot
+path: K3 query embedding (GloVe gather -> BiLSTM -> Linear) -> K4 fused distance / moment-mean /
+top-100 over the whole bank (-> all-gather + K7 merge when the bank is sharded over N GPUs).
+Strong scaling: the bank is fixed and split by contiguous video ranges over the ranks.
+
+value      = batch * 21 M pairs / step time, inputs (token ids) already resident in HBM.
+e2e        = the same through the public host-buffer call (MomentRetriever.search ->
+             vfr_search_host): pinned host token ids in, host top-k lists out, copies inside the
+             timed region.
+roofline   = the dominant kernel (K4 score+top-k) timed with CUDA events inside the steps.
+cpu_baseline / --impl reference = the oracle's op-for-op port of the reference's python loop
+             (model/evaluate.py:42-80) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_VIDEOS = 1_000_000
+N_SEG = 6
+DIM = 100
+VOCAB = 10_000
+TOPK = 100
+MOMENTS_PER_VIDEO = N_SEG * (N_SEG + 1) // 2
+BANK_BLOCKS = 64          # the synthetic bank is generated in fixed blocks so any sharding sees the same data
+SEED = 123
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="queries per step")
+    ap.add_argument("--videos", type=int, default=N_VIDEOS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data (seeded; identical for every N)
+# ------------------------------------------------------------------------------------------------
+def make_model(device):
+    import vfr_b200  # noqa: F401
+    from vfr_b200 import models
+    torch.manual_seed(SEED)
+    table = torch.randn(VOCAB, 100) * 0.4
+    table[0] = 0
+    model = models.CALModel(visual_input_dim=2 * 4096 + 2, pretrained_emb=table)
+    return model.to(device).eval()
+
+
+def make_tokens(n, seed):
+    rng = np.random.default_rng(seed)
+    tok = np.zeros((n, 20), dtype=np.int64)
+    lens = np.clip(rng.poisson(6.5, size=n) + 1, 1, 20)
+    for i in range(n):
+        tok[i, :lens[i]] = rng.integers(1, VOCAB, size=lens[i])
+    return tok
+
+
+def bank_block(block, n_videos, device):
+    """Clip embeddings of one fixed block of videos (shared per-video component + per-clip part)."""
+    v0, v1 = (n_videos * block) // BANK_BLOCKS, (n_videos * (block + 1)) // BANK_BLOCKS
+    g = torch.Generator(device=device).manual_seed(SEED * 1000 + block)
+    base = torch.randn((v1 - v0, 1, DIM), device=device, generator=g)
+    clip = torch.randn((v1 - v0, N_SEG, DIM), device=device, generator=g)
+    return ((base + 0.6 * clip) * 0.05).reshape(-1, DIM), v0, v1
+
+
+def make_shard(n_videos, rank, world, device):
+    from vfr_b200.retrieval import shard_range
+    v0, v1 = shard_range(n_videos, rank, world)
+    parts = []
+    for b in range(BANK_BLOCKS):
+        b0, b1 = (n_videos * b) // BANK_BLOCKS, (n_videos * (b + 1)) // BANK_BLOCKS
+        lo, hi = max(b0, v0), min(b1, v1)
+        if lo >= hi:
+            continue
+        emb, _, _ = bank_block(b, n_videos, device)
+        parts.append(emb[(lo - b0) * N_SEG:(hi - b0) * N_SEG])
+    clips = torch.cat(parts, dim=0)
+    vid_off = np.arange(v1 - v0 + 1, dtype=np.int64) * N_SEG
+    return clips, vid_off, v0 * MOMENTS_PER_VIDEO
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own loop (oracle port), bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+class ReferenceArm:
+    """One step = `n_q` queries, each embedded at batch 1 (model/evaluate.py:44), scored against
+    `n_v` videos of the bank with one index_select().mean().item() per moment (:53-58), then
+    np.argsort over all the distances (:71) - the oracle's op-for-op port of the reference loop."""
+
+    def __init__(self, n_videos, n_q=2, n_v=3000):
+        from oracle import cal_oracle as orc
+        self.orc = orc
+        self.n_q, self.n_v = n_q, min(n_v, n_videos)
+        model = make_model("cpu")
+        self.sd = {k: v.detach() for k, v in model.state_dict().items()}
+        emb, _, _ = bank_block(0, n_videos, "cpu")
+        self.videos = [emb[i * N_SEG:(i + 1) * N_SEG].contiguous() for i in range(self.n_v)]
+        self.moments = orc.generate_moments(N_SEG)
+        self.step_idx = 0
+        self.pairs_per_step = self.n_q * self.n_v * MOMENTS_PER_VIDEO
+
+    def step(self):
+        tok = make_tokens(self.n_q, 10_000 + self.step_idx)
+        self.step_idx += 1
+        best = []
+        with torch.no_grad():
+            for q in range(self.n_q):
+                q_emb = self.orc.text_embed(self.sd, tok[q:q + 1])
+                distances = []
+                for v in self.videos:
+                    distances.extend(self.orc.moment_scores_loop(v, q_emb, self.moments))
+                order = np.argsort(distances)
+                best.append(order[:TOPK])
+        return best
+
+    def describe(self):
+        return (f"{self.n_q} queries x {self.n_v} videos x {MOMENTS_PER_VIDEO} moments per step "
+                f"(bank block 0 of the bench bank), oracle port of model/evaluate.py:42-80")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arm = ReferenceArm(args.videos)
+    for _ in range(args.warmup):
+        arm.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        arm.step()
+    dt = time.perf_counter() - t0
+    value = arm.pairs_per_step * args.steps / dt
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "query-moment pairs scored/sec", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world=args.gpus),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": arm.describe(),
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "corpus retrieval: 100k queries x %d videos x 21 moments (6 clips, D=100), top-%d, "
+                        "query batches of %d (BASELINE configs[4])" % (args.videos, TOPK, args.batch),
+            "query_batch": args.batch, "n_videos": args.videos, "n_moments": args.videos * MOMENTS_PER_VIDEO,
+            "dim": DIM, "topk": TOPK, "parallelism": f"bank sharded by video range over {world} GPU(s), queries replicated",
+            "l2": "inputs larger than L2: the packed bank shard (%.2f GB) is streamed every step"
+                  % (args.videos / world * N_SEG * DIM * 4 / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import vfr_b200  # noqa: F401
+    from vfr_b200 import _lib
+    from vfr_b200.retrieval import MomentRetriever
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (ours) needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+
+    model = make_model(device)
+    clips, vid_off, id_base = make_shard(args.videos, rank, world, device)
+    retr = MomentRetriever(model, clips, vid_off, id_base=id_base, max_queries=args.batch, k=TOPK)
+    del clips
+    n_batches = args.warmup + args.steps
+    tokens_host = [torch.from_numpy(make_tokens(args.batch, 1000 + i)).pin_memory() for i in range(n_batches)]
+    tokens_dev = [t.to(device) for t in tokens_host]
+    pairs_per_step = args.batch * args.videos * MOMENTS_PER_VIDEO
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident steps (value) + per-kernel events (roofline) ----
+    for i in range(args.warmup):
+        retr.search_device(tokens_dev[i])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        retr.search_device(tokens_dev[args.warmup + i])
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop()
+
+    # ---- the dominant kernel alone, inside the same steps: K4 through its own C entry point ----
+    from vfr_b200 import ops
+    q_emb = retr.q_emb[:args.batch]
+    k4_ms = []
+    for i in range(args.steps):
+        retr.search_device(tokens_dev[args.warmup + i])        # keeps the step's cache/clock state
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        qp = ops.pack_queries(q_emb)
+        a.record()
+        _lib.call("vfr_score_topk", retr.bank.packed.data_ptr(), retr.bank.vid_off.data_ptr(), retr.bank.mom_off.data_ptr(),
+                  retr.bank.n_videos, retr.bank.n_max, retr.bank.dim, qp.data_ptr(), args.batch, TOPK, id_base,
+                  retr.out_s.data_ptr(), retr.out_i.data_ptr(), retr.topk_ws.data_ptr(), 0,
+                  torch.cuda.current_stream().cuda_stream)
+        b.record()
+        torch.cuda.synchronize()
+        k4_ms.append(a.elapsed_time(b))
+    k4 = max_over_ranks(float(np.mean(k4_ms)))
+
+    # ---- end to end through the host-buffer API ----
+    for i in range(args.warmup):
+        retr.search(tokens_host[i])
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        s, ids = retr.search(tokens_host[args.warmup + i])
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+    checksum = float(s[:, 0].double().sum().item())
+
+    pk = peaks()
+    local_pairs = args.batch * retr.bank.m_total                 # pairs this rank's K4 launch scores
+    flop_per_pair = 4.0 * DIM / (N_SEG + 1)                      # 2*D*S / (S(S+1)/2)
+    achieved_tflops = local_pairs * flop_per_pair / (k4 * 1e-3) / 1e12
+    roofline = {
+        "kernel": "vfr_score_topk (score_kernel<TOPK> + topk_finish_kernel)", "bound": "tensor",
+        "achieved": achieved_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": achieved_tflops / pk["bf16_tflops_sustained"], "traffic": None,
+        "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+        "ms_per_launch": k4, "algorithmic_flop_per_pair": flop_per_pair,
+        "note": "exact-fp32 CUDA-core path (FADD+FFMA direct-difference form): 2 fp32 instr per (clip, dim); "
+                "fp32 FFMA peak ~72 TFLOP/s is the real ceiling of this path",
+        "share_of_step": k4 * args.steps / ms_total,
+    }
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = ReferenceArm(args.videos, n_q=2, n_v=3000)
+        arm.step()
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < 12.0:
+            arm.step()
+            n += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": arm.pairs_per_step * n / dt, "unit": "pairs/s", "cores": torch.get_num_threads(),
+                        "kind": "port", "sample": arm.describe() + f", {n} steps in {dt:.1f} s",
+                        "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": "query-moment pairs scored/sec", "value": pairs_per_step * args.steps / (ms_total * 1e-3),
+            "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": pairs_per_step * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": retr.h2d_bytes(args.batch), "d2h_bytes_per_step": retr.d2h_bytes(args.batch),
+                    "ms_per_step": e2e_ms / args.steps, "api": "MomentRetriever.search -> vfr_search_host"},
+            "gpu_launches": retr.launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "checksum_top1": checksum,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -177,6 +177,31 @@ int vfr_ranking_loss_bwd(const float* posit, const float* intra, const float* in
                          void* workspace, const float* grad_out, float* grad_posit, float* grad_intra,
                          float* grad_inter, float* grad_lang, vfr_stream_t stream);
 
+/* ---- retrieval step: K3 -> K4 behind one call --------------------------------------------------
+ * The serving form of model/evaluate.py:42-80: one batch of tokenised queries against the resident
+ * bank.  All pointers inside the plan are DEVICE pointers supplied by the caller (weights as for
+ * vfr_text_embed, bank as for vfr_score_topk, scratch sized for max_queries):
+ *   tokens_dev int64 [max_queries, seq_len]; q_emb fp32 [max_queries, dim];
+ *   q_packed vfr_query_pack_bytes(max_queries, dim); text_ws vfr_text_embed_bytes(max_queries, ...);
+ *   topk_ws vfr_score_topk_bytes(max_queries, n_split); out_*_dev [max_queries, k]. */
+typedef struct vfr_search_plan {
+  const float* table; int64_t vocab; const float* length_table; int emb;
+  const float* lstm_fwd; const float* lstm_bwd; int hidden;
+  const float* fc_w; const float* fc_b; int dim; int seq_len;
+  const float* bank_packed; const int32_t* vid_off; const int64_t* mom_off;
+  int64_t n_videos; int n_max; int64_t id_base;
+  int64_t* tokens_dev; float* q_emb; float* q_packed; void* text_ws; void* topk_ws;
+  float* out_scores_dev; int64_t* out_ids_dev; int n_split; int64_t max_queries;
+} vfr_search_plan;
+
+/* device-resident inputs/outputs; asynchronous */
+int vfr_search_device(const vfr_search_plan* plan, const int64_t* tokens_dev, int64_t n_queries, int k,
+                      float* out_scores_dev, int64_t* out_ids_dev, vfr_stream_t stream);
+/* HOST token ids in, HOST top-k out (copies on `stream` inside the call); returns after the
+ * results have landed (synchronises the stream). */
+int vfr_search_host(const vfr_search_plan* plan, const int64_t* tokens_host, int64_t n_queries, int k,
+                    float* out_scores_host, int64_t* out_ids_host, vfr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

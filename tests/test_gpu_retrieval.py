@@ -1,0 +1,65 @@
+"""GPU tests of the retrieval step (K3 -> K4 behind vfr_search_device / vfr_search_host)."""
+import numpy as np
+import pytest
+import torch
+
+import vfr_b200  # noqa: F401
+from vfr_b200 import models, ops, synth
+from vfr_b200.retrieval import MomentRetriever, shard_range
+from oracle import cal_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _setup(seed=21, V=300, Q=70, vocab=400):
+    sd = synth.make_state_dict(seed, 8, vocab, spread=4.0)
+    model = models.CALModel(visual_input_dim=18, pretrained_emb=torch.from_numpy(sd["word_embedding.weight"]))
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.to(DEV).eval()
+    clips = synth.make_bank(seed, V, 6, 100)
+    videos = synth.make_videos(seed, 4, 8)
+    tokens = synth.make_queries(seed, videos, Q, vocab)["tokens"]
+    return sd, model, clips, tokens
+
+
+def test_search_host_matches_oracle_and_device_path():
+    sd, model, clips, tokens = _setup()
+    V = clips.shape[0] // 6
+    vid_off = np.arange(V + 1) * 6
+    retr = MomentRetriever(model, torch.from_numpy(clips).to(DEV), vid_off, max_queries=128, k=10)
+    s, i = retr.search(tokens)
+    sd_, id_ = retr.search_device(torch.from_numpy(tokens).to(DEV))
+    assert torch.equal(s, sd_.cpu()) and torch.equal(i, id_.cpu())
+    q_emb = orc.text_embed(sd, tokens)
+    full = orc.score_matrix(clips, vid_off, q_emb).numpy()
+    order = np.argsort(full, axis=1, kind="stable")[:, :10]
+    want = np.take_along_axis(full, order, axis=1)
+    np.testing.assert_allclose(s.numpy(), want, rtol=1e-5)
+    # ids agree wherever the neighbouring scores are separated by more than the tolerance
+    gap_ok = np.abs(np.diff(np.take_along_axis(full, np.argsort(full, axis=1)[:, :11], axis=1), axis=1)) > 1e-5 * want
+    agree = (i.numpy() == order)
+    assert agree[gap_ok & np.roll(gap_ok, 1, axis=1)].mean() > 0.99
+    with pytest.raises(ValueError):
+        retr.search(np.zeros((200, 20), dtype=np.int64))
+    bad = tokens.copy()
+    bad[3, 0] = 10 ** 6
+    with pytest.raises(IndexError):
+        retr.search(bad)
+
+
+def test_sharded_search_equals_single_bank_search():
+    sd, model, clips, tokens = _setup(seed=22, V=1000)
+    V = clips.shape[0] // 6
+    full = MomentRetriever(model, torch.from_numpy(clips).to(DEV), np.arange(V + 1) * 6, max_queries=128, k=100)
+    s, i = full.search_device(torch.from_numpy(tokens).to(DEV))
+    parts_s, parts_i = [], []
+    for r in range(4):
+        v0, v1 = shard_range(V, r, 4)
+        shard = MomentRetriever(model, torch.from_numpy(clips[v0 * 6:v1 * 6]).to(DEV), np.arange(v1 - v0 + 1) * 6,
+                                id_base=v0 * 21, max_queries=128, k=100)
+        ps, pi = shard.search_device(torch.from_numpy(tokens).to(DEV))
+        parts_s.append(ps.clone())
+        parts_i.append(pi.clone())
+    ms, mi = ops.topk_merge(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(ms, s) and torch.equal(mi, i)

@@ -27,6 +27,17 @@ _l = C.c_int64
 _z = C.c_size_t
 _f = C.c_float
 
+class SearchPlan(C.Structure):
+    """Mirror of ``vfr_search_plan`` (include/vfr.h)."""
+    _fields_ = [("table", _p), ("vocab", _l), ("length_table", _p), ("emb", _i),
+                ("lstm_fwd", _p), ("lstm_bwd", _p), ("hidden", _i),
+                ("fc_w", _p), ("fc_b", _p), ("dim", _i), ("seq_len", _i),
+                ("bank_packed", _p), ("vid_off", _p), ("mom_off", _p),
+                ("n_videos", _l), ("n_max", _i), ("id_base", _l),
+                ("tokens_dev", _p), ("q_emb", _p), ("q_packed", _p), ("text_ws", _p), ("topk_ws", _p),
+                ("out_scores_dev", _p), ("out_ids_dev", _p), ("n_split", _i), ("max_queries", _l)]
+
+
 # name -> (restype, argtypes); kept in the order of include/vfr.h
 PROTOTYPES = {
     "vfr_last_error": (C.c_char_p, []),
@@ -56,6 +67,8 @@ PROTOTYPES = {
     "vfr_ranking_loss_bytes": (_z, [_i, _i, _i, _i]),
     "vfr_ranking_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p]),
     "vfr_ranking_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "vfr_search_device": (_i, [C.POINTER(SearchPlan), _p, _l, _i, _p, _p, _p]),
+    "vfr_search_host": (_i, [C.POINTER(SearchPlan), _p, _l, _i, _p, _p, _p]),
 }
 
 _lib = None

@@ -1,0 +1,51 @@
+// Retrieval step = K3 (query embedding) -> K4 (fused score + top-k) behind one C call, with a
+// HOST-buffer flavour (pinned or pageable host pointers in, host pointers out; the H2D / D2H copies
+// are issued on the caller's stream inside the call).  This is the serving form of the hot loop of
+// reference model/evaluate.py:42-80: one batch of tokenised queries against the resident bank.
+#include "vfr_common.cuh"
+
+using namespace vfr;
+
+static int check_plan(const vfr_search_plan* p, int64_t n_queries, int k) {
+  VFR_REQUIRE(p, VFR_ERR_INVALID, "vfr_search: null plan");
+  VFR_REQUIRE(p->table && p->lstm_fwd && p->lstm_bwd && p->fc_w && p->fc_b && p->bank_packed && p->vid_off && p->mom_off,
+              VFR_ERR_INVALID, "vfr_search: null model/bank pointer in plan");
+  VFR_REQUIRE(p->tokens_dev && p->q_emb && p->q_packed && p->text_ws && p->topk_ws && p->out_scores_dev && p->out_ids_dev,
+              VFR_ERR_INVALID, "vfr_search: null scratch pointer in plan");
+  VFR_REQUIRE(n_queries > 0 && n_queries <= p->max_queries, VFR_ERR_INVALID,
+              "vfr_search: n_queries=%lld exceeds plan capacity %lld", (long long)n_queries, (long long)p->max_queries);
+  VFR_REQUIRE(k >= 1 && k <= VFR_TOPK_MAX, VFR_ERR_UNSUPPORTED, "vfr_search: k=%d", k);
+  return VFR_OK;
+}
+
+extern "C" int vfr_search_device(const vfr_search_plan* p, const int64_t* tokens_dev, int64_t n_queries, int k,
+                                 float* out_scores_dev, int64_t* out_ids_dev, vfr_stream_t stream) {
+  int rc = check_plan(p, n_queries, k);
+  if (rc) return rc;
+  VFR_REQUIRE(tokens_dev && out_scores_dev && out_ids_dev, VFR_ERR_INVALID, "vfr_search_device: null pointer");
+  rc = vfr_text_embed(tokens_dev, n_queries, p->seq_len, p->table, p->vocab, p->length_table, p->emb, p->lstm_fwd,
+                      p->lstm_bwd, p->hidden, p->fc_w, p->fc_b, p->dim, p->text_ws, p->q_emb, stream);
+  if (rc) return rc;
+  rc = vfr_query_pack(p->q_emb, n_queries, p->dim, p->q_packed, stream);
+  if (rc) return rc;
+  return vfr_score_topk(p->bank_packed, p->vid_off, p->mom_off, p->n_videos, p->n_max, p->dim, p->q_packed, n_queries,
+                        k, p->id_base, out_scores_dev, out_ids_dev, p->topk_ws, p->n_split, stream);
+}
+
+extern "C" int vfr_search_host(const vfr_search_plan* p, const int64_t* tokens_host, int64_t n_queries, int k,
+                               float* out_scores_host, int64_t* out_ids_host, vfr_stream_t stream) {
+  int rc = check_plan(p, n_queries, k);
+  if (rc) return rc;
+  VFR_REQUIRE(tokens_host && out_scores_host && out_ids_host, VFR_ERR_INVALID, "vfr_search_host: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  VFR_CUDA(cudaMemcpyAsync(p->tokens_dev, tokens_host, (size_t)n_queries * p->seq_len * sizeof(int64_t),
+                           cudaMemcpyHostToDevice, st));
+  rc = vfr_search_device(p, p->tokens_dev, n_queries, k, p->out_scores_dev, p->out_ids_dev, stream);
+  if (rc) return rc;
+  VFR_CUDA(cudaMemcpyAsync(out_scores_host, p->out_scores_dev, (size_t)n_queries * k * sizeof(float),
+                           cudaMemcpyDeviceToHost, st));
+  VFR_CUDA(cudaMemcpyAsync(out_ids_host, p->out_ids_dev, (size_t)n_queries * k * sizeof(int64_t),
+                           cudaMemcpyDeviceToHost, st));
+  VFR_CUDA(cudaStreamSynchronize(st));
+  return VFR_OK;
+}

@@ -1,0 +1,121 @@
+"""Corpus-scale moment retrieval (BASELINE config 5): tokenised queries -> global top-k moments.
+
+The reference has no serving entry point - its corpus protocol is the python loop of
+``model/evaluate.py:42-80`` (every query scored against every moment of every video, then sorted).
+``MomentRetriever`` is that loop as a service: the bank of clip embeddings stays resident in HBM
+(as the reference keeps its ``videos`` dict), each ``search`` call embeds a batch of queries (K3),
+scores it against the bank with the fused top-k (K4) and returns the k best (score, moment id).
+
+Multi-GPU: the bank is partitioned by contiguous video ranges across the ranks of
+one NVSwitch box, queries are replicated, every rank computes its local top-k with GLOBAL moment ids
+and the per-rank lists are exchanged with ONE ``all_gather`` over NCCL/NVLink and merged (K7).
+Moment id = ``mom_off[video] + moment_index`` over the WHOLE corpus, so results do not depend on the
+number of ranks.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+
+
+def shard_range(n_videos, rank, world):
+    """Contiguous video range [v0, v1) of ``rank``."""
+    return (n_videos * rank) // world, (n_videos * (rank + 1)) // world
+
+
+class MomentRetriever:
+
+    def __init__(self, model, clips, vid_off, id_base=0, max_queries=4096, k=100, n_split=0, group=None):
+        """``model``: a ``CALModel`` (text branch used); ``clips`` fp32 [C_local, D] + ``vid_off`` =
+        this rank's bank shard; ``id_base`` = global moment id of the shard's first moment."""
+        self.model = model
+        self.bank = ops.Bank(clips, vid_off)
+        self.k = int(k)
+        self.max_queries = int(max_queries)
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev = self.bank.device
+        self.device = dev
+        self.seq_len = 20
+        lib = _lib.load()
+        fwd, bwd = model._packed_lstm()
+        table = model.word_embedding.weight.detach().float().contiguous()
+        length = model.learnable_length.weight.detach().float().reshape(-1).contiguous() if model.normalize_lang else None
+        fc_w = model.lang_fc.weight.detach().float().contiguous()
+        fc_b = model.lang_fc.bias.detach().float().contiguous()
+        H, E, D = model.hidden_size, table.shape[1], fc_w.shape[0]
+        mq = self.max_queries
+        self._keep = [fwd, bwd, table, length, fc_w, fc_b]
+        self.tokens_dev = torch.empty((mq, self.seq_len), dtype=torch.int64, device=dev)
+        self.q_emb = torch.empty((mq, D), dtype=torch.float32, device=dev)
+        self.q_packed = torch.empty(lib.vfr_query_pack_bytes(mq, D) // 4, dtype=torch.float32, device=dev)
+        self.text_ws = torch.empty(lib.vfr_text_embed_bytes(mq, self.seq_len, H, E) // 4, dtype=torch.float32, device=dev)
+        self.topk_ws = torch.empty(lib.vfr_score_topk_bytes(mq, n_split), dtype=torch.uint8, device=dev)
+        self.out_s = torch.empty((mq, self.k), dtype=torch.float32, device=dev)
+        self.out_i = torch.empty((mq, self.k), dtype=torch.int64, device=dev)
+        p = _lib.SearchPlan()
+        p.table, p.vocab, p.length_table, p.emb = table.data_ptr(), table.shape[0], (length.data_ptr() if length is not None else None), E
+        p.lstm_fwd, p.lstm_bwd, p.hidden = fwd.data_ptr(), bwd.data_ptr(), H
+        p.fc_w, p.fc_b, p.dim, p.seq_len = fc_w.data_ptr(), fc_b.data_ptr(), D, self.seq_len
+        p.bank_packed, p.vid_off, p.mom_off = self.bank.packed.data_ptr(), self.bank.vid_off.data_ptr(), self.bank.mom_off.data_ptr()
+        p.n_videos, p.n_max, p.id_base = self.bank.n_videos, self.bank.n_max, int(id_base)
+        p.tokens_dev, p.q_emb, p.q_packed = self.tokens_dev.data_ptr(), self.q_emb.data_ptr(), self.q_packed.data_ptr()
+        p.text_ws, p.topk_ws = self.text_ws.data_ptr(), self.topk_ws.data_ptr()
+        p.out_scores_dev, p.out_ids_dev = self.out_s.data_ptr(), self.out_i.data_ptr()
+        p.n_split, p.max_queries = int(n_split), mq
+        self.plan = p
+        if self.world > 1:
+            self.gather_s = torch.empty((self.world, mq, self.k), dtype=torch.float32, device=dev)
+            self.gather_i = torch.empty((self.world, mq, self.k), dtype=torch.int64, device=dev)
+        # pinned staging for the host-buffer path
+        self.host_tokens = torch.empty((mq, self.seq_len), dtype=torch.int64).pin_memory()
+        self.host_s = torch.empty((mq, self.k), dtype=torch.float32).pin_memory()
+        self.host_i = torch.empty((mq, self.k), dtype=torch.int64).pin_memory()
+        # kernels launched per search step: gather + 20 LSTM steps + 2 fc + query pack + score + finish (+ merge)
+        self.launches_per_step = 1 + self.seq_len + 2 + 1 + 1 + 1 + (1 if self.world > 1 else 0)
+
+    # -- device-resident step ---------------------------------------------------------------------
+    def search_device(self, tokens_dev):
+        """tokens int64 [Q, 20] on the device -> (scores fp32 [Q, k], ids int64 [Q, k]) on the device."""
+        Q = tokens_dev.shape[0]
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.call("vfr_search_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.k, self.out_s.data_ptr(),
+                  self.out_i.data_ptr(), stream)
+        if self.world == 1:
+            return self.out_s[:Q], self.out_i[:Q]
+        gs, gi = self.gather_s[:, :Q].contiguous(), self.gather_i[:, :Q].contiguous()
+        dist.all_gather_into_tensor(gs, self.out_s[:Q].contiguous(), group=self.group)
+        dist.all_gather_into_tensor(gi, self.out_i[:Q].contiguous(), group=self.group)
+        return ops.topk_merge(gs, gi)
+
+    # -- host-buffer step (the call a user makes) -------------------------------------------------------
+    def search(self, tokens):
+        """tokens: int64 [Q, 20] HOST tensor/array -> (scores, ids) HOST tensors [Q, k]."""
+        tokens = torch.as_tensor(tokens, dtype=torch.int64)
+        Q = tokens.shape[0]
+        if Q > self.max_queries:
+            raise ValueError(f"batch of {Q} queries exceeds max_queries={self.max_queries}")
+        self.host_tokens[:Q].copy_(tokens)
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.world == 1:
+            _lib.call("vfr_search_host", C.byref(self.plan), self.host_tokens.data_ptr(), Q, self.k,
+                      self.host_s.data_ptr(), self.host_i.data_ptr(), stream)
+        else:
+            self.tokens_dev[:Q].copy_(self.host_tokens[:Q], non_blocking=True)
+            s, i = self.search_device(self.tokens_dev[:Q])
+            self.host_s[:Q].copy_(s, non_blocking=True)
+            self.host_i[:Q].copy_(i, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        bad = int(self.text_ws[-4:].view(torch.int32)[0].item())
+        if bad:
+            raise IndexError("index out of range in self")
+        return self.host_s[:Q], self.host_i[:Q]
+
+    def h2d_bytes(self, Q):
+        return Q * self.seq_len * 8
+
+    def d2h_bytes(self, Q):
+        return Q * self.k * (4 + 8)
