@@ -139,7 +139,7 @@ int vfr_visual_embed(const float* x, int64_t n_rows, int in_dim, const float* w1
  * update by vfr_lstm_pack ([W_hh | W_ih] rows interleaved by gate, bias = b_ih + b_hh;
  * vfr_lstm_pack_bytes bytes).  tokens int64 [B, L]; table fp32 [vocab, emb] (row 0 = pad);
  * length_table fp32 [vocab] or NULL (the normalize_lang variant, models.py:62-64);
- * fc_w fp32 [dim, 2*hidden]; out fp32 [B, dim]; workspace vfr_text_embed_bytes bytes whose LAST
+ * fc_w fp32 [dim, 2*hidden]; out fp32 [B, dim]; workspace vfr_text_embed_bytes bytes whose FIRST
  * int32 is set to 1 if a token id was outside [0, vocab) (the reference raises IndexError). */
 size_t vfr_lstm_pack_bytes(int hidden, int emb);
 int vfr_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int hidden,

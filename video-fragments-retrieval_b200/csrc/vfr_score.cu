@@ -555,15 +555,32 @@ static int launch_score(const ScoreParams& p, int n_split, cudaStream_t st) {
   return check_launch("score_kernel");
 }
 
+// Bank splits per query tile.  The kernel runs 2 CTAs per SM (launch bounds + 103 KB smem), so the
+// grid is sized to fill whole waves of 2 x SMs CTAs: a grid of 1.08 waves costs as much as 2 waves.
+static int wave_split(int64_t n_queries, int n_tiles, int max_split) {
+  const int64_t qtiles = (n_queries + TQ - 1) / TQ;
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t slots = 2LL * sms;
+  int best = 1;
+  double best_util = 0.0;
+  for (int w = 1; w <= 4; ++w) {
+    int64_t ns = slots * w / qtiles;
+    if (ns < 1) ns = 1;
+    if (ns > n_tiles) ns = n_tiles;
+    if (ns > max_split) ns = max_split;
+    const int64_t ctas = ns * qtiles;
+    const int64_t waves = (ctas + slots - 1) / slots;
+    const double util = (double)ctas / (double)(waves * slots);
+    if (util > best_util + 0.02) { best_util = util; best = (int)ns; }
+  }
+  return best;
+}
+
 static int auto_split(int64_t n_queries, int n_tiles, int n_split) {
   if (n_split > 0) return n_split < n_tiles ? n_split : n_tiles;
-  // fill ~2 CTAs/SM x 148 SMs, a few waves
-  const int64_t qtiles = (n_queries + TQ - 1) / TQ;
-  int64_t want = (2 * 148 * 2 + qtiles - 1) / qtiles;
-  if (want < 1) want = 1;
-  if (want > n_tiles) want = n_tiles;
-  if (want > 64) want = 64;
-  return (int)want;
+  return wave_split(n_queries, n_tiles, 64);
 }
 
 }  // namespace vfr
@@ -665,11 +682,7 @@ extern "C" int vfr_score_count(const float* bank_packed, const int32_t* vid_off,
 
 static int topk_split(int64_t n_queries, int n_split) {
   if (n_split > 0) return n_split;
-  const int64_t qtiles = (n_queries + TQ - 1) / TQ;
-  int64_t want = (2 * 148 + qtiles - 1) / qtiles;
-  if (want < 1) want = 1;
-  if (want > 32) want = 32;
-  return (int)want;
+  return wave_split(n_queries, 1 << 30, 32);
 }
 
 extern "C" size_t vfr_score_topk_bytes(int64_t n_queries, int n_split) {

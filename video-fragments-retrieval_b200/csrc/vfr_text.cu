@@ -146,11 +146,11 @@ extern "C" int vfr_text_embed(const int64_t* tokens, int64_t n_queries, int seq_
               "vfr_text_embed: hidden and hidden+emb must be multiples of 4");
   cudaStream_t st = (cudaStream_t)stream;
   const int B = (int)n_queries, L = seq_len, H = hidden, E = emb, K = H + E;
-  float* ws = reinterpret_cast<float*>(workspace);
+  int* bad = reinterpret_cast<int*>(workspace);          // first 16 bytes: out-of-range-token flag
+  float* ws = reinterpret_cast<float*>(workspace) + 4;
   const size_t hx_sz = (size_t)(L + 1) * B * K;
   float* hx[2] = {ws, ws + hx_sz};
   float* c[2] = {ws + 2 * hx_sz, ws + 2 * hx_sz + (size_t)B * H};
-  int* bad = reinterpret_cast<int*>(ws + 2 * hx_sz + 2 * (size_t)B * H);
   VFR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
   {
     const int64_t warps = (int64_t)B * L;
@@ -185,6 +185,6 @@ extern "C" int vfr_text_embed(const int64_t* tokens, int64_t n_queries, int seq_
     if (rc) return rc;
   }
   // out-of-range token ids (the reference raises IndexError) are clamped to the pad row and flagged
-  // in the LAST int32 of the workspace; the call stays asynchronous, the caller inspects the flag.
+  // in the FIRST int32 of the workspace; the call stays asynchronous, the caller inspects the flag.
   return VFR_OK;
 }

@@ -253,7 +253,7 @@ def text_embed(tokens, table, length_table, packed_fwd, packed_bwd, hidden, fc_w
         _lib.call("vfr_text_embed", _ptr(tokens[b0:b0 + nb]), nb, L, _ptr(table), table.shape[0], _ptr(lt), E,
                   _ptr(packed_fwd), _ptr(packed_bwd), hidden, _ptr(fc_w), _ptr(fc_b), D, _ptr(ws),
                   _ptr(out[b0:b0 + nb]), _stream())
-        if check_tokens and int(ws[-4:].view(torch.int32)[0].item()) != 0:
+        if check_tokens and int(ws[:4].view(torch.int32)[0].item()) != 0:
             raise IndexError("index out of range in self")   # what nn.Embedding raises in the reference
     return out
 

@@ -109,7 +109,7 @@ class MomentRetriever:
             self.host_s[:Q].copy_(s, non_blocking=True)
             self.host_i[:Q].copy_(i, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-        bad = int(self.text_ws[-4:].view(torch.int32)[0].item())
+        bad = int(self.text_ws[:4].view(torch.int32)[0].item())
         if bad:
             raise IndexError("index out of range in self")
         return self.host_s[:Q], self.host_i[:Q]
