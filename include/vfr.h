@@ -97,6 +97,32 @@ int vfr_score_topk(const float* bank_packed, const int32_t* vid_off, const int64
 int vfr_topk_merge(const float* in_scores, const int64_t* in_ids, int n_parts, int64_t n_queries, int k,
                    float* out_scores, int64_t* out_ids, vfr_stream_t stream);
 
+/* ---- K4, tensor-core path (tcgen05 / TMEM / TMA) ----------------------------------------------------
+ * Same outputs as vfr_score_topk / vfr_score_full at the north-star tolerance (fp32 scores within
+ * 1e-5 of the reference): the query x clip contraction runs as a split-bf16 GEMM (n_terms = 3:
+ * qh.vh + ql.vh + qh.vl, fp32 accumulation in TMEM) with an exact-fp32 recompute of near-duplicate
+ * pairs; n_terms = 1 is the plain-bf16 variant (1e-2 tolerance).  Videos of at most 6 clips
+ * (fixed 6-slot layout), dim <= 125.  Means are sum * fl(1/len), sqrt is sqrt.approx (<= 2 ulp).
+ * Packed operands: vfr_tc_bank_bytes / vfr_tc_query_bytes; `bank`, `queries`, `vid_off`, `mom_off`
+ * are the unpacked arrays (read only on the exact-fallback / append paths); uniform != 0 asserts that
+ * every video has exactly 6 clips. */
+size_t vfr_tc_bank_bytes(int64_t n_videos);
+int vfr_tc_bank_pack(const float* bank, const int32_t* vid_off, int64_t n_videos, int n_max, int dim,
+                     int n_terms, void* packed, vfr_stream_t stream);
+size_t vfr_tc_query_bytes(int64_t n_queries);
+int vfr_tc_query_pack(const float* queries, int64_t n_queries, int dim, int n_terms, void* packed,
+                      vfr_stream_t stream);
+size_t vfr_score_topk_tc_bytes(int64_t n_queries, int64_t n_videos, int n_split);
+int vfr_score_topk_tc(const void* bank_packed, const float* bank, const int32_t* vid_off,
+                      const int64_t* mom_off, int64_t n_videos, int uniform, int dim, int n_terms,
+                      const void* query_packed, const float* queries, int64_t n_queries, int k,
+                      int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, int n_split,
+                      vfr_stream_t stream);
+int vfr_score_full_tc(const void* bank_packed, const float* bank, const int32_t* vid_off,
+                      const int64_t* mom_off, int64_t n_videos, int uniform, int dim, int n_terms,
+                      const void* query_packed, const float* queries, int64_t n_queries, float* out,
+                      int64_t m_total, vfr_stream_t stream);
+
 /* ---- K5 : integer-exact temporal IoU, ground truth, rank statistics -------------------------
  * times int32 [Q, n_annot, 2] inclusive (start, end), absent annotators = (-1, -1);
  * q_nseg int32 [Q] = clips of the query's own video; own_scores fp32 [Q, m_stride] (vfr_score_own);

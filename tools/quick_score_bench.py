@@ -26,3 +26,7 @@ tau = torch.full((Q, 2), 1.0, device="cuda")
 qv = torch.zeros(Q, dtype=torch.int32, device="cuda")
 t = timeit(lambda: ops.score_count(bank, q, tau, qv))
 print(f"count V={V} Q={Q}: {t:.2f} ms  {pairs / t / 1e6:.1f} Gpairs/s")
+t = timeit(lambda: ops.score_topk_tc(bank, q, k))
+print(f"tc topk V={V} Q={Q}: {t:.2f} ms  {pairs / t / 1e6:.1f} Gpairs/s  clip-pairs/s {Q*V*S/t/1e6:.1f} G")
+t = timeit(lambda: ops.score_topk_tc(bank, q, k, n_terms=1))
+print(f"tc topk bf16 V={V} Q={Q}: {t:.2f} ms  {pairs / t / 1e6:.1f} Gpairs/s")

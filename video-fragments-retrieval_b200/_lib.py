@@ -53,6 +53,13 @@ PROTOTYPES = {
     "vfr_score_topk_bytes": (_z, [_l, _i]),
     "vfr_score_topk": (_i, [_p, _p, _p, _l, _i, _i, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
     "vfr_topk_merge": (_i, [_p, _p, _i, _l, _i, _p, _p, _p]),
+    "vfr_tc_bank_bytes": (_z, [_l]),
+    "vfr_tc_bank_pack": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),
+    "vfr_tc_query_bytes": (_z, [_l]),
+    "vfr_tc_query_pack": (_i, [_p, _l, _i, _i, _p, _p]),
+    "vfr_score_topk_tc_bytes": (_z, [_l, _l, _i]),
+    "vfr_score_topk_tc": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
+    "vfr_score_full_tc": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _l, _p, _l, _p]),
     "vfr_gt_select": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p, _p]),
     "vfr_rank_order": (_i, [_p, _i, _p, _l, _i, _p, _p]),
     "vfr_single_metrics": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p]),

@@ -17,6 +17,7 @@
 // shared memory to the moment phase, where a thread owns ONE query (so count / top-k state is
 // thread-private: no atomics in the loop) and walks the tile's videos.
 #include "vfr_common.cuh"
+#include "vfr_topk.cuh"
 #include <math_constants.h>
 
 namespace vfr {
@@ -31,7 +32,6 @@ constexpr int Q_STAGE = KC * TQ;    // floats
 constexpr int V_STAGE = KC * TC;    // floats
 constexpr int STAGE_FLOATS = Q_STAGE + V_STAGE;
 constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * 4;
-constexpr int CAP = VFR_TOPK_CAP;   // 256
 constexpr int CAP_HI = CAP - VFR_MAX_SEG;  // compaction trigger: at most 32 appends between checks
 
 enum Mode { MODE_FULL = 0, MODE_COUNT = 1, MODE_TOPK = 2 };
@@ -121,88 +121,6 @@ __global__ void pack_query_kernel(const float* __restrict__ q, int64_t n_queries
   if (threadIdx.x < TQ) {
     const int64_t qi = tile * TQ + threadIdx.x;
     rowsum[tile * TQ + threadIdx.x] = (qi < n_queries) ? row_sum(q + qi * dim, dim) : 0.f;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// warp-cooperative compaction of one thread-private candidate list (top-k mode)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cswap(unsigned long long& a, unsigned long long& b, bool asc) {
-  const bool sw = (a > b) == asc;
-  const unsigned long long t = a;
-  a = sw ? b : a;
-  b = sw ? t : b;
-}
-
-// bitonic sort of 256 keys held 8 per lane, element index e = slot*32 + lane, ascending in e
-__device__ __forceinline__ void warp_sort256(unsigned long long (&key)[8], int lane) {
-#pragma unroll
-  for (int size = 2; size <= 256; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride >= 32) {
-        const int ss = stride >> 5;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (!(i & ss)) {
-            const bool asc = (size == 256) ? true : !((i << 5) & size);
-            cswap(key[i], key[i | ss], asc);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[i], stride);
-          const int e = (i << 5) | lane;
-          const bool asc = (size == 256) ? true : !(e & size);
-          const bool lower = !(lane & stride);
-          const bool take_min = (lower == asc);
-          const unsigned long long mn = key[i] < other ? key[i] : other;
-          const unsigned long long mx = key[i] < other ? other : key[i];
-          key[i] = take_min ? mn : mx;
-        }
-      }
-    }
-  }
-}
-
-// Every lane calls this (warp-uniform call site).  For each lane whose `need` is set the whole warp
-// sorts that lane's list and keeps the k smallest (score, id) keys, sorted, at its front.
-__device__ __forceinline__ void compact_lists(unsigned long long* list, int& cnt, float& tau, int k,
-                                              bool need, int lane) {
-  unsigned mask = __ballot_sync(0xffffffffu, need);
-  while (mask) {
-    const int src = __ffs(mask) - 1;
-    mask &= mask - 1;
-    unsigned long long* lp =
-        reinterpret_cast<unsigned long long*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(list), src));
-    const int n = __shfl_sync(0xffffffffu, cnt, src);
-    __syncwarp();
-    unsigned long long key[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = (i << 5) | lane;
-      key[i] = idx < n ? lp[idx] : ~0ull;
-    }
-    warp_sort256(key, lane);
-    const int keep = n < k ? n : k;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = (i << 5) | lane;
-      if (idx < keep) lp[idx] = key[i];
-    }
-    // k-th smallest (rank k-1) lives in slot (k-1)>>5 of lane (k-1)&31
-    unsigned long long kth = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const unsigned long long cand = __shfl_sync(0xffffffffu, key[i], (k - 1) & 31);
-      if (i == ((k - 1) >> 5)) kth = cand;
-    }
-    __syncwarp();
-    if (lane == src) {
-      cnt = keep;
-      tau = (n >= k) ? __uint_as_float((unsigned)(kth >> 32)) : CUDART_INF_F;
-    }
   }
 }
 
@@ -583,6 +501,13 @@ static int auto_split(int64_t n_queries, int n_tiles, int n_split) {
   return wave_split(n_queries, n_tiles, 64);
 }
 
+int launch_topk_finish(const unsigned long long* cand, const int32_t* cand_cnt, int n_parts, int k, int64_t id_base,
+                       int64_t n_queries, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  topk_finish_kernel<<<(unsigned)n_queries, MERGE_THREADS, 0, st>>>(cand, cand_cnt, n_parts, k, id_base, out_scores,
+                                                                   out_ids);
+  return check_launch("topk_finish_kernel");
+}
+
 }  // namespace vfr
 
 using namespace vfr;
@@ -714,9 +639,7 @@ extern "C" int vfr_score_topk(const float* bank_packed, const int32_t* vid_off, 
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_score<MODE_TOPK, 1>(p, ns_eff, st);
   if (rc) return rc;
-  topk_finish_kernel<<<(unsigned)n_queries, MERGE_THREADS, 0, st>>>(p.cand, p.cand_cnt, p.n_parts, k, id_base,
-                                                                   out_scores, out_ids);
-  return check_launch("topk_finish_kernel");
+  return launch_topk_finish(p.cand, p.cand_cnt, p.n_parts, k, id_base, n_queries, out_scores, out_ids, st);
 }
 
 extern "C" int vfr_score_own(const float* bank, const int32_t* vid_off, int dim, const float* queries,

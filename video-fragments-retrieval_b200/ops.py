@@ -66,6 +66,23 @@ class Bank:
     def device(self):
         return self.clips.device
 
+    def tc(self, n_terms=3):
+        """Packed operand of the tensor-core scoring path (built lazily, cached per n_terms)."""
+        cache = self.__dict__.setdefault("_tc", {})
+        if n_terms not in cache:
+            if self.n_max > 6:
+                raise _lib.VfrError("the tensor-core scoring path holds videos of at most 6 clips")
+            nbytes = _lib.load().vfr_tc_bank_bytes(self.n_videos)
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.call("vfr_tc_bank_pack", _ptr(self.clips), _ptr(self.vid_off), self.n_videos, self.n_max, self.dim,
+                      n_terms, _ptr(packed), _stream())
+            cache[n_terms] = packed
+        return cache[n_terms]
+
+    @property
+    def uniform6(self):
+        return int(bool((self.nseg_host == 6).all()))
+
 
 def pack_queries(queries):
     _need_cuda(queries)
@@ -124,6 +141,37 @@ def score_topk(bank, queries, k, id_base=0, n_split=0):
     out_i = torch.empty((Q, k), dtype=torch.int64, device=bank.device)
     _lib.call("vfr_score_topk", _ptr(bank.packed), _ptr(bank.vid_off), _ptr(bank.mom_off), bank.n_videos,
               bank.n_max, bank.dim, _ptr(qp), Q, k, id_base, _ptr(out_s), _ptr(out_i), _ptr(ws), n_split, _stream())
+    return out_s, out_i
+
+
+def pack_queries_tc(queries, n_terms=3):
+    _need_cuda(queries)
+    q = _f32c(queries)
+    packed = torch.empty(_lib.load().vfr_tc_query_bytes(q.shape[0]), dtype=torch.uint8, device=q.device)
+    _lib.call("vfr_tc_query_pack", _ptr(q), q.shape[0], q.shape[1], n_terms, _ptr(packed), _stream())
+    return q, packed
+
+
+def score_full_tc(bank, queries, n_terms=3):
+    """Tensor-core path: all scores -> fp32 [Q, M_total] (moments of padded slots are not written)."""
+    q, qp = pack_queries_tc(queries, n_terms)
+    Q = q.shape[0]
+    out = torch.full((Q, bank.m_total), float("nan"), dtype=torch.float32, device=bank.device)
+    _lib.call("vfr_score_full_tc", _ptr(bank.tc(n_terms)), _ptr(bank.clips), _ptr(bank.vid_off), _ptr(bank.mom_off),
+              bank.n_videos, bank.uniform6, bank.dim, n_terms, _ptr(qp), _ptr(q), Q, _ptr(out), bank.m_total, _stream())
+    return out
+
+
+def score_topk_tc(bank, queries, k, id_base=0, n_split=0, n_terms=3):
+    """Tensor-core path: fused top-k -> (scores fp32 [Q, k], ids int64 [Q, k])."""
+    q, qp = pack_queries_tc(queries, n_terms)
+    Q = q.shape[0]
+    ws = torch.empty(_lib.load().vfr_score_topk_tc_bytes(Q, bank.n_videos, n_split), dtype=torch.uint8, device=bank.device)
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=bank.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=bank.device)
+    _lib.call("vfr_score_topk_tc", _ptr(bank.tc(n_terms)), _ptr(bank.clips), _ptr(bank.vid_off), _ptr(bank.mom_off),
+              bank.n_videos, bank.uniform6, bank.dim, n_terms, _ptr(qp), _ptr(q), Q, k, id_base, _ptr(out_s), _ptr(out_i),
+              _ptr(ws), n_split, _stream())
     return out_s, out_i
 
 
