@@ -64,6 +64,7 @@ struct ScoreParams {
   unsigned long long* cand;
   int32_t* cand_cnt;
   int n_parts;
+  unsigned* tau_g;            // [Qpad] shared per-query threshold
 };
 
 static inline int nkc_of(int dim) { return (dim + KC - 1) / KC; }
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) score_kernel(const ScoreParams p)
     }
     __syncthreads();  // ds complete; also releases stage s
 
+    if (MODE == MODE_TOPK) my_tau = fminf(my_tau, tau_fetch(p.tau_g + q_global));
     // ---- moment phase: thread = (query mq, half) walks the videos of the tile ----
     const int tile = tile_begin + it / p.nkc;
     const int64_t v0 = (int64_t)tile * p.vt;
@@ -282,7 +284,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) score_kernel(const ScoreParams p)
             }
           }
         }
-        if (MODE == MODE_TOPK) compact_lists(my_list, my_cnt, my_tau, p.k, my_cnt > CAP_HI, lane);
+        if (MODE == MODE_TOPK) {
+          const float before = my_tau;
+          compact_lists(my_list, my_cnt, my_tau, p.k, my_cnt > CAP_HI, lane);
+          if (my_tau < before) tau_publish(p.tau_g + q_global, my_tau);
+        }
       }
     }
     __syncthreads();  // ds free for the next tile
@@ -501,6 +507,14 @@ static int auto_split(int64_t n_queries, int n_tiles, int n_split) {
   return wave_split(n_queries, n_tiles, 64);
 }
 
+__global__ void fill_u32_kernel(unsigned* dst, unsigned value, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = value;
+}
+int launch_fill_u32(unsigned* dst, unsigned value, size_t n, cudaStream_t st) {
+  fill_u32_kernel<<<(unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, st>>>(dst, value, n);
+  return check_launch("fill_u32_kernel");
+}
+
 int launch_topk_finish(const unsigned long long* cand, const int32_t* cand_cnt, int n_parts, int k, int64_t id_base,
                        int64_t n_queries, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   topk_finish_kernel<<<(unsigned)n_queries, MERGE_THREADS, 0, st>>>(cand, cand_cnt, n_parts, k, id_base, out_scores,
@@ -615,7 +629,7 @@ extern "C" size_t vfr_score_topk_bytes(int64_t n_queries, int n_split) {
   const int ns = topk_split(n_queries, n_split);
   const size_t qpad = (size_t)((n_queries + TQ - 1) / TQ) * TQ;
   const size_t parts = (size_t)ns * 2;
-  return qpad * parts * CAP * sizeof(unsigned long long) + qpad * parts * sizeof(int32_t);
+  return qpad * parts * CAP * sizeof(unsigned long long) + qpad * parts * sizeof(int32_t) + qpad * sizeof(unsigned);
 }
 
 extern "C" int vfr_score_topk(const float* bank_packed, const int32_t* vid_off, const int64_t* mom_off,
@@ -636,7 +650,10 @@ extern "C" int vfr_score_topk(const float* bank_packed, const int32_t* vid_off, 
   p.n_parts = ns_eff * 2;
   p.cand = reinterpret_cast<unsigned long long*>(workspace);
   p.cand_cnt = reinterpret_cast<int32_t*>(p.cand + qpad * (size_t)ns_req * 2 * CAP);
+  p.tau_g = reinterpret_cast<unsigned*>(p.cand_cnt + qpad * (size_t)ns_req * 2);
   cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad, st);
+  if (rc) return rc;
   rc = launch_score<MODE_TOPK, 1>(p, ns_eff, st);
   if (rc) return rc;
   return launch_topk_finish(p.cand, p.cand_cnt, p.n_parts, k, id_base, n_queries, out_scores, out_ids, st);

@@ -72,6 +72,7 @@ struct TcParams {
   unsigned long long* cand;
   int32_t* cand_cnt;
   int n_parts;
+  unsigned* tau_g;            // [Qpad] shared per-query threshold
   // FULL
   float* out_full;
   int64_t m_total;
@@ -277,6 +278,74 @@ __device__ __noinline__ float exact_distance(const float* __restrict__ vr, const
   return __fsqrt_rn(fmaxf(__fadd_rn(acc, corr), 0.f));
 }
 
+// cold paths of the epilogue, kept out of line so the hot loop stays small in the instruction cache
+__device__ __noinline__ int append_video(unsigned long long* list, int cnt, float tau, int n, unsigned mbase, float d0,
+                                         float d1, float d2, float d3, float d4, float d5) {
+  const float d[TC_S] = {d0, d1, d2, d3, d4, d5};
+  const float rcp[TC_S] = {1.f, 0.5f, 1.f / 3.f, 0.25f, 0.2f, 1.f / 6.f};
+#pragma unroll
+  for (int s = 0; s < TC_S; ++s) {
+    float run = 0.f;
+#pragma unroll
+    for (int e = s; e < TC_S; ++e) {
+      run += d[e];
+      const float score = run * rcp[e - s];
+      if (e < n && score <= tau)
+        list[cnt++] = ((unsigned long long)__float_as_uint(score) << 32) | (mbase + (unsigned)moment_index(n, s, e));
+    }
+  }
+  return cnt;
+}
+
+__device__ __noinline__ void write_video_scores(float* o, int n, float d0, float d1, float d2, float d3, float d4,
+                                                float d5) {
+  const float d[TC_S] = {d0, d1, d2, d3, d4, d5};
+  const float rcp[TC_S] = {1.f, 0.5f, 1.f / 3.f, 0.25f, 0.2f, 1.f / 6.f};
+#pragma unroll
+  for (int s = 0; s < TC_S; ++s) {
+    float run = 0.f;
+#pragma unroll
+    for (int e = s; e < TC_S; ++e) {
+      run += d[e];
+      if (e < n) o[moment_index(n, s, e)] = run * rcp[e - s];
+    }
+  }
+}
+
+__device__ __noinline__ void compact_lists_noinline(unsigned long long* list, int& cnt, float& tau, int k, bool need,
+                                                    int lane) {
+  compact_lists(list, cnt, tau, k, need, lane);
+}
+
+// mbarrier wait with nanosleep back-off (single-lane producer / MMA threads must not steal issue slots
+// from the epilogue warps of their SM sub-partition) and a watchdog: a protocol bug traps instead of hanging
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t done = 0;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(ns);
+    if ((spin & 0xfff) == 0xfff) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {   // 4 s
+        printf("vfr: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -334,7 +403,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int row = (tile_begin + t) * TC_N;
         for (int c = 0; c < b_chunks; ++c, ++it) {
           const int s = it % TC_STAGES;
-          mbar_wait_wd(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+          mbar_wait_sleep(&empty[s], ((it / TC_STAGES) & 1) ^ 1, 64);
           mbar_expect_tx(&full[s], TC_B_CHUNK);
           const int seg = c / seg_chunks, cc = c % seg_chunks;
           tma_load_2d(smem_b + s * TC_B_CHUNK, &tm_b, seg * TC_KSEG + cc * 64, row, &full[s]);
@@ -345,18 +414,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // ================= MMA issuer =================
     if (lane == 0 && n_my_tiles > 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-      mbar_wait_wd(a_full, 0);
+      mbar_wait_sleep(a_full, 0, 64);
       tc_fence_after();
       int it = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
         const int buf = t & 1;
-        mbar_wait_wd(&tmem_empty[buf], ((t >> 1) & 1) ^ 1);
+        mbar_wait_sleep(&tmem_empty[buf], ((t >> 1) & 1) ^ 1, 32);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256;
         uint32_t accumulate = 0;
         for (int c = 0; c < b_chunks; ++c, ++it) {
           const int s = it % TC_STAGES;
-          mbar_wait_wd(&full[s], (it / TC_STAGES) & 1);
+          mbar_wait_sleep(&full[s], (it / TC_STAGES) & 1, 32);
           tc_fence_after();
           const int seg = c / seg_chunks, cc = c % seg_chunks;
           const int ks = (cc == 0) ? min(p.ksteps, 4) : (p.ksteps - 4);
@@ -393,12 +462,20 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     for (int l = 0; l < TC_S; ++l) thr[l] = CUDART_INF_F;
     if (MODE == TC_TOPK) my_list = p.cand + ((int64_t)q_global * p.n_parts + part) * CAP;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const float rcp[TC_S] = {1.f, 0.5f, 1.f / 3.f, 0.25f, 0.2f, 1.f / 6.f};
+    constexpr int VSUB = TC_SUB / TC_S;           // 4 videos per sub-block
 
     for (int t = 0; t < n_my_tiles; ++t) {
       const int buf = t & 1;
       const int tile = tile_begin + t;
-      mbar_wait_wd(&tmem_full[buf], (t >> 1) & 1);
+      if (MODE == TC_TOPK) {
+        const float tg = tau_fetch(p.tau_g + q_global);
+        if (tg < my_tau) {
+          my_tau = tg;
+#pragma unroll
+          for (int l = 0; l < TC_S; ++l) thr[l] = my_tau * (float)(l + 1) * 1.000001f;
+        }
+      }
+      mbar_wait_sleep(&tmem_full[buf], (t >> 1) & 1, 20);
       tc_fence_after();
       for (int sb = 0; sb < TC_SUBS; ++sb) {
         float acc[TC_SUB];
@@ -406,83 +483,94 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         tmem_ld16(lane_addr + col, acc, 0);
         tmem_ld8(lane_addr + col + 16, acc, 16);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int64_t v_first = (int64_t)tile * TC_VID + half * (TC_VID / 2) + sb * (TC_SUB / TC_S);
+        const int64_t v_first = (int64_t)tile * TC_VID + half * (TC_VID / 2) + sb * VSUB;
+        // ---- hot path: 24 distances, 4 x 21 threshold tests; everything else is behind `flags` ----
+        float d[VSUB][TC_S];
+        unsigned flags = 0;                       // bit j: video j has a candidate; bit 4+j: needs the exact fallback
 #pragma unroll
-        for (int j = 0; j < TC_SUB / TC_S; ++j) {
-          const int64_t v = v_first + j;
-          float d[TC_S];
-          bool need_exact = false;
+        for (int j = 0; j < VSUB; ++j) {
+          bool ex = false;
 #pragma unroll
           for (int i = 0; i < TC_S; ++i) {
             const float d2 = acc[j * TC_S + i] + nq;
-            need_exact |= d2 < gq;
-            d[i] = sqrt_approx(fmaxf(d2, 0.f));
+            ex |= d2 < gq;
+            d[j][i] = sqrt_approx(fmaxf(d2, 0.f));
           }
-          int n = TC_S;
-          if (!p.uniform) n = (v < p.n_videos) ? (int)p.nseg[v] : 0;
-          else if (v >= p.n_videos) n = 0;
-          if (need_exact && n > 0) {
-            // near-duplicate embeddings: the GEMM expansion cancels; redo those clips exactly
-            const int c0 = p.vid_off[v];
+          flags |= ex ? (16u << j) : 0u;
+        }
+        // ragged banks / the padded tail of the last tile: mask the clip slots a video does not have
+        const bool ragged = (!p.uniform) || (v_first + VSUB > p.n_videos);
+        int nn[VSUB];
+#pragma unroll
+        for (int j = 0; j < VSUB; ++j) nn[j] = TC_S;
+        if (ragged) {
+#pragma unroll
+          for (int j = 0; j < VSUB; ++j) {
+            const int64_t v = v_first + j;
+            nn[j] = (v < p.n_videos) ? (int)p.nseg[v] : 0;
+#pragma unroll
+            for (int i = 0; i < TC_S; ++i)
+              if (i >= nn[j]) d[j][i] = CUDART_INF_F;
+          }
+        }
+        if (flags >> 4) {
+          // near-duplicate embeddings: the GEMM expansion cancels; redo those clips with the exact form
+          if (q_valid) {
             const float* qr = p.queries + q_global * p.dim;
-            if (q_valid) {
 #pragma unroll
-              for (int i = 0; i < TC_S; ++i)
-                if (i < n && (acc[j * TC_S + i] + nq) < gq) d[i] = exact_distance(p.bank + (int64_t)(c0 + i) * p.dim, qr, p.dim);
-            }
-          }
+            for (int j = 0; j < VSUB; ++j) {
+              if ((flags >> (4 + j)) & 1u) {
+                const int64_t v = v_first + j;
+                if (v < p.n_videos) {
+                  const int c0 = p.vid_off[v];
 #pragma unroll
-          for (int i = 0; i < TC_S; ++i)
-            if (i >= n) d[i] = CUDART_INF_F;
-
-          if (MODE == TC_FULL) {
-            if (q_valid && n > 0) {
-              float* o = p.out_full + q_global * p.m_total + p.mom_off[v];
-#pragma unroll
-              for (int s = 0; s < TC_S; ++s) {
-                float run = 0.f;
-#pragma unroll
-                for (int e = s; e < TC_S; ++e) {
-                  run += d[e];
-                  if (e < n) o[moment_index(n, s, e)] = run * rcp[e - s];
+                  for (int i = 0; i < TC_S; ++i)
+                    if (i < nn[j] && (acc[j * TC_S + i] + nq) < gq)
+                      d[j][i] = exact_distance(p.bank + (int64_t)(c0 + i) * p.dim, qr, p.dim);
                 }
               }
             }
-          } else {
+          }
+        }
+        if (MODE == TC_FULL) {
+          if (q_valid) {
+#pragma unroll
+            for (int j = 0; j < VSUB; ++j)
+              if (nn[j] > 0)
+                write_video_scores(p.out_full + q_global * p.m_total + p.mom_off[v_first + j], nn[j], d[j][0], d[j][1],
+                                   d[j][2], d[j][3], d[j][4], d[j][5]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < VSUB; ++j) {
             bool any = false;
 #pragma unroll
             for (int s = 0; s < TC_S; ++s) {
               float run = 0.f;
 #pragma unroll
               for (int e = s; e < TC_S; ++e) {
-                run += d[e];
+                run += d[j][e];
                 any |= run <= thr[e - s];
               }
             }
-            if (any) {
-              const int64_t mbase = p.mom_off[v];
-#pragma unroll
-              for (int s = 0; s < TC_S; ++s) {
-                float run = 0.f;
-#pragma unroll
-                for (int e = s; e < TC_S; ++e) {
-                  run += d[e];
-                  const float score = run * rcp[e - s];
-                  if (e < n && score <= my_tau)
-                    my_list[my_cnt++] = ((unsigned long long)__float_as_uint(score) << 32) |
-                                        (unsigned)(mbase + moment_index(n, s, e));
-                }
-              }
-            }
+            flags |= any ? (1u << j) : 0u;
           }
-        }
-        if (MODE == TC_TOPK) {
-          const float tau_before = my_tau;
-          compact_lists(my_list, my_cnt, my_tau, p.k, my_cnt > TC_CAP_HI, lane);
-          if (my_tau != tau_before) {
-            // sum <= tau * len, slightly inclusive; the exact `score <= tau` test is redone on append
+          if (flags & 15u) {
 #pragma unroll
-            for (int l = 0; l < TC_S; ++l) thr[l] = my_tau * (float)(l + 1) * 1.000001f;
+            for (int j = 0; j < VSUB; ++j)
+              if ((flags >> j) & 1u)
+                my_cnt = append_video(my_list, my_cnt, my_tau, nn[j], (unsigned)p.mom_off[v_first + j], d[j][0], d[j][1],
+                                      d[j][2], d[j][3], d[j][4], d[j][5]);
+          }
+          if (__any_sync(0xffffffffu, my_cnt > TC_CAP_HI)) {
+            const float tau_before = my_tau;
+            compact_lists_noinline(my_list, my_cnt, my_tau, p.k, my_cnt > TC_CAP_HI, lane);
+            if (my_tau != tau_before) {
+              tau_publish(p.tau_g + q_global, my_tau);
+              // sum <= tau * len, slightly inclusive; the exact `score <= tau` test is redone on append
+#pragma unroll
+              for (int l = 0; l < TC_S; ++l) thr[l] = my_tau * (float)(l + 1) * 1.000001f;
+            }
           }
         }
       }
@@ -491,7 +579,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
     if (MODE == TC_TOPK) {
-      compact_lists(my_list, my_cnt, my_tau, p.k, true, lane);
+      compact_lists_noinline(my_list, my_cnt, my_tau, p.k, true, lane);
       p.cand_cnt[q_global * p.n_parts + part] = my_cnt;
     }
   }
@@ -539,7 +627,9 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t 
 static int64_t tc_tiles(int64_t n_videos) { return (n_videos + TC_VID - 1) / TC_VID; }
 static int64_t tc_qtiles(int64_t n_queries) { return (n_queries + TC_M - 1) / TC_M; }
 
-// splits so that qtiles * splits fills whole waves of one CTA per SM
+// Bank splits per query tile (one CTA per SM).  Every split adds two candidate lists per query, and the
+// filter threshold of a list only tightens with the moments that list has seen, so prefer the FEWEST
+// splits that still keep >= 85 % of the SMs busy; with >= #SM query tiles there is no split at all.
 static int tc_split(int64_t n_queries, int64_t n_tiles, int n_split) {
   if (n_split > 0) return (int)(n_split < n_tiles ? n_split : n_tiles);
   const int64_t qt = tc_qtiles(n_queries);
@@ -547,15 +637,12 @@ static int tc_split(int64_t n_queries, int64_t n_tiles, int n_split) {
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int best = 1;
   double best_util = 0.0;
-  for (int w = 1; w <= 8; ++w) {
-    int64_t ns = (int64_t)sms * w / qt;
-    if (ns < 1) ns = 1;
-    if (ns > n_tiles) ns = n_tiles;
-    if (ns > 64) ns = 64;
+  for (int ns = 1; ns <= 64 && ns <= n_tiles; ++ns) {
     const int64_t ctas = ns * qt;
     const int64_t waves = (ctas + sms - 1) / sms;
     const double util = (double)ctas / (double)(waves * sms);
-    if (util > best_util + 0.01) { best_util = util; best = (int)ns; }
+    if (util >= 0.85) return ns;
+    if (util > best_util) { best_util = util; best = ns; }
   }
   return best;
 }
@@ -646,7 +733,7 @@ extern "C" size_t vfr_score_topk_tc_bytes(int64_t n_queries, int64_t n_videos, i
   const int ns = tc_split(n_queries, tc_tiles(n_videos), n_split);
   const size_t qpad = (size_t)tc_qtiles(n_queries) * TC_M;
   const size_t parts = (size_t)ns * 2;
-  return qpad * parts * CAP * sizeof(unsigned long long) + qpad * parts * sizeof(int32_t);
+  return qpad * parts * CAP * sizeof(unsigned long long) + qpad * parts * sizeof(int32_t) + qpad * sizeof(unsigned);
 }
 
 extern "C" int vfr_score_topk_tc(const void* bank_packed, const float* bank, const int32_t* vid_off,
@@ -669,7 +756,10 @@ extern "C" int vfr_score_topk_tc(const void* bank_packed, const float* bank, con
   p.n_parts = ns * 2;
   p.cand = reinterpret_cast<unsigned long long*>(workspace);
   p.cand_cnt = reinterpret_cast<int32_t*>(p.cand + qpad * (size_t)ns_req * 2 * CAP);
+  p.tau_g = reinterpret_cast<unsigned*>(p.cand_cnt + qpad * (size_t)ns_req * 2);
   cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad, st);
+  if (rc) return rc;
   VFR_CUDA(cudaFuncSetAttribute(score_tc_kernel<TC_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   score_tc_kernel<TC_TOPK><<<(unsigned)(p.n_qtiles * ns), TC_THREADS, TC_SMEM, st>>>(ma, mb, p);
   rc = check_launch("score_tc_kernel<TOPK>");

@@ -91,6 +91,18 @@ __device__ __forceinline__ void compact_lists(unsigned long long* list, int& cnt
 }
 
 
+// Per-query threshold shared by all part lists of a query (non-negative fp32 compared as uint32).
+// Each list's k-th best score is an upper bound of the GLOBAL k-th best, so publishing it with an
+// atomic min lets every other list filter with it: appends per query drop from
+// parts * k ln(N/(parts k)) to ~k ln(N/k), which keeps the append branch rare per WARP as well.
+__device__ __forceinline__ void tau_publish(unsigned* tau_g, float tau) {
+  if (tau < CUDART_INF_F) atomicMin(tau_g, __float_as_uint(tau));
+}
+__device__ __forceinline__ float tau_fetch(const unsigned* tau_g) {
+  return __uint_as_float(*reinterpret_cast<const volatile unsigned*>(tau_g));
+}
+int launch_fill_u32(unsigned* dst, unsigned value, size_t n, cudaStream_t st);
+
 // merges the part lists of every query: out [Q, k] ascending by (score, id); defined in vfr_score.cu
 int launch_topk_finish(const unsigned long long* cand, const int32_t* cand_cnt, int n_parts, int k, int64_t id_base,
                        int64_t n_queries, float* out_scores, int64_t* out_ids, cudaStream_t st);
