@@ -37,7 +37,7 @@ extern "C" {
 #define VFR_TILE_Q 128    /* queries per scoring tile */
 #define VFR_TILE_C 96     /* clip columns per scoring tile */
 #define VFR_TOPK_MAX 128  /* largest k of the fused top-k */
-#define VFR_TOPK_CAP 256  /* candidate slots per (query, part) list in the top-k workspace */
+#define VFR_TOPK_CAP 512  /* candidate slots per (query, part) list in the top-k workspace */
 #define VFR_MAX_TAU 16    /* thresholds per query in count mode */
 
 typedef void* vfr_stream_t;

@@ -5,7 +5,7 @@ import numpy as np, torch
 import vfr_b200
 from vfr_b200 import ops
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 250000
-Q = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+Q = int(sys.argv[2]) if len(sys.argv) > 2 else 18944
 g = torch.Generator(device="cuda").manual_seed(0)
 clips = torch.randn(V * 6, 100, device="cuda", generator=g) * 0.25
 q = torch.randn(Q, 100, device="cuda", generator=g) * 0.25

@@ -305,10 +305,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) score_kernel(const ScoreParams p)
       }
     }
   }
-  if (MODE == MODE_TOPK) {
-    compact_lists(my_list, my_cnt, my_tau, p.k, true, lane);
-    p.cand_cnt[q_global * p.n_parts + part] = my_cnt;
-  }
+  if (MODE == MODE_TOPK) p.cand_cnt[q_global * p.n_parts + part] = my_cnt;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -374,6 +371,9 @@ __device__ __forceinline__ void block_sort(unsigned long long* keys /*MERGE_N*/)
   __syncthreads();
 }
 
+// Part lists are unsorted and hold up to CAP keys each.  All keys of a query are streamed through a
+// 2048-key shared-memory bitonic sort: slots [0,128) carry the running best, slots [128,2048) the
+// next batch.
 __global__ void __launch_bounds__(MERGE_THREADS) topk_finish_kernel(const unsigned long long* __restrict__ cand,
                                                                      const int32_t* __restrict__ cand_cnt,
                                                                      int n_parts, int k, int64_t id_base,
@@ -381,23 +381,29 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_finish_kernel(const unsign
                                                                      int64_t* __restrict__ out_ids) {
   __shared__ unsigned long long keys[MERGE_N];
   const int64_t q = blockIdx.x;
-  for (int i = threadIdx.x; i < MERGE_N; i += MERGE_THREADS) keys[i] = ~0ull;
-  __syncthreads();
-  const int per_pass = (MERGE_N - VFR_TOPK_MAX) / VFR_TOPK_MAX;  // lists per pass (each <= 128 kept)
-  for (int p0 = 0; p0 < n_parts; p0 += per_pass) {
-    const int np = min(per_pass, n_parts - p0);
-    for (int i = threadIdx.x; i < np * VFR_TOPK_MAX; i += MERGE_THREADS) {
-      const int pl = i / VFR_TOPK_MAX, j = i % VFR_TOPK_MAX;
-      const int64_t li = q * n_parts + p0 + pl;
-      const int cnt = min(cand_cnt[li], k);
-      keys[VFR_TOPK_MAX + i] = (j < cnt) ? cand[li * CAP + j] : ~0ull;
-    }
-    for (int i = VFR_TOPK_MAX + np * VFR_TOPK_MAX + threadIdx.x; i < MERGE_N; i += MERGE_THREADS) keys[i] = ~0ull;
-    block_sort(keys);
-    // keep the best k at the front; slots k..127 must be empty for the next pass
-    for (int i = k + threadIdx.x; i < VFR_TOPK_MAX; i += MERGE_THREADS) keys[i] = ~0ull;
+  constexpr int BATCH = MERGE_N - VFR_TOPK_MAX;
+  for (int i = threadIdx.x; i < VFR_TOPK_MAX; i += MERGE_THREADS) keys[i] = ~0ull;
+  int part = 0, pos = 0;          // stream position: next key is cand[(q*n_parts+part)*CAP + pos]
+  while (part < n_parts) {
     __syncthreads();
+    // every thread walks the same (part, pos) sequence; thread i of the batch takes the i-th key
+    int filled = 0, pp = part, po = pos;
+    while (pp < n_parts && filled < BATCH) {
+      const int64_t li = q * n_parts + pp;
+      const int cnt = min(cand_cnt[li], CAP);
+      const int take = min(cnt - po, BATCH - filled);
+      for (int i = threadIdx.x; i < take; i += MERGE_THREADS) keys[VFR_TOPK_MAX + filled + i] = cand[li * CAP + po + i];
+      filled += take;
+      po += take;
+      if (po >= cnt) { ++pp; po = 0; }
+    }
+    for (int i = VFR_TOPK_MAX + filled + threadIdx.x; i < MERGE_N; i += MERGE_THREADS) keys[i] = ~0ull;
+    part = pp;
+    pos = po;
+    block_sort(keys);
+    for (int i = k + threadIdx.x; i < VFR_TOPK_MAX; i += MERGE_THREADS) keys[i] = ~0ull;
   }
+  __syncthreads();
   for (int i = threadIdx.x; i < k; i += MERGE_THREADS) {
     const unsigned long long key = keys[i];
     const bool ok = key != ~0ull;

@@ -578,10 +578,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
-    if (MODE == TC_TOPK) {
-      compact_lists_noinline(my_list, my_cnt, my_tau, p.k, true, lane);
-      p.cand_cnt[q_global * p.n_parts + part] = my_cnt;
-    }
+    if (MODE == TC_TOPK) p.cand_cnt[q_global * p.n_parts + part] = my_cnt;
   }
 
   tc_fence_before();
