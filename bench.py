@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="queries per step")
+    ap.add_argument("--batch", type=int, default=18944, help="queries per step (148 query tiles of 128 = one per SM)")
+    ap.add_argument("--engine", type=str, default="tc", choices=["tc", "tc_bf16", "exact"])
     ap.add_argument("--videos", type=int, default=N_VIDEOS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -225,7 +226,7 @@ def workload_config(args, world):
     return {"workload": "corpus retrieval: 100k queries x %d videos x 21 moments (6 clips, D=100), top-%d, "
                         "query batches of %d (BASELINE configs[4])" % (args.videos, TOPK, args.batch),
             "query_batch": args.batch, "n_videos": args.videos, "n_moments": args.videos * MOMENTS_PER_VIDEO,
-            "dim": DIM, "topk": TOPK, "parallelism": f"bank sharded by video range over {world} GPU(s), queries replicated",
+            "dim": DIM, "topk": TOPK, "parallelism": f"bank sharded by video range over {world} GPU(s), queries replicated", "engine": getattr(args, "engine", "tc"),
             "l2": "inputs larger than L2: the packed bank shard (%.2f GB) is streamed every step"
                   % (args.videos / world * N_SEG * DIM * 4 / 1e9)}
 
@@ -252,7 +253,7 @@ def run_ours(args):
 
     model = make_model(device)
     clips, vid_off, id_base = make_shard(args.videos, rank, world, device)
-    retr = MomentRetriever(model, clips, vid_off, id_base=id_base, max_queries=args.batch, k=TOPK)
+    retr = MomentRetriever(model, clips, vid_off, id_base=id_base, max_queries=args.batch, k=TOPK, engine=args.engine)
     del clips
     n_batches = args.warmup + args.steps
     tokens_host = [torch.from_numpy(make_tokens(args.batch, 1000 + i)).pin_memory() for i in range(n_batches)]
@@ -288,18 +289,12 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # ---- the dominant kernel alone, inside the same steps: K4 through its own C entry point ----
-    from vfr_b200 import ops
-    q_emb = retr.q_emb[:args.batch]
     k4_ms = []
     for i in range(args.steps):
         retr.search_device(tokens_dev[args.warmup + i])        # keeps the step's cache/clock state
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        qp = ops.pack_queries(q_emb)
         a.record()
-        _lib.call("vfr_score_topk", retr.bank.packed.data_ptr(), retr.bank.vid_off.data_ptr(), retr.bank.mom_off.data_ptr(),
-                  retr.bank.n_videos, retr.bank.n_max, retr.bank.dim, qp.data_ptr(), args.batch, TOPK, id_base,
-                  retr.out_s.data_ptr(), retr.out_i.data_ptr(), retr.topk_ws.data_ptr(), 0,
-                  torch.cuda.current_stream().cuda_stream)
+        retr.score_only(args.batch)
         b.record()
         torch.cuda.synchronize()
         k4_ms.append(a.elapsed_time(b))
@@ -323,14 +318,19 @@ def run_ours(args):
     local_pairs = args.batch * retr.bank.m_total                 # pairs this rank's K4 launch scores
     flop_per_pair = 4.0 * DIM / (N_SEG + 1)                      # 2*D*S / (S(S+1)/2)
     achieved_tflops = local_pairs * flop_per_pair / (k4 * 1e-3) / 1e12
+    tc = args.engine != "exact"
     roofline = {
-        "kernel": "vfr_score_topk (score_kernel<TOPK> + topk_finish_kernel)", "bound": "tensor",
-        "achieved": achieved_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "kernel": ("vfr_score_topk_tc (score_tc_kernel<TOPK> + threshold init + topk_finish_kernel)" if tc else
+                   "vfr_score_topk (score_kernel<TOPK> + topk_finish_kernel)"),
+        "bound": "tensor", "achieved": achieved_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved_tflops / pk["bf16_tflops_sustained"], "traffic": None,
         "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
         "ms_per_launch": k4, "algorithmic_flop_per_pair": flop_per_pair,
-        "note": "exact-fp32 CUDA-core path (FADD+FFMA direct-difference form): 2 fp32 instr per (clip, dim); "
-                "fp32 FFMA peak ~72 TFLOP/s is the real ceiling of this path",
+        "note": ("tcgen05 split-bf16 GEMM (3 MMA passes, K=112 each) + fused sqrt / moment-mean / top-k epilogue; "
+                 "algorithmic FLOPs count ONE fp32 pass (4D/(S+1) per pair), so frac understates tensor-pipe use 3.4x; "
+                 "the kernel is epilogue-ALU bound (SURVEY H2)") if tc else
+                ("exact-fp32 CUDA-core path (FADD+FFMA direct-difference form): 2 fp32 instr per (clip, dim); "
+                 "fp32 FFMA peak ~72 TFLOP/s is the real ceiling of this path"),
         "share_of_step": k4 * args.steps / ms_total,
     }
 
@@ -353,7 +353,8 @@ def run_ours(args):
             "metric": "query-moment pairs scored/sec", "value": pairs_per_step * args.steps / (ms_total * 1e-3),
             "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": {"tc": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate; fp32 scores within 1e-5)", "tc_bf16": "bf16", "exact": "f32"}[args.engine],
+            "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks,
             "e2e": {"value": pairs_per_step * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": retr.h2d_bytes(args.batch), "d2h_bytes_per_step": retr.d2h_bytes(args.batch),

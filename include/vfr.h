@@ -209,7 +209,8 @@ int vfr_ranking_loss_bwd(const float* posit, const float* intra, const float* in
  * vfr_text_embed, bank as for vfr_score_topk, scratch sized for max_queries):
  *   tokens_dev int64 [max_queries, seq_len]; q_emb fp32 [max_queries, dim];
  *   q_packed vfr_query_pack_bytes(max_queries, dim); text_ws vfr_text_embed_bytes(max_queries, ...);
- *   topk_ws vfr_score_topk_bytes(max_queries, n_split); out_*_dev [max_queries, k]. */
+ *   topk_ws vfr_score_topk_bytes(max_queries, n_split); out_*_dev [max_queries, k].
+ * bank_packed / q_packed are only needed by engine 0. */
 typedef struct vfr_search_plan {
   const float* table; int64_t vocab; const float* length_table; int emb;
   const float* lstm_fwd; const float* lstm_bwd; int hidden;
@@ -218,6 +219,11 @@ typedef struct vfr_search_plan {
   int64_t n_videos; int n_max; int64_t id_base;
   int64_t* tokens_dev; float* q_emb; float* q_packed; void* text_ws; void* topk_ws;
   float* out_scores_dev; int64_t* out_ids_dev; int n_split; int64_t max_queries;
+  /* scoring engine: 0 = exact-fp32 CUDA-core path (vfr_score_topk); 3 = tensor-core split-bf16 path,
+   * 1 = tensor-core plain-bf16 path (vfr_score_topk_tc with n_terms = engine).  Engines 1/3 need:
+   * bank_tc (vfr_tc_bank_pack), bank_clips fp32 [C, dim] (exact fallback), uniform6, q_tc
+   * (vfr_tc_query_bytes(max_queries)) and topk_ws sized by vfr_score_topk_tc_bytes. */
+  int engine; const void* bank_tc; const float* bank_clips; int uniform6; void* q_tc;
 } vfr_search_plan;
 
 /* device-resident inputs/outputs; asynchronous */

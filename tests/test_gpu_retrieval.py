@@ -23,11 +23,13 @@ def _setup(seed=21, V=300, Q=70, vocab=400):
     return sd, model, clips, tokens
 
 
-def test_search_host_matches_oracle_and_device_path():
+@pytest.mark.parametrize("engine", ["exact", "tc"])
+def test_search_host_matches_oracle_and_device_path(engine):
     sd, model, clips, tokens = _setup()
     V = clips.shape[0] // 6
     vid_off = np.arange(V + 1) * 6
-    retr = MomentRetriever(model, torch.from_numpy(clips).to(DEV), vid_off, max_queries=128, k=10)
+    retr = MomentRetriever(model, torch.from_numpy(clips).to(DEV), vid_off, max_queries=128, k=10, engine=engine)
+    assert retr.engine == engine
     s, i = retr.search(tokens)
     sd_, id_ = retr.search_device(torch.from_numpy(tokens).to(DEV))
     assert torch.equal(s, sd_.cpu()) and torch.equal(i, id_.cpu())
@@ -48,16 +50,18 @@ def test_search_host_matches_oracle_and_device_path():
         retr.search(bad)
 
 
-def test_sharded_search_equals_single_bank_search():
+@pytest.mark.parametrize("engine", ["exact", "tc", "tc_bf16"])
+def test_sharded_search_equals_single_bank_search(engine):
     sd, model, clips, tokens = _setup(seed=22, V=1000)
     V = clips.shape[0] // 6
-    full = MomentRetriever(model, torch.from_numpy(clips).to(DEV), np.arange(V + 1) * 6, max_queries=128, k=100)
+    full = MomentRetriever(model, torch.from_numpy(clips).to(DEV), np.arange(V + 1) * 6, max_queries=128, k=100,
+                           engine=engine)
     s, i = full.search_device(torch.from_numpy(tokens).to(DEV))
     parts_s, parts_i = [], []
     for r in range(4):
         v0, v1 = shard_range(V, r, 4)
         shard = MomentRetriever(model, torch.from_numpy(clips[v0 * 6:v1 * 6]).to(DEV), np.arange(v1 - v0 + 1) * 6,
-                                id_base=v0 * 21, max_queries=128, k=100)
+                                id_base=v0 * 21, max_queries=128, k=100, engine=engine)
         ps, pi = shard.search_device(torch.from_numpy(tokens).to(DEV))
         parts_s.append(ps.clone())
         parts_i.append(pi.clone())

@@ -35,7 +35,8 @@ class SearchPlan(C.Structure):
                 ("bank_packed", _p), ("vid_off", _p), ("mom_off", _p),
                 ("n_videos", _l), ("n_max", _i), ("id_base", _l),
                 ("tokens_dev", _p), ("q_emb", _p), ("q_packed", _p), ("text_ws", _p), ("topk_ws", _p),
-                ("out_scores_dev", _p), ("out_ids_dev", _p), ("n_split", _i), ("max_queries", _l)]
+                ("out_scores_dev", _p), ("out_ids_dev", _p), ("n_split", _i), ("max_queries", _l),
+                ("engine", _i), ("bank_tc", _p), ("bank_clips", _p), ("uniform6", _i), ("q_tc", _p)]
 
 
 # name -> (restype, argtypes); kept in the order of include/vfr.h

@@ -8,10 +8,15 @@ using namespace vfr;
 
 static int check_plan(const vfr_search_plan* p, int64_t n_queries, int k) {
   VFR_REQUIRE(p, VFR_ERR_INVALID, "vfr_search: null plan");
-  VFR_REQUIRE(p->table && p->lstm_fwd && p->lstm_bwd && p->fc_w && p->fc_b && p->bank_packed && p->vid_off && p->mom_off,
+  VFR_REQUIRE(p->table && p->lstm_fwd && p->lstm_bwd && p->fc_w && p->fc_b && p->vid_off && p->mom_off,
               VFR_ERR_INVALID, "vfr_search: null model/bank pointer in plan");
-  VFR_REQUIRE(p->tokens_dev && p->q_emb && p->q_packed && p->text_ws && p->topk_ws && p->out_scores_dev && p->out_ids_dev,
+  VFR_REQUIRE(p->tokens_dev && p->q_emb && p->text_ws && p->topk_ws && p->out_scores_dev && p->out_ids_dev,
               VFR_ERR_INVALID, "vfr_search: null scratch pointer in plan");
+  VFR_REQUIRE(p->engine == 0 || p->engine == 1 || p->engine == 3, VFR_ERR_INVALID, "vfr_search: engine=%d", p->engine);
+  if (p->engine == 0)
+    VFR_REQUIRE(p->bank_packed && p->q_packed, VFR_ERR_INVALID, "vfr_search: engine 0 needs bank_packed and q_packed");
+  else
+    VFR_REQUIRE(p->bank_tc && p->bank_clips && p->q_tc, VFR_ERR_INVALID, "vfr_search: tensor-core engine needs bank_tc, bank_clips, q_tc");
   VFR_REQUIRE(n_queries > 0 && n_queries <= p->max_queries, VFR_ERR_INVALID,
               "vfr_search: n_queries=%lld exceeds plan capacity %lld", (long long)n_queries, (long long)p->max_queries);
   VFR_REQUIRE(k >= 1 && k <= VFR_TOPK_MAX, VFR_ERR_UNSUPPORTED, "vfr_search: k=%d", k);
@@ -26,6 +31,13 @@ extern "C" int vfr_search_device(const vfr_search_plan* p, const int64_t* tokens
   rc = vfr_text_embed(tokens_dev, n_queries, p->seq_len, p->table, p->vocab, p->length_table, p->emb, p->lstm_fwd,
                       p->lstm_bwd, p->hidden, p->fc_w, p->fc_b, p->dim, p->text_ws, p->q_emb, stream);
   if (rc) return rc;
+  if (p->engine != 0) {
+    rc = vfr_tc_query_pack(p->q_emb, n_queries, p->dim, p->engine, p->q_tc, stream);
+    if (rc) return rc;
+    return vfr_score_topk_tc(p->bank_tc, p->bank_clips, p->vid_off, p->mom_off, p->n_videos, p->uniform6, p->dim,
+                             p->engine, p->q_tc, p->q_emb, n_queries, k, p->id_base, out_scores_dev, out_ids_dev,
+                             p->topk_ws, p->n_split, stream);
+  }
   rc = vfr_query_pack(p->q_emb, n_queries, p->dim, p->q_packed, stream);
   if (rc) return rc;
   return vfr_score_topk(p->bank_packed, p->vid_off, p->mom_off, p->n_videos, p->n_max, p->dim, p->q_packed, n_queries,

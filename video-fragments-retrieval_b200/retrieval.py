@@ -28,9 +28,15 @@ def shard_range(n_videos, rank, world):
 
 class MomentRetriever:
 
-    def __init__(self, model, clips, vid_off, id_base=0, max_queries=4096, k=100, n_split=0, group=None):
+    ENGINES = {"exact": 0, "tc": 3, "tc_bf16": 1}
+
+    def __init__(self, model, clips, vid_off, id_base=0, max_queries=4096, k=100, n_split=0, group=None,
+                 engine="auto"):
         """``model``: a ``CALModel`` (text branch used); ``clips`` fp32 [C_local, D] + ``vid_off`` =
-        this rank's bank shard; ``id_base`` = global moment id of the shard's first moment."""
+        this rank's bank shard; ``id_base`` = global moment id of the shard's first moment.
+        ``engine``: "exact" (fp32 CUDA-core scoring, bit-identical to the evaluation path), "tc"
+        (tcgen05 split-bf16 scoring, fp32 scores within 1e-5), "tc_bf16" (plain bf16, 1e-2), or
+        "auto" = "tc" whenever the bank fits its layout (videos of <= 6 clips, D <= 125)."""
         self.model = model
         self.bank = ops.Bank(clips, vid_off)
         self.k = int(k)
@@ -51,9 +57,20 @@ class MomentRetriever:
         self._keep = [fwd, bwd, table, length, fc_w, fc_b]
         self.tokens_dev = torch.empty((mq, self.seq_len), dtype=torch.int64, device=dev)
         self.q_emb = torch.empty((mq, D), dtype=torch.float32, device=dev)
-        self.q_packed = torch.empty(lib.vfr_query_pack_bytes(mq, D) // 4, dtype=torch.float32, device=dev)
         self.text_ws = torch.empty(lib.vfr_text_embed_bytes(mq, self.seq_len, H, E) // 4, dtype=torch.float32, device=dev)
-        self.topk_ws = torch.empty(lib.vfr_score_topk_bytes(mq, n_split), dtype=torch.uint8, device=dev)
+        if engine == "auto":
+            engine = "tc" if (self.bank.n_max <= 6 and D <= 125) else "exact"
+        self.engine = engine
+        eng = self.ENGINES[engine]
+        if eng == 0:
+            self.q_packed = torch.empty(lib.vfr_query_pack_bytes(mq, D) // 4, dtype=torch.float32, device=dev)
+            self.topk_ws = torch.empty(lib.vfr_score_topk_bytes(mq, n_split), dtype=torch.uint8, device=dev)
+            self.q_tc = None
+        else:
+            self.q_packed = None
+            self.q_tc = torch.empty(lib.vfr_tc_query_bytes(mq), dtype=torch.uint8, device=dev)
+            self.topk_ws = torch.empty(lib.vfr_score_topk_tc_bytes(mq, self.bank.n_videos, n_split), dtype=torch.uint8,
+                                       device=dev)
         self.out_s = torch.empty((mq, self.k), dtype=torch.float32, device=dev)
         self.out_i = torch.empty((mq, self.k), dtype=torch.int64, device=dev)
         p = _lib.SearchPlan()
@@ -61,8 +78,13 @@ class MomentRetriever:
         p.lstm_fwd, p.lstm_bwd, p.hidden = fwd.data_ptr(), bwd.data_ptr(), H
         p.fc_w, p.fc_b, p.dim, p.seq_len = fc_w.data_ptr(), fc_b.data_ptr(), D, self.seq_len
         p.bank_packed, p.vid_off, p.mom_off = self.bank.packed.data_ptr(), self.bank.vid_off.data_ptr(), self.bank.mom_off.data_ptr()
+        p.engine = eng
+        if eng:
+            p.bank_tc, p.bank_clips = self.bank.tc(eng).data_ptr(), self.bank.clips.data_ptr()
+            p.uniform6, p.q_tc = self.bank.uniform6, self.q_tc.data_ptr()
         p.n_videos, p.n_max, p.id_base = self.bank.n_videos, self.bank.n_max, int(id_base)
-        p.tokens_dev, p.q_emb, p.q_packed = self.tokens_dev.data_ptr(), self.q_emb.data_ptr(), self.q_packed.data_ptr()
+        p.tokens_dev, p.q_emb = self.tokens_dev.data_ptr(), self.q_emb.data_ptr()
+        p.q_packed = self.q_packed.data_ptr() if self.q_packed is not None else None
         p.text_ws, p.topk_ws = self.text_ws.data_ptr(), self.topk_ws.data_ptr()
         p.out_scores_dev, p.out_ids_dev = self.out_s.data_ptr(), self.out_i.data_ptr()
         p.n_split, p.max_queries = int(n_split), mq
@@ -74,8 +96,21 @@ class MomentRetriever:
         self.host_tokens = torch.empty((mq, self.seq_len), dtype=torch.int64).pin_memory()
         self.host_s = torch.empty((mq, self.k), dtype=torch.float32).pin_memory()
         self.host_i = torch.empty((mq, self.k), dtype=torch.int64).pin_memory()
-        # kernels launched per search step: gather + 20 LSTM steps + 2 fc + query pack + score + finish (+ merge)
-        self.launches_per_step = 1 + self.seq_len + 2 + 1 + 1 + 1 + (1 if self.world > 1 else 0)
+        # kernels launched per search step: gather + 20 LSTM steps + 2 fc + query pack + (threshold init) + score + finish (+ merge)
+        self.launches_per_step = 1 + self.seq_len + 2 + 1 + 1 + 1 + 1 + (1 if self.world > 1 else 0)
+
+    def score_only(self, n_queries):
+        """K4 alone (query pack excluded) on the query embeddings left in ``q_emb`` by the previous
+        search - used by bench.py to time the dominant kernel inside the steps."""
+        lib_stream = torch.cuda.current_stream().cuda_stream
+        b, p = self.bank, self.plan
+        if p.engine:
+            _lib.call("vfr_score_topk_tc", p.bank_tc, p.bank_clips, p.vid_off, p.mom_off, b.n_videos, p.uniform6, b.dim,
+                      p.engine, p.q_tc, p.q_emb, n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev,
+                      p.topk_ws, p.n_split, lib_stream)
+        else:
+            _lib.call("vfr_score_topk", p.bank_packed, p.vid_off, p.mom_off, b.n_videos, b.n_max, b.dim, p.q_packed,
+                      n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev, p.topk_ws, p.n_split, lib_stream)
 
     # -- device-resident step ---------------------------------------------------------------------
     def search_device(self, tokens_dev):
