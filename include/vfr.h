@@ -176,6 +176,30 @@ int vfr_text_embed(const int64_t* tokens, int64_t n_queries, int seq_len, const 
                    int hidden, const float* fc_w, const float* fc_b, int dim, void* workspace, float* out,
                    vfr_stream_t stream);
 
+/* ---- K2 / K3, tensor-core path: split-bf16 GEMMs on tcgen05 (fp32 accuracy) ------------------------
+ * Every fp32 operand is stored as a bf16 (hi, lo) pair and the product is accumulated in fp32 in TMEM
+ * as Ah.Bh + Al.Bh + Ah.Bl (csrc/vfr_gemm_tc.cuh).
+ * vfr_linear_tc: out = act(x W^T + b) with W packed once by vfr_tc_weight_pack; workspace
+ * vfr_linear_tc_bytes(n_rows, in_dim) holds the split copy of x. */
+size_t vfr_tc_weight_bytes(int out_dim, int in_dim);
+int vfr_tc_weight_pack(const float* w, int out_dim, int in_dim, void* packed, vfr_stream_t stream);
+size_t vfr_linear_tc_bytes(int64_t n_rows, int in_dim);
+int vfr_linear_tc(const float* x, int64_t n_rows, int in_dim, int64_t ldx, const void* w_packed,
+                  const float* bias, int out_dim, int relu, float* out, int64_t ldo, void* workspace,
+                  vfr_stream_t stream);
+/* K3 on tensor cores: same contract as vfr_text_embed; `packed` (vfr_text_pack_tc_bytes) holds both
+ * LSTM directions and lang_fc, re-packed once per weight update; workspace vfr_text_embed_tc_bytes
+ * whose FIRST int32 flags out-of-range token ids. */
+size_t vfr_text_pack_tc_bytes(int hidden, int emb, int dim);
+int vfr_text_pack_tc(const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
+                     const float* w_ih_b, const float* w_hh_b, const float* b_ih_b, const float* b_hh_b,
+                     const float* fc_w, const float* fc_b, int hidden, int emb, int dim, void* packed,
+                     vfr_stream_t stream);
+size_t vfr_text_embed_tc_bytes(int64_t n_queries, int seq_len, int hidden, int emb);
+int vfr_text_embed_tc(const int64_t* tokens, int64_t n_queries, int seq_len, const float* table,
+                      int64_t vocab, const float* length_table, int emb, const void* packed, int hidden,
+                      int dim, void* workspace, float* out, vfr_stream_t stream);
+
 /* ---- K1 : frame -> segment pooling --------------------------------------------------------------
  * replaces model/data.py:142-188.  frames fp32 [sum_v F_v, dim] (the get_rgb_features.py .npy rows
  * of all videos back to back), frame_off int64 [V+1].  mode 0 = avg, 1 = max (.npy branch,
@@ -224,6 +248,10 @@ typedef struct vfr_search_plan {
    * bank_tc (vfr_tc_bank_pack), bank_clips fp32 [C, dim] (exact fallback), uniform6, q_tc
    * (vfr_tc_query_bytes(max_queries)) and topk_ws sized by vfr_score_topk_tc_bytes. */
   int engine; const void* bank_tc; const float* bank_clips; int uniform6; void* q_tc;
+  /* text engine: 0 = exact-fp32 CUDA-core K3 (lstm_fwd/lstm_bwd/fc_w/fc_b, text_ws =
+   * vfr_text_embed_bytes); 3 = tensor-core K3 (text_tc = vfr_text_pack_tc blob, text_ws =
+   * vfr_text_embed_tc_bytes). */
+  int text_engine; const void* text_tc;
 } vfr_search_plan;
 
 /* device-resident inputs/outputs; asynchronous */

@@ -1,0 +1,88 @@
+"""GPU tests of the split-bf16 tcgen05 GEMM and of the tensor-core K3 built on it."""
+import numpy as np
+import pytest
+import torch
+
+import vfr_b200  # noqa: F401
+from vfr_b200 import models, ops, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+# stated tolerance of the tensor-core (split-bf16) query-embedding engine against the fp32 reference,
+# relative to the largest embedding component: 20 chained recurrent GEMMs, each ~5e-6 (see below).
+# (The north star allows 1e-2 for bf16 embeddings; the exact-fp32 engine stays at 1e-5.)
+TC_TEXT_TOL = 3e-5
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 5, 3), (257, 257, 33), (300, 501, 777), (1000, 100, 2000), (513, 500, 8194)])
+def test_linear_tc_fp32_accuracy(m, n, k):
+    g = torch.Generator(device=DEV).manual_seed(m * 7 + n)
+    x = torch.randn(m, k, device=DEV, generator=g)
+    w = torch.randn(n, k, device=DEV, generator=g) * 0.05
+    b = torch.randn(n, device=DEV, generator=g)
+    want = x.double() @ w.double().t() + b.double()
+    wp = ops.pack_weight_tc(w)
+    got = ops.linear_tc(x, wp, n, b)
+    scale = want.abs().max().item()
+    err = (got.double() - want).abs().max().item()
+    # split-bf16 keeps 16 mantissa bits per operand (~2e-6); on top of that the TMEM accumulator truncates
+    # instead of rounding, which adds a bias that grows with the number of accumulated k-steps (3K/16)
+    tol = 1e-5 if k <= 2048 else 5e-5
+    assert err <= tol * scale, (err, scale)
+    # the exact-fp32 CUDA-core GEMM agrees with it to the same tolerance
+    ref32 = ops.linear(x, w, b)
+    assert (ref32 - got).abs().max().item() <= tol * scale
+    got_relu = ops.linear_tc(x, wp, n, b, relu=True)
+    assert torch.equal(got_relu, got.clamp_min(0))
+
+
+def _model(sd, feat_dim, normalize_lang=False):
+    m = models.CALModel(visual_input_dim=2 * feat_dim + 2, pretrained_emb=torch.from_numpy(sd["word_embedding.weight"]),
+                        normalize_lang=normalize_lang)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return m.to(DEV).eval()
+
+
+def test_text_embed_tc_matches_reference(golden):
+    z, meta = golden("tiny_eval")
+    videos = synth.make_videos(meta["seed"], meta["n_videos"], meta["feat_dim"], tuple(meta["seg_choices"]), tuple(meta["seg_probs"]))
+    queries = synth.make_queries(meta["seed"], videos, meta["n_queries"], meta["vocab"])
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], spread=meta["spread"])
+    model = _model(sd, meta["feat_dim"])
+    tok = torch.from_numpy(queries["tokens"]).to(DEV)
+    with torch.no_grad():
+        exact = model(tok, False, DEV)
+        model.engine = "tc"
+        got = model(tok, False, DEV)
+    scale = np.abs(z["query_emb"]).max()
+    assert np.abs(got.cpu().numpy() - z["query_emb"]).max() <= TC_TEXT_TOL * scale
+    assert (got - exact).abs().max().item() <= TC_TEXT_TOL * scale
+
+
+@pytest.mark.parametrize("nl", [0, 1])
+def test_text_embed_tc_normalize_lang_and_bad_tokens(golden, nl):
+    z, meta = golden(f"text_nl{nl}")
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], normalize_lang=bool(nl))
+    q = synth.make_queries(meta["seed"], synth.make_videos(meta["seed"], 4, meta["feat_dim"]), meta["n_queries"], meta["vocab"])
+    model = _model(sd, meta["feat_dim"], bool(nl))
+    model.engine = "tc"
+    with torch.no_grad():
+        emb = model(torch.from_numpy(q["tokens"]).to(DEV), False, DEV)
+    scale = np.abs(z["emb_batch1"]).max()
+    assert np.abs(emb.cpu().numpy() - z["emb_batch1"]).max() <= TC_TEXT_TOL * scale
+    bad = torch.from_numpy(q["tokens"]).clone()
+    bad[2, 1] = -3
+    with pytest.raises(IndexError):
+        model(bad.to(DEV), False, DEV)
+
+
+def test_text_embed_tc_large_batch_vs_exact():
+    sd = synth.make_state_dict(5, 8, 3000)
+    model = _model(sd, 8)
+    rng = np.random.default_rng(0)
+    tok = torch.from_numpy(rng.integers(1, 3000, size=(700, 20))).to(DEV)    # not a multiple of the 256-row tile
+    with torch.no_grad():
+        exact = model(tok, False, DEV)
+        model.engine = "tc"
+        got = model(tok, False, DEV)
+    assert (got - exact).abs().max().item() <= TC_TEXT_TOL * exact.abs().max().item()

@@ -28,8 +28,9 @@ def test_search_host_matches_oracle_and_device_path(engine):
     sd, model, clips, tokens = _setup()
     V = clips.shape[0] // 6
     vid_off = np.arange(V + 1) * 6
-    retr = MomentRetriever(model, torch.from_numpy(clips).to(DEV), vid_off, max_queries=128, k=10, engine=engine)
-    assert retr.engine == engine
+    retr = MomentRetriever(model, torch.from_numpy(clips).to(DEV), vid_off, max_queries=128, k=10, engine=engine,
+                           text_engine=engine)
+    assert retr.engine == engine and retr.text_engine == engine
     s, i = retr.search(tokens)
     sd_, id_ = retr.search_device(torch.from_numpy(tokens).to(DEV))
     assert torch.equal(s, sd_.cpu()) and torch.equal(i, id_.cpu())

@@ -36,7 +36,8 @@ class SearchPlan(C.Structure):
                 ("n_videos", _l), ("n_max", _i), ("id_base", _l),
                 ("tokens_dev", _p), ("q_emb", _p), ("q_packed", _p), ("text_ws", _p), ("topk_ws", _p),
                 ("out_scores_dev", _p), ("out_ids_dev", _p), ("n_split", _i), ("max_queries", _l),
-                ("engine", _i), ("bank_tc", _p), ("bank_clips", _p), ("uniform6", _i), ("q_tc", _p)]
+                ("engine", _i), ("bank_tc", _p), ("bank_clips", _p), ("uniform6", _i), ("q_tc", _p),
+                ("text_engine", _i), ("text_tc", _p)]
 
 
 # name -> (restype, argtypes); kept in the order of include/vfr.h
@@ -70,6 +71,14 @@ PROTOTYPES = {
     "vfr_lstm_pack": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "vfr_text_embed_bytes": (_z, [_l, _i, _i, _i]),
     "vfr_text_embed": (_i, [_p, _l, _i, _p, _l, _p, _i, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
+    "vfr_tc_weight_bytes": (_z, [_i, _i]),
+    "vfr_tc_weight_pack": (_i, [_p, _i, _i, _p, _p]),
+    "vfr_linear_tc_bytes": (_z, [_l, _i]),
+    "vfr_linear_tc": (_i, [_p, _l, _i, _l, _p, _p, _i, _i, _p, _l, _p, _p]),
+    "vfr_text_pack_tc_bytes": (_z, [_i, _i, _i]),
+    "vfr_text_pack_tc": (_i, [_p] * 10 + [_i, _i, _i, _p, _p]),
+    "vfr_text_embed_tc_bytes": (_z, [_l, _i, _i, _i]),
+    "vfr_text_embed_tc": (_i, [_p, _l, _i, _p, _l, _p, _i, _p, _i, _i, _p, _p, _p]),
     "vfr_segment_pool_bytes": (_z, [_l, _i, _i]),
     "vfr_segment_pool": (_i, [_p, _p, _l, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
     "vfr_ranking_loss_bytes": (_z, [_i, _i, _i, _i]),

@@ -1,0 +1,256 @@
+// Split-bf16 tensor-core GEMM  C[M,N] = A[M,K] * B[N,K]^T  at fp32 accuracy (tcgen05 / TMEM / TMA).
+//
+// Each fp32 operand x is stored as a bf16 pair (hi = bf16(x), lo = bf16(x - hi)); a packed row is
+// [hi(0..Kp) | lo(0..Kp)] bf16, Kp = K rounded up to 32.  The product is accumulated in fp32 in TMEM as
+//     A.B^T ~= Ah.Bh^T + Al.Bh^T + Ah.Bl^T        (relative error ~2^-17 / sqrt(K) per dot product)
+// One CTA computes a 256 x 256 output tile as two 128-row accumulators (2 x 256 TMEM columns), so a
+// K-chunk of 32 needs (256 + 256) rows x (hi + lo) x 64 B = 64 KB of operands for 12 MMAs of
+// 128x256x16 - the same bytes-per-MAC as a cta_group::2 pair, without a cluster.  Operands arrive by
+// TMA (SWIZZLE_64B boxes) through a 3-stage mbarrier ring; one thread issues the MMAs; 8 epilogue warps
+// read the accumulators (tcgen05.ld 32x32b.x16, thread = output row) and apply a fused epilogue functor.
+#pragma once
+#include "vfr_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace vfr {
+
+constexpr int GT_BM = 256, GT_BN = 256, GT_BK = 32, GT_STAGES = 3;
+constexpr int GT_THREADS = 320;
+constexpr int GT_A_SUB = 128 * GT_BK * 2;                 // one [128 x 32] bf16 box = 8 KB
+constexpr int GT_B_BOX = GT_BN * GT_BK * 2;               // one [256 x 32] bf16 box = 16 KB
+constexpr int GT_STAGE = 4 * GT_A_SUB + 2 * GT_B_BOX;     // Ah0 Ah1 Al0 Al1 Bh Bl = 64 KB
+constexpr uint32_t GT_SMEM = GT_STAGES * GT_STAGE + 1024 + 256;
+
+struct GemmTcMaps {          // up to two problems per launch (blockIdx.z)
+  CUtensorMap a[2];
+  CUtensorMap b[2];
+};
+
+__device__ __forceinline__ void gt_tma_load(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void gt_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void gt_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void gt_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void gt_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major SWIZZLE_64B operand tile: rows of 64 B, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t gt_desc(const void* smem_ptr) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                         // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void gt_wait(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t done = 0;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(ns);
+    if ((spin & 0xfff) == 0xfff) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("vfr: gemm_tc mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void gt_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split an fp32 value into its bf16 hi / lo pair
+__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// Epi: struct with  __device__ void operator()(int z, int m, int n0, const float (&v)[16]) const
+//      called for 16 consecutive output columns n0..n0+15 of row m (m < M guaranteed, columns not).
+template <class Epi>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M, int k_chunks, int kp, Epi epi) {
+  extern __shared__ uint8_t gt_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gt_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + GT_STAGES;
+  uint64_t* acc_full = bars + 2 * GT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * GT_BN;
+  const CUtensorMap* ma = &maps.a[z];
+  const CUtensorMap* mb = &maps.b[z];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  gt_fence_before();
+  __syncthreads();
+  gt_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 0; c < k_chunks; ++c) {
+        const int s = c % GT_STAGES;
+        gt_wait(&empty[s], ((c / GT_STAGES) & 1) ^ 1, 64);
+        uint8_t* st = smem + s * GT_STAGE;
+        mbar_expect_tx(&full[s], GT_STAGE);
+        const int kc = c * GT_BK;
+        gt_tma_load(st + 0 * GT_A_SUB, ma, kc, m0, &full[s]);              // Ah rows m0..+127
+        gt_tma_load(st + 1 * GT_A_SUB, ma, kc, m0 + 128, &full[s]);        // Ah rows m0+128..
+        gt_tma_load(st + 2 * GT_A_SUB, ma, kp + kc, m0, &full[s]);         // Al
+        gt_tma_load(st + 3 * GT_A_SUB, ma, kp + kc, m0 + 128, &full[s]);
+        gt_tma_load(st + 4 * GT_A_SUB, mb, kc, n0, &full[s]);              // Bh
+        gt_tma_load(st + 4 * GT_A_SUB + GT_B_BOX, mb, kp + kc, n0, &full[s]);  // Bl
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GT_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int c = 0; c < k_chunks; ++c) {
+        const int s = c % GT_STAGES;
+        gt_wait(&full[s], (c / GT_STAGES) & 1, 32);
+        gt_fence_after();
+        uint8_t* st = smem + s * GT_STAGE;
+        const uint64_t bh = gt_desc(st + 4 * GT_A_SUB), bl = gt_desc(st + 4 * GT_A_SUB + GT_B_BOX);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const uint64_t ah = gt_desc(st + sub * GT_A_SUB), al = gt_desc(st + (2 + sub) * GT_A_SUB);
+          const uint32_t d = tmem_base + (uint32_t)sub * 256;
+#pragma unroll
+          for (int k = 0; k < GT_BK / 16; ++k) {
+            gt_mma(d, ah + 2 * k, bh + 2 * k, idesc, (c | k) ? 1u : 0u);
+            gt_mma(d, al + 2 * k, bh + 2 * k, idesc, 1u);
+            gt_mma(d, ah + 2 * k, bl + 2 * k, idesc, 1u);
+          }
+        }
+        gt_commit(&empty[s]);
+      }
+      gt_commit(acc_full);
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int sub = ew >> 2;
+    const int m = m0 + sub * 128 + quarter * 32 + lane;
+    gt_wait(acc_full, 0, 256);
+    gt_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)sub * 256;
+    for (int c = 0; c < GT_BN / 16; ++c) {
+      float v[16];
+      gt_ld16(taddr + c * 16, v);
+      if (m < M) epi(z, m, n0 + c * 16, v);
+    }
+  }
+  gt_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// ---- host helpers ---------------------------------------------------------------------------------
+typedef CUresult (*GtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline GtEncodeFn gt_encode_fn() {
+  static GtEncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<GtEncodeFn>(ptr);
+  }
+  return fn;
+}
+
+// packed operand [rows, ld_elems] bf16 (ld_elems >= 2*kp); box = [32 k] x [box_rows]; rows beyond `rows` read as 0
+static inline int gt_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
+  GtEncodeFn enc = gt_encode_fn();
+  VFR_REQUIRE(enc, VFR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)ld_elems, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {GT_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VFR_REQUIRE(r == CUDA_SUCCESS, VFR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return VFR_OK;
+}
+
+static inline int gt_kp(int k) { return (k + GT_BK - 1) / GT_BK * GT_BK; }
+
+// A: packed [M, lda] (lda >= 2*kp), B: packed [N, ldb]; batch <= 2 problems with identical shapes
+template <class Epi>
+static int launch_gemm_tc(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda,
+                          int64_t ldb, Epi epi, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || kp <= 0) return VFR_OK;
+  VFR_REQUIRE(batch >= 1 && batch <= 2 && kp % GT_BK == 0 && lda >= 2 * kp && ldb >= 2 * kp && lda % 8 == 0 && ldb % 8 == 0,
+              VFR_ERR_INVALID, "launch_gemm_tc: bad operand layout");
+  GemmTcMaps maps;
+  for (int z = 0; z < batch; ++z) {
+    int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128);
+    if (rc) return rc;
+    rc = gt_make_map(&maps.b[z], b[z], (uint64_t)N, (uint64_t)ldb, GT_BN);
+    if (rc) return rc;
+  }
+  if (batch == 1) { maps.a[1] = maps.a[0]; maps.b[1] = maps.b[0]; }
+  VFR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
+  dim3 grid((N + GT_BN - 1) / GT_BN, (M + GT_BM - 1) / GT_BM, batch);
+  gemm_tc_kernel<Epi><<<grid, GT_THREADS, GT_SMEM, st>>>(maps, M, kp / GT_BK, kp, epi);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace vfr

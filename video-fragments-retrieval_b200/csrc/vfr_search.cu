@@ -8,8 +8,12 @@ using namespace vfr;
 
 static int check_plan(const vfr_search_plan* p, int64_t n_queries, int k) {
   VFR_REQUIRE(p, VFR_ERR_INVALID, "vfr_search: null plan");
-  VFR_REQUIRE(p->table && p->lstm_fwd && p->lstm_bwd && p->fc_w && p->fc_b && p->vid_off && p->mom_off,
-              VFR_ERR_INVALID, "vfr_search: null model/bank pointer in plan");
+  VFR_REQUIRE(p->table && p->vid_off && p->mom_off, VFR_ERR_INVALID, "vfr_search: null model/bank pointer in plan");
+  VFR_REQUIRE(p->text_engine == 0 || p->text_engine == 3, VFR_ERR_INVALID, "vfr_search: text_engine=%d", p->text_engine);
+  if (p->text_engine == 0)
+    VFR_REQUIRE(p->lstm_fwd && p->lstm_bwd && p->fc_w && p->fc_b, VFR_ERR_INVALID, "vfr_search: null text weights");
+  else
+    VFR_REQUIRE(p->text_tc, VFR_ERR_INVALID, "vfr_search: text engine 3 needs text_tc");
   VFR_REQUIRE(p->tokens_dev && p->q_emb && p->text_ws && p->topk_ws && p->out_scores_dev && p->out_ids_dev,
               VFR_ERR_INVALID, "vfr_search: null scratch pointer in plan");
   VFR_REQUIRE(p->engine == 0 || p->engine == 1 || p->engine == 3, VFR_ERR_INVALID, "vfr_search: engine=%d", p->engine);
@@ -28,8 +32,12 @@ extern "C" int vfr_search_device(const vfr_search_plan* p, const int64_t* tokens
   int rc = check_plan(p, n_queries, k);
   if (rc) return rc;
   VFR_REQUIRE(tokens_dev && out_scores_dev && out_ids_dev, VFR_ERR_INVALID, "vfr_search_device: null pointer");
-  rc = vfr_text_embed(tokens_dev, n_queries, p->seq_len, p->table, p->vocab, p->length_table, p->emb, p->lstm_fwd,
-                      p->lstm_bwd, p->hidden, p->fc_w, p->fc_b, p->dim, p->text_ws, p->q_emb, stream);
+  if (p->text_engine == 3)
+    rc = vfr_text_embed_tc(tokens_dev, n_queries, p->seq_len, p->table, p->vocab, p->length_table, p->emb, p->text_tc,
+                           p->hidden, p->dim, p->text_ws, p->q_emb, stream);
+  else
+    rc = vfr_text_embed(tokens_dev, n_queries, p->seq_len, p->table, p->vocab, p->length_table, p->emb, p->lstm_fwd,
+                        p->lstm_bwd, p->hidden, p->fc_w, p->fc_b, p->dim, p->text_ws, p->q_emb, stream);
   if (rc) return rc;
   if (p->engine != 0) {
     rc = vfr_tc_query_pack(p->q_emb, n_queries, p->dim, p->engine, p->q_tc, stream);

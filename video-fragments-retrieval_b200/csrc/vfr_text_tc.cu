@@ -1,0 +1,337 @@
+// K3 (tensor-core path): query embedding  GloVe gather -> BiLSTM -> Linear  with every GEMM on
+// tcgen05 as a split-bf16 product (vfr_gemm_tc.cuh), fp32 accumulation and fp32 cell state.
+// Same contract as vfr_text_embed (reference model/models.py:33-48,61-66).
+//
+// Layout: per direction L slots [B][2*Kp] bf16, Kp = Hp + Ep (H, E rounded up to 32); slot t holds
+// the split operand [h_{t-1} | x_t] = (hi | lo), so one recurrent step is ONE GEMM against the packed
+// weights [W_hh | W_ih] (rows interleaved 4j+g) whose epilogue adds the bias, applies the LSTM cell and
+// writes h_t, already split into bf16 hi/lo, straight into slot t+1 (the last step writes into the
+// [h_fwd | h_bwd] operand of the final projection).  Both directions share a launch (grid z).
+#include "vfr_gemm_tc.cuh"
+
+namespace vfr {
+
+struct TextTcDims {
+  int H, E, D, L;
+  int Hp, Ep, Kp;        // padded widths
+  int Np;                // 4H rounded up to 256 rows
+  int Dp;                // D rounded up to 256 rows
+  int Kf;                // 2*Hp : K of the final projection
+};
+
+static TextTcDims text_dims(int hidden, int emb, int dim, int seq_len) {
+  TextTcDims d;
+  d.H = hidden; d.E = emb; d.D = dim; d.L = seq_len;
+  d.Hp = gt_kp(hidden); d.Ep = gt_kp(emb); d.Kp = d.Hp + d.Ep;
+  d.Np = (4 * hidden + GT_BN - 1) / GT_BN * GT_BN;
+  d.Dp = (dim + GT_BN - 1) / GT_BN * GT_BN;
+  d.Kf = 2 * d.Hp;
+  return d;
+}
+
+// packed model blob: [W fwd | W bwd | fc | bias fwd | bias bwd | fc bias]
+struct TextTcBlob {
+  const __nv_bfloat16* w[2];
+  const __nv_bfloat16* fc;
+  const float* bias[2];
+  const float* fc_b;
+  size_t bytes;
+};
+static TextTcBlob text_blob(const void* base, const TextTcDims& d) {
+  TextTcBlob b;
+  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base);
+  const size_t wsz = (size_t)d.Np * 2 * d.Kp;
+  b.w[0] = p;
+  b.w[1] = p + wsz;
+  b.fc = p + 2 * wsz;
+  const float* f = reinterpret_cast<const float*>(b.fc + (size_t)d.Dp * 2 * d.Kf);
+  b.bias[0] = f;
+  b.bias[1] = f + 4 * d.H;
+  b.fc_b = f + 8 * d.H;
+  b.bytes = (2 * wsz + (size_t)d.Dp * 2 * d.Kf) * 2 + ((size_t)8 * d.H + d.D) * 4;
+  return b;
+}
+
+__global__ void tc_text_pack_lstm_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                         const float* __restrict__ b_ih, const float* __restrict__ b_hh, TextTcDims d,
+                                         __nv_bfloat16* __restrict__ w, float* __restrict__ bias) {
+  const int64_t total = (int64_t)4 * d.H * d.Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int rp = (int)(i / d.Kp), k = (int)(i % d.Kp);
+    const int j = rp >> 2, g = rp & 3, r = g * d.H + j;
+    float x = 0.f;
+    if (k < d.H) x = w_hh[(int64_t)r * d.H + k];
+    else if (k >= d.Hp && k < d.Hp + d.E) x = w_ih[(int64_t)r * d.E + (k - d.Hp)];
+    __nv_bfloat16 hi, lo;
+    split2(x, hi, lo);
+    w[(int64_t)rp * 2 * d.Kp + k] = hi;
+    w[(int64_t)rp * 2 * d.Kp + d.Kp + k] = lo;
+    if (k == 0) bias[rp] = b_ih[r] + b_hh[r];
+  }
+}
+
+__global__ void tc_text_pack_fc_kernel(const float* __restrict__ fc_w, const float* __restrict__ fc_b, TextTcDims d,
+                                       __nv_bfloat16* __restrict__ w, float* __restrict__ bias) {
+  const int64_t total = (int64_t)d.D * d.Kf;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / d.Kf), k = (int)(i % d.Kf);
+    const int dir = k / d.Hp, kk = k % d.Hp;
+    float x = 0.f;
+    if (kk < d.H) x = fc_w[(int64_t)r * 2 * d.H + dir * d.H + kk];
+    __nv_bfloat16 hi, lo;
+    split2(x, hi, lo);
+    w[(int64_t)r * 2 * d.Kf + k] = hi;
+    w[(int64_t)r * 2 * d.Kf + d.Kf + k] = lo;
+    if (k == 0) bias[r] = fc_b[r];
+  }
+}
+
+// x part of every slot of both directions; one warp per (b, t)
+__global__ void tc_text_gather_kernel(const int64_t* __restrict__ tokens, int64_t B, TextTcDims d,
+                                      const float* __restrict__ table, int64_t vocab, const float* __restrict__ length,
+                                      __nv_bfloat16* __restrict__ slots_f, __nv_bfloat16* __restrict__ slots_b,
+                                      int* __restrict__ bad_token) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= B * d.L) return;
+  const int64_t b = w / d.L;
+  const int t = (int)(w % d.L);
+  int64_t id = tokens[b * d.L + t];
+  if (id < 0 || id >= vocab) { if (lane == 0) atomicExch(bad_token, 1); id = 0; }
+  const float* row = table + id * d.E;
+  float denom = 1.f, len = 1.f;
+  if (length) {
+    float ss = 0.f;
+    for (int k = lane; k < d.E; k += 32) ss = __fmaf_rn(row[k], row[k], ss);
+    ss = warp_sum(ss);
+    denom = __fadd_rn(__fsqrt_rn(ss), VFR_NORM_EPS);
+    len = length[id];
+  }
+  const int64_t ld = 2 * (int64_t)d.Kp;
+  __nv_bfloat16* df = slots_f + ((int64_t)t * B + b) * ld + d.Hp;              // forward consumes x_t at step t
+  __nv_bfloat16* db = slots_b + ((int64_t)(d.L - 1 - t) * B + b) * ld + d.Hp;  // backward consumes x_{L-1-t}
+  for (int k = lane; k < d.E; k += 32) {
+    float v = row[k];
+    if (length) v = __fmul_rn(__fdiv_rn(v, denom), len);
+    __nv_bfloat16 hi, lo;
+    split2(v, hi, lo);
+    df[k] = hi; df[d.Kp + k] = lo;
+    db[k] = hi; db[d.Kp + k] = lo;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.f * sigmoid_fast(2.f * x) - 1.f; }
+
+struct EpiLstmTc {
+  const float* bias[2];
+  float* c[2];                 // [B, H] fp32
+  __nv_bfloat16* dst[2];       // where h_t goes: row stride ld, hi at column col0 + j, lo at + lo_off
+  int64_t ld;
+  int col0[2];
+  int lo_off;
+  int H;
+  int first;
+  __device__ __forceinline__ void operator()(int z, int m, int n0, const float (&v)[16]) const {
+    const int j0 = n0 >> 2;
+    if (j0 >= H) return;
+    const float4* bz = reinterpret_cast<const float4*>(bias[z] + n0);
+    float4* cp = reinterpret_cast<float4*>(c[z] + (int64_t)m * H + j0);
+    float4 c_prev = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!first) c_prev = *cp;
+    const float cpv[4] = {c_prev.x, c_prev.y, c_prev.z, c_prev.w};
+    float cn[4];
+    __nv_bfloat16 hh[4], hl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 bb = __ldg(bz + u);
+      const float gi = v[4 * u + 0] + bb.x, gf = v[4 * u + 1] + bb.y, gg = v[4 * u + 2] + bb.z, go = v[4 * u + 3] + bb.w;
+      cn[u] = sigmoid_fast(gf) * cpv[u] + sigmoid_fast(gi) * tanh_fast(gg);
+      const float h = sigmoid_fast(go) * tanh_fast(cn[u]);
+      split2(h, hh[u], hl[u]);
+    }
+    *cp = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    __nv_bfloat16* o = dst[z] + (int64_t)m * ld + col0[z] + j0;
+    *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
+    *reinterpret_cast<uint2*>(o + lo_off) = make_uint2(pack_bf16x2(hl[0], hl[1]), pack_bf16x2(hl[2], hl[3]));
+  }
+};
+
+struct EpiBiasOutTc {
+  float* out;
+  int64_t ldo;
+  int N;
+  const float* bias;
+  int relu;
+  __device__ __forceinline__ void operator()(int, int m, int n0, const float (&v)[16]) const {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int n = n0 + j;
+      if (n < N) {
+        float x = v[j] + (bias ? __ldg(bias + n) : 0.f);
+        if (relu) x = fmaxf(x, 0.f);
+        out[(int64_t)m * ldo + n] = x;
+      }
+    }
+  }
+};
+
+// fp32 rows -> split bf16 packed rows (generic operand preparation, one warp per row)
+__global__ void tc_split_rows_kernel(const float* __restrict__ x, int64_t rows, int k, int64_t ldx, int kp,
+                                     __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* src = x + r * ldx;
+  __nv_bfloat16* dst = out + r * 2 * (int64_t)kp;
+  for (int c = lane; c < kp; c += 32) {
+    __nv_bfloat16 hi, lo;
+    split2(c < k ? src[c] : 0.f, hi, lo);
+    dst[c] = hi;
+    dst[kp + c] = lo;
+  }
+}
+
+}  // namespace vfr
+
+using namespace vfr;
+
+// ---------------------------------------------------------------------------------------------
+// generic split-bf16 linear layer (building block of the K2 tensor-core path; also the GEMM self-test)
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t vfr_tc_weight_bytes(int out_dim, int in_dim) {
+  if (out_dim <= 0 || in_dim <= 0) return 0;
+  return (size_t)out_dim * 2 * gt_kp(in_dim) * 2;
+}
+
+extern "C" int vfr_tc_weight_pack(const float* w, int out_dim, int in_dim, void* packed, vfr_stream_t stream) {
+  VFR_REQUIRE(w && packed && out_dim > 0 && in_dim > 0, VFR_ERR_INVALID, "vfr_tc_weight_pack: bad argument");
+  tc_split_rows_kernel<<<(out_dim + 7) / 8, 256, 0, (cudaStream_t)stream>>>(w, out_dim, in_dim, in_dim, gt_kp(in_dim),
+                                                                            reinterpret_cast<__nv_bfloat16*>(packed));
+  return check_launch("tc_split_rows_kernel");
+}
+
+extern "C" size_t vfr_linear_tc_bytes(int64_t n_rows, int in_dim) {
+  if (n_rows <= 0 || in_dim <= 0) return 0;
+  return (size_t)n_rows * 2 * gt_kp(in_dim) * 2;
+}
+
+extern "C" int vfr_linear_tc(const float* x, int64_t n_rows, int in_dim, int64_t ldx, const void* w_packed,
+                             const float* bias, int out_dim, int relu, float* out, int64_t ldo, void* workspace,
+                             vfr_stream_t stream) {
+  VFR_REQUIRE(x && w_packed && out && workspace, VFR_ERR_INVALID, "vfr_linear_tc: null pointer");
+  VFR_REQUIRE(n_rows >= 0 && n_rows < (int64_t(1) << 31) && in_dim > 0 && out_dim > 0 && ldx >= in_dim && ldo >= out_dim,
+              VFR_ERR_INVALID, "vfr_linear_tc: bad shape");
+  if (n_rows == 0) return VFR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kp = gt_kp(in_dim);
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(workspace);
+  tc_split_rows_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(x, n_rows, in_dim, ldx, kp, xs);
+  int rc = check_launch("tc_split_rows_kernel");
+  if (rc) return rc;
+  const void* a[1] = {xs};
+  const void* b[1] = {w_packed};
+  EpiBiasOutTc epi{out, ldo, out_dim, bias, relu};
+  return launch_gemm_tc(a, b, 1, (int)n_rows, out_dim, kp, 2 * (int64_t)kp, 2 * (int64_t)kp, epi, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t vfr_text_pack_tc_bytes(int hidden, int emb, int dim) {
+  if (hidden <= 0 || emb <= 0 || dim <= 0) return 0;
+  const TextTcDims d = text_dims(hidden, emb, dim, 1);
+  return text_blob(nullptr, d).bytes;
+}
+
+extern "C" int vfr_text_pack_tc(const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
+                                const float* w_ih_b, const float* w_hh_b, const float* b_ih_b, const float* b_hh_b,
+                                const float* fc_w, const float* fc_b, int hidden, int emb, int dim, void* packed,
+                                vfr_stream_t stream) {
+  VFR_REQUIRE(w_ih_f && w_hh_f && b_ih_f && b_hh_f && w_ih_b && w_hh_b && b_ih_b && b_hh_b && fc_w && fc_b && packed,
+              VFR_ERR_INVALID, "vfr_text_pack_tc: null pointer");
+  VFR_REQUIRE(hidden > 0 && hidden % 4 == 0 && emb > 0 && dim > 0, VFR_ERR_UNSUPPORTED,
+              "vfr_text_pack_tc: hidden must be a positive multiple of 4");
+  const TextTcDims d = text_dims(hidden, emb, dim, 1);
+  const TextTcBlob blob = text_blob(packed, d);
+  cudaStream_t st = (cudaStream_t)stream;
+  VFR_CUDA(cudaMemsetAsync(packed, 0, blob.bytes, st));
+  const float* wi[2] = {w_ih_f, w_ih_b};
+  const float* wh[2] = {w_hh_f, w_hh_b};
+  const float* bi[2] = {b_ih_f, b_ih_b};
+  const float* bh[2] = {b_hh_f, b_hh_b};
+  for (int z = 0; z < 2; ++z) {
+    tc_text_pack_lstm_kernel<<<1184, 256, 0, st>>>(wi[z], wh[z], bi[z], bh[z], d, const_cast<__nv_bfloat16*>(blob.w[z]),
+                                                   const_cast<float*>(blob.bias[z]));
+    int rc = check_launch("tc_text_pack_lstm_kernel");
+    if (rc) return rc;
+  }
+  tc_text_pack_fc_kernel<<<296, 256, 0, st>>>(fc_w, fc_b, d, const_cast<__nv_bfloat16*>(blob.fc),
+                                              const_cast<float*>(blob.fc_b));
+  return check_launch("tc_text_pack_fc_kernel");
+}
+
+extern "C" size_t vfr_text_embed_tc_bytes(int64_t n_queries, int seq_len, int hidden, int emb) {
+  if (n_queries <= 0 || seq_len <= 0 || hidden <= 0 || emb <= 0) return 0;
+  const TextTcDims d = text_dims(hidden, emb, 1, seq_len);
+  const size_t slots = (size_t)2 * seq_len * n_queries * 2 * d.Kp * 2;    // bf16
+  const size_t hcat = (size_t)n_queries * 2 * d.Kf * 2;
+  const size_t c = (size_t)2 * n_queries * hidden * 4;
+  return 16 + slots + hcat + c;
+}
+
+extern "C" int vfr_text_embed_tc(const int64_t* tokens, int64_t n_queries, int seq_len, const float* table,
+                                 int64_t vocab, const float* length_table, int emb, const void* packed, int hidden,
+                                 int dim, void* workspace, float* out, vfr_stream_t stream) {
+  VFR_REQUIRE(tokens && table && packed && workspace && out, VFR_ERR_INVALID, "vfr_text_embed_tc: null pointer");
+  VFR_REQUIRE(n_queries > 0 && n_queries < (int64_t(1) << 31) && seq_len > 0 && hidden > 0 && hidden % 4 == 0 && emb > 0 &&
+                  dim > 0 && vocab > 0,
+              VFR_ERR_INVALID, "vfr_text_embed_tc: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const TextTcDims d = text_dims(hidden, emb, dim, seq_len);
+  const TextTcBlob blob = text_blob(packed, d);
+  const int64_t B = n_queries;
+  const int64_t ld = 2 * (int64_t)d.Kp;
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  int* bad = reinterpret_cast<int*>(base);
+  __nv_bfloat16* slots[2];
+  slots[0] = reinterpret_cast<__nv_bfloat16*>(base + 16);
+  slots[1] = slots[0] + (size_t)seq_len * B * ld;
+  __nv_bfloat16* hcat = slots[1] + (size_t)seq_len * B * ld;
+  float* c0 = reinterpret_cast<float*>(hcat + (size_t)B * 2 * d.Kf);
+  float* c[2] = {c0, c0 + (size_t)B * hidden};
+  // zero: flag, all operand slots (h_{-1} = 0 and every pad column) and the final operand
+  VFR_CUDA(cudaMemsetAsync(base, 0, 16 + ((size_t)2 * seq_len * B * ld + (size_t)B * 2 * d.Kf) * 2, st));
+  {
+    const int64_t warps = B * seq_len;
+    tc_text_gather_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(tokens, B, d, table, vocab, length_table, slots[0],
+                                                                     slots[1], bad);
+    int rc = check_launch("tc_text_gather_kernel");
+    if (rc) return rc;
+  }
+  for (int t = 0; t < seq_len; ++t) {
+    const void* a[2] = {slots[0] + (size_t)t * B * ld, slots[1] + (size_t)t * B * ld};
+    const void* b[2] = {blob.w[0], blob.w[1]};
+    EpiLstmTc epi{};
+    const bool last = (t == seq_len - 1);
+    for (int z = 0; z < 2; ++z) {
+      epi.bias[z] = blob.bias[z];
+      epi.c[z] = c[z];
+      epi.dst[z] = last ? hcat : slots[z] + (size_t)(t + 1) * B * ld;
+      epi.col0[z] = last ? z * d.Hp : 0;
+    }
+    epi.ld = last ? 2 * (int64_t)d.Kf : ld;
+    epi.lo_off = last ? d.Kf : d.Kp;
+    epi.H = hidden;
+    epi.first = (t == 0);
+    int rc = launch_gemm_tc(a, b, 2, (int)B, 4 * hidden, d.Kp, ld, ld, epi, st);
+    if (rc) return rc;
+  }
+  const void* a[1] = {hcat};
+  const void* b[1] = {blob.fc};
+  EpiBiasOutTc epi{out, dim, dim, blob.fc_b, 0};
+  return launch_gemm_tc(a, b, 1, (int)B, dim, d.Kf, 2 * (int64_t)d.Kf, 2 * (int64_t)d.Kf, epi, st);
+}

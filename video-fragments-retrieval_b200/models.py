@@ -85,6 +85,9 @@ class CALModel(nn.Module):
             self.lang_fc = nn.Linear(hidden_size * 2, emb_dim)
             self.lang_fc.apply(init_weights)
         self._packed = None   # (version key, packed fwd, packed bwd)
+        self._packed_tc = None
+        # "exact": fp32 CUDA-core GEMMs (default, parity-critical evaluation); "tc": tcgen05 split-bf16 GEMMs
+        self.engine = "exact"
 
     def init_hidden(self, batch_size, device):
         """Zero (h0, c0) of the BiLSTM (models.py:50-52); the kernels start from zeros implicitly."""
@@ -107,9 +110,20 @@ class CALModel(nn.Module):
             self._packed = (key, ops.lstm_pack(*[p.detach() for p in ps[:4]]), ops.lstm_pack(*[p.detach() for p in ps[4:]]))
         return self._packed[1], self._packed[2]
 
+    def _packed_text_tc(self):
+        ps = self._text_params()[:10]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._packed_tc is None or self._packed_tc[0] != key:
+            d = [p.detach() for p in ps]
+            self._packed_tc = (key, ops.text_pack_tc(d[:4], d[4:8], d[8], d[9]))
+        return self._packed_tc[1]
+
     def _text_forward_kernels(self, tokens):
-        fwd, bwd = self._packed_lstm()
         length = self.learnable_length.weight.detach() if self.normalize_lang else None
+        if self.engine == "tc":
+            return ops.text_embed_tc(tokens, self.word_embedding.weight.detach(), length, self._packed_text_tc(),
+                                     self.hidden_size, self.lang_fc.weight.shape[0])
+        fwd, bwd = self._packed_lstm()
         return ops.text_embed(tokens, self.word_embedding.weight.detach(), length, fwd, bwd, self.hidden_size,
                               self.lang_fc.weight.detach(), self.lang_fc.bias.detach())
 

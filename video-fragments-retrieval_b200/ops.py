@@ -306,6 +306,57 @@ def text_embed(tokens, table, length_table, packed_fwd, packed_bwd, hidden, fc_w
     return out
 
 
+def pack_weight_tc(weight):
+    _need_cuda(weight)
+    w = _f32c(weight)
+    packed = torch.empty(_lib.load().vfr_tc_weight_bytes(w.shape[0], w.shape[1]), dtype=torch.uint8, device=w.device)
+    _lib.call("vfr_tc_weight_pack", _ptr(w), w.shape[0], w.shape[1], _ptr(packed), _stream())
+    return packed
+
+
+def linear_tc(x, w_packed, out_dim, bias=None, relu=False):
+    """Tensor-core (split-bf16, fp32-accurate) ``x @ W.T + b``; ``w_packed`` from ``pack_weight_tc``."""
+    _need_cuda(x, w_packed, bias)
+    x = _f32c(x)
+    b = None if bias is None else _f32c(bias)
+    n, k = x.shape
+    out = torch.empty((n, out_dim), dtype=torch.float32, device=x.device)
+    if n:
+        ws = torch.empty(_lib.load().vfr_linear_tc_bytes(n, k), dtype=torch.uint8, device=x.device)
+        _lib.call("vfr_linear_tc", _ptr(x), n, k, k, _ptr(w_packed), _ptr(b), out_dim, int(bool(relu)), _ptr(out), out_dim,
+                  _ptr(ws), _stream())
+    return out
+
+
+def text_pack_tc(params_fwd, params_bwd, fc_w, fc_b):
+    """Pack (w_ih, w_hh, b_ih, b_hh) of both directions + lang_fc for the tensor-core K3."""
+    ts = [_f32c(t) for t in (*params_fwd, *params_bwd, fc_w, fc_b)]
+    _need_cuda(*ts)
+    H, E, D = ts[1].shape[1], ts[0].shape[1], ts[8].shape[0]
+    packed = torch.empty(_lib.load().vfr_text_pack_tc_bytes(H, E, D), dtype=torch.uint8, device=ts[0].device)
+    _lib.call("vfr_text_pack_tc", *[_ptr(t) for t in ts], H, E, D, _ptr(packed), _stream())
+    return packed
+
+
+def text_embed_tc(tokens, table, length_table, packed, hidden, dim, check_tokens=True, max_batch=32768):
+    """K3 on tensor cores: tokens int64 [B, L] -> fp32 [B, D]."""
+    _need_cuda(tokens, table, packed)
+    tokens = tokens.to(torch.int64).contiguous()
+    B, L = tokens.shape
+    table = _f32c(table)
+    E = table.shape[1]
+    lt = None if length_table is None else _f32c(length_table).reshape(-1)
+    out = torch.empty((B, dim), dtype=torch.float32, device=tokens.device)
+    for b0 in range(0, B, max_batch):
+        nb = min(max_batch, B - b0)
+        ws = torch.empty(_lib.load().vfr_text_embed_tc_bytes(nb, L, hidden, E), dtype=torch.uint8, device=tokens.device)
+        _lib.call("vfr_text_embed_tc", _ptr(tokens[b0:b0 + nb]), nb, L, _ptr(table), table.shape[0], _ptr(lt), E,
+                  _ptr(packed), hidden, dim, _ptr(ws), _ptr(out[b0:b0 + nb]), _stream())
+        if check_tokens and int(ws[:4].view(torch.int32)[0].item()) != 0:
+            raise IndexError("index out of range in self")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # K1 : frame -> segment pooling
 # ---------------------------------------------------------------------------------------------

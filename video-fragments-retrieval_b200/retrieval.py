@@ -31,7 +31,7 @@ class MomentRetriever:
     ENGINES = {"exact": 0, "tc": 3, "tc_bf16": 1}
 
     def __init__(self, model, clips, vid_off, id_base=0, max_queries=4096, k=100, n_split=0, group=None,
-                 engine="auto"):
+                 engine="auto", text_engine="auto"):
         """``model``: a ``CALModel`` (text branch used); ``clips`` fp32 [C_local, D] + ``vid_off`` =
         this rank's bank shard; ``id_base`` = global moment id of the shard's first moment.
         ``engine``: "exact" (fp32 CUDA-core scoring, bit-identical to the evaluation path), "tc"
@@ -57,7 +57,15 @@ class MomentRetriever:
         self._keep = [fwd, bwd, table, length, fc_w, fc_b]
         self.tokens_dev = torch.empty((mq, self.seq_len), dtype=torch.int64, device=dev)
         self.q_emb = torch.empty((mq, D), dtype=torch.float32, device=dev)
-        self.text_ws = torch.empty(lib.vfr_text_embed_bytes(mq, self.seq_len, H, E) // 4, dtype=torch.float32, device=dev)
+        if text_engine == "auto":
+            text_engine = "tc" if H % 4 == 0 else "exact"
+        self.text_engine = text_engine
+        if text_engine == "tc":
+            self.text_tc = model._packed_text_tc()
+            self.text_ws = torch.empty(lib.vfr_text_embed_tc_bytes(mq, self.seq_len, H, E) // 4 + 1, dtype=torch.float32, device=dev)
+        else:
+            self.text_tc = None
+            self.text_ws = torch.empty(lib.vfr_text_embed_bytes(mq, self.seq_len, H, E) // 4, dtype=torch.float32, device=dev)
         if engine == "auto":
             engine = "tc" if (self.bank.n_max <= 6 and D <= 125) else "exact"
         self.engine = engine
@@ -78,6 +86,8 @@ class MomentRetriever:
         p.lstm_fwd, p.lstm_bwd, p.hidden = fwd.data_ptr(), bwd.data_ptr(), H
         p.fc_w, p.fc_b, p.dim, p.seq_len = fc_w.data_ptr(), fc_b.data_ptr(), D, self.seq_len
         p.bank_packed, p.vid_off, p.mom_off = self.bank.packed.data_ptr(), self.bank.vid_off.data_ptr(), self.bank.mom_off.data_ptr()
+        p.text_engine = 3 if text_engine == "tc" else 0
+        p.text_tc = self.text_tc.data_ptr() if self.text_tc is not None else None
         p.engine = eng
         if eng:
             p.bank_tc, p.bank_clips = self.bank.tc(eng).data_ptr(), self.bank.clips.data_ptr()
