@@ -320,21 +320,23 @@ __device__ __noinline__ void compact_lists_noinline(unsigned long long* list, in
 // mbarrier wait with nanosleep back-off (single-lane producer / MMA threads must not steal issue slots
 // from the epilogue warps of their SM sub-partition) and a watchdog: a protocol bug traps instead of hanging
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the
+  // hint expires), so single-lane producer / MMA threads do not steal issue slots from the epilogue warps
   uint32_t done = 0;
   unsigned long long t0 = 0;
+  (void)ns;
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
         : "memory");
     if (done) return;
-    __nanosleep(ns);
-    if ((spin & 0xfff) == 0xfff) {
+    if ((spin & 0x3f) == 0x3f) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
@@ -349,7 +351,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -457,9 +459,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     unsigned long long* my_list = nullptr;
     int my_cnt = 0;
     float my_tau = CUDART_INF_F;
-    float thr[TC_S];
-#pragma unroll
-    for (int l = 0; l < TC_S; ++l) thr[l] = CUDART_INF_F;
+    float thr = CUDART_INF_F;     // tau * (1 + 2e-6): slightly inclusive filter threshold
     if (MODE == TC_TOPK) my_list = p.cand + ((int64_t)q_global * p.n_parts + part) * CAP;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     constexpr int VSUB = TC_SUB / TC_S;           // 4 videos per sub-block
@@ -471,8 +471,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const float tg = tau_fetch(p.tau_g + q_global);
         if (tg < my_tau) {
           my_tau = tg;
-#pragma unroll
-          for (int l = 0; l < TC_S; ++l) thr[l] = my_tau * (float)(l + 1) * 1.000001f;
+          thr = my_tau * 1.000002f;
         }
       }
       mbar_wait_sleep(&tmem_full[buf], (t >> 1) & 1, 20);
@@ -494,7 +493,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           for (int i = 0; i < TC_S; ++i) {
             const float d2 = acc[j * TC_S + i] + nq;
             ex |= d2 < gq;
-            d[j][i] = sqrt_approx(fmaxf(d2, 0.f));
+            // split mode: every d2 < gq (negatives included) is redone exactly below, so no clamp
+            d[j][i] = sqrt_approx(SPLIT ? d2 : fmaxf(d2, 0.f));
           }
           flags |= ex ? (16u << j) : 0u;
         }
@@ -541,19 +541,24 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                                    d[j][2], d[j][3], d[j][4], d[j][5]);
           }
         } else {
+          // A moment (s, e) passes  mean(d[s..e]) <= tau  iff  sum_{i=s..e} (d_i - tau) <= 0, so a video has a
+          // candidate iff the MINIMUM-SUM SUBARRAY of x_i = d_i - tau is <= 0: Kadane's recurrence, 4 ops per
+          // clip instead of 15 adds + 21 compares per video.  (tau is padded by 2e-6; the exact test is
+          // redone on the cold path.)
+          float best[VSUB];
 #pragma unroll
           for (int j = 0; j < VSUB; ++j) {
-            bool any = false;
+            float cur = d[j][0] - thr;
+            best[j] = cur;
 #pragma unroll
-            for (int s = 0; s < TC_S; ++s) {
-              float run = 0.f;
-#pragma unroll
-              for (int e = s; e < TC_S; ++e) {
-                run += d[j][e];
-                any |= run <= thr[e - s];
-              }
+            for (int i = 1; i < TC_S; ++i) {
+              cur = (d[j][i] - thr) + fminf(cur, 0.f);
+              best[j] = fminf(best[j], cur);
             }
-            flags |= any ? (1u << j) : 0u;
+          }
+          if (fminf(fminf(best[0], best[1]), fminf(best[2], best[3])) <= 0.f) {
+#pragma unroll
+            for (int j = 0; j < VSUB; ++j) flags |= (best[j] <= 0.f) ? (1u << j) : 0u;
           }
           if (flags & 15u) {
 #pragma unroll
@@ -567,9 +572,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             compact_lists_noinline(my_list, my_cnt, my_tau, p.k, my_cnt > TC_CAP_HI, lane);
             if (my_tau != tau_before) {
               tau_publish(p.tau_g + q_global, my_tau);
-              // sum <= tau * len, slightly inclusive; the exact `score <= tau` test is redone on append
-#pragma unroll
-              for (int l = 0; l < TC_S; ++l) thr[l] = my_tau * (float)(l + 1) * 1.000001f;
+              thr = my_tau * 1.000002f;
             }
           }
         }
@@ -757,8 +760,10 @@ extern "C" int vfr_score_topk_tc(const void* bank_packed, const float* bank, con
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad, st);
   if (rc) return rc;
-  VFR_CUDA(cudaFuncSetAttribute(score_tc_kernel<TC_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-  score_tc_kernel<TC_TOPK><<<(unsigned)(p.n_qtiles * ns), TC_THREADS, TC_SMEM, st>>>(ma, mb, p);
+  VFR_CUDA(cudaFuncSetAttribute(score_tc_kernel<TC_TOPK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  VFR_CUDA(cudaFuncSetAttribute(score_tc_kernel<TC_TOPK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  if (n_terms == 3) score_tc_kernel<TC_TOPK, true><<<(unsigned)(p.n_qtiles * ns), TC_THREADS, TC_SMEM, st>>>(ma, mb, p);
+  else score_tc_kernel<TC_TOPK, false><<<(unsigned)(p.n_qtiles * ns), TC_THREADS, TC_SMEM, st>>>(ma, mb, p);
   rc = check_launch("score_tc_kernel<TOPK>");
   if (rc) return rc;
   return launch_topk_finish(p.cand, p.cand_cnt, p.n_parts, k, id_base, n_queries, out_scores, out_ids, st);
@@ -780,7 +785,9 @@ extern "C" int vfr_score_full_tc(const void* bank_packed, const float* bank, con
   p.out_full = out;
   p.m_total = m_total;
   cudaStream_t st = (cudaStream_t)stream;
-  VFR_CUDA(cudaFuncSetAttribute(score_tc_kernel<TC_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-  score_tc_kernel<TC_FULL><<<(unsigned)(p.n_qtiles * ns), TC_THREADS, TC_SMEM, st>>>(ma, mb, p);
+  VFR_CUDA(cudaFuncSetAttribute(score_tc_kernel<TC_FULL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  VFR_CUDA(cudaFuncSetAttribute(score_tc_kernel<TC_FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  if (n_terms == 3) score_tc_kernel<TC_FULL, true><<<(unsigned)(p.n_qtiles * ns), TC_THREADS, TC_SMEM, st>>>(ma, mb, p);
+  else score_tc_kernel<TC_FULL, false><<<(unsigned)(p.n_qtiles * ns), TC_THREADS, TC_SMEM, st>>>(ma, mb, p);
   return check_launch("score_tc_kernel<FULL>");
 }
