@@ -254,6 +254,12 @@ typedef struct vfr_search_plan {
   int text_engine; const void* text_tc;
 } vfr_search_plan;
 
+/* the two stages separately (multi-GPU: every rank embeds its slice of the batch, the embeddings are
+ * all-gathered into plan->q_emb, then every rank scores the whole batch against its bank shard) */
+int vfr_search_embed_device(const vfr_search_plan* plan, const int64_t* tokens_dev, int64_t n_queries,
+                            float* q_emb_out, vfr_stream_t stream);
+int vfr_search_score_device(const vfr_search_plan* plan, int64_t n_queries, int k, float* out_scores_dev,
+                            int64_t* out_ids_dev, vfr_stream_t stream);
 /* device-resident inputs/outputs; asynchronous */
 int vfr_search_device(const vfr_search_plan* plan, const int64_t* tokens_dev, int64_t n_queries, int k,
                       float* out_scores_dev, int64_t* out_ids_dev, vfr_stream_t stream);

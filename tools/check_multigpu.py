@@ -1,0 +1,38 @@
+"""Run under torchrun on N GPUs: sharded retrieval (local top-k -> NCCL all-gather -> K7 merge) must equal
+the single-bank search computed on every rank from the full bank."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+import vfr_b200
+from vfr_b200 import models, synth
+from vfr_b200.retrieval import MomentRetriever, shard_range
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+V, S, Q, k = 60000, 6, 1000, 100
+sd = synth.make_state_dict(3, 8, 500, spread=4.0)
+model = models.CALModel(visual_input_dim=18, pretrained_emb=torch.from_numpy(sd["word_embedding.weight"]))
+model.load_state_dict({n: torch.from_numpy(v) for n, v in sd.items()})
+model = model.to(dev).eval()
+clips = torch.from_numpy(synth.make_bank(3, V, S, 100)).to(dev)
+tokens = synth.make_queries(3, synth.make_videos(3, 4, 8), Q, 500)["tokens"]
+ok = True
+for engine in ("tc", "exact"):
+    v0, v1 = shard_range(V, rank, world)
+    shard = MomentRetriever(model, clips[v0 * S:v1 * S], np.arange(v1 - v0 + 1) * S, id_base=v0 * 21, max_queries=Q, k=k,
+                            engine=engine, text_engine=engine)
+    s, i = shard.search(tokens)                      # host in, host out, all-gather + merge inside
+    s, i = s.clone(), i.clone()
+    full = MomentRetriever(model, clips, np.arange(V + 1) * S, max_queries=Q, k=k, engine=engine, text_engine=engine)
+    full.world = 1                                   # single-bank reference on every rank
+    fs, fi = full.search(tokens)
+    same = torch.equal(s, fs) and torch.equal(i, fi)
+    t = torch.tensor([int(same)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"engine={engine}: sharded({world}) == single bank: {bool(t.item())}")
+    ok = ok and bool(t.item())
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

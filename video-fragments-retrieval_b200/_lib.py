@@ -84,6 +84,8 @@ PROTOTYPES = {
     "vfr_ranking_loss_bytes": (_z, [_i, _i, _i, _i]),
     "vfr_ranking_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p]),
     "vfr_ranking_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "vfr_search_embed_device": (_i, [C.POINTER(SearchPlan), _p, _l, _p, _p]),
+    "vfr_search_score_device": (_i, [C.POINTER(SearchPlan), _l, _i, _p, _p, _p]),
     "vfr_search_device": (_i, [C.POINTER(SearchPlan), _p, _l, _i, _p, _p, _p]),
     "vfr_search_host": (_i, [C.POINTER(SearchPlan), _p, _l, _i, _p, _p, _p]),
 }

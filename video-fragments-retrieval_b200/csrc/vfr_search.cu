@@ -27,18 +27,25 @@ static int check_plan(const vfr_search_plan* p, int64_t n_queries, int k) {
   return VFR_OK;
 }
 
-extern "C" int vfr_search_device(const vfr_search_plan* p, const int64_t* tokens_dev, int64_t n_queries, int k,
-                                 float* out_scores_dev, int64_t* out_ids_dev, vfr_stream_t stream) {
+// stage 1: K3 only - tokens -> query embeddings (q_emb_out fp32 [n_queries, dim], may be a slice of plan->q_emb)
+extern "C" int vfr_search_embed_device(const vfr_search_plan* p, const int64_t* tokens_dev, int64_t n_queries,
+                                       float* q_emb_out, vfr_stream_t stream) {
+  int rc = check_plan(p, n_queries, 1);
+  if (rc) return rc;
+  VFR_REQUIRE(tokens_dev && q_emb_out, VFR_ERR_INVALID, "vfr_search_embed_device: null pointer");
+  if (p->text_engine == 3)
+    return vfr_text_embed_tc(tokens_dev, n_queries, p->seq_len, p->table, p->vocab, p->length_table, p->emb, p->text_tc,
+                             p->hidden, p->dim, p->text_ws, q_emb_out, stream);
+  return vfr_text_embed(tokens_dev, n_queries, p->seq_len, p->table, p->vocab, p->length_table, p->emb, p->lstm_fwd,
+                        p->lstm_bwd, p->hidden, p->fc_w, p->fc_b, p->dim, p->text_ws, q_emb_out, stream);
+}
+
+// stage 2: K4 only - the first n_queries rows of plan->q_emb against the resident bank
+extern "C" int vfr_search_score_device(const vfr_search_plan* p, int64_t n_queries, int k, float* out_scores_dev,
+                                       int64_t* out_ids_dev, vfr_stream_t stream) {
   int rc = check_plan(p, n_queries, k);
   if (rc) return rc;
-  VFR_REQUIRE(tokens_dev && out_scores_dev && out_ids_dev, VFR_ERR_INVALID, "vfr_search_device: null pointer");
-  if (p->text_engine == 3)
-    rc = vfr_text_embed_tc(tokens_dev, n_queries, p->seq_len, p->table, p->vocab, p->length_table, p->emb, p->text_tc,
-                           p->hidden, p->dim, p->text_ws, p->q_emb, stream);
-  else
-    rc = vfr_text_embed(tokens_dev, n_queries, p->seq_len, p->table, p->vocab, p->length_table, p->emb, p->lstm_fwd,
-                        p->lstm_bwd, p->hidden, p->fc_w, p->fc_b, p->dim, p->text_ws, p->q_emb, stream);
-  if (rc) return rc;
+  VFR_REQUIRE(out_scores_dev && out_ids_dev, VFR_ERR_INVALID, "vfr_search_score_device: null pointer");
   if (p->engine != 0) {
     rc = vfr_tc_query_pack(p->q_emb, n_queries, p->dim, p->engine, p->q_tc, stream);
     if (rc) return rc;
@@ -50,6 +57,15 @@ extern "C" int vfr_search_device(const vfr_search_plan* p, const int64_t* tokens
   if (rc) return rc;
   return vfr_score_topk(p->bank_packed, p->vid_off, p->mom_off, p->n_videos, p->n_max, p->dim, p->q_packed, n_queries,
                         k, p->id_base, out_scores_dev, out_ids_dev, p->topk_ws, p->n_split, stream);
+}
+
+extern "C" int vfr_search_device(const vfr_search_plan* p, const int64_t* tokens_dev, int64_t n_queries, int k,
+                                 float* out_scores_dev, int64_t* out_ids_dev, vfr_stream_t stream) {
+  int rc = check_plan(p, n_queries, k);
+  if (rc) return rc;
+  rc = vfr_search_embed_device(p, tokens_dev, n_queries, p->q_emb, stream);
+  if (rc) return rc;
+  return vfr_search_score_device(p, n_queries, k, out_scores_dev, out_ids_dev, stream);
 }
 
 extern "C" int vfr_search_host(const vfr_search_plan* p, const int64_t* tokens_host, int64_t n_queries, int k,

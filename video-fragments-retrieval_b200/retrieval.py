@@ -102,6 +102,9 @@ class MomentRetriever:
         if self.world > 1:
             self.gather_s = torch.empty((self.world, mq, self.k), dtype=torch.float32, device=dev)
             self.gather_i = torch.empty((self.world, mq, self.k), dtype=torch.int64, device=dev)
+            per = (mq + self.world - 1) // self.world
+            self.q_slice = torch.zeros((per, D), dtype=torch.float32, device=dev)
+            self.q_gather = torch.empty((self.world * per, D), dtype=torch.float32, device=dev)
         # pinned staging for the host-buffer path
         self.host_tokens = torch.empty((mq, self.seq_len), dtype=torch.int64).pin_memory()
         self.host_s = torch.empty((mq, self.k), dtype=torch.float32).pin_memory()
@@ -124,13 +127,30 @@ class MomentRetriever:
 
     # -- device-resident step ---------------------------------------------------------------------
     def search_device(self, tokens_dev):
-        """tokens int64 [Q, 20] on the device -> (scores fp32 [Q, k], ids int64 [Q, k]) on the device."""
+        """tokens int64 [Q, 20] on the device -> (scores fp32 [Q, k], ids int64 [Q, k]) on the device.
+
+        One GPU: K3 -> K4 in one C call.  N GPUs: every rank embeds its slice of the batch (K3 is
+        data-parallel over queries), ONE all-gather replicates the embeddings, every rank scores the
+        whole batch against its bank shard (K4), ONE all-gather exchanges the per-shard top-k lists,
+        K7 merges them."""
         Q = tokens_dev.shape[0]
         stream = torch.cuda.current_stream().cuda_stream
-        _lib.call("vfr_search_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.k, self.out_s.data_ptr(),
-                  self.out_i.data_ptr(), stream)
         if self.world == 1:
+            _lib.call("vfr_search_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.k, self.out_s.data_ptr(),
+                      self.out_i.data_ptr(), stream)
             return self.out_s[:Q], self.out_i[:Q]
+        rank = dist.get_rank(self.group)
+        per = (Q + self.world - 1) // self.world                      # queries embedded per rank
+        q0, q1 = min(rank * per, Q), min((rank + 1) * per, Q)
+        mine = self.q_slice[:per]
+        if q1 > q0:
+            _lib.call("vfr_search_embed_device", C.byref(self.plan), tokens_dev[q0:q1].data_ptr(), q1 - q0,
+                      mine.data_ptr(), stream)
+        gathered = self.q_gather[:self.world * per]
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        self.q_emb[:Q].copy_(gathered[:Q])
+        _lib.call("vfr_search_score_device", C.byref(self.plan), Q, self.k, self.out_s.data_ptr(), self.out_i.data_ptr(),
+                  stream)
         gs, gi = self.gather_s[:, :Q].contiguous(), self.gather_i[:, :Q].contiguous()
         dist.all_gather_into_tensor(gs, self.out_s[:Q].contiguous(), group=self.group)
         dist.all_gather_into_tensor(gi, self.out_i[:Q].contiguous(), group=self.group)
