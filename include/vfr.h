@@ -123,6 +123,34 @@ int vfr_score_full_tc(const void* bank_packed, const float* bank, const int32_t*
                       const void* query_packed, const float* queries, int64_t n_queries, float* out,
                       int64_t m_total, vfr_stream_t stream);
 
+/* ---- K4, filter + refine top-k (one fp16 tcgen05 pass + exact fp32 re-scoring) ------------------------
+ * Same contract and the SAME BITS as vfr_score_topk (reference model/evaluate.py:49-58,71-80): a
+ * moment's score is the mean of its clips' distances, so the k best moments all live in videos that own
+ * one of the ~k closest clips.  Stage 1 finds those clips with a single fp16 GEMM pass (fp32
+ * accumulation in TMEM) whose rounding error is bounded rigorously per query; every clip inside the
+ * bound of the k-th smallest squared distance survives.  Stage 2 re-scores all moments of the surviving
+ * videos with the exact-fp32 arithmetic of vfr_score_topk and selects the k best by (score, moment id).
+ * Any number of clips per video (<= 32), dim <= 125; the bank is packed by clip rows (no video padding).
+ *   packed bank    vfr_sel_bank_bytes(n_clips)   <- vfr_sel_bank_pack (once per bank)
+ *   packed queries vfr_sel_query_bytes(n_queries) <- vfr_sel_query_pack (per batch; reads the bank's scales)
+ *   workspace      vfr_sel_topk_bytes(max n_queries, n_clips, n_split)
+ * vfr_sel_flags(query_packed, n_queries) -> device pointer to int32 [n_queries] written by the last
+ * vfr_sel_query_pack / vfr_sel_topk on that buffer: 0 = result guaranteed exact; 1 = the query's or the
+ * bank's magnitudes do not fit the fp16 operand scales, 2 / 3 = more candidates inside the error band than
+ * the stage-1 lists / stage-2 buffer hold (mass duplicates).  Flagged queries must be re-run through
+ * vfr_score_topk by the caller (vfr_b200.retrieval does). */
+size_t vfr_sel_bank_bytes(int64_t n_clips);
+int vfr_sel_bank_pack(const float* bank, int64_t n_clips, int dim, void* packed, vfr_stream_t stream);
+size_t vfr_sel_query_bytes(int64_t n_queries);
+int vfr_sel_query_pack(const float* queries, int64_t n_queries, int dim, const void* bank_packed,
+                       int64_t n_clips, void* packed, vfr_stream_t stream);
+size_t vfr_sel_topk_bytes(int64_t n_queries, int64_t n_clips, int n_split);
+int vfr_sel_topk(const void* bank_packed, const float* bank, const int32_t* vid_off, const int64_t* mom_off,
+                 int64_t n_videos, int64_t n_clips, int n_max, int dim, void* query_packed,
+                 const float* queries, int64_t n_queries, int k, int64_t id_base, float* out_scores,
+                 int64_t* out_ids, void* workspace, int n_split, vfr_stream_t stream);
+const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries);
+
 /* ---- K5 : integer-exact temporal IoU, ground truth, rank statistics -------------------------
  * times int32 [Q, n_annot, 2] inclusive (start, end), absent annotators = (-1, -1);
  * q_nseg int32 [Q] = clips of the query's own video; own_scores fp32 [Q, m_stride] (vfr_score_own);

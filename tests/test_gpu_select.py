@@ -1,0 +1,197 @@
+"""GPU parity tests of the filter + refine top-k (vfr_sel_topk: one fp16 tcgen05 pass + exact fp32
+re-scoring).  The bar is BIT equality with the exact-fp32 engine (vfr_score_topk / vfr_score_full),
+which the other test files hold to the reference's own scores; plus a direct check that the rigorous
+error bound of the fp16 pass holds with margin."""
+import numpy as np
+import pytest
+import torch
+
+import vfr_b200  # noqa: F401
+from vfr_b200 import _lib, ops
+from oracle import cal_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+CAP = 1024
+
+
+def _ragged_bank(rng, n_videos, dim, seg_choices, scale=0.25, shared=1.0):
+    nseg = rng.choice(np.asarray(seg_choices), size=n_videos)
+    vid_off = np.concatenate([[0], np.cumsum(nseg)])
+    base = np.repeat(rng.standard_normal((n_videos, dim), dtype=np.float32), nseg, axis=0)
+    clips = (shared * base + 0.6 * rng.standard_normal((int(vid_off[-1]), dim), dtype=np.float32)) * scale
+    return clips.astype(np.float32), vid_off
+
+
+def _assert_same_as_exact(bank, q, k, n_split=0, id_base=0):
+    es, ei = ops.score_topk(bank, q, k, id_base=id_base)
+    gs, gi, flags, _ = ops.score_topk_sel(bank, q, k, id_base=id_base, n_split=n_split, return_flags=True)
+    assert int(flags.abs().sum().item()) == 0, flags.unique()
+    assert torch.equal(gi, ei), f"{(gi != ei).sum().item()} ids differ"
+    assert torch.equal(gs.view(torch.int32), es.view(torch.int32))
+
+
+def test_sel_matches_reference_scores(golden):
+    """Top-k of the reference's own score lists (golden val_eval: ragged 5/6-clip videos)."""
+    z, meta = golden("val_eval")
+    bank = ops.Bank(torch.from_numpy(z["video_emb"]).to(DEV), z["vid_off"])
+    n_keep = z["scores"].shape[0]
+    q = torch.from_numpy(z["query_emb"][:n_keep]).to(DEV)
+    k = 100
+    gs, gi = ops.score_topk_sel(bank, q, k)
+    ref = torch.from_numpy(z["scores"]).to(DEV)
+    ws, wi = torch.sort(ref, dim=1, stable=True)
+    rel = ((gs - ws[:, :k]).abs() / ws[:, :k]).max().item()
+    assert rel < 1e-5, rel
+    # the reference's scores of the returned moments are inside its own top-k up to the score tolerance
+    ref_of_ids = torch.gather(ref, 1, gi)
+    assert bool((ref_of_ids <= ws[:, k - 1:k] * (1 + 4e-5)).all())
+    assert (gi == wi[:, :k]).float().mean().item() > 0.97
+
+
+@pytest.mark.parametrize("k", [1, 10, 100, 128])
+def test_sel_equals_exact_engine_val(golden, k):
+    z, meta = golden("val_eval")
+    bank = ops.Bank(torch.from_numpy(z["video_emb"]).to(DEV), z["vid_off"])
+    q = torch.from_numpy(z["query_emb"]).to(DEV)           # 48 queries: ragged last query tile
+    for n_split in (0, 1, 3):
+        _assert_same_as_exact(bank, q, k, n_split=n_split)
+
+
+@pytest.mark.parametrize("seg,n_videos,n_queries", [((6, 5), 30000, 700), ((1, 2, 3, 6), 9000, 129), ((30,), 3000, 260),
+                                                     ((32, 7, 1), 2500, 64)])
+def test_sel_equals_exact_engine_ragged(seg, n_videos, n_queries):
+    rng = np.random.default_rng(11)
+    clips, vid_off = _ragged_bank(rng, n_videos, 100, seg)
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    q = torch.from_numpy((rng.standard_normal((n_queries, 100), dtype=np.float32) * 0.3)).to(DEV)
+    _assert_same_as_exact(bank, q, 100, id_base=12345678901)
+
+
+@pytest.mark.parametrize("dim", [17, 64, 100, 125])
+def test_sel_other_dims(dim):
+    rng = np.random.default_rng(5)
+    clips, vid_off = _ragged_bank(rng, 4000, dim, (6, 5))
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    q = torch.from_numpy(rng.standard_normal((200, dim), dtype=np.float32) * 0.25).to(DEV)
+    _assert_same_as_exact(bank, q, 50)
+
+
+def test_sel_near_duplicates_and_ties():
+    """Queries that (almost) coincide with bank clips, exact duplicates inside the bank (tied scores:
+    the order must be by moment id) and a bank smaller than k."""
+    rng = np.random.default_rng(3)
+    D = 100
+    qs = rng.standard_normal((40, D), dtype=np.float32)
+    near = np.repeat(qs, 6, axis=0) + 1e-3 * rng.standard_normal((240, D), dtype=np.float32)
+    near[::7] = np.repeat(qs, 6, axis=0)[::7]                     # exact hits: d^2 = D eps^2
+    other, _ = _ragged_bank(rng, 300, D, (6,), scale=1.0)
+    dup = np.tile(other[:60], (3, 1))                              # three identical copies of 10 videos
+    clips = np.concatenate([near, other, dup]).astype(np.float32)
+    vid_off = np.arange(clips.shape[0] // 6 + 1) * 6
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    _assert_same_as_exact(bank, torch.from_numpy(qs).to(DEV), 100)
+    tiny = ops.Bank(torch.from_numpy(clips[:12]).to(DEV), np.arange(3) * 6)     # 42 moments < k
+    gs, gi = ops.score_topk_sel(tiny, torch.from_numpy(qs).to(DEV), 100)
+    es, ei = ops.score_topk(tiny, torch.from_numpy(qs).to(DEV), 100)
+    assert torch.equal(gi, ei) and torch.equal(gs.view(torch.int32), es.view(torch.int32))
+    assert bool((gi[:, 42:] == -1).all()) and bool(torch.isinf(gs[:, 42:]).all())
+
+
+@pytest.mark.parametrize("bank_scale,query_scale", [(1e-3, 1e-3), (30.0, 0.02), (0.01, 5.0), (1e4, 1e4)])
+def test_sel_operand_scales(bank_scale, query_scale):
+    """Power-of-two operand scaling keeps magnitudes far from 1 inside fp16's range."""
+    rng = np.random.default_rng(8)
+    clips, vid_off = _ragged_bank(rng, 6000, 100, (6, 5), scale=bank_scale)
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    q = torch.from_numpy(rng.standard_normal((150, 100), dtype=np.float32) * query_scale).to(DEV)
+    _assert_same_as_exact(bank, q, 100)
+
+
+def test_sel_offset_embeddings():
+    """A large common offset (all-positive embeddings, as after a ReLU) is the worst case of the error
+    bound: the dot products are large and d^2 is a small difference."""
+    rng = np.random.default_rng(9)
+    clips, vid_off = _ragged_bank(rng, 8000, 100, (6, 5), scale=0.05)
+    clips = (clips + 1.0).astype(np.float32)
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    q = torch.from_numpy((rng.standard_normal((130, 100), dtype=np.float32) * 0.05 + 1.0)).to(DEV)
+    _assert_same_as_exact(bank, q, 100)
+
+
+@pytest.mark.parametrize("offset", [0.0, 1.0])
+def test_sel_error_bound_holds(offset):
+    """With fewer clips per candidate list than k nothing is ever dropped, so the stage-1 lists hold the
+    approximate d^2 of EVERY (query, clip) pair: compare them with float64 and with the bound E."""
+    rng = np.random.default_rng(21)
+    D, C, Q, k = 100, 128, 128, 128
+    clips = (rng.standard_normal((C, D)) * np.exp(rng.uniform(-3, 1, size=(C, 1))) + offset).astype(np.float32)
+    qs = (rng.standard_normal((Q, D)) * np.exp(rng.uniform(-3, 1, size=(Q, 1))) + offset).astype(np.float32)
+    qs[:8] = np.abs(clips[:8])          # aligned all-positive pairs: sum |q_k v_k| = |q||v|
+    clips[:8] = np.abs(clips[:8])
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), np.arange(C // 4 + 1) * 4)
+    gs, gi, flags, (qp, ws) = ops.score_topk_sel(bank, torch.from_numpy(qs).to(DEV), k, return_flags=True)
+    assert int(flags.abs().sum().item()) == 0
+    n_parts, qpad = 2, 256
+    cand = ws[:qpad * n_parts * CAP * 8].view(torch.int64).view(qpad, n_parts, CAP).cpu().numpy()
+    cnt = ws[qpad * n_parts * CAP * 8:qpad * n_parts * (CAP * 8 + 4)].view(torch.int32).view(qpad, n_parts).cpu().numpy()
+    assert cnt[:Q].sum(axis=1).tolist() == [C] * Q
+    qmeta = qp[qpad * 256:qpad * 256 + qpad * 16].view(torch.float32).view(qpad, 4).cpu().numpy()
+    eps = 1e-6
+    d2 = (((clips[None, :, :].astype(np.float64) - qs[:, None, :].astype(np.float64) + eps) ** 2).sum(-1))
+    worst = 0.0
+    for qi in range(Q):
+        keys = np.concatenate([cand[qi, p, :cnt[qi, p]] for p in range(n_parts)])
+        ids = (keys & 0xffffffff).astype(np.int64)
+        approx = (keys >> 32).astype(np.uint32).view(np.float32).astype(np.float64)
+        assert sorted(ids.tolist()) == list(range(C))
+        err = np.abs(approx - d2[qi, ids])
+        E = qmeta[qi, 3] / 2
+        worst = max(worst, float((err / E).max()))
+    assert worst < 0.5, worst          # observed error stays below half the rigorous bound
+
+
+def test_sel_sharded_merge_equals_single_bank():
+    rng = np.random.default_rng(4)
+    clips, vid_off = _ragged_bank(rng, 20000, 100, (6, 5))
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    q = torch.from_numpy(rng.standard_normal((300, 100), dtype=np.float32) * 0.3).to(DEV)
+    want_s, want_i = ops.score_topk(bank, q, 100)
+    P = 4
+    parts_s, parts_i = [], []
+    for r in range(P):
+        v0, v1 = 20000 * r // P, 20000 * (r + 1) // P
+        c0, c1 = int(vid_off[v0]), int(vid_off[v1])
+        shard = ops.Bank(torch.from_numpy(clips[c0:c1]).to(DEV), vid_off[v0:v1 + 1] - c0)
+        s, i = ops.score_topk_sel(shard, q, 100, id_base=int(bank.mom_off_host[v0]))
+        parts_s.append(s)
+        parts_i.append(i)
+    ms, mi = ops.topk_merge(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(mi, want_i) and torch.equal(ms.view(torch.int32), want_s.view(torch.int32))
+
+
+def test_sel_large_properties():
+    """131 k videos x 2 k queries (beyond the oracle's reach): sortedness, id range, no duplicates, and
+    the oracle's re-scoring of the winners."""
+    g = torch.Generator(device=DEV).manual_seed(1)
+    V, Q, k = 131072, 2048, 100
+    clips = (torch.randn(V, 1, 100, device=DEV, generator=g) + 0.6 * torch.randn(V, 6, 100, device=DEV, generator=g)).reshape(-1, 100) * 0.05
+    bank = ops.Bank(clips, np.arange(V + 1) * 6)
+    q = torch.randn(Q, 100, device=DEV, generator=g) * 0.06
+    gs, gi, flags, _ = ops.score_topk_sel(bank, q, k, return_flags=True)
+    assert int(flags.abs().sum().item()) == 0
+    es, ei = ops.score_topk(bank, q, k)
+    assert torch.equal(gi, ei) and torch.equal(gs.view(torch.int32), es.view(torch.int32))
+    assert bool((gs[:, 1:] >= gs[:, :-1]).all()) and bool((gi >= 0).all()) and bool((gi < bank.m_total).all())
+    for row in gi[:8].cpu().tolist():
+        assert len(set(row)) == k
+    vid = (gi[:4, :5] // 21).cpu().numpy()
+    mom = (gi[:4, :5] % 21).cpu().numpy()
+    moments = orc.generate_moments(6)
+    c = clips.cpu().numpy()
+    qq = q[:4].cpu().numpy()
+    for a in range(4):
+        for b in range(5):
+            s, e = moments[mom[a, b]]
+            want = orc.moment_scores_loop(torch.from_numpy(c[vid[a, b] * 6:vid[a, b] * 6 + 6]), torch.from_numpy(qq[a:a + 1]), [(s, e)])[0]
+            assert abs(want - gs[a, b].item()) / want < 1e-5

@@ -62,6 +62,13 @@ PROTOTYPES = {
     "vfr_score_topk_tc_bytes": (_z, [_l, _l, _i]),
     "vfr_score_topk_tc": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
     "vfr_score_full_tc": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _l, _p, _l, _p]),
+    "vfr_sel_bank_bytes": (_z, [_l]),
+    "vfr_sel_bank_pack": (_i, [_p, _l, _i, _p, _p]),
+    "vfr_sel_query_bytes": (_z, [_l]),
+    "vfr_sel_query_pack": (_i, [_p, _l, _i, _p, _l, _p, _p]),
+    "vfr_sel_topk_bytes": (_z, [_l, _l, _i]),
+    "vfr_sel_topk": (_i, [_p, _p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
+    "vfr_sel_flags": (_p, [_p, _l]),
     "vfr_gt_select": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p, _p]),
     "vfr_rank_order": (_i, [_p, _i, _p, _l, _i, _p, _p]),
     "vfr_single_metrics": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p]),

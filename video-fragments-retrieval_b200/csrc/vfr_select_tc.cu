@@ -1,0 +1,1248 @@
+// K4 (filter + refine): the k best moments of every query over the whole bank, bit-identical to the
+// exact-fp32 engine (vfr_score_topk), at ONE fp16 tensor-core pass per (query, clip).
+// Replaces reference model/evaluate.py:49-58 (distance + moment means) and :71-80 (argsort, top-k).
+//
+// Idea.  A moment's score is the MEAN of its clips' distances (evaluate.py:58), so it is >= the distance
+// of its closest clip.  Single clips are moments themselves, hence the k-th best moment score tau_k is
+// <= c_k, the k-th smallest clip distance of the bank.  Every moment of the final top-k therefore
+// belongs to a video that owns a clip with distance <= c_k: the search over 21 M moments reduces to
+//   stage 1 (filter)  find, per query, all clips whose squared distance is <= c_k^2        [tensor cores]
+//   stage 2 (refine)  score all moments of the <= ~k videos owning those clips exactly      [CUDA cores]
+// Stage 1 needs neither the sqrt nor the moment means: it is a GEMM whose epilogue is one 3-input min
+// per two accumulator elements and one compare per 64.
+//
+// Stage 1 arithmetic.  fp16 operands (11-bit significands), exact products, fp32 accumulation in TMEM:
+//   acc[r][c] = sum_k A[r][k] B[c][k]        A[r] = [ q_r 2^sq_r | 2^(sq_r+t) x3 ]   B[c] = [ -2 v_c 2^sb | nv_c 2^(sb-t) as an fp16 triple ]
+//   (q, v here are CENTRED on the bank mean - d^2 is translation invariant - so a common offset of the embeddings does not inflate |q||v|)
+//             = 2^(sq_r+sb) ( |v_c + eps|^2 - 2 q_r.v_c )  =  2^(sq_r+sb) ( d^2 - nq_r )       (+ rounding)
+// with power-of-two scales (per bank: sb, t; per query: sq_r) that keep the operands in fp16's normal
+// range.  The rounding error of the approximate d^2 is bounded RIGOROUSLY per query by
+//   E_r = 1.05 * 2^-10 * |q_r| * 2 max|v|  + (sub-normal, triple, accumulation and key-rounding terms)
+// and the filter keeps every clip with  d2~ <= tau2 + 2 E_r  where tau2 is the k-th smallest d2~ seen so
+// far: if S is the set of the k smallest d2~, their exact d^2 are <= tau2 + E, so c_k^2 <= tau2 + E, and a
+// clip with exact d^2 <= c_k^2 has d2~ <= tau2 + 2E.  No exact candidate can be lost; stage 2 recomputes
+// everything that survives with the arithmetic of vfr_score.cu (sequential fp32 FADD/FFMA over k,
+// IEEE sqrt and division), so scores, ids and tie order equal the exact engine's bit for bit.
+//
+// Stage 1 pipeline (one CTA per SM, 320 threads, warp-specialised):
+//   warp 0       TMA producer: the CTA's query tiles (R x 128 rows, resident) once, then bank tiles of 256
+//                clip rows as two [256 x 64] fp16 boxes (SWIZZLE_128B) through an mbarrier ring
+//   warp 1       MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=256, K=16; 7 per (tile, query
+//                tile) at D=100; the 512 TMEM columns hold two accumulators (ping-pong)
+//   warps 2..9   epilogue, two sets of four warps (one warp per TMEM lane quarter); set s owns TMEM buffer
+//                s, so a thread sees ALL 256 columns of ONE query row and keeps ONE candidate list:
+//                tcgen05.ld 32x32b.x32 double-buffered in registers (the next 64 columns load while the
+//                current 64 go through an FMNMX3 tree and one compare against the query's threshold);
+//                the rare hit appends (d2~, clip id) to the list (band-preserving radix-select
+//                compaction, cf. vfr_topk.cuh); the TMEM buffer is released after the last load
+// R = 2 query tiles share every bank tile in shared memory, halving the L2 -> SM traffic per MMA
+// (set s = query tile s); with R = 1 the two sets take the bank tiles of even / odd parity.
+#include "vfr_common.cuh"
+#include "vfr_topk.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+#include <stdlib.h>
+
+namespace vfr {
+
+constexpr int SL_N = 256;                 // clip rows per bank tile (MMA N)
+constexpr int SL_M = 128;                 // query rows per MMA
+constexpr int SL_ROW = 128;               // fp16 columns per packed row (D + 3 <= 128)
+constexpr int SL_A_CHUNK = SL_M * 128;    // bytes of one [128 x 64 fp16] box
+constexpr int SL_B_CHUNK = SL_N * 128;    // bytes of one [256 x 64 fp16] box = 32 KB
+constexpr int SL_SET_WARPS = 4;           // one epilogue warp per TMEM lane quarter ...
+constexpr int SL_THREADS = 64 + 2 * SL_SET_WARPS * 32;   // ... in two sets (one per TMEM buffer): 320 threads
+constexpr int SL_CAP = 1024;              // candidate slots per (query, part) list
+constexpr int SL_CAP_HI = SL_CAP - SL_N;  // a tile can append at most SL_N keys to a list
+constexpr int SL_QPAD = 256;              // packed query rows are padded to a multiple of this
+
+struct SlBankMeta {          // written by the bank pack kernels, read by the query pack kernel
+  unsigned vmax_abs_bits;    // max |v_k|                    (fp32 bit patterns: non-negative, so uint order)
+  unsigned vnorm_max_bits;   // max ||v_c||
+  unsigned nv_max_bits;      // max nv_c = |v_c + eps|^2
+  unsigned vsum_abs_max_bits;// max_c sum_k |v_ck|
+  int sb;                    // operand scale exponent of the bank
+  int t;                     // exponent of the nv columns
+  int pad[2];
+  double colsum[SL_ROW];     // column sums of the bank (pack-time scratch)
+  float center[SL_ROW];      // bank mean: both operands are centred on it (d^2 is translation invariant), which
+                             // keeps |q'||v'| - and with it the error bound - small for embeddings with a common offset
+};
+
+struct SlParams {
+  const float4* qmeta;       // [Qpad] {nq, scale = 2^(sq+sb), 1/scale, band2 = 2E}
+  int64_t n_clips;
+  int64_t n_queries;
+  int n_qgroups;             // CTAs along the query dimension (R query tiles each)
+  int n_tiles;
+  int tiles_per_split;
+  int ksteps;                // 16-wide k steps (ceil((D+3)/16))
+  int k;
+  unsigned long long* cand;  // [Qpad][n_parts][SL_CAP]  (d2~ bits << 32 | clip id)
+  int32_t* cand_cnt;         // [Qpad][n_parts]
+  int n_parts;
+  unsigned* tau_g;           // [Qpad] k-th smallest d2~ published by any list of the query
+  int wait_mode;             // mbarrier wait flavour (see sl_wait)
+  int32_t* flags;            // [Qpad] != 0: a candidate list overflowed / scales out of range (see vfr.h)
+};
+
+// ---------------------------------------------------------------------------------------------
+// packing
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_pos(unsigned* dst, float v) { atomicMax(dst, __float_as_uint(fmaxf(v, 0.f))); }
+
+// column sums of the bank -> its mean (the centre)
+__global__ void sl_bank_colsum_kernel(const float* __restrict__ bank, int64_t n_clips, int dim, SlBankMeta* meta) {
+  const int k = threadIdx.x & (SL_ROW - 1);
+  const int r = threadIdx.x >> 7;                       // 256 threads = 2 rows x 128 columns
+  double s = 0.0;
+  if (k < dim)
+    for (int64_t c = (int64_t)blockIdx.x * 2 + r; c < n_clips; c += (int64_t)gridDim.x * 2) s += (double)bank[c * dim + k];
+  if (k < dim) atomicAdd(&meta->colsum[k], s);
+}
+__global__ void sl_bank_center_kernel(int64_t n_clips, int dim, SlBankMeta* meta) {
+  const int k = threadIdx.x;
+  meta->center[k] = (k < dim) ? (float)(meta->colsum[k] / (double)n_clips) : 0.f;
+}
+
+// one warp per clip row: maxima the scales and the error bound are derived from (centred values)
+__global__ void sl_bank_stats_kernel(const float* __restrict__ bank, int64_t n_clips, int dim, SlBankMeta* meta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float m_abs = 0.f, m_norm = 0.f, m_nv = 0.f, m_sum = 0.f;
+  for (int64_t c = warp0; c < n_clips; c += nwarps) {
+    const float* src = bank + c * dim;
+    double ss = 0.0, sm = 0.0;
+    float sa = 0.f, ma = 0.f;
+    for (int k = lane; k < dim; k += 32) {
+      const float x = __fsub_rn(src[k], meta->center[k]);
+      ss += (double)x * x;
+      sm += (double)x;
+      sa += fabsf(x);
+      ma = fmaxf(ma, fabsf(x));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    }
+    const double eps = (double)VFR_PAIRWISE_EPS;
+    const double nv = ss + 2.0 * eps * sm + (double)dim * eps * eps;
+    m_abs = fmaxf(m_abs, ma);
+    m_norm = fmaxf(m_norm, (float)(sqrt(ss) * 1.0000002));
+    m_nv = fmaxf(m_nv, (float)(nv * 1.0000002));
+    m_sum = fmaxf(m_sum, sa * 1.00001f);
+  }
+  if (lane == 0) {
+    atomic_max_pos(&meta->vmax_abs_bits, m_abs);
+    atomic_max_pos(&meta->vnorm_max_bits, m_norm);
+    atomic_max_pos(&meta->nv_max_bits, m_nv);
+    atomic_max_pos(&meta->vsum_abs_max_bits, m_sum);
+  }
+}
+
+__global__ void sl_bank_scales_kernel(SlBankMeta* meta) {
+  const float vmax = __uint_as_float(meta->vmax_abs_bits);
+  const float nvmax = __uint_as_float(meta->nv_max_bits);
+  int sb = 0, t = 0;
+  if (vmax > 0.f && vmax < CUDART_INF_F) sb = 6 - ilogbf(vmax);          // 2 |v| 2^sb < 2^8
+  sb = max(-60, min(60, sb));
+  if (nvmax > 0.f && nvmax < CUDART_INF_F) t = ilogbf(nvmax) + sb - 13;  // nv 2^(sb-t) < 2^14
+  t = max(-120, min(120, t));
+  meta->sb = sb;
+  meta->t = t;
+}
+
+// x (>= 0, < 2^15) as the sum of three fp16 values
+__device__ __forceinline__ void split3_h(double x, __half& a, __half& b, __half& c) {
+  a = __double2half(x);
+  const double r1 = x - (double)__half2float(a);
+  b = __double2half(r1);
+  c = __double2half(r1 - (double)__half2float(b));
+}
+
+// one warp per packed row (rows >= n_clips are padding: zero operands, nv = 2^15)
+__global__ void sl_bank_pack_kernel(const float* __restrict__ bank, int64_t n_clips, int64_t n_rows_pad, int dim,
+                                    const SlBankMeta* __restrict__ meta, __half* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= n_rows_pad) return;
+  __half* row = out + c * SL_ROW;
+  const __half zero = __float2half_rn(0.f);
+  if (c >= n_clips) {
+    for (int k = lane; k < SL_ROW; k += 32) row[k] = (k == dim) ? __float2half_rn(32768.f) : zero;
+    return;
+  }
+  const int sb = meta->sb, t = meta->t;
+  const float* src = bank + c * dim;
+  double ss = 0.0, sm = 0.0;
+  for (int k = lane; k < SL_ROW; k += 32) {
+    __half h = zero;
+    if (k < dim) {
+      const float x = __fsub_rn(src[k], meta->center[k]);
+      ss += (double)x * x;
+      sm += (double)x;
+      h = __float2half_rn(scalbnf(-2.f * x, sb));
+    }
+    if (k < dim || k >= dim + 3) row[k] = h;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  }
+  if (lane == 0) {
+    const double eps = (double)VFR_PAIRWISE_EPS;
+    const double nv = ss + 2.0 * eps * sm + (double)dim * eps * eps;
+    __half a, b, c3;
+    split3_h(scalbn(nv, sb - t), a, b, c3);
+    row[dim] = a;
+    row[dim + 1] = b;
+    row[dim + 2] = c3;
+  }
+}
+
+// one warp per query row
+__global__ void sl_query_pack_kernel(const float* __restrict__ q, int64_t n_queries, int64_t n_rows_pad, int dim,
+                                     const SlBankMeta* __restrict__ meta, __half* __restrict__ out,
+                                     float4* __restrict__ qmeta, int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows_pad) return;
+  __half* row = out + r * SL_ROW;
+  const __half zero = __float2half_rn(0.f);
+  if (r >= n_queries) {
+    for (int k = lane; k < SL_ROW; k += 32) row[k] = zero;
+    if (lane == 0) { qmeta[r] = make_float4(0.f, 1.f, 1.f, 0.f); flags[r] = 0; }
+    return;
+  }
+  const float* src = q + r * dim;
+  double ss = 0.0, sm = 0.0;
+  float sa = 0.f, ma = 0.f;
+  for (int k = lane; k < dim; k += 32) {
+    const float x = __fsub_rn(src[k], meta->center[k]);
+    ss += (double)x * x;
+    sm += (double)x;
+    sa += fabsf(x);
+    ma = fmaxf(ma, fabsf(x));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+  }
+  const int sb = meta->sb, t = meta->t;
+  int sq = 0, bad = 0;
+  if (ma > 0.f && ma < CUDART_INF_F) sq = 7 - ilogbf(ma);      // |q| 2^sq < 2^8
+  if (!(ma < CUDART_INF_F) || !(ss < 1e300)) bad = 1;          // inf / nan in the query
+  sq = min(sq, 14 - t);                                          // the nv multiplier 2^(sq+t) must fit fp16
+  if (sq + t < -24 || sq + sb > 100 || sq + sb < -100) { bad = 1; sq = 0; }
+  for (int k = lane; k < SL_ROW; k += 32) {
+    __half h = zero;
+    if (k < dim) h = __float2half_rn(scalbnf(__fsub_rn(src[k], meta->center[k]), sq));
+    else if (k < dim + 3) h = bad ? zero : __float2half_rn(scalbnf(1.f, sq + t));
+    row[k] = h;
+  }
+  if (lane == 0) {
+    const double eps = (double)VFR_PAIRWISE_EPS;
+    const double nq = ss - 2.0 * eps * sm;
+    const double qn = sqrt(ss);
+    const double vn = (double)__uint_as_float(meta->vnorm_max_bits);
+    const double nvm = (double)__uint_as_float(meta->nv_max_bits);
+    const double vsa = (double)__uint_as_float(meta->vsum_abs_max_bits);
+    // rigorous bound of |d2~ - d^2| (see the header): operand rounding, sub-normal operands, the nv
+    // triple, fp32 accumulation inside the tensor core (2^-18 of the absolute sum: >= 32 x its observed
+    // error) and the rounding of the key / threshold arithmetic
+    const double main_term = 1.05 * (1.0 / 1024.0) * (1.0 + 1.0 / 4096.0) * qn * 2.0 * vn;
+    const double sub_term = 1.001 * ldexp(1.0, -25) * (ldexp((double)sa, -sb) + ldexp(2.0 * vsa, -sq));
+    const double nv_term = ldexp(nvm, -30) + ldexp(1.0, t - sb - 24);
+    const double acc_term = ldexp(2.0 * qn * vn + nvm, -18);
+    const double key_term = ldexp(fabs(nq) + nvm + 2.0 * qn * vn, -21);
+    const double ctr_term = ldexp((qn + vn) * (qn + vn), -22);   // fp32 rounding of the centring subtractions
+    const double E = main_term + sub_term + nv_term + acc_term + key_term + ctr_term;
+    const float scale = scalbnf(1.f, sq + sb);
+    qmeta[r] = make_float4((float)nq, scale, scalbnf(1.f, -(sq + sb)), (float)(2.0 * E * 1.0001));
+    flags[r] = bad;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMA primitives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sl_tma_load(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void sl_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void sl_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void sl_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sl_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t sl_desc(const void* smem_ptr) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void sl_ld32(uint32_t taddr, float (&v)[64], int off) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[off + i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// mbarrier wait with a watchdog (a protocol bug traps instead of hanging the GPU).  mode 0: try_wait with a
+// suspend-time hint (the thread sleeps in hardware); mode 1: plain try_wait loop; mode 2: short hint
+__device__ __forceinline__ void sl_wait(uint64_t* bar, uint32_t parity, int mode) {
+  uint32_t done = 0;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    if (mode == 1) {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(parity)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(parity), "r"(mode == 0 ? 1000000u : 200u)
+          : "memory");
+    }
+    if (done) return;
+    if ((spin & 0x3fff) == 0x3fff) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("vfr: select_tc mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+
+// threshold of the accumulator domain, rounded up:  (tau2 + band2 - nq) * scale
+__device__ __forceinline__ float sl_threshold(float tau2, float band2, float nq, float scale) {
+  return __fmul_ru(__fsub_ru(__fadd_ru(tau2, band2), nq), scale);
+}
+
+// Band-preserving compaction of thread-private candidate lists (cf. compact_lists in vfr_topk.cuh, here for
+// SL_CAP keys).  For each lane whose `need` is set the warp finds the k-th smallest key of that lane's list
+// (most-significant-bit-first radix select on the d2~ word), makes it the lane's tau and keeps every key
+// <= min(tau, tau_shared) + band2.
+constexpr int SL_SLOTS = SL_CAP / 32;   // keys per lane
+
+__device__ __forceinline__ unsigned sl_radix_kth(const unsigned (&w)[SL_SLOTS], unsigned candmask, int kk, int m) {
+  unsigned a = 0xffffffffu, o = 0u;
+#pragma unroll
+  for (int s = 0; s < SL_SLOTS; ++s)
+    if ((candmask >> s) & 1u) { a &= w[s]; o |= w[s]; }
+  a = warp_and(a);
+  o = warp_or(o);
+  const unsigned diff = a ^ o;
+  if (diff == 0u) return a;
+  const int top = 31 - __clz(diff);
+  unsigned value = a & ~((2u << top) - 1u);
+  int bit = top;
+  for (; bit >= 0 && m > 1; --bit) {
+    unsigned ones = 0u;
+#pragma unroll
+    for (int s = 0; s < SL_SLOTS; ++s) ones |= ((w[s] >> bit) & 1u) << s;
+    const int c0 = warp_sum_int(__popc(candmask & ~ones));
+    if (kk <= c0) { m = c0; candmask &= ~ones; }
+    else { kk -= c0; m -= c0; candmask &= ones; value |= 1u << bit; }
+  }
+  if (bit >= 0) {
+    unsigned mine = 0u;
+#pragma unroll
+    for (int s = 0; s < SL_SLOTS; ++s)
+      if ((candmask >> s) & 1u) mine = w[s];
+    const unsigned who = __ballot_sync(0xffffffffu, candmask != 0u);
+    value = __shfl_sync(0xffffffffu, mine, __ffs(who) - 1);
+  }
+  return value;
+}
+
+__device__ __noinline__ void sl_compact(unsigned long long* list, int& cnt, float& tau_own, float tau_shared, float band2,
+                                        int k, bool need, int lane) {
+  unsigned mask = __ballot_sync(0xffffffffu, need);
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    unsigned long long* lp =
+        reinterpret_cast<unsigned long long*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(list), src));
+    const int n = __shfl_sync(0xffffffffu, cnt, src);
+    const float ts = __shfl_sync(0xffffffffu, tau_shared, src);
+    const float b2 = __shfl_sync(0xffffffffu, band2, src);
+    if (n <= k) continue;
+    __syncwarp();
+    unsigned hi[SL_SLOTS], lo[SL_SLOTS];
+    unsigned candmask = 0u;
+#pragma unroll
+    for (int s = 0; s < SL_SLOTS; ++s) {
+      const int idx = (s << 5) | lane;
+      unsigned long long key = ~0ull;
+      if (idx < n) { key = lp[idx]; candmask |= 1u << s; }
+      hi[s] = (unsigned)(key >> 32);
+      lo[s] = (unsigned)key;
+    }
+    const unsigned kth_hi = sl_radix_kth(hi, candmask, k, n);
+    const float kth = __uint_as_float(kth_hi);
+    const unsigned keep_bits = __float_as_uint(__fadd_ru(fminf(kth, ts), b2));
+    __syncwarp();
+    int base = 0;
+#pragma unroll
+    for (int s = 0; s < SL_SLOTS; ++s) {
+      const int idx = (s << 5) | lane;
+      const bool keep = idx < n && hi[s] <= keep_bits;
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) lp[base + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)hi[s] << 32) | lo[s];
+      base += __popc(bal);
+    }
+    __syncwarp();
+    if (lane == src) {
+      cnt = base;
+      tau_own = kth;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 1: the filter kernel
+// ---------------------------------------------------------------------------------------------
+template <int R>
+struct SlCfg {
+  static constexpr int STAGES = (R == 1) ? 6 : 5;
+  static constexpr uint32_t SMEM = R * 2 * SL_A_CHUNK + STAGES * SL_B_CHUNK + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// per-thread state of the epilogue: one query row, one candidate list
+struct SlRow {
+  unsigned long long* list;
+  int cnt;
+  float tau_own;     // k-th smallest d2~ of this list (inf until it has been compacted once)
+  float tau_use;     // min(tau_own, the query's shared tau): what the filter currently uses
+  float thr;         // the same in the accumulator domain, band included
+  float nq, inv_scale, scale, band2;   // the query's qmeta
+  int64_t q;
+  int64_t clip0;     // first clip of the current tile
+};
+
+__device__ __forceinline__ void sl_append(SlRow& st, float x, int64_t clip, const SlParams& p) {
+  if (clip < p.n_clips) {
+    const float key = fmaxf(__fmaf_rn(x, st.inv_scale, st.nq), 0.f);
+    st.list[st.cnt++] = ((unsigned long long)__float_as_uint(key) << 32) | (unsigned)clip;
+  }
+}
+
+// Cold path of sl_process: some of the 64 columns pass the filter.  Branch-free pass mask (FSETP + predicated
+// LOP3, four independent chains); the usual case is ONE passing column, whose value is the minimum the hot path
+// already holds, so no dynamic register indexing is needed.  Several passing columns (start of the scan) go
+// through a local-memory copy.
+__device__ __forceinline__ void sl_cold(const float (&v)[64], float m, int coff, SlRow& st, const SlParams& p) {
+  unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    m0 |= (v[j] <= st.thr) ? (1u << j) : 0u;
+    m1 |= (v[16 + j] <= st.thr) ? (1u << (16 + j)) : 0u;
+    m2 |= (v[32 + j] <= st.thr) ? (1u << j) : 0u;
+    m3 |= (v[48 + j] <= st.thr) ? (1u << (16 + j)) : 0u;
+  }
+  unsigned lo = m0 | m1, hi = m2 | m3;
+  const int64_t c0 = st.clip0 + coff;
+  if (__popc(lo) + __popc(hi) == 1) {
+    const int idx = lo ? (__ffs(lo) - 1) : (31 + __ffs(hi));
+    sl_append(st, m, c0 + idx, p);
+  } else {
+    float vl[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) vl[j] = v[j];
+    while (lo) {
+      const int idx = __ffs(lo) - 1;
+      lo &= lo - 1;
+      sl_append(st, vl[idx], c0 + idx, p);
+    }
+    while (hi) {
+      const int idx = __ffs(hi) - 1;
+      hi &= hi - 1;
+      sl_append(st, vl[32 + idx], c0 + 32 + idx, p);
+    }
+  }
+}
+
+// 64 accumulator columns of one query row: FMNMX3 tree and one compare
+__device__ __forceinline__ void sl_process(const float (&v)[64], int coff, SlRow& st, const SlParams& p) {
+  float g[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = fmin3(v[8 * i], v[8 * i + 1], v[8 * i + 2]);
+    const float b = fmin3(v[8 * i + 3], v[8 * i + 4], v[8 * i + 5]);
+    g[i] = fmin3(a, b, fminf(v[8 * i + 6], v[8 * i + 7]));
+  }
+  const float m = fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), fminf(g[6], g[7]));
+  if (m <= st.thr) sl_cold(v, m, coff, st, p);
+}
+
+template <int R>
+__global__ void __launch_bounds__(SL_THREADS, 1)
+sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const SlParams p) {
+  constexpr int STAGES = SlCfg<R>::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                   // [R][2 chunks]
+  uint8_t* smem_b = smem + R * 2 * SL_A_CHUNK;              // [STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * SL_B_CHUNK);
+  uint64_t* full = bars;                        // [STAGES]
+  uint64_t* empty = bars + STAGES;              // [STAGES]
+  uint64_t* a_full = bars + 2 * STAGES;         // [1]
+  uint64_t* tmem_full = a_full + 1;             // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qgroup = blockIdx.x % p.n_qgroups;
+  const int split = blockIdx.x / p.n_qgroups;
+  const int tile_begin = split * p.tiles_per_split;
+  const int tile_end = min(tile_begin + p.tiles_per_split, p.n_tiles);
+  const int n_my_tiles = max(tile_end - tile_begin, 0);
+  const int b_chunks = (p.ksteps > 4) ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], SL_SET_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  sl_fence_before();
+  __syncthreads();
+  sl_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0 && n_my_tiles > 0) {
+      mbar_expect_tx(a_full, (uint32_t)(R * b_chunks) * SL_A_CHUNK);
+      for (int r = 0; r < R; ++r)
+        for (int c = 0; c < b_chunks; ++c)
+          sl_tma_load(smem_a + (r * 2 + c) * SL_A_CHUNK, &tm_a, c * 64, (qgroup * R + r) * SL_M, a_full);
+      int it = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const int row = (tile_begin + t) * SL_N;
+        for (int c = 0; c < b_chunks; ++c, ++it) {
+          const int s = it % STAGES;
+          sl_wait(&empty[s], ((it / STAGES) & 1) ^ 1, p.wait_mode);
+          mbar_expect_tx(&full[s], SL_B_CHUNK);
+          sl_tma_load(smem_b + s * SL_B_CHUNK, &tm_b, c * 64, row, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0 && n_my_tiles > 0) {
+      // kind::f16, fp16 x fp16 -> fp32, K-major A and B, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(SL_N >> 3) << 17) | ((uint32_t)(SL_M >> 4) << 24);
+      sl_wait(a_full, 0, p.wait_mode);
+      sl_fence_after();
+      int it = 0, job = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const int s0 = it % STAGES, ph0 = (it / STAGES) & 1;
+        const int s1 = (it + 1) % STAGES, ph1 = ((it + 1) / STAGES) & 1;
+        it += b_chunks;
+        for (int r = 0; r < R; ++r, ++job) {
+          const int buf = job & 1;                 // R = 2: buffer = query tile; R = 1: buffer = tile parity
+          sl_wait(&tmem_empty[buf], ((job >> 1) & 1) ^ 1, p.wait_mode);
+          sl_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)buf * SL_N;
+          uint32_t accumulate = 0;
+          for (int c = 0; c < b_chunks; ++c) {
+            if (r == 0) {
+              sl_wait(&full[c ? s1 : s0], c ? ph1 : ph0, p.wait_mode);
+              sl_fence_after();
+            }
+            const int ks = (c == 0) ? min(p.ksteps, 4) : (p.ksteps - 4);
+            const uint64_t adesc = sl_desc(smem_a + (r * 2 + c) * SL_A_CHUNK);
+            const uint64_t bdesc = sl_desc(smem_b + (c ? s1 : s0) * SL_B_CHUNK);
+            for (int k = 0; k < ks; ++k) {
+              sl_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          sl_commit(&tmem_full[buf]);
+        }
+        sl_commit(&empty[s0]);
+        if (b_chunks == 2) sl_commit(&empty[s1]);
+      }
+    }
+  } else {
+    // ================= epilogue: two sets of four warps, set s owns TMEM buffer s =================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int set = ew >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * SL_N);
+    // R = 2: set s serves query tile s on every bank tile; R = 1: set s serves the tiles of parity s
+    const int qtile = (R == 2) ? (qgroup * 2 + set) : qgroup;
+    const int part = (R == 2) ? split : (split * 2 + set);
+    SlRow st;
+    st.q = (int64_t)qtile * SL_M + quarter * 32 + lane;
+    const bool valid = st.q < p.n_queries;
+    st.list = p.cand + ((int64_t)st.q * p.n_parts + part) * SL_CAP;
+    st.cnt = 0;
+    {
+      const float4 qm = __ldg(p.qmeta + st.q);
+      st.nq = qm.x; st.scale = qm.y; st.inv_scale = qm.z; st.band2 = qm.w;
+    }
+    st.tau_own = CUDART_INF_F;
+    st.tau_use = valid ? CUDART_INF_F : -1.f;
+    st.thr = valid ? CUDART_INF_F : -CUDART_INF_F;
+    const int t_first = (R == 2) ? 0 : set;
+    const int t_step = (R == 2) ? 1 : 2;
+
+    int visit = 0;
+    for (int t = t_first; t < n_my_tiles; t += t_step, ++visit) {
+      st.clip0 = (int64_t)(tile_begin + t) * SL_N;
+      if ((visit & 3) == 0) {
+        // the other lists of this query (other bank splits / tile parities) may have tightened the threshold
+        const float tg = tau_fetch(p.tau_g + st.q);
+        if (tg < st.tau_use) {
+          st.tau_use = tg;
+          st.thr = sl_threshold(tg, st.band2, st.nq, st.scale);
+        }
+      }
+      sl_wait(&tmem_full[set], visit & 1, p.wait_mode);
+      sl_fence_after();
+      float va[64], vb[64];
+      sl_ld32(lane_addr, va, 0);
+      sl_ld32(lane_addr + 32, va, 32);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      sl_ld32(lane_addr + 64, vb, 0);          // in flight while the first 64 columns are processed
+      sl_ld32(lane_addr + 96, vb, 32);
+      sl_process(va, 0, st, p);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      sl_ld32(lane_addr + 128, va, 0);
+      sl_ld32(lane_addr + 160, va, 32);
+      sl_process(vb, 64, st, p);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      sl_ld32(lane_addr + 192, vb, 0);
+      sl_ld32(lane_addr + 224, vb, 32);
+      sl_process(va, 128, st, p);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // the whole accumulator has been read: hand the TMEM buffer back to the MMA warp
+      sl_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[set]);
+      sl_process(vb, 192, st, p);
+
+      if (__any_sync(0xffffffffu, st.cnt > SL_CAP_HI)) {
+        const float before = st.tau_own;
+        // (copies: taking the address of a member would push the whole per-thread state into local memory)
+        int cnt = st.cnt;
+        float tau_own = st.tau_own;
+        sl_compact(st.list, cnt, tau_own, st.tau_use, st.band2, p.k, cnt > SL_CAP_HI, lane);
+        const bool over = cnt > SL_CAP_HI;
+        if (__any_sync(0xffffffffu, over)) {
+          // more than CAP_HI keys inside the band (mass duplicates): keep the list bounded and flag the query
+          if (over) p.flags[st.q] = 2;
+          sl_compact(st.list, cnt, tau_own, st.tau_use, 0.f, p.k, over, lane);
+          if (over) cnt = min(cnt, SL_CAP_HI);
+        }
+        st.cnt = cnt;
+        st.tau_own = tau_own;
+        if (st.tau_own < before) {
+          tau_publish(p.tau_g + st.q, st.tau_own);
+          if (st.tau_own < st.tau_use) {
+            st.tau_use = st.tau_own;
+            st.thr = sl_threshold(st.tau_own, st.band2, st.nq, st.scale);
+          }
+        }
+      }
+    }
+    // a list that ends with more than k keys still tightens the query's threshold for stage 2
+    if (__any_sync(0xffffffffu, st.cnt > p.k)) {
+      const float before = st.tau_own;
+      int cnt = st.cnt;
+      float tau_own = st.tau_own;
+      sl_compact(st.list, cnt, tau_own, st.tau_use, st.band2, p.k, cnt > p.k, lane);
+      st.cnt = cnt;
+      st.tau_own = tau_own;
+      if (st.tau_own < before) tau_publish(p.tau_g + st.q, st.tau_own);
+    }
+    p.cand_cnt[st.q * p.n_parts + part] = st.cnt;
+  }
+
+  sl_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 2: exact refine - all moments of the candidate videos, arithmetic of vfr_score.cu
+// ---------------------------------------------------------------------------------------------
+constexpr int RF_THREADS = 256;
+constexpr int RF_MAXC = 1024;      // candidate clips (and videos) per query
+constexpr int RF_KEYS = 2048;      // sort buffer: [0, 128) running best, [128, 2048) the next batch
+constexpr int RF_BATCH = RF_KEYS - VFR_TOPK_MAX;
+constexpr int RF_DIST = 1024;      // clip distances per chunk of videos
+
+struct RfParams {
+  const float* bank;           // fp32 [C, dim]
+  const float* queries;        // fp32 [Q, dim]
+  const int32_t* vid_off;      // [V+1]
+  const int64_t* mom_off;      // [V+1]
+  int64_t n_videos;
+  int n_max;
+  int dim;
+  const float4* qmeta;
+  const unsigned long long* cand;
+  const int32_t* cand_cnt;
+  int n_parts;
+  const unsigned* tau_g;
+  int32_t* flags;
+  int k;
+  int64_t id_base;
+  float* out_scores;
+  int64_t* out_ids;
+};
+
+// exact fp32 distance of one (query, clip) pair: the arithmetic of score_kernel / score_own_kernel in
+// vfr_score.cu (direct-difference form, k strictly sequential).  The bank row is fetched in batches of
+// 32 floats (8 independent 128-bit loads in flight) because the rows of the candidates are scattered
+// over the whole bank: the loop is bound by DRAM latency, not by the 100 dependent FFMAs.
+__device__ __forceinline__ float rf_distance(const float* __restrict__ vr, const float* qr, float sq, int dim) {
+  float acc = 0.f, sv = 0.f;
+  int k0 = 0;
+  if ((reinterpret_cast<uintptr_t>(vr) & 15u) == 0) {
+    for (; k0 + 32 <= dim; k0 += 32) {
+      float4 x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __ldg(reinterpret_cast<const float4*>(vr + k0) + j);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xs[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float d = __fsub_rn(xs[i], qr[k0 + 4 * j + i]);
+          acc = __fmaf_rn(d, d, acc);
+          sv = __fadd_rn(sv, xs[i]);
+        }
+      }
+    }
+  }
+  for (int k = k0; k < dim; ++k) {
+    const float x = __ldg(vr + k);
+    const float d = __fsub_rn(x, qr[k]);
+    acc = __fmaf_rn(d, d, acc);
+    sv = __fadd_rn(sv, x);
+  }
+  const float corr = __fmaf_rn(2.f * VFR_PAIRWISE_EPS, __fsub_rn(sv, sq), (float)dim * VFR_PAIRWISE_EPS * VFR_PAIRWISE_EPS);
+  return __fsqrt_rn(fmaxf(__fadd_rn(acc, corr), 0.f));
+}
+
+// block-wide bitonic sort of keys[0, n), n a power of two
+template <typename T>
+__device__ __forceinline__ void rf_block_sort(T* keys, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n / 2; i += RF_THREADS) {
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        const int hi = lo | stride;
+        const bool asc = !(lo & size) || size == n;
+        const T a = keys[lo], b = keys[hi];
+        if ((a > b) == asc) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ int rf_pow2(int x, int lo) {
+  int n = lo;
+  while (n < x) n <<= 1;
+  return n;
+}
+// merge the batch keys[128, 128 + count) into the running best keys[0, k): sort, trim, new threshold
+__device__ __forceinline__ void rf_merge_batch(unsigned long long* keys, int count, int k, int* s_cnt, float* s_tau) {
+  const int n = rf_pow2(VFR_TOPK_MAX + count, 256);
+  for (int i = VFR_TOPK_MAX + count + threadIdx.x; i < n; i += RF_THREADS) keys[i] = ~0ull;
+  rf_block_sort(keys, n);
+  for (int i = k + threadIdx.x; i < VFR_TOPK_MAX; i += RF_THREADS) keys[i] = ~0ull;
+  if (threadIdx.x == 0) {
+    *s_cnt = 0;
+    const unsigned long long kth = keys[k - 1];
+    if (kth != ~0ull) *s_tau = fminf(*s_tau, __uint_as_float((unsigned)(kth >> 32)));
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p) {
+  __shared__ unsigned long long keys[RF_KEYS];
+  __shared__ int vids[RF_MAXC];
+  __shared__ int uvid[RF_MAXC];
+  __shared__ float dist[RF_DIST];
+  __shared__ float qrow[SL_ROW];
+  __shared__ int warp_tot[RF_THREADS / 32];
+  __shared__ int s_n, s_cnt;
+  __shared__ float s_sq, s_tau;
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  // ---- 0. the query row and its sequential row sum ----
+  for (int i = tid; i < p.dim; i += RF_THREADS) qrow[i] = p.queries[q * p.dim + i];
+  if (tid == 0) { s_n = 0; s_cnt = 0; s_tau = CUDART_INF_F; }
+  for (int i = tid; i < RF_MAXC; i += RF_THREADS) vids[i] = INT_MAX;
+  for (int i = tid; i < VFR_TOPK_MAX; i += RF_THREADS) keys[i] = ~0ull;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int k = 0; k < p.dim; ++k) s = __fadd_rn(s, qrow[k]);
+    s_sq = s;
+  }
+
+  // ---- 1. candidate clips.  The k-th smallest d2~ over the UNION of the query's lists (each list only
+  //         knows its own) gives the final band; every key inside it -> video index ----
+  const float4 qm = p.qmeta[q];
+  const float tau_pub = tau_fetch(p.tau_g + q);
+  const unsigned pre_bits = __float_as_uint(__fadd_ru(tau_pub, qm.w));
+  float tau_fin = tau_pub;
+  int total = 0;
+  for (int part = 0; part < p.n_parts; ++part) total += min(p.cand_cnt[q * p.n_parts + part], SL_CAP);
+  const bool one_batch = total <= RF_BATCH;
+  {
+    int filled = 0;
+    for (int part = 0; part < p.n_parts; ++part) {
+      const int64_t li = q * p.n_parts + part;
+      const int n = min(p.cand_cnt[li], SL_CAP);
+      if (filled + n > RF_BATCH) {
+        __syncthreads();
+        rf_merge_batch(keys, s_cnt, p.k, &s_cnt, &s_tau);
+        filled = 0;
+      }
+      for (int i = tid; i < n; i += RF_THREADS) {
+        const unsigned long long key = p.cand[li * SL_CAP + i];
+        if ((unsigned)(key >> 32) <= pre_bits) keys[VFR_TOPK_MAX + atomicAdd(&s_cnt, 1)] = key;
+      }
+      filled += n;
+    }
+    __syncthreads();
+  }
+  const int gathered = s_cnt;                       // (one_batch: every key of the band is in keys[128, 128 + gathered))
+  const int n_sorted = rf_pow2(VFR_TOPK_MAX + gathered, 256);
+  {
+    for (int i = VFR_TOPK_MAX + gathered + tid; i < n_sorted; i += RF_THREADS) keys[i] = ~0ull;
+    rf_block_sort(keys, n_sorted);
+    const unsigned long long kth_key = keys[p.k - 1];
+    if (kth_key != ~0ull) tau_fin = fminf(tau_pub, __uint_as_float((unsigned)(kth_key >> 32)));
+  }
+  const unsigned keep_bits = __float_as_uint(__fadd_ru(tau_fin, qm.w));
+  // no moment scoring above this can be among the k best: the k closest clips are moments themselves
+  const float s_max = (tau_fin < CUDART_INF_F) ? __fmul_ru(__fsqrt_ru(__fadd_ru(tau_fin, qm.w)), 1.00001f) : CUDART_INF_F;
+  if (one_batch) {
+    // the sorted keys ARE the band: a prefix of keys[]
+    for (int i = tid; i < VFR_TOPK_MAX + gathered; i += RF_THREADS) {
+      const unsigned long long key = keys[i];
+      if (key != ~0ull && (unsigned)(key >> 32) <= keep_bits) {
+        const int clip = (int)(unsigned)key;
+        int lo = 0, hi = (int)p.n_videos;            // largest v with vid_off[v] <= clip
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(p.vid_off + mid) <= clip) lo = mid; else hi = mid;
+        }
+        const int pos = atomicAdd(&s_n, 1);
+        if (pos < RF_MAXC) vids[pos] = lo;
+      }
+    }
+  } else {
+    for (int part = 0; part < p.n_parts; ++part) {
+      const int64_t li = q * p.n_parts + part;
+      const int n = min(p.cand_cnt[li], SL_CAP);
+      for (int i = tid; i < n; i += RF_THREADS) {
+        const unsigned long long key = p.cand[li * SL_CAP + i];
+        if ((unsigned)(key >> 32) <= keep_bits) {
+          const int clip = (int)(unsigned)key;
+          int lo = 0, hi = (int)p.n_videos;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(p.vid_off + mid) <= clip) lo = mid; else hi = mid;
+          }
+          const int pos = atomicAdd(&s_n, 1);
+          if (pos < RF_MAXC) vids[pos] = lo;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < VFR_TOPK_MAX; i += RF_THREADS) keys[i] = ~0ull;
+  if (tid == 0) { s_cnt = 0; s_tau = CUDART_INF_F; }
+  __syncthreads();
+  if (s_n > RF_MAXC && tid == 0) p.flags[q] = 3;   // more candidates than the refine stage holds
+  rf_block_sort(vids, rf_pow2(min(s_n, RF_MAXC), 32));
+
+  // ---- 2. unique videos, ascending ----
+  constexpr int PER = RF_MAXC / RF_THREADS;
+  int flagsum = 0;
+  bool isnew[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = tid * PER + j;
+    const int v = vids[i];
+    isnew[j] = v != INT_MAX && (i == 0 || vids[i - 1] != v);
+    flagsum += isnew[j] ? 1 : 0;
+  }
+  int incl = flagsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  int base = incl - flagsum;
+  int n_unique = 0;
+#pragma unroll
+  for (int w = 0; w < RF_THREADS / 32; ++w) {
+    if (w < wid) base += warp_tot[w];
+    n_unique += warp_tot[w];
+  }
+#pragma unroll
+  for (int j = 0; j < PER; ++j)
+    if (isnew[j]) uvid[base++] = vids[tid * PER + j];
+  __syncthreads();
+
+  // ---- 3. chunks of videos: exact clip distances, exact moment means, streaming top-k ----
+  const int mom_max = num_moments(p.n_max);
+  const int vch = max(1, min(RF_DIST / p.n_max, RF_BATCH / mom_max));
+  const float sq = s_sq;
+  for (int v0 = 0; v0 < n_unique; v0 += vch) {
+    const int nv = min(vch, n_unique - v0);
+    if (s_cnt + nv * mom_max > RF_BATCH) rf_merge_batch(keys, s_cnt, p.k, &s_cnt, &s_tau);
+    for (int idx = tid; idx < nv * p.n_max; idx += RF_THREADS) {
+      const int vi = idx / p.n_max, c = idx - vi * p.n_max;
+      const int v = uvid[v0 + vi];
+      const int c0 = __ldg(p.vid_off + v);
+      const int n = __ldg(p.vid_off + v + 1) - c0;
+      if (c < n) dist[idx] = rf_distance(p.bank + (int64_t)(c0 + c) * p.dim, qrow, sq, p.dim);
+    }
+    __syncthreads();
+    const float tau = fminf(s_tau, s_max);
+    for (int idx = tid; idx < nv * p.n_max; idx += RF_THREADS) {
+      const int vi = idx / p.n_max, s = idx - vi * p.n_max;
+      const int v = uvid[v0 + vi];
+      const int n = __ldg(p.vid_off + v + 1) - __ldg(p.vid_off + v);
+      if (s < n) {
+        float run = 0.f;
+        for (int e = s; e < n; ++e) {
+          run = __fadd_rn(run, dist[vi * p.n_max + e]);
+          const float score = __fdiv_rn(run, (float)(e - s + 1));
+          if (score <= tau) {
+            const int pos = atomicAdd(&s_cnt, 1);
+            keys[VFR_TOPK_MAX + pos] =
+                ((unsigned long long)__float_as_uint(score) << 32) | (unsigned)(((v0 + vi) << 10) | moment_index(n, s, e));
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  rf_merge_batch(keys, s_cnt, p.k, &s_cnt, &s_tau);
+
+  // ---- 4. output: ascending (score, global moment id) ----
+  for (int i = tid; i < p.k; i += RF_THREADS) {
+    const unsigned long long key = keys[i];
+    const bool ok = key != ~0ull;
+    float score = CUDART_INF_F;
+    int64_t id = -1;
+    if (ok) {
+      const unsigned low = (unsigned)key;
+      score = __uint_as_float((unsigned)(key >> 32));
+      id = p.id_base + __ldg(p.mom_off + uvid[low >> 10]) + (int64_t)(low & 1023u);
+    }
+    p.out_scores[q * p.k + i] = score;
+    p.out_ids[q * p.k + i] = id;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*SlEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static SlEncodeFn sl_get_encode() {
+  static SlEncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<SlEncodeFn>(ptr);
+  }
+  return fn;
+}
+
+static int sl_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+  SlEncodeFn enc = sl_get_encode();
+  VFR_REQUIRE(enc, VFR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)SL_ROW, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)SL_ROW * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VFR_REQUIRE(r == CUDA_SUCCESS, VFR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return VFR_OK;
+}
+
+static int64_t sl_tiles(int64_t n_clips) { return (n_clips + SL_N - 1) / SL_N; }
+static int64_t sl_qrows(int64_t n_queries) { return (n_queries + SL_QPAD - 1) / SL_QPAD * SL_QPAD; }
+
+// query tiles per CTA: two whenever that still fills the machine (halves the L2 -> SM bank traffic)
+static int sl_rows(int64_t n_queries) {
+  const char* env = getenv("VFR_SEL_R");
+  if (env && (env[0] == '1' || env[0] == '2')) return env[0] - '0';
+  return (n_queries > SL_M) ? 2 : 1;
+}
+
+// bank splits per query group (one CTA per SM): the fewest that keep >= 85 % of the SMs busy
+static int sl_split(int64_t n_qgroups, int64_t n_tiles, int n_split) {
+  if (n_split > 0) return (int)(n_split < n_tiles ? n_split : n_tiles);
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int best = 1;
+  double best_util = 0.0;
+  for (int ns = 1; ns <= 148 && ns <= n_tiles; ++ns) {
+    const int64_t ctas = ns * n_qgroups;
+    const int64_t waves = (ctas + sms - 1) / sms;
+    const double util = (double)ctas / (double)(waves * sms);
+    if (util >= 0.85) return ns;
+    if (util > best_util) { best_util = util; best = ns; }
+  }
+  return best;
+}
+
+struct SlPlan {
+  int R, n_qgroups, ns, tiles_per_split, n_parts;
+  int64_t n_tiles, qrows;
+};
+
+static SlPlan sl_plan(int64_t n_queries, int64_t n_clips, int n_split) {
+  SlPlan pl;
+  pl.R = sl_rows(n_queries);
+  pl.n_tiles = sl_tiles(n_clips);
+  pl.qrows = sl_qrows(n_queries);
+  const int64_t qtiles = (n_queries + SL_M - 1) / SL_M;
+  pl.n_qgroups = (int)((qtiles + pl.R - 1) / pl.R);
+  const int ns_req = sl_split(pl.n_qgroups, pl.n_tiles, n_split);
+  pl.tiles_per_split = (int)((pl.n_tiles + ns_req - 1) / ns_req);
+  pl.ns = (int)((pl.n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
+  pl.n_parts = pl.ns * (pl.R == 2 ? 1 : 2);
+  return pl;
+}
+
+}  // namespace vfr
+
+using namespace vfr;
+
+extern "C" size_t vfr_sel_bank_bytes(int64_t n_clips) {
+  if (n_clips <= 0) return 0;
+  return (size_t)sl_tiles(n_clips) * SL_N * SL_ROW * 2 + sizeof(SlBankMeta);
+}
+
+extern "C" int vfr_sel_bank_pack(const float* bank, int64_t n_clips, int dim, void* packed, vfr_stream_t stream) {
+  VFR_REQUIRE(bank && packed, VFR_ERR_INVALID, "vfr_sel_bank_pack: null pointer");
+  VFR_REQUIRE(n_clips > 0 && n_clips < (int64_t(1) << 31) - SL_N, VFR_ERR_UNSUPPORTED,
+              "vfr_sel_bank_pack: n_clips=%lld out of range", (long long)n_clips);
+  VFR_REQUIRE(dim >= 1 && dim + 3 <= SL_ROW, VFR_ERR_UNSUPPORTED, "vfr_sel_bank_pack: dim=%d must be <= %d", dim, SL_ROW - 3);
+  const int64_t rows = sl_tiles(n_clips) * SL_N;
+  __half* out = reinterpret_cast<__half*>(packed);
+  SlBankMeta* meta = reinterpret_cast<SlBankMeta*>(out + rows * SL_ROW);
+  cudaStream_t st = (cudaStream_t)stream;
+  VFR_CUDA(cudaMemsetAsync(meta, 0, sizeof(SlBankMeta), st));
+  const int64_t sum_blocks = (n_clips + 1) / 2 < 148 * 8 ? (n_clips + 1) / 2 : 148 * 8;
+  sl_bank_colsum_kernel<<<(unsigned)sum_blocks, 256, 0, st>>>(bank, n_clips, dim, meta);
+  int rc0 = check_launch("sl_bank_colsum_kernel");
+  if (rc0) return rc0;
+  sl_bank_center_kernel<<<1, SL_ROW, 0, st>>>(n_clips, dim, meta);
+  rc0 = check_launch("sl_bank_center_kernel");
+  if (rc0) return rc0;
+  const int64_t stat_blocks = (n_clips + 7) / 8 < 148 * 16 ? (n_clips + 7) / 8 : 148 * 16;
+  sl_bank_stats_kernel<<<(unsigned)stat_blocks, 256, 0, st>>>(bank, n_clips, dim, meta);
+  int rc = check_launch("sl_bank_stats_kernel");
+  if (rc) return rc;
+  sl_bank_scales_kernel<<<1, 1, 0, st>>>(meta);
+  rc = check_launch("sl_bank_scales_kernel");
+  if (rc) return rc;
+  sl_bank_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(bank, n_clips, rows, dim, meta, out);
+  return check_launch("sl_bank_pack_kernel");
+}
+
+extern "C" size_t vfr_sel_query_bytes(int64_t n_queries) {
+  if (n_queries <= 0) return 0;
+  const size_t rows = (size_t)sl_qrows(n_queries);
+  return rows * SL_ROW * 2 + rows * sizeof(float4) + rows * sizeof(int32_t);
+}
+
+extern "C" int vfr_sel_query_pack(const float* queries, int64_t n_queries, int dim, const void* bank_packed,
+                                  int64_t n_clips, void* packed, vfr_stream_t stream) {
+  VFR_REQUIRE(queries && bank_packed && packed, VFR_ERR_INVALID, "vfr_sel_query_pack: null pointer");
+  VFR_REQUIRE(n_queries > 0 && n_clips > 0 && dim >= 1 && dim + 3 <= SL_ROW, VFR_ERR_UNSUPPORTED,
+              "vfr_sel_query_pack: bad shape");
+  const int64_t rows = sl_qrows(n_queries);
+  const SlBankMeta* meta =
+      reinterpret_cast<const SlBankMeta*>(reinterpret_cast<const __half*>(bank_packed) + sl_tiles(n_clips) * SL_N * SL_ROW);
+  __half* out = reinterpret_cast<__half*>(packed);
+  float4* qmeta = reinterpret_cast<float4*>(out + rows * SL_ROW);
+  int32_t* flags = reinterpret_cast<int32_t*>(qmeta + rows);
+  sl_query_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(queries, n_queries, rows, dim, meta,
+                                                                                     out, qmeta, flags);
+  return check_launch("sl_query_pack_kernel");
+}
+
+extern "C" size_t vfr_sel_topk_bytes(int64_t n_queries, int64_t n_clips, int n_split) {
+  if (n_queries <= 0 || n_clips <= 0) return 0;
+  // the plan (query tiles per CTA, bank splits) depends on the batch size: size for the worst batch <= n_queries
+  size_t worst = 0;
+  const int64_t qtiles = (n_queries + SL_M - 1) / SL_M;
+  for (int64_t qt = 1; qt <= qtiles; ++qt) {
+    const SlPlan pl = sl_plan(qt == qtiles ? n_queries : qt * SL_M, n_clips, n_split);
+    const size_t qpad = (size_t)pl.qrows;
+    const size_t need = qpad * pl.n_parts * SL_CAP * sizeof(unsigned long long) + qpad * pl.n_parts * sizeof(int32_t) + qpad * sizeof(unsigned);
+    if (need > worst) worst = need;
+  }
+  return worst;
+}
+
+extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const int32_t* vid_off, const int64_t* mom_off,
+                            int64_t n_videos, int64_t n_clips, int n_max, int dim, void* query_packed,
+                            const float* queries, int64_t n_queries, int k, int64_t id_base, float* out_scores,
+                            int64_t* out_ids, void* workspace, int n_split, vfr_stream_t stream) {
+  VFR_REQUIRE(bank_packed && bank && vid_off && mom_off && query_packed && queries && out_scores && out_ids && workspace,
+              VFR_ERR_INVALID, "vfr_sel_topk: null pointer");
+  VFR_REQUIRE(n_videos > 0 && n_clips > 0 && n_queries > 0, VFR_ERR_INVALID, "vfr_sel_topk: empty bank or batch");
+  VFR_REQUIRE(n_clips < (int64_t(1) << 31) - SL_N && n_videos < (int64_t(1) << 31) - 1, VFR_ERR_UNSUPPORTED,
+              "vfr_sel_topk: bank shard too large");
+  VFR_REQUIRE(dim >= 1 && dim + 3 <= SL_ROW, VFR_ERR_UNSUPPORTED, "vfr_sel_topk: dim=%d must be <= %d", dim, SL_ROW - 3);
+  VFR_REQUIRE(n_max >= 1 && n_max <= VFR_MAX_SEG, VFR_ERR_UNSUPPORTED, "vfr_sel_topk: n_max=%d", n_max);
+  VFR_REQUIRE(k >= 1 && k <= VFR_TOPK_MAX, VFR_ERR_UNSUPPORTED, "k=%d not in [1,%d]", k, VFR_TOPK_MAX);
+  const SlPlan pl = sl_plan(n_queries, n_clips, n_split);
+  const int64_t rows = pl.n_tiles * SL_N;
+  CUtensorMap ma, mb;
+  int rc = sl_make_map(&ma, query_packed, (uint64_t)pl.qrows, SL_M);
+  if (rc) return rc;
+  rc = sl_make_map(&mb, bank_packed, (uint64_t)rows, SL_N);
+  if (rc) return rc;
+  __half* qp = reinterpret_cast<__half*>(query_packed);
+  SlParams p{};
+  p.qmeta = reinterpret_cast<const float4*>(qp + pl.qrows * SL_ROW);
+  p.flags = reinterpret_cast<int32_t*>(const_cast<float4*>(p.qmeta) + pl.qrows);
+  p.n_clips = n_clips;
+  p.n_queries = n_queries;
+  p.n_qgroups = pl.n_qgroups;
+  p.n_tiles = (int)pl.n_tiles;
+  p.tiles_per_split = pl.tiles_per_split;
+  p.ksteps = (dim + 3 + 15) / 16;
+  p.k = k;
+  p.n_parts = pl.n_parts;
+  { const char* wm = getenv("VFR_SEL_WAIT"); p.wait_mode = wm ? atoi(wm) : 0; }
+  const size_t qpad = (size_t)pl.qrows;
+  p.cand = reinterpret_cast<unsigned long long*>(workspace);
+  p.cand_cnt = reinterpret_cast<int32_t*>(p.cand + qpad * (size_t)pl.n_parts * SL_CAP);
+  p.tau_g = reinterpret_cast<unsigned*>(p.cand_cnt + qpad * (size_t)pl.n_parts);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad, st);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
+  if (pl.R == 2) {
+    VFR_CUDA(cudaFuncSetAttribute(sl_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SlCfg<2>::SMEM));
+    sl_filter_kernel<2><<<grid, SL_THREADS, SlCfg<2>::SMEM, st>>>(ma, mb, p);
+  } else {
+    VFR_CUDA(cudaFuncSetAttribute(sl_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SlCfg<1>::SMEM));
+    sl_filter_kernel<1><<<grid, SL_THREADS, SlCfg<1>::SMEM, st>>>(ma, mb, p);
+  }
+  rc = check_launch("sl_filter_kernel");
+  if (rc) return rc;
+  RfParams r{};
+  r.bank = bank;
+  r.queries = queries;
+  r.vid_off = vid_off;
+  r.mom_off = mom_off;
+  r.n_videos = n_videos;
+  r.n_max = n_max;
+  r.dim = dim;
+  r.qmeta = p.qmeta;
+  r.cand = p.cand;
+  r.cand_cnt = p.cand_cnt;
+  r.n_parts = p.n_parts;
+  r.tau_g = p.tau_g;
+  r.flags = p.flags;
+  r.k = k;
+  r.id_base = id_base;
+  r.out_scores = out_scores;
+  r.out_ids = out_ids;
+  sl_refine_kernel<<<(unsigned)n_queries, RF_THREADS, 0, st>>>(r);
+  return check_launch("sl_refine_kernel");
+}
+
+// flags of the last vfr_sel_topk on this packed query buffer: device pointer to int32 [n_queries]
+// (0 = exact result; 1 = operand scales out of fp16 range, 2 = candidate list overflow, 3 = refine overflow)
+extern "C" const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries) {
+  if (!query_packed || n_queries <= 0) return nullptr;
+  const int64_t rows = sl_qrows(n_queries);
+  const __half* qp = reinterpret_cast<const __half*>(query_packed);
+  return reinterpret_cast<const int32_t*>(reinterpret_cast<const float4*>(qp + rows * SL_ROW) + rows);
+}

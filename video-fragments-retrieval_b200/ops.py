@@ -79,6 +79,17 @@ class Bank:
             cache[n_terms] = packed
         return cache[n_terms]
 
+    def sel(self):
+        """Packed fp16 operand of the filter + refine top-k (vfr_sel_topk); built lazily, cached."""
+        if "_sel" not in self.__dict__:
+            if self.dim > 125:
+                raise _lib.VfrError("the filter + refine top-k holds embeddings of at most 125 dimensions")
+            n_clips = int(self.clips.shape[0])
+            packed = torch.empty(_lib.load().vfr_sel_bank_bytes(n_clips), dtype=torch.uint8, device=self.device)
+            _lib.call("vfr_sel_bank_pack", _ptr(self.clips), n_clips, self.dim, _ptr(packed), _stream())
+            self.__dict__["_sel"] = packed
+        return self.__dict__["_sel"]
+
     @property
     def uniform6(self):
         return int(bool((self.nseg_host == 6).all()))
@@ -173,6 +184,30 @@ def score_topk_tc(bank, queries, k, id_base=0, n_split=0, n_terms=3):
               bank.n_videos, bank.uniform6, bank.dim, n_terms, _ptr(qp), _ptr(q), Q, k, id_base, _ptr(out_s), _ptr(out_i),
               _ptr(ws), n_split, _stream())
     return out_s, out_i
+
+
+def score_topk_sel(bank, queries, k, id_base=0, n_split=0, return_flags=False):
+    """Filter + refine path (one fp16 tensor-core pass + exact fp32 re-scoring of the survivors):
+    (scores fp32 [Q, k], ids int64 [Q, k]) bit-identical to ``score_topk``.  ``flags`` int32 [Q] is 0 for
+    every query whose result is guaranteed exact (see include/vfr.h, vfr_sel_flags)."""
+    _need_cuda(queries)
+    q = _f32c(queries)
+    Q = q.shape[0]
+    lib = _lib.load()
+    n_clips = int(bank.clips.shape[0])
+    qp = torch.empty(lib.vfr_sel_query_bytes(Q), dtype=torch.uint8, device=bank.device)
+    _lib.call("vfr_sel_query_pack", _ptr(q), Q, bank.dim, _ptr(bank.sel()), n_clips, _ptr(qp), _stream())
+    ws = torch.empty(lib.vfr_sel_topk_bytes(Q, n_clips, n_split), dtype=torch.uint8, device=bank.device)
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=bank.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=bank.device)
+    _lib.call("vfr_sel_topk", _ptr(bank.sel()), _ptr(bank.clips), _ptr(bank.vid_off), _ptr(bank.mom_off), bank.n_videos,
+              n_clips, bank.n_max, bank.dim, _ptr(qp), _ptr(q), Q, k, id_base, _ptr(out_s), _ptr(out_i), _ptr(ws),
+              n_split, _stream())
+    if not return_flags:
+        return out_s, out_i
+    off = lib.vfr_sel_flags(_ptr(qp), Q) - qp.data_ptr()
+    flags = qp[off:off + 4 * Q].view(torch.int32).clone()
+    return out_s, out_i, flags, (qp, ws)
 
 
 def topk_merge(scores, ids):
