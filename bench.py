@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=18944, help="queries per step (148 query tiles of 128 = one per SM)")
-    ap.add_argument("--engine", type=str, default="tc", choices=["tc", "tc_bf16", "exact"])
+    ap.add_argument("--engine", type=str, default="sel", choices=["sel", "tc", "tc_bf16", "exact"])
     ap.add_argument("--videos", type=int, default=N_VIDEOS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -226,7 +226,7 @@ def workload_config(args, world):
     return {"workload": "corpus retrieval: 100k queries x %d videos x 21 moments (6 clips, D=100), top-%d, "
                         "query batches of %d (BASELINE configs[4])" % (args.videos, TOPK, args.batch),
             "query_batch": args.batch, "n_videos": args.videos, "n_moments": args.videos * MOMENTS_PER_VIDEO,
-            "dim": DIM, "topk": TOPK, "parallelism": f"bank sharded by video range over {world} GPU(s), queries replicated", "engine": getattr(args, "engine", "tc"),
+            "dim": DIM, "topk": TOPK, "parallelism": f"bank sharded by video range over {world} GPU(s), queries replicated", "engine": getattr(args, "engine", "sel"),
             "l2": "inputs larger than L2: the packed bank shard (%.2f GB) is streamed every step"
                   % (args.videos / world * N_SEG * DIM * 4 / 1e9)}
 
@@ -318,19 +318,27 @@ def run_ours(args):
     local_pairs = args.batch * retr.bank.m_total                 # pairs this rank's K4 launch scores
     flop_per_pair = 4.0 * DIM / (N_SEG + 1)                      # 2*D*S / (S(S+1)/2)
     achieved_tflops = local_pairs * flop_per_pair / (k4 * 1e-3) / 1e12
-    tc = args.engine != "exact"
+    kernel_names = {
+        "sel": "vfr_sel_topk (sl_filter_kernel: fp16 tcgen05 GEMM + min/threshold epilogue; sl_refine_kernel: exact fp32 re-scoring)",
+        "tc": "vfr_score_topk_tc (score_tc_kernel<TOPK> + threshold init + topk_finish_kernel)",
+        "tc_bf16": "vfr_score_topk_tc (score_tc_kernel<TOPK>, plain bf16)",
+        "exact": "vfr_score_topk (score_kernel<TOPK> + topk_finish_kernel)"}
+    notes = {
+        "sel": "one fp16 tcgen05 pass (K padded 100 -> 112: 224 executed FLOP per (query, clip) vs 200 algorithmic), the k best "
+               "moments are provably inside the videos of the ~k closest clips, which are re-scored exactly in fp32; results "
+               "bit-identical to the exact engine",
+        "tc": "tcgen05 split-bf16 GEMM (3 MMA passes, K=112 each) + fused sqrt / moment-mean / top-k epilogue; algorithmic FLOPs "
+              "count ONE fp32 pass (4D/(S+1) per pair), so frac understates tensor-pipe use 3.4x",
+        "tc_bf16": "tcgen05 plain-bf16 GEMM + fused epilogue (1e-2 tolerance)",
+        "exact": "exact-fp32 CUDA-core path (FADD+FFMA direct-difference form): 2 fp32 instr per (clip, dim); fp32 FFMA peak "
+                 "~72 TFLOP/s is the real ceiling of this path"}
     roofline = {
-        "kernel": ("vfr_score_topk_tc (score_tc_kernel<TOPK> + threshold init + topk_finish_kernel)" if tc else
-                   "vfr_score_topk (score_kernel<TOPK> + topk_finish_kernel)"),
+        "kernel": kernel_names[args.engine],
         "bound": "tensor", "achieved": achieved_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved_tflops / pk["bf16_tflops_sustained"], "traffic": None,
         "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
         "ms_per_launch": k4, "algorithmic_flop_per_pair": flop_per_pair,
-        "note": ("tcgen05 split-bf16 GEMM (3 MMA passes, K=112 each) + fused sqrt / moment-mean / top-k epilogue; "
-                 "algorithmic FLOPs count ONE fp32 pass (4D/(S+1) per pair), so frac understates tensor-pipe use 3.4x; "
-                 "the kernel is epilogue-ALU bound (SURVEY H2)") if tc else
-                ("exact-fp32 CUDA-core path (FADD+FFMA direct-difference form): 2 fp32 instr per (clip, dim); "
-                 "fp32 FFMA peak ~72 TFLOP/s is the real ceiling of this path"),
+        "note": notes[args.engine],
         "share_of_step": k4 * args.steps / ms_total,
     }
 
@@ -353,7 +361,8 @@ def run_ours(args):
             "metric": "query-moment pairs scored/sec", "value": pairs_per_step * args.steps / (ms_total * 1e-3),
             "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"tc": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate; fp32 scores within 1e-5)", "tc_bf16": "bf16", "exact": "f32"}[args.engine],
+            "dtype": {"sel": "f16 tensor-core filter (fp32 accumulate, rigorous error band) + f32 exact re-scoring: scores bit-identical to the fp32 path",
+                      "tc": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate; fp32 scores within 1e-5)", "tc_bf16": "bf16", "exact": "f32"}[args.engine],
             "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks,
             "e2e": {"value": pairs_per_step * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",

@@ -280,6 +280,10 @@ typedef struct vfr_search_plan {
    * vfr_text_embed_bytes); 3 = tensor-core K3 (text_tc = vfr_text_pack_tc blob, text_ws =
    * vfr_text_embed_tc_bytes). */
   int text_engine; const void* text_tc;
+  /* engine 4 = filter + refine top-k (vfr_sel_topk): bank_tc = vfr_sel_bank_pack blob, q_tc =
+   * vfr_sel_query_bytes(max_queries), topk_ws = vfr_sel_topk_bytes(max_queries, n_clips, n_split),
+   * bank_clips fp32 [n_clips, dim]; any clip count per video <= 32.  Per-query flags: vfr_sel_flags(q_tc, n). */
+  int64_t n_clips;
 } vfr_search_plan;
 
 /* the two stages separately (multi-GPU: every rank embeds its slice of the batch, the embeddings are

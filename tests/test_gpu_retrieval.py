@@ -23,14 +23,15 @@ def _setup(seed=21, V=300, Q=70, vocab=400):
     return sd, model, clips, tokens
 
 
-@pytest.mark.parametrize("engine", ["exact", "tc"])
+@pytest.mark.parametrize("engine", ["exact", "tc", "sel"])
 def test_search_host_matches_oracle_and_device_path(engine):
     sd, model, clips, tokens = _setup()
     V = clips.shape[0] // 6
     vid_off = np.arange(V + 1) * 6
+    text_engine = "tc" if engine == "sel" else engine
     retr = MomentRetriever(model, torch.from_numpy(clips).to(DEV), vid_off, max_queries=128, k=10, engine=engine,
-                           text_engine=engine)
-    assert retr.engine == engine and retr.text_engine == engine
+                           text_engine=text_engine)
+    assert retr.engine == engine and retr.text_engine == text_engine
     s, i = retr.search(tokens)
     sd_, id_ = retr.search_device(torch.from_numpy(tokens).to(DEV))
     assert torch.equal(s, sd_.cpu()) and torch.equal(i, id_.cpu())
@@ -51,7 +52,7 @@ def test_search_host_matches_oracle_and_device_path(engine):
         retr.search(bad)
 
 
-@pytest.mark.parametrize("engine", ["exact", "tc", "tc_bf16"])
+@pytest.mark.parametrize("engine", ["exact", "tc", "tc_bf16", "sel"])
 def test_sharded_search_equals_single_bank_search(engine):
     sd, model, clips, tokens = _setup(seed=22, V=1000)
     V = clips.shape[0] // 6
@@ -68,3 +69,24 @@ def test_sharded_search_equals_single_bank_search(engine):
         parts_i.append(pi.clone())
     ms, mi = ops.topk_merge(torch.stack(parts_s), torch.stack(parts_i))
     assert torch.equal(ms, s) and torch.equal(mi, i)
+
+
+def test_sel_engine_equals_exact_engine_and_fixes_up_flagged_queries():
+    """The default engine ("auto" -> filter + refine) returns the exact engine's bits; queries it cannot
+    certify (here: a bank scaled so far from the queries that the fp16 operand scales do not fit) are
+    re-run through the exact engine by the retriever."""
+    sd, model, clips, tokens = _setup(seed=23, V=2000, Q=100)
+    V = clips.shape[0] // 6
+    vid_off = np.arange(V + 1) * 6
+    tok = torch.from_numpy(tokens).to(DEV)
+    for scale, expect_fixups in ((1.0, False), (1e33, True)):
+        bank = torch.from_numpy(clips * np.float32(scale)).to(DEV)
+        exact = MomentRetriever(model, bank, vid_off, max_queries=128, k=100, engine="exact", text_engine="tc")
+        auto = MomentRetriever(model, bank, vid_off, max_queries=128, k=100, text_engine="tc")
+        assert auto.engine == "sel"
+        es, ei = exact.search_device(tok)
+        gs, gi = auto.search_device(tok)
+        assert torch.equal(gi, ei) and torch.equal(gs.view(torch.int32), es.view(torch.int32))
+        assert (getattr(auto, "n_fixups", 0) > 0) == expect_fixups
+        hs, hi = auto.search(tokens)
+        assert torch.equal(hi, ei.cpu()) and torch.equal(hs.view(torch.int32), es.cpu().view(torch.int32))

@@ -37,7 +37,7 @@ class SearchPlan(C.Structure):
                 ("tokens_dev", _p), ("q_emb", _p), ("q_packed", _p), ("text_ws", _p), ("topk_ws", _p),
                 ("out_scores_dev", _p), ("out_ids_dev", _p), ("n_split", _i), ("max_queries", _l),
                 ("engine", _i), ("bank_tc", _p), ("bank_clips", _p), ("uniform6", _i), ("q_tc", _p),
-                ("text_engine", _i), ("text_tc", _p)]
+                ("text_engine", _i), ("text_tc", _p), ("n_clips", _l)]
 
 
 # name -> (restype, argtypes); kept in the order of include/vfr.h

@@ -16,7 +16,9 @@ static int check_plan(const vfr_search_plan* p, int64_t n_queries, int k) {
     VFR_REQUIRE(p->text_tc, VFR_ERR_INVALID, "vfr_search: text engine 3 needs text_tc");
   VFR_REQUIRE(p->tokens_dev && p->q_emb && p->text_ws && p->topk_ws && p->out_scores_dev && p->out_ids_dev,
               VFR_ERR_INVALID, "vfr_search: null scratch pointer in plan");
-  VFR_REQUIRE(p->engine == 0 || p->engine == 1 || p->engine == 3, VFR_ERR_INVALID, "vfr_search: engine=%d", p->engine);
+  VFR_REQUIRE(p->engine == 0 || p->engine == 1 || p->engine == 3 || p->engine == 4, VFR_ERR_INVALID, "vfr_search: engine=%d",
+              p->engine);
+  if (p->engine == 4) VFR_REQUIRE(p->n_clips > 0, VFR_ERR_INVALID, "vfr_search: engine 4 needs n_clips");
   if (p->engine == 0)
     VFR_REQUIRE(p->bank_packed && p->q_packed, VFR_ERR_INVALID, "vfr_search: engine 0 needs bank_packed and q_packed");
   else
@@ -46,6 +48,13 @@ extern "C" int vfr_search_score_device(const vfr_search_plan* p, int64_t n_queri
   int rc = check_plan(p, n_queries, k);
   if (rc) return rc;
   VFR_REQUIRE(out_scores_dev && out_ids_dev, VFR_ERR_INVALID, "vfr_search_score_device: null pointer");
+  if (p->engine == 4) {
+    rc = vfr_sel_query_pack(p->q_emb, n_queries, p->dim, p->bank_tc, p->n_clips, p->q_tc, stream);
+    if (rc) return rc;
+    return vfr_sel_topk(p->bank_tc, p->bank_clips, p->vid_off, p->mom_off, p->n_videos, p->n_clips, p->n_max, p->dim,
+                        p->q_tc, p->q_emb, n_queries, k, p->id_base, out_scores_dev, out_ids_dev, p->topk_ws, p->n_split,
+                        stream);
+  }
   if (p->engine != 0) {
     rc = vfr_tc_query_pack(p->q_emb, n_queries, p->dim, p->engine, p->q_tc, stream);
     if (rc) return rc;

@@ -28,7 +28,7 @@ def shard_range(n_videos, rank, world):
 
 class MomentRetriever:
 
-    ENGINES = {"exact": 0, "tc": 3, "tc_bf16": 1}
+    ENGINES = {"exact": 0, "tc": 3, "tc_bf16": 1, "sel": 4}
 
     def __init__(self, model, clips, vid_off, id_base=0, max_queries=4096, k=100, n_split=0, group=None,
                  engine="auto", text_engine="auto"):
@@ -36,7 +36,9 @@ class MomentRetriever:
         this rank's bank shard; ``id_base`` = global moment id of the shard's first moment.
         ``engine``: "exact" (fp32 CUDA-core scoring, bit-identical to the evaluation path), "tc"
         (tcgen05 split-bf16 scoring, fp32 scores within 1e-5), "tc_bf16" (plain bf16, 1e-2), or
-        "auto" = "tc" whenever the bank fits its layout (videos of <= 6 clips, D <= 125)."""
+        "sel" (filter + refine: one fp16 tcgen05 pass with a rigorous error band + exact fp32 re-scoring of the
+        survivors; results bit-identical to "exact", any clip count per video), or "auto" = "sel" whenever
+        D <= 125."""
         self.model = model
         self.bank = ops.Bank(clips, vid_off)
         self.k = int(k)
@@ -67,13 +69,18 @@ class MomentRetriever:
             self.text_tc = None
             self.text_ws = torch.empty(lib.vfr_text_embed_bytes(mq, self.seq_len, H, E) // 4, dtype=torch.float32, device=dev)
         if engine == "auto":
-            engine = "tc" if (self.bank.n_max <= 6 and D <= 125) else "exact"
+            engine = "sel" if D <= 125 else "exact"
         self.engine = engine
         eng = self.ENGINES[engine]
         if eng == 0:
             self.q_packed = torch.empty(lib.vfr_query_pack_bytes(mq, D) // 4, dtype=torch.float32, device=dev)
             self.topk_ws = torch.empty(lib.vfr_score_topk_bytes(mq, n_split), dtype=torch.uint8, device=dev)
             self.q_tc = None
+        elif eng == 4:
+            self.n_clips = int(self.bank.clips.shape[0])
+            self.q_packed = None
+            self.q_tc = torch.empty(lib.vfr_sel_query_bytes(mq), dtype=torch.uint8, device=dev)
+            self.topk_ws = torch.empty(lib.vfr_sel_topk_bytes(mq, self.n_clips, n_split), dtype=torch.uint8, device=dev)
         else:
             self.q_packed = None
             self.q_tc = torch.empty(lib.vfr_tc_query_bytes(mq), dtype=torch.uint8, device=dev)
@@ -89,7 +96,10 @@ class MomentRetriever:
         p.text_engine = 3 if text_engine == "tc" else 0
         p.text_tc = self.text_tc.data_ptr() if self.text_tc is not None else None
         p.engine = eng
-        if eng:
+        if eng == 4:
+            p.bank_tc, p.bank_clips = self.bank.sel().data_ptr(), self.bank.clips.data_ptr()
+            p.q_tc, p.n_clips = self.q_tc.data_ptr(), self.n_clips
+        elif eng:
             p.bank_tc, p.bank_clips = self.bank.tc(eng).data_ptr(), self.bank.clips.data_ptr()
             p.uniform6, p.q_tc = self.bank.uniform6, self.q_tc.data_ptr()
         p.n_videos, p.n_max, p.id_base = self.bank.n_videos, self.bank.n_max, int(id_base)
@@ -109,7 +119,7 @@ class MomentRetriever:
         self.host_tokens = torch.empty((mq, self.seq_len), dtype=torch.int64).pin_memory()
         self.host_s = torch.empty((mq, self.k), dtype=torch.float32).pin_memory()
         self.host_i = torch.empty((mq, self.k), dtype=torch.int64).pin_memory()
-        # kernels launched per search step: gather + 20 LSTM steps + 2 fc + query pack + (threshold init) + score + finish (+ merge)
+        # kernels launched per search step: gather + 20 LSTM steps + 2 fc + query pack + threshold init + score (filter) + finish (refine) (+ merge)
         self.launches_per_step = 1 + self.seq_len + 2 + 1 + 1 + 1 + 1 + (1 if self.world > 1 else 0)
 
     def score_only(self, n_queries):
@@ -117,13 +127,37 @@ class MomentRetriever:
         search - used by bench.py to time the dominant kernel inside the steps."""
         lib_stream = torch.cuda.current_stream().cuda_stream
         b, p = self.bank, self.plan
-        if p.engine:
+        if p.engine == 4:
+            _lib.call("vfr_sel_topk", p.bank_tc, p.bank_clips, p.vid_off, p.mom_off, b.n_videos, self.n_clips, b.n_max,
+                      b.dim, p.q_tc, p.q_emb, n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev, p.topk_ws,
+                      p.n_split, lib_stream)
+        elif p.engine:
             _lib.call("vfr_score_topk_tc", p.bank_tc, p.bank_clips, p.vid_off, p.mom_off, b.n_videos, p.uniform6, b.dim,
                       p.engine, p.q_tc, p.q_emb, n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev,
                       p.topk_ws, p.n_split, lib_stream)
         else:
             _lib.call("vfr_score_topk", p.bank_packed, p.vid_off, p.mom_off, b.n_videos, b.n_max, b.dim, p.q_packed,
                       n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev, p.topk_ws, p.n_split, lib_stream)
+
+    def _sel_flags(self, Q):
+        """int32 [Q] view of the per-query flags of the last filter + refine call (0 = guaranteed exact)."""
+        off = _lib.load().vfr_sel_flags(self.q_tc.data_ptr(), Q) - self.q_tc.data_ptr()
+        return self.q_tc[off:off + 4 * Q].view(torch.int32)
+
+    def _sel_fixup(self, Q):
+        """Queries the filter + refine engine could not certify (operand magnitudes outside the fp16 scales, or
+        more candidates inside the error band than its lists hold - mass duplicates) are re-run through the
+        exact engine.  One 4-byte read-back per step when nothing is flagged."""
+        if self.plan.engine != 4:
+            return
+        flags = self._sel_flags(Q)
+        if int((flags != 0).any().item()) == 0:
+            return
+        idx = torch.nonzero(flags != 0).reshape(-1)
+        s, i = ops.score_topk(self.bank, self.q_emb[:Q][idx].contiguous(), self.k, id_base=int(self.plan.id_base))
+        self.out_s[:Q][idx] = s
+        self.out_i[:Q][idx] = i
+        self.n_fixups = getattr(self, "n_fixups", 0) + int(idx.numel())
 
     # -- device-resident step ---------------------------------------------------------------------
     def search_device(self, tokens_dev):
@@ -138,6 +172,7 @@ class MomentRetriever:
         if self.world == 1:
             _lib.call("vfr_search_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.k, self.out_s.data_ptr(),
                       self.out_i.data_ptr(), stream)
+            self._sel_fixup(Q)
             return self.out_s[:Q], self.out_i[:Q]
         rank = dist.get_rank(self.group)
         per = (Q + self.world - 1) // self.world                      # queries embedded per rank
@@ -151,6 +186,7 @@ class MomentRetriever:
         self.q_emb[:Q].copy_(gathered[:Q])
         _lib.call("vfr_search_score_device", C.byref(self.plan), Q, self.k, self.out_s.data_ptr(), self.out_i.data_ptr(),
                   stream)
+        self._sel_fixup(Q)
         gs, gi = self.gather_s[:, :Q].contiguous(), self.gather_i[:, :Q].contiguous()
         dist.all_gather_into_tensor(gs, self.out_s[:Q].contiguous(), group=self.group)
         dist.all_gather_into_tensor(gi, self.out_i[:Q].contiguous(), group=self.group)
@@ -168,6 +204,11 @@ class MomentRetriever:
         if self.world == 1:
             _lib.call("vfr_search_host", C.byref(self.plan), self.host_tokens.data_ptr(), Q, self.k,
                       self.host_s.data_ptr(), self.host_i.data_ptr(), stream)
+            if self.plan.engine == 4 and int((self._sel_flags(Q) != 0).any().item()):
+                self._sel_fixup(Q)
+                self.host_s[:Q].copy_(self.out_s[:Q])
+                self.host_i[:Q].copy_(self.out_i[:Q])
+                torch.cuda.current_stream().synchronize()
         else:
             self.tokens_dev[:Q].copy_(self.host_tokens[:Q], non_blocking=True)
             s, i = self.search_device(self.tokens_dev[:Q])
