@@ -11,6 +11,6 @@ clips = ((torch.randn(V, 1, 100, device="cuda", generator=g) + 0.6 * torch.randn
 q = torch.randn(Q, 100, device="cuda", generator=g) * 0.06
 bank = ops.Bank(clips, np.arange(V + 1) * 6)
 for _ in range(2):
-    s, i = ops.score_topk_sel(bank, q, 100)
+    s, i = ops.score_topk_sel(bank, q, int(os.environ.get("K", "100")))
 torch.cuda.synchronize()
 print("ok", float(s[:, 0].sum()))

@@ -5,7 +5,7 @@ import numpy as np, torch
 import vfr_b200
 from vfr_b200 import ops, _lib
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-S, D, k = 6, 100, 100
+S, D, k = 6, int(os.environ.get("D", "100")), int(os.environ.get("K", "100"))
 g = torch.Generator(device="cuda").manual_seed(0)
 clips = ((torch.randn(V, 1, D, device="cuda", generator=g) + 0.6 * torch.randn(V, S, D, device="cuda", generator=g)) * 0.05).reshape(-1, D)
 bank = ops.Bank(clips, np.arange(V + 1) * S)
@@ -20,5 +20,5 @@ for Q in [int(x) for x in (sys.argv[2:] or ["4096", "18944"])]:
     q = torch.randn(Q, D, device="cuda", generator=g) * 0.06
     t = timeit(lambda: ops.score_topk_sel(bank, q, k))
     s, i, flags, (qp, ws) = ops.score_topk_sel(bank, q, k, return_flags=True)
-    print(f"sel topk V={V} Q={Q} R={os.environ.get('VFR_SEL_R','auto')}: {t:.2f} ms  {Q*V*21/t/1e6:.1f} Gpairs/s  clip-pairs {Q*V*S/t/1e6:.1f} G/s  "
+    print(f"sel topk k={k} V={V} Q={Q} R={os.environ.get('VFR_SEL_R','auto')}: {t:.2f} ms  {Q*V*21/t/1e6:.1f} Gpairs/s  clip-pairs {Q*V*S/t/1e6:.1f} G/s  "
           f"per SM-clk@1.9GHz {Q*V*S/t/1e6/148/1.9:.2f}  flags={int(flags.abs().sum())} ws={ws.numel()/1e6:.0f}MB", flush=True)

@@ -1,0 +1,27 @@
+"""Timeline of CTA 0 of the filter kernel (development aid): VFR_SEL_DBG points the kernel at a debug buffer."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import vfr_b200
+from vfr_b200 import ops
+V, Q, k = 1000000, 18944, int(os.environ.get("K", "1"))
+D = int(os.environ.get("D", "100"))
+g = torch.Generator(device="cuda").manual_seed(0)
+clips = ((torch.randn(V, 1, D, device="cuda", generator=g) + 0.6 * torch.randn(V, 6, D, device="cuda", generator=g)) * 0.05).reshape(-1, D)
+q = torch.randn(Q, D, device="cuda", generator=g) * 0.06
+bank = ops.Bank(clips, np.arange(V + 1) * 6)
+ops.score_topk_sel(bank, q, k)
+dbg = torch.zeros(9 * 256 * 4, dtype=torch.int64, device="cuda")
+os.environ["VFR_SEL_DBG"] = hex(dbg.data_ptr())
+ops.score_topk_sel(bank, q, k)
+torch.cuda.synchronize()
+d = dbg.cpu().numpy().reshape(9, 256, 4)
+t0 = d[0, 0, 0]
+print("MMA thread (job = tile*2 + r): wait_start wait_end issued(commit) | wait issue")
+for j in range(40, 48):
+    print("  job %3d buf %d  %8d %8d %8d | wait %5d issue %5d" % (j, d[0, j, 3], d[0, j, 0] - t0, d[0, j, 1] - t0, d[0, j, 2] - t0, d[0, j, 1] - d[0, j, 0], d[0, j, 2] - d[0, j, 1]))
+for s in (0, 1):
+    print("epilogue set %d: per warp (ew) full_seen / released / done, visits 20..22" % s)
+    for v in range(20, 23):
+        print("  visit %d: " % v + "  ".join("ew%d %d/%d/%d" % (w, d[1 + w, v, 1] - t0, d[1 + w, v, 2] - t0, d[1 + w, v, 3] - t0) for w in range(4 * s, 4 * s + 4)))
+print("steady state: %.0f cycles per job" % ((d[0, 200, 0] - d[0, 40, 0]) / 160.0))

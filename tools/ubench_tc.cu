@@ -93,7 +93,7 @@ ubench_kernel(int mode, int reader_warps, int ld_iters, int mma_n, int mma_count
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (uint32_t)i * 0x00010001u;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -106,7 +106,7 @@ ubench_kernel(int mode, int reader_warps, int ld_iters, int mma_n, int mma_count
 
   if (warp == 0) {
     if (lane == 0 && (mode & 2)) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | ((wait_every & 1) ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // wait_every odd: bf16, even: fp16
       const uint64_t adesc = make_desc(smem), bdesc = make_desc(smem + 16384);
       const long long t0 = clock64();
       for (int i = 0; i < mma_count; ++i) tc_mma(tmem_base + (uint32_t)((i & 1) * 256), adesc + (uint64_t)((i & 3) * 2), bdesc + (uint64_t)((i & 3) * 2), idesc, i > 1);
@@ -114,6 +114,22 @@ ubench_kernel(int mode, int reader_warps, int ld_iters, int mma_n, int mma_count
       mbar_wait(&bar, 0);
       const long long t1 = clock64();
       out_mma[blockIdx.x] = t1 - t0;
+      if (mma_count == 7) {   // cost of waiting on an ALREADY COMPLETE barrier, and of a commit + wait round trip
+        const long long w0 = clock64();
+        for (int i = 0; i < 64; ++i) mbar_wait(&bar, 0);
+        const long long w1 = clock64();
+        long long acc = 0;
+        uint32_t ph = 1;
+        for (int i = 0; i < 16; ++i) {
+          tc_mma(tmem_base, adesc, bdesc, idesc, 0);
+          const long long c0 = clock64();
+          tc_commit(&bar);
+          mbar_wait(&bar, ph);
+          acc += clock64() - c0;
+          ph ^= 1;
+        }
+        if (blockIdx.x == 0) printf("wait on complete barrier: %.1f cyc; 1 MMA + commit + wait: %.1f cyc\n", (double)(w1 - w0) / 64.0, (double)acc / 16.0);
+      }
     }
   } else if (warp >= 2 && warp < 2 + reader_warps && (mode & 1)) {
     const int quarter = warp & 3;
@@ -168,7 +184,8 @@ static void run(int mode, int reader_warps, int ld_iters, int mma_n, int mma_cou
   cudaFree(d_ld); cudaFree(d_mma); cudaFree(sink);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) { run<32>(2, 4, 0, 256, 7, 1); for (int n : {128, 240, 256}) { run<32>(2, 4, 0, n, 4000, 1); run<32>(2, 4, 0, n, 4000, 2); } for (int readers : {8}) { run<32>(3, readers, 4000, 256, 8000, 1); run<32>(3, readers, 4000, 256, 8000, 2); } return 0; }
   for (int readers : {4, 8, 16}) {
     for (int we : {1, 2}) {
       run<16>(1, readers, 4000, 240, 0, we);

@@ -84,6 +84,7 @@ struct SlParams {
   int n_parts;
   unsigned* tau_g;           // [Qpad] k-th smallest d2~ published by any list of the query
   int wait_mode;             // mbarrier wait flavour (see sl_wait)
+  long long* dbg;            // optional timeline of CTA 0 (development aid): [9 roles][256 events][4]
   int32_t* flags;            // [Qpad] != 0: a candidate list overflowed / scales out of range (see vfr.h)
 };
 
@@ -368,6 +369,21 @@ __device__ __forceinline__ void sl_wait(uint64_t* bar, uint32_t parity, int mode
   }
 }
 
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool sl_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 // threshold of the accumulator domain, rounded up:  (tau2 + band2 - nq) * scale
 __device__ __forceinline__ float sl_threshold(float tau2, float band2, float nq, float scale) {
   return __fmul_ru(__fsub_ru(__fadd_ru(tau2, band2), nq), scale);
@@ -596,34 +612,71 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint32_t idesc = (1u << 4) | ((uint32_t)(SL_N >> 3) << 17) | ((uint32_t)(SL_M >> 4) << 24);
       sl_wait(a_full, 0, p.wait_mode);
       sl_fence_after();
-      int it = 0, job = 0;
-      for (int t = 0; t < n_my_tiles; ++t) {
-        const int s0 = it % STAGES, ph0 = (it / STAGES) & 1;
-        const int s1 = (it + 1) % STAGES, ph1 = ((it + 1) / STAGES) & 1;
-        it += b_chunks;
-        for (int r = 0; r < R; ++r, ++job) {
-          const int buf = job & 1;                 // R = 2: buffer = query tile; R = 1: buffer = tile parity
-          sl_wait(&tmem_empty[buf], ((job >> 1) & 1) ^ 1, p.wait_mode);
-          sl_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)buf * SL_N;
-          uint32_t accumulate = 0;
-          for (int c = 0; c < b_chunks; ++c) {
-            if (r == 0) {
-              sl_wait(&full[c ? s1 : s0], c ? ph1 : ph0, p.wait_mode);
-              sl_fence_after();
-            }
-            const int ks = (c == 0) ? min(p.ksteps, 4) : (p.ksteps - 4);
-            const uint64_t adesc = sl_desc(smem_a + (r * 2 + c) * SL_A_CHUNK);
-            const uint64_t bdesc = sl_desc(smem_b + (c ? s1 : s0) * SL_B_CHUNK);
-            for (int k = 0; k < ks; ++k) {
-              sl_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
-              accumulate = 1;
-            }
-          }
-          sl_commit(&tmem_full[buf]);
+      // A barrier wait issued right after a tcgen05.commit stalls the thread ~250 cycles (until the MMAs ahead
+      // of the commit have drained), which is a third of a job.  So the commit of job j is issued AFTER the
+      // waits of job j+1 - unless one of them really has to block, then the commit goes first.
+      int it = 0;
+      int s0 = 0, s1 = 0, ph0 = 0, ph1 = 0;
+      int pend_buf = -1, pend_s0 = 0, pend_s1 = 0;
+      bool pend_release = false;
+      const int n_jobs = n_my_tiles * R;
+      for (int job = 0; job < n_jobs; ++job) {
+        const int r = (R == 2) ? (job & 1) : 0;
+        const int buf = job & 1;                   // R = 2: buffer = query tile; R = 1: buffer = tile parity
+        const long long tm0 = p.dbg ? clock64() : 0;
+        if (r == 0) {
+          s0 = it % STAGES; ph0 = (it / STAGES) & 1;
+          s1 = (it + 1) % STAGES; ph1 = ((it + 1) / STAGES) & 1;
+          it += b_chunks;
         }
-        sl_commit(&empty[s0]);
-        if (b_chunks == 2) sl_commit(&empty[s1]);
+        const uint32_t pe = ((job >> 1) & 1) ^ 1;
+        bool ready = sl_test(&tmem_empty[buf], pe);
+        if (r == 0) {
+          ready = ready && sl_test(&full[s0], ph0);
+          if (b_chunks == 2) ready = ready && sl_test(&full[s1], ph1);
+        }
+        if (!ready || pend_buf < 0) {
+          if (pend_buf >= 0) {
+            sl_commit(&tmem_full[pend_buf]);
+            if (pend_release) { sl_commit(&empty[pend_s0]); if (b_chunks == 2) sl_commit(&empty[pend_s1]); }
+            pend_buf = -1;
+          }
+          if (r == 0) {
+            sl_wait(&full[s0], ph0, p.wait_mode);
+            if (b_chunks == 2) sl_wait(&full[s1], ph1, p.wait_mode);
+          }
+          sl_wait(&tmem_empty[buf], pe, p.wait_mode);
+        }
+        sl_fence_after();
+        if (pend_buf >= 0) {
+          sl_commit(&tmem_full[pend_buf]);
+          if (pend_release) { sl_commit(&empty[pend_s0]); if (b_chunks == 2) sl_commit(&empty[pend_s1]); }
+        }
+        const long long tm1 = p.dbg ? clock64() : 0;
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * SL_N;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < b_chunks; ++c) {
+          const int ks = (c == 0) ? min(p.ksteps, 4) : (p.ksteps - 4);
+          const uint64_t adesc = sl_desc(smem_a + (r * 2 + c) * SL_A_CHUNK);
+          const uint64_t bdesc = sl_desc(smem_b + (c ? s1 : s0) * SL_B_CHUNK);
+          for (int k = 0; k < ks; ++k) {
+            sl_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        pend_buf = buf;
+        pend_s0 = s0;
+        pend_s1 = s1;
+        pend_release = (r == R - 1);
+        const int job0 = n_jobs - 256;
+        if (p.dbg && blockIdx.x == 0 && job >= job0) {
+          long long* d = p.dbg + (0 * 256 + (job - job0)) * 4;
+          d[0] = tm0; d[1] = tm1; d[2] = clock64(); d[3] = buf;
+        }
+      }
+      if (pend_buf >= 0) {
+        sl_commit(&tmem_full[pend_buf]);
+        if (pend_release) { sl_commit(&empty[pend_s0]); if (b_chunks == 2) sl_commit(&empty[pend_s1]); }
       }
     }
   } else {
@@ -661,8 +714,10 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           st.thr = sl_threshold(tg, st.band2, st.nq, st.scale);
         }
       }
+      const long long te0 = p.dbg ? clock64() : 0;
       sl_wait(&tmem_full[set], visit & 1, p.wait_mode);
       sl_fence_after();
+      const long long te1 = p.dbg ? clock64() : 0;
       float va[64], vb[64];
       sl_ld32(lane_addr, va, 0);
       sl_ld32(lane_addr + 32, va, 32);
@@ -683,7 +738,13 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       sl_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[set]);
+      const long long te2 = p.dbg ? clock64() : 0;
       sl_process(vb, 192, st, p);
+      const int visit0 = (n_my_tiles - t_first + t_step - 1) / t_step - 128;
+      if (p.dbg && blockIdx.x == 0 && visit >= visit0 && lane == 0) {
+        long long* d = p.dbg + ((1 + ew) * 256 + (visit - visit0)) * 4;
+        d[0] = te0; d[1] = te1; d[2] = te2; d[3] = clock64();
+      }
 
       if (__any_sync(0xffffffffu, st.cnt > SL_CAP_HI)) {
         const float before = st.tau_own;
@@ -1199,6 +1260,7 @@ extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const in
   p.k = k;
   p.n_parts = pl.n_parts;
   { const char* wm = getenv("VFR_SEL_WAIT"); p.wait_mode = wm ? atoi(wm) : 0; }
+  { const char* dg = getenv("VFR_SEL_DBG"); p.dbg = dg ? reinterpret_cast<long long*>(strtoull(dg, nullptr, 0)) : nullptr; }
   const size_t qpad = (size_t)pl.qrows;
   p.cand = reinterpret_cast<unsigned long long*>(workspace);
   p.cand_cnt = reinterpret_cast<int32_t*>(p.cand + qpad * (size_t)pl.n_parts * SL_CAP);
