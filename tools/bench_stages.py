@@ -1,0 +1,82 @@
+"""Per-stage timings of the hot path at the BASELINE shapes: K1 pooling, K2 visual embedding,
+K3 text embedding, K5 metrics, K6 ranking loss fwd+bwd, K4 variants.  Prints one JSON line per stage with the
+achieved figure next to the roofline that bounds it (peaks from MEASURED_PEAKS.json)."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import vfr_b200
+from vfr_b200 import ops, models, synth, data as vdata, main as vmain
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
+dev = "cuda"
+
+def timeit(f, n=5, warm=2):
+    for _ in range(warm): f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): f()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+g = torch.Generator(device=dev).manual_seed(1)
+# ---- K1: frame -> segment pooling (val shape x 8: 8752 videos of 150 frames x 4096) ----
+V, F, DIMF = 2048, 150, 4096
+frames = torch.rand(V * F, DIMF, device=dev, generator=g)
+frame_off = torch.arange(V + 1, dtype=torch.int64) * F
+t = timeit(lambda: ops.segment_pool(frames, frame_off.numpy(), "avg", 25), n=3, warm=1)
+bytes_ = V * (4.0 * F * DIMF + 3 * 4.0 * 7 * DIMF)
+emit(stage="K1 segment_pool", shape=f"{V} videos x {F} frames x {DIMF}", ms=t, achieved_gbs=bytes_ / t / 1e6, peak_gbs=pk["hbm_gbs"], frac=bytes_ / t / 1e6 / pk["hbm_gbs"], bound="hbm",
+     note="includes the host-side offset upload of ops.segment_pool")
+del frames
+# ---- model ----
+torch.manual_seed(123)
+table = torch.randn(10000, 100) * 0.4; table[0] = 0
+model = models.CALModel(visual_input_dim=2 * 4096 + 2, pretrained_emb=table).to(dev).eval()
+# ---- K2: visual embedding of 6382 x 16 clips ([N, 8194] rows as the reference feeds them) ----
+N = 6382 * 4
+x = torch.rand(N, 8194, device=dev, generator=g)
+with torch.no_grad():
+    t = timeit(lambda: model(x), n=3, warm=1)
+flop = 2.0 * N * (8194 * 500 + 500 * 100)
+emit(stage="K2 visual_embed", shape=f"{N} clips x 8194", ms=t, achieved_tflops=flop / t / 1e9, peak_tflops=pk["bf16_tflops_sustained"], frac=flop / t / 1e9 / pk["bf16_tflops_sustained"], bound="tensor (split-bf16: 3 passes executed per algorithmic FLOP)")
+del x
+# ---- K3: text embedding of 18944 queries ----
+B = 18944
+tok = torch.from_numpy(np.random.default_rng(0).integers(1, 10000, size=(B, 20))).to(dev)
+with torch.no_grad():
+    t = timeit(lambda: model(tok, False, dev), n=3, warm=1)
+flop = B * (2.0 * 20 * 2 * 4000 * 1100 + 2 * 2000 * 100)
+emit(stage="K3 text_embed", shape=f"{B} queries x 20 tokens", ms=t, achieved_tflops=flop / t / 1e9, peak_tflops=pk["bf16_tflops_sustained"], frac=flop / t / 1e9 / pk["bf16_tflops_sustained"], bound="tensor (split-bf16: 3 passes executed per algorithmic FLOP)")
+# ---- K6: ranking loss forward + backward at the training shape ----
+R_, Bq = 123, 87
+maskp = torch.sort(torch.randint(0, Bq, (R_,), device=dev, generator=g)).values
+maskp[:Bq] = torch.arange(Bq, device=dev); maskp = torch.sort(maskp).values
+embs = [torch.randn(R_, 100, device=dev, generator=g, requires_grad=True) for _ in range(3)]
+lang = torch.randn(Bq, 100, device=dev, generator=g, requires_grad=True)
+tr = vmain.Trainer(device=dev) if hasattr(vmain, "Trainer") else None
+if tr is not None:
+    def step():
+        loss, n = tr.ranking_loss(embs[0], embs[1], embs[2], lang, maskp, maskp)
+        loss.backward()
+    try:
+        t = timeit(step, n=20, warm=3)
+        emit(stage="K6 ranking_loss fwd+bwd", shape=f"R={R_} rows x3, B={Bq} queries", us=t * 1e3, bound="latency")
+    except Exception as e:
+        emit(stage="K6 ranking_loss", error=str(e)[:200])
+# ---- K4 variants on the val shape and the long-video shape ----
+for name, nv, seg, Q in (("val", 1094, (6, 5), 4180), ("long", 1094, (30,), 4180)):
+    rng = np.random.default_rng(5)
+    nseg = rng.choice(np.asarray(seg), size=nv)
+    vo = np.concatenate([[0], np.cumsum(nseg)])
+    clips = torch.randn(int(vo[-1]), 100, device=dev, generator=g) * 0.25
+    bank = ops.Bank(clips, vo)
+    q = torch.randn(Q, 100, device=dev, generator=g) * 0.25
+    t_full = timeit(lambda: ops.score_full(bank, q), n=3, warm=1)
+    t_sel = timeit(lambda: ops.score_topk_sel(bank, q, 100), n=3, warm=1)
+    pairs = Q * bank.m_total
+    emit(stage=f"K4 {name} eval", shape=f"{Q} queries x {nv} videos ({bank.m_total} moments)", ms_score_full_exact=t_full, pairs_per_s_full=pairs / t_full * 1e3, ms_topk_sel=t_sel, pairs_per_s_topk=pairs / t_sel * 1e3)

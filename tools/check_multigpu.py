@@ -19,13 +19,14 @@ model = model.to(dev).eval()
 clips = torch.from_numpy(synth.make_bank(3, V, S, 100)).to(dev)
 tokens = synth.make_queries(3, synth.make_videos(3, 4, 8), Q, 500)["tokens"]
 ok = True
-for engine in ("tc", "exact"):
+for engine in ("sel", "tc", "exact"):
     v0, v1 = shard_range(V, rank, world)
     shard = MomentRetriever(model, clips[v0 * S:v1 * S], np.arange(v1 - v0 + 1) * S, id_base=v0 * 21, max_queries=Q, k=k,
-                            engine=engine, text_engine=engine)
+                            engine=engine, text_engine="tc" if engine == "sel" else engine)
     s, i = shard.search(tokens)                      # host in, host out, all-gather + merge inside
     s, i = s.clone(), i.clone()
-    full = MomentRetriever(model, clips, np.arange(V + 1) * S, max_queries=Q, k=k, engine=engine, text_engine=engine)
+    full = MomentRetriever(model, clips, np.arange(V + 1) * S, max_queries=Q, k=k, engine=engine,
+                           text_engine="tc" if engine == "sel" else engine)
     full.world = 1                                   # single-bank reference on every rank
     fs, fi = full.search(tokens)
     same = torch.equal(s, fs) and torch.equal(i, fi)
