@@ -86,3 +86,30 @@ def test_text_embed_tc_large_batch_vs_exact():
         model.engine = "tc"
         got = model(tok, False, DEV)
     assert (got - exact).abs().max().item() <= TC_TEXT_TOL * exact.abs().max().item()
+
+
+@pytest.mark.parametrize("nl", [False, True])
+def test_text_embed_tc_padding_aware_rows(nl):
+    """The tensor-core K3 orders rows by length and lets a query join the backward recurrence at its first
+    real token with the state an all-padding row has reached (reference: padding is fed through the LSTM,
+    models.py:65).  Every length 0..20, zeros INSIDE a query, a non-zero embedding for the padding id and
+    batch composition must not change a query's embedding."""
+    sd = synth.make_state_dict(7, 8, 600, normalize_lang=nl)
+    sd["word_embedding.weight"][0] = 0.3 * np.random.default_rng(1).standard_normal(100).astype(np.float32)
+    model = _model(sd, 8, nl)
+    rng = np.random.default_rng(2)
+    tok = np.zeros((300, 20), dtype=np.int64)
+    for i in range(300):
+        n = i % 21                                       # every length, including 0 (all padding) and 20
+        tok[i, :n] = rng.integers(1, 600, size=n)
+    tok[40:60, 2] = 0                                    # padding id in the middle of a query
+    t = torch.from_numpy(tok).to(DEV)
+    with torch.no_grad():
+        exact = model(t, False, DEV)
+        model.engine = "tc"
+        got = model(t, False, DEV)
+        alone = torch.cat([model(t[i:i + 1], False, DEV) for i in (0, 1, 20, 21, 45, 299)])
+        shuffled = model(t.flip(0), False, DEV).flip(0)
+    assert (got - exact).abs().max().item() <= TC_TEXT_TOL * exact.abs().max().item()
+    assert torch.equal(alone, got[[0, 1, 20, 21, 45, 299]])
+    assert torch.equal(shuffled, got)

@@ -110,7 +110,8 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
 //      called for 16 consecutive output columns n0..n0+15 of row m (m < M guaranteed, columns not).
 template <class Epi>
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M, int k_chunks, int kp, Epi epi) {
+gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __restrict__ m_limit, int k_chunks, int kp,
+               Epi epi) {
   extern __shared__ uint8_t gt_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gt_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE);
@@ -122,6 +123,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M, int k_chunks, int
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
   const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * GT_BN;
+  // rows of problem z that are live in this launch (device-side count: no host sync); a tile past it retires
+  const int M = m_limit ? min(M_all, m_limit[z]) : M_all;
+  if (m0 >= M) return;
   const CUtensorMap* ma = &maps.a[z];
   const CUtensorMap* mb = &maps.b[z];
 
@@ -235,7 +239,7 @@ static inline int gt_kp(int k) { return (k + GT_BK - 1) / GT_BK * GT_BK; }
 // A: packed [M, lda] (lda >= 2*kp), B: packed [N, ldb]; batch <= 2 problems with identical shapes
 template <class Epi>
 static int launch_gemm_tc(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda,
-                          int64_t ldb, Epi epi, cudaStream_t st) {
+                          int64_t ldb, Epi epi, cudaStream_t st, const int* m_limit = nullptr) {
   if (M <= 0 || N <= 0 || kp <= 0) return VFR_OK;
   VFR_REQUIRE(batch >= 1 && batch <= 2 && kp % GT_BK == 0 && lda >= 2 * kp && ldb >= 2 * kp && lda % 8 == 0 && ldb % 8 == 0,
               VFR_ERR_INVALID, "launch_gemm_tc: bad operand layout");
@@ -249,7 +253,7 @@ static int launch_gemm_tc(const void* const* a, const void* const* b, int batch,
   if (batch == 1) { maps.a[1] = maps.a[0]; maps.b[1] = maps.b[0]; }
   VFR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
   dim3 grid((N + GT_BN - 1) / GT_BN, (M + GT_BM - 1) / GT_BM, batch);
-  gemm_tc_kernel<Epi><<<grid, GT_THREADS, GT_SMEM, st>>>(maps, M, kp / GT_BK, kp, epi);
+  gemm_tc_kernel<Epi><<<grid, GT_THREADS, GT_SMEM, st>>>(maps, M, m_limit, kp / GT_BK, kp, epi);
   return check_launch("gemm_tc_kernel");
 }
 

@@ -86,17 +86,67 @@ __global__ void tc_text_pack_fc_kernel(const float* __restrict__ fc_w, const flo
   }
 }
 
-// x part of every slot of both directions; one warp per (b, t)
+// ---- padding-aware row order ------------------------------------------------------------------------
+// The reference feeds the zero padding through the LSTM (models.py:65, no packing).  In the BACKWARD direction
+// a query of length len starts with L - len padding steps from the zero state: that prefix is the same for
+// every query, so it is computed ONCE (row 0 of the batch is an all-padding query) and a query joins the
+// recurrence at its first real token with the state row 0 has reached.  Rows are ordered by descending length,
+// so the live rows of backward step t are a prefix [0, n_active[t]) and the GEMM tiles past it retire at once:
+// the backward direction costs sum(len) instead of B * L cell updates (~ -30 % of K3 at DiDeMo's lengths).
+struct TextOrder {
+  int* len;        // [B]     tokens up to the last non-zero id
+  int* perm;       // [B + 1] row -> query (row 0 = the padding row, -1)
+  int* hist;       // [L + 1] queries per length
+  int* cursor;     // [L + 1] next free row of each length bucket
+  int* n_active;   // [L]     live backward rows of step t (padding row included)
+  int* limits;     // [L][2]  per-step row limits of the two GEMM problems {forward, backward}
+};
+
+__global__ void tc_text_len_kernel(const int64_t* __restrict__ tokens, int64_t B, int L, TextOrder o) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int len = 0;
+  for (int t = 0; t < L; ++t)
+    if (tokens[b * L + t] != 0) len = t + 1;
+  o.len[b] = len;
+  atomicAdd(&o.hist[len], 1);
+}
+
+__global__ void tc_text_scan_kernel(int64_t B, int L, TextOrder o) {
+  if (threadIdx.x != 0) return;
+  int rows = 1;                                    // row 0 = the padding row
+  for (int len = L; len >= 0; --len) {             // descending length
+    o.cursor[len] = rows;
+    rows += o.hist[len];
+    if (len >= 1) {                                // step t = L - len is the first one that needs length-len rows
+      const int t = L - len;
+      o.n_active[t] = rows;
+      o.limits[2 * t] = (int)B + 1;
+      o.limits[2 * t + 1] = rows;
+    }
+  }
+  o.perm[0] = -1;
+}
+
+__global__ void tc_text_perm_kernel(int64_t B, TextOrder o) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  o.perm[atomicAdd(&o.cursor[o.len[b]], 1)] = (int)b;
+}
+
+// x part of every slot of both directions; one warp per (row, t); row r holds query perm[r]
 __global__ void tc_text_gather_kernel(const int64_t* __restrict__ tokens, int64_t B, TextTcDims d,
                                       const float* __restrict__ table, int64_t vocab, const float* __restrict__ length,
-                                      __nv_bfloat16* __restrict__ slots_f, __nv_bfloat16* __restrict__ slots_b,
-                                      int* __restrict__ bad_token) {
+                                      const int* __restrict__ perm, __nv_bfloat16* __restrict__ slots_f,
+                                      __nv_bfloat16* __restrict__ slots_b, int* __restrict__ bad_token) {
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= B * d.L) return;
-  const int64_t b = w / d.L;
+  const int64_t Bp = B + 1;
+  if (w >= Bp * d.L) return;
+  const int64_t r = w / d.L;
   const int t = (int)(w % d.L);
-  int64_t id = tokens[b * d.L + t];
+  const int qi = perm[r];
+  int64_t id = (qi < 0) ? 0 : tokens[(int64_t)qi * d.L + t];
   if (id < 0 || id >= vocab) { if (lane == 0) atomicExch(bad_token, 1); id = 0; }
   const float* row = table + id * d.E;
   float denom = 1.f, len = 1.f;
@@ -108,8 +158,8 @@ __global__ void tc_text_gather_kernel(const int64_t* __restrict__ tokens, int64_
     len = length[id];
   }
   const int64_t ld = 2 * (int64_t)d.Kp;
-  __nv_bfloat16* df = slots_f + ((int64_t)t * B + b) * ld + d.Hp;              // forward consumes x_t at step t
-  __nv_bfloat16* db = slots_b + ((int64_t)(d.L - 1 - t) * B + b) * ld + d.Hp;  // backward consumes x_{L-1-t}
+  __nv_bfloat16* df = slots_f + ((int64_t)t * Bp + r) * ld + d.Hp;              // forward consumes x_t at step t
+  __nv_bfloat16* db = slots_b + ((int64_t)(d.L - 1 - t) * Bp + r) * ld + d.Hp;  // backward consumes x_{L-1-t}
   for (int k = lane; k < d.E; k += 32) {
     float v = row[k];
     if (length) v = __fmul_rn(__fdiv_rn(v, denom), len);
@@ -117,6 +167,28 @@ __global__ void tc_text_gather_kernel(const int64_t* __restrict__ tokens, int64_
     split2(v, hi, lo);
     df[k] = hi; df[d.Kp + k] = lo;
     db[k] = hi; db[d.Kp + k] = lo;
+  }
+}
+
+// rows [lo, hi) take over the state of row 0 (the padding row): h (split bf16, hi and lo segments) into dst,
+// c into the cell array.  lo / hi come from device memory (n_active); one warp per row.
+__global__ void tc_text_join_kernel(const int* __restrict__ lo_p, const int* __restrict__ hi_p, int hi_default,
+                                    __nv_bfloat16* __restrict__ dst, int64_t ld, int col0, int lo_off, int Hp,
+                                    float* __restrict__ c, int H) {
+  const int lane = threadIdx.x & 31;
+  const int lo = lo_p ? *lo_p : 0;
+  const int hi = hi_p ? *hi_p : hi_default;
+  const int r = lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= hi || r == 0) return;
+  const uint2* s_hi = reinterpret_cast<const uint2*>(dst + col0);
+  const uint2* s_lo = reinterpret_cast<const uint2*>(dst + col0 + lo_off);
+  uint2* d_hi = reinterpret_cast<uint2*>(dst + (int64_t)r * ld + col0);
+  uint2* d_lo = reinterpret_cast<uint2*>(dst + (int64_t)r * ld + col0 + lo_off);
+  for (int k = lane; k < Hp / 4; k += 32) { d_hi[k] = s_hi[k]; d_lo[k] = s_lo[k]; }
+  if (c) {
+    const float4* sc = reinterpret_cast<const float4*>(c);
+    float4* dc = reinterpret_cast<float4*>(c + (int64_t)r * H);
+    for (int k = lane; k < H / 4; k += 32) dc[k] = sc[k];
   }
 }
 
@@ -134,14 +206,12 @@ struct EpiLstmTc {
   int col0[2];
   int lo_off;
   int H;
-  int first;
   __device__ __forceinline__ void operator()(int z, int m, int n0, const float (&v)[16]) const {
     const int j0 = n0 >> 2;
     if (j0 >= H) return;
     const float4* bz = reinterpret_cast<const float4*>(bias[z] + n0);
     float4* cp = reinterpret_cast<float4*>(c[z] + (int64_t)m * H + j0);
-    float4 c_prev = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!first) c_prev = *cp;
+    const float4 c_prev = *cp;                   // (the cell arrays start zeroed)
     const float cpv[4] = {c_prev.x, c_prev.y, c_prev.z, c_prev.w};
     float cn[4];
     __nv_bfloat16 hh[4], hl[4];
@@ -166,7 +236,12 @@ struct EpiBiasOutTc {
   int N;
   const float* bias;
   int relu;
+  const int* row_map;          // optional: output row of GEMM row m (negative = no output)
   __device__ __forceinline__ void operator()(int, int m, int n0, const float (&v)[16]) const {
+    if (row_map) {
+      m = row_map[m];
+      if (m < 0) return;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int n = n0 + j;
@@ -234,7 +309,7 @@ extern "C" int vfr_linear_tc(const float* x, int64_t n_rows, int in_dim, int64_t
   if (rc) return rc;
   const void* a[1] = {xs};
   const void* b[1] = {w_packed};
-  EpiBiasOutTc epi{out, ldo, out_dim, bias, relu};
+  EpiBiasOutTc epi{out, ldo, out_dim, bias, relu, nullptr};
   return launch_gemm_tc(a, b, 1, (int)n_rows, out_dim, kp, 2 * (int64_t)kp, 2 * (int64_t)kp, epi, st);
 }
 
@@ -277,61 +352,93 @@ extern "C" int vfr_text_pack_tc(const float* w_ih_f, const float* w_hh_f, const 
 extern "C" size_t vfr_text_embed_tc_bytes(int64_t n_queries, int seq_len, int hidden, int emb) {
   if (n_queries <= 0 || seq_len <= 0 || hidden <= 0 || emb <= 0) return 0;
   const TextTcDims d = text_dims(hidden, emb, 1, seq_len);
-  const size_t slots = (size_t)2 * seq_len * n_queries * 2 * d.Kp * 2;    // bf16
-  const size_t hcat = (size_t)n_queries * 2 * d.Kf * 2;
-  const size_t c = (size_t)2 * n_queries * hidden * 4;
-  return 16 + slots + hcat + c;
+  const size_t rows = (size_t)n_queries + 1;                                // + the padding row
+  const size_t slots = (size_t)2 * seq_len * rows * 2 * d.Kp * 2;          // bf16
+  const size_t hcat = rows * 2 * d.Kf * 2;
+  const size_t c = (size_t)2 * rows * hidden * 4;
+  const size_t order = ((size_t)2 * rows + 6 * ((size_t)seq_len + 1) + 16) * 4;
+  return 16 + slots + hcat + c + order;
 }
 
 extern "C" int vfr_text_embed_tc(const int64_t* tokens, int64_t n_queries, int seq_len, const float* table,
                                  int64_t vocab, const float* length_table, int emb, const void* packed, int hidden,
                                  int dim, void* workspace, float* out, vfr_stream_t stream) {
   VFR_REQUIRE(tokens && table && packed && workspace && out, VFR_ERR_INVALID, "vfr_text_embed_tc: null pointer");
-  VFR_REQUIRE(n_queries > 0 && n_queries < (int64_t(1) << 31) && seq_len > 0 && hidden > 0 && hidden % 4 == 0 && emb > 0 &&
-                  dim > 0 && vocab > 0,
+  VFR_REQUIRE(n_queries > 0 && n_queries < (int64_t(1) << 31) - 1 && seq_len > 0 && hidden > 0 && hidden % 4 == 0 &&
+                  emb > 0 && dim > 0 && vocab > 0,
               VFR_ERR_INVALID, "vfr_text_embed_tc: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const TextTcDims d = text_dims(hidden, emb, dim, seq_len);
   const TextTcBlob blob = text_blob(packed, d);
-  const int64_t B = n_queries;
+  const int64_t B = n_queries, Bp = n_queries + 1;
+  const int L = seq_len;
   const int64_t ld = 2 * (int64_t)d.Kp;
   uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
   int* bad = reinterpret_cast<int*>(base);
   __nv_bfloat16* slots[2];
   slots[0] = reinterpret_cast<__nv_bfloat16*>(base + 16);
-  slots[1] = slots[0] + (size_t)seq_len * B * ld;
-  __nv_bfloat16* hcat = slots[1] + (size_t)seq_len * B * ld;
-  float* c0 = reinterpret_cast<float*>(hcat + (size_t)B * 2 * d.Kf);
-  float* c[2] = {c0, c0 + (size_t)B * hidden};
-  // zero: flag, all operand slots (h_{-1} = 0 and every pad column) and the final operand
-  VFR_CUDA(cudaMemsetAsync(base, 0, 16 + ((size_t)2 * seq_len * B * ld + (size_t)B * 2 * d.Kf) * 2, st));
+  slots[1] = slots[0] + (size_t)L * Bp * ld;
+  __nv_bfloat16* hcat = slots[1] + (size_t)L * Bp * ld;
+  float* c0 = reinterpret_cast<float*>(hcat + (size_t)Bp * 2 * d.Kf);
+  float* c[2] = {c0, c0 + (size_t)Bp * hidden};
+  int* ints = reinterpret_cast<int*>(c0 + (size_t)2 * Bp * hidden);
+  TextOrder o;
+  o.len = ints;
+  o.perm = o.len + Bp;
+  o.hist = o.perm + Bp;
+  o.cursor = o.hist + (L + 1);
+  o.n_active = o.cursor + (L + 1);
+  o.limits = o.n_active + (L + 1);
+  // zero: flag, all operand slots (h_{-1} = 0 and every pad column), the final operand, the cell states, the counters
+  VFR_CUDA(cudaMemsetAsync(base, 0, vfr_text_embed_tc_bytes(n_queries, seq_len, hidden, emb), st));
+  tc_text_len_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(tokens, B, L, o);
+  int rc = check_launch("tc_text_len_kernel");
+  if (rc) return rc;
+  tc_text_scan_kernel<<<1, 32, 0, st>>>(B, L, o);
+  rc = check_launch("tc_text_scan_kernel");
+  if (rc) return rc;
+  tc_text_perm_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, o);
+  rc = check_launch("tc_text_perm_kernel");
+  if (rc) return rc;
   {
-    const int64_t warps = B * seq_len;
-    tc_text_gather_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(tokens, B, d, table, vocab, length_table, slots[0],
-                                                                     slots[1], bad);
-    int rc = check_launch("tc_text_gather_kernel");
+    const int64_t warps = Bp * L;
+    tc_text_gather_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(tokens, B, d, table, vocab, length_table, o.perm,
+                                                                     slots[0], slots[1], bad);
+    rc = check_launch("tc_text_gather_kernel");
     if (rc) return rc;
   }
-  for (int t = 0; t < seq_len; ++t) {
-    const void* a[2] = {slots[0] + (size_t)t * B * ld, slots[1] + (size_t)t * B * ld};
+  const unsigned join_blocks = (unsigned)((Bp + 7) / 8);
+  for (int t = 0; t < L; ++t) {
+    if (t > 0) {
+      // rows whose first real token is consumed by backward step t join with the padding row's state
+      tc_text_join_kernel<<<join_blocks, 256, 0, st>>>(o.n_active + (t - 1), o.n_active + t, 0,
+                                                       slots[1] + (size_t)t * Bp * ld, ld, 0, d.Kp, d.Hp, c[1], hidden);
+      rc = check_launch("tc_text_join_kernel");
+      if (rc) return rc;
+    }
+    const void* a[2] = {slots[0] + (size_t)t * Bp * ld, slots[1] + (size_t)t * Bp * ld};
     const void* b[2] = {blob.w[0], blob.w[1]};
     EpiLstmTc epi{};
-    const bool last = (t == seq_len - 1);
+    const bool last = (t == L - 1);
     for (int z = 0; z < 2; ++z) {
       epi.bias[z] = blob.bias[z];
       epi.c[z] = c[z];
-      epi.dst[z] = last ? hcat : slots[z] + (size_t)(t + 1) * B * ld;
+      epi.dst[z] = last ? hcat : slots[z] + (size_t)(t + 1) * Bp * ld;
       epi.col0[z] = last ? z * d.Hp : 0;
     }
     epi.ld = last ? 2 * (int64_t)d.Kf : ld;
     epi.lo_off = last ? d.Kf : d.Kp;
     epi.H = hidden;
-    epi.first = (t == 0);
-    int rc = launch_gemm_tc(a, b, 2, (int)B, 4 * hidden, d.Kp, ld, ld, epi, st);
+    rc = launch_gemm_tc(a, b, 2, (int)Bp, 4 * hidden, d.Kp, ld, ld, epi, st, o.limits + 2 * t);
     if (rc) return rc;
   }
+  // all-padding queries never joined: their backward state is the padding row's final one
+  tc_text_join_kernel<<<join_blocks, 256, 0, st>>>(o.n_active + (L - 1), nullptr, (int)Bp, hcat, 2 * (int64_t)d.Kf, d.Hp, d.Kf,
+                                                   d.Hp, nullptr, hidden);
+  rc = check_launch("tc_text_join_kernel");
+  if (rc) return rc;
   const void* a[1] = {hcat};
   const void* b[1] = {blob.fc};
-  EpiBiasOutTc epi{out, dim, dim, blob.fc_b, 0};
-  return launch_gemm_tc(a, b, 1, (int)B, dim, d.Kf, 2 * (int64_t)d.Kf, 2 * (int64_t)d.Kf, epi, st);
+  EpiBiasOutTc epi{out, dim, dim, blob.fc_b, 0, o.perm};
+  return launch_gemm_tc(a, b, 1, (int)Bp, dim, d.Kf, 2 * (int64_t)d.Kf, 2 * (int64_t)d.Kf, epi, st);
 }
