@@ -83,6 +83,7 @@ struct SlParams {
   int32_t* cand_cnt;         // [Qpad][n_parts]
   int n_parts;
   unsigned* tau_g;           // [Qpad] k-th smallest d2~ published by any list of the query
+  float* tau_part;           // [Qpad][n_parts] ceil(k / n_parts)-th smallest d2~ of each list (inf until compacted)
   int wait_mode;             // mbarrier wait flavour (see sl_wait)
   long long* dbg;            // optional timeline of CTA 0 (development aid): [9 roles][256 events][4]
   int32_t* flags;            // [Qpad] != 0: a candidate list overflowed / scales out of range (see vfr.h)
@@ -392,7 +393,9 @@ __device__ __forceinline__ float sl_threshold(float tau2, float band2, float nq,
 // Band-preserving compaction of thread-private candidate lists (cf. compact_lists in vfr_topk.cuh, here for
 // SL_CAP keys).  For each lane whose `need` is set the warp finds the k-th smallest key of that lane's list
 // (most-significant-bit-first radix select on the d2~ word), makes it the lane's tau and keeps every key
-// <= min(tau, tau_shared) + band2.
+// <= min(tau, tau_shared) + band2.  tau_part receives the ceil(k / P)-th smallest, P = lists per query: every list
+// holds >= k/P keys under its own tau_part, so the LARGEST tau_part of the P lists bounds the k-th smallest d2~ of
+// the whole bank - far tighter than any single list's k-th, which only knows 1/P of the clips.
 constexpr int SL_SLOTS = SL_CAP / 32;   // keys per lane
 
 __device__ __forceinline__ unsigned sl_radix_kth(const unsigned (&w)[SL_SLOTS], unsigned candmask, int kk, int m) {
@@ -426,8 +429,8 @@ __device__ __forceinline__ unsigned sl_radix_kth(const unsigned (&w)[SL_SLOTS], 
   return value;
 }
 
-__device__ __noinline__ void sl_compact(unsigned long long* list, int& cnt, float& tau_own, float tau_shared, float band2,
-                                        int k, bool need, int lane) {
+__device__ __noinline__ void sl_compact(unsigned long long* list, int& cnt, float& tau_own, float& tau_part, float tau_shared,
+                                        float band2, int k, int k_part, bool need, int lane) {
   unsigned mask = __ballot_sync(0xffffffffu, need);
   while (mask) {
     const int src = __ffs(mask) - 1;
@@ -451,6 +454,7 @@ __device__ __noinline__ void sl_compact(unsigned long long* list, int& cnt, floa
     }
     const unsigned kth_hi = sl_radix_kth(hi, candmask, k, n);
     const float kth = __uint_as_float(kth_hi);
+    const float kpart = (k_part < k) ? __uint_as_float(sl_radix_kth(hi, candmask, k_part, n)) : kth;
     const unsigned keep_bits = __float_as_uint(__fadd_ru(fminf(kth, ts), b2));
     __syncwarp();
     int base = 0;
@@ -466,6 +470,7 @@ __device__ __noinline__ void sl_compact(unsigned long long* list, int& cnt, floa
     if (lane == src) {
       cnt = base;
       tau_own = kth;
+      tau_part = kpart;
     }
   }
 }
@@ -751,21 +756,33 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // (copies: taking the address of a member would push the whole per-thread state into local memory)
         int cnt = st.cnt;
         float tau_own = st.tau_own;
-        sl_compact(st.list, cnt, tau_own, st.tau_use, st.band2, p.k, cnt > SL_CAP_HI, lane);
+        float tau_part = CUDART_INF_F;
+        const int k_part = (p.k + p.n_parts - 1) / p.n_parts;
+        sl_compact(st.list, cnt, tau_own, tau_part, st.tau_use, st.band2, p.k, k_part, cnt > SL_CAP_HI, lane);
         const bool over = cnt > SL_CAP_HI;
         if (__any_sync(0xffffffffu, over)) {
           // more than CAP_HI keys inside the band (mass duplicates): keep the list bounded and flag the query
           if (over) p.flags[st.q] = 2;
-          sl_compact(st.list, cnt, tau_own, st.tau_use, 0.f, p.k, over, lane);
+          float dummy = CUDART_INF_F;
+          sl_compact(st.list, cnt, tau_own, dummy, st.tau_use, 0.f, p.k, p.k, over, lane);
           if (over) cnt = min(cnt, SL_CAP_HI);
         }
         st.cnt = cnt;
         st.tau_own = tau_own;
         if (st.tau_own < before) {
-          tau_publish(p.tau_g + st.q, st.tau_own);
-          if (st.tau_own < st.tau_use) {
-            st.tau_use = st.tau_own;
-            st.thr = sl_threshold(st.tau_own, st.band2, st.nq, st.scale);
+          float best = st.tau_own;
+          if (p.n_parts > 1 && tau_part < CUDART_INF_F) {
+            // publish this list's share and bound the query's k-th smallest by the largest share of all its lists
+            volatile float* tp = p.tau_part + st.q * p.n_parts;
+            tp[part] = tau_part;
+            float worst = tau_part;
+            for (int j = 0; j < p.n_parts; ++j) worst = fmaxf(worst, tp[j]);
+            best = fminf(best, worst);
+          }
+          tau_publish(p.tau_g + st.q, best);
+          if (best < st.tau_use) {
+            st.tau_use = best;
+            st.thr = sl_threshold(best, st.band2, st.nq, st.scale);
           }
         }
       }
@@ -775,7 +792,8 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const float before = st.tau_own;
       int cnt = st.cnt;
       float tau_own = st.tau_own;
-      sl_compact(st.list, cnt, tau_own, st.tau_use, st.band2, p.k, cnt > p.k, lane);
+      float dummy = CUDART_INF_F;
+      sl_compact(st.list, cnt, tau_own, dummy, st.tau_use, st.band2, p.k, p.k, cnt > p.k, lane);
       st.cnt = cnt;
       st.tau_own = tau_own;
       if (st.tau_own < before) tau_publish(p.tau_g + st.q, st.tau_own);
@@ -1222,7 +1240,8 @@ extern "C" size_t vfr_sel_topk_bytes(int64_t n_queries, int64_t n_clips, int n_s
   for (int64_t qt = 1; qt <= qtiles; ++qt) {
     const SlPlan pl = sl_plan(qt == qtiles ? n_queries : qt * SL_M, n_clips, n_split);
     const size_t qpad = (size_t)pl.qrows;
-    const size_t need = qpad * pl.n_parts * SL_CAP * sizeof(unsigned long long) + qpad * pl.n_parts * sizeof(int32_t) + qpad * sizeof(unsigned);
+    const size_t need = qpad * pl.n_parts * SL_CAP * sizeof(unsigned long long) + qpad * pl.n_parts * sizeof(int32_t) +
+                        qpad * sizeof(unsigned) + qpad * pl.n_parts * sizeof(float);
     if (need > worst) worst = need;
   }
   return worst;
@@ -1266,7 +1285,8 @@ extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const in
   p.cand_cnt = reinterpret_cast<int32_t*>(p.cand + qpad * (size_t)pl.n_parts * SL_CAP);
   p.tau_g = reinterpret_cast<unsigned*>(p.cand_cnt + qpad * (size_t)pl.n_parts);
   cudaStream_t st = (cudaStream_t)stream;
-  rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad, st);
+  p.tau_part = reinterpret_cast<float*>(p.tau_g + qpad);
+  rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad * (1 + (size_t)pl.n_parts), st);   // tau_g and tau_part: +inf
   if (rc) return rc;
   const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
   if (pl.R == 2) {
