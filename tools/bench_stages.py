@@ -43,13 +43,17 @@ x = torch.rand(N, 8194, device=dev, generator=g)
 with torch.no_grad():
     t = timeit(lambda: model(x), n=3, warm=1)
 flop = 2.0 * N * (8194 * 500 + 500 * 100)
-emit(stage="K2 visual_embed", shape=f"{N} clips x 8194", ms=t, achieved_tflops=flop / t / 1e9, peak_tflops=pk["bf16_tflops_sustained"], frac=flop / t / 1e9 / pk["bf16_tflops_sustained"], bound="tensor (split-bf16: 3 passes executed per algorithmic FLOP)")
+emit(stage="K2 visual_embed (exact fp32 CUDA-core path, model default)", shape=f"{N} clips x 8194", ms=t, achieved_tflops=flop / t / 1e9, bound="fp32 FFMA (~72 TFLOP/s)")
+model.engine = "tc"
+with torch.no_grad():
+    t = timeit(lambda: model(x), n=3, warm=1)
+emit(stage="K2 visual_embed (engine tc: split-bf16 tcgen05)", shape=f"{N} clips x 8194", ms=t, achieved_tflops=flop / t / 1e9, peak_tflops=pk["bf16_tflops_sustained"], frac=flop / t / 1e9 / pk["bf16_tflops_sustained"], bound="tensor (split-bf16: 3 passes executed per algorithmic FLOP)")
 del x
 # ---- K3: text embedding of 18944 queries ----
 B = 18944
 tok = torch.from_numpy(np.random.default_rng(0).integers(1, 10000, size=(B, 20))).to(dev)
 with torch.no_grad():
-    t = timeit(lambda: model(tok, False, dev), n=3, warm=1)
+    t = timeit(lambda: model(tok, False, dev), n=3, warm=1)      # engine "tc" (set above)
 flop = B * (2.0 * 20 * 2 * 4000 * 1100 + 2 * 2000 * 100)
 emit(stage="K3 text_embed", shape=f"{B} queries x 20 tokens", ms=t, achieved_tflops=flop / t / 1e9, peak_tflops=pk["bf16_tflops_sustained"], frac=flop / t / 1e9 / pk["bf16_tflops_sustained"], bound="tensor (split-bf16: 3 passes executed per algorithmic FLOP)")
 # ---- K6: ranking loss forward + backward at the training shape ----

@@ -86,7 +86,9 @@ class CALModel(nn.Module):
             self.lang_fc.apply(init_weights)
         self._packed = None   # (version key, packed fwd, packed bwd)
         self._packed_tc = None
-        # "exact": fp32 CUDA-core GEMMs (default, parity-critical evaluation); "tc": tcgen05 split-bf16 GEMMs
+        self._packed_vis = None
+        # "exact": fp32 CUDA-core GEMMs (default, parity-critical evaluation); "tc": tcgen05 split-bf16 GEMMs for both
+        # embedding branches (K2 and K3), fp32-accurate (<= 1e-5 of the embedding scale)
         self.engine = "exact"
 
     def init_hidden(self, batch_size, device):
@@ -136,6 +138,22 @@ class CALModel(nn.Module):
             _, hidden = self.lstm(embedded)
         return self.lang_fc(hidden[0].transpose(0, 1).reshape(tokens.size(0), 2 * self.hidden_size))
 
+    # -- visual branch -----------------------------------------------------------------------
+    def _visual_forward_kernels(self, batch):
+        lin1, lin2 = self.visual_fc[0], self.visual_fc[2]
+        if self.engine == "tc":
+            # K2 on tensor cores: two split-bf16 tcgen05 GEMMs (fp32-accurate), bias + ReLU in the epilogue
+            ps = (lin1.weight, lin2.weight)
+            key = tuple((p.data_ptr(), p._version) for p in ps)
+            if self._packed_vis is None or self._packed_vis[0] != key:
+                self._packed_vis = (key, ops.pack_weight_tc(lin1.weight.detach()), ops.pack_weight_tc(lin2.weight.detach()))
+            if batch.dim() != 2 or batch.shape[1] != lin1.weight.shape[1]:
+                raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(batch.shape)} and "
+                                   f"{tuple(lin1.weight.t().shape)})")
+            hidden = ops.linear_tc(batch, self._packed_vis[1], lin1.weight.shape[0], lin1.bias.detach(), relu=True)
+            return ops.linear_tc(hidden, self._packed_vis[2], lin2.weight.shape[0], lin2.bias.detach())
+        return ops.visual_embed(batch, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+
     # -- forward -----------------------------------------------------------------------------
     def forward(self, batch, visual=True, device=None, bert=False):
         if not batch.is_cuda:
@@ -146,7 +164,7 @@ class CALModel(nn.Module):
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.visual_fc.parameters()):
                 out = _VisualEmbed.apply(batch, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
             else:
-                out = ops.visual_embed(batch, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+                out = self._visual_forward_kernels(batch)
             return drop(out)            # identity in eval mode; torch RNG mask in train mode (models.py:25)
         if bert:
             if torch.is_grad_enabled() and self.lang_fc.weight.requires_grad:
