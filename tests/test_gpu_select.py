@@ -132,7 +132,7 @@ def test_sel_error_bound_holds(offset):
     bank = ops.Bank(torch.from_numpy(clips).to(DEV), np.arange(C // 4 + 1) * 4)
     gs, gi, flags, (qp, ws) = ops.score_topk_sel(bank, torch.from_numpy(qs).to(DEV), k, return_flags=True)
     assert int(flags.abs().sum().item()) == 0
-    n_parts, qpad = 2, 256
+    n_parts, qpad = 2, 512
     cand = ws[:qpad * n_parts * CAP * 8].view(torch.int64).view(qpad, n_parts, CAP).cpu().numpy()
     cnt = ws[qpad * n_parts * CAP * 8:qpad * n_parts * (CAP * 8 + 4)].view(torch.int32).view(qpad, n_parts).cpu().numpy()
     assert cnt[:Q].sum(axis=1).tolist() == [C] * Q
@@ -195,3 +195,15 @@ def test_sel_large_properties():
             s, e = moments[mom[a, b]]
             want = orc.moment_scores_loop(torch.from_numpy(c[vid[a, b] * 6:vid[a, b] * 6 + 6]), torch.from_numpy(qq[a:a + 1]), [(s, e)])[0]
             assert abs(want - gs[a, b].item()) / want < 1e-5
+
+
+def test_sel_cluster_multicast_variant(monkeypatch):
+    """VFR_SEL_CL=2: CTA pairs share every bank tile through TMA multicast (odd query-group counts get an idle
+    partner CTA).  Same bits as the exact engine."""
+    monkeypatch.setenv("VFR_SEL_CL", "2")
+    rng = np.random.default_rng(12)
+    clips, vid_off = _ragged_bank(rng, 20000, 100, (6, 5))
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    for n_queries in (700, 300, 129):            # 3, 2 (odd -> padded) and 1 query groups of 256
+        q = torch.from_numpy((rng.standard_normal((n_queries, 100), dtype=np.float32) * 0.3)).to(DEV)
+        _assert_same_as_exact(bank, q, 100)

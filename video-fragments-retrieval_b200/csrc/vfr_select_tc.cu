@@ -55,7 +55,7 @@ constexpr int SL_SET_WARPS = 4;           // one epilogue warp per TMEM lane qua
 constexpr int SL_THREADS = 64 + 2 * SL_SET_WARPS * 32;   // ... in two sets (one per TMEM buffer): 320 threads
 constexpr int SL_CAP = 1024;              // candidate slots per (query, part) list
 constexpr int SL_CAP_HI = SL_CAP - SL_N;  // a tile can append at most SL_N keys to a list
-constexpr int SL_QPAD = 256;              // packed query rows are padded to a multiple of this
+constexpr int SL_QPAD = 512;              // packed query rows are padded to a multiple of this (R x 128 rows x CTA pair)
 
 struct SlBankMeta {          // written by the bank pack kernels, read by the query pack kernel
   unsigned vmax_abs_bits;    // max |v_k|                    (fp32 bit patterns: non-negative, so uint order)
@@ -300,6 +300,28 @@ __device__ __forceinline__ void sl_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// the same load delivered to the same shared-memory offsets (data and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void sl_tma_load_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void sl_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void sl_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ int sl_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return (int)r;
+}
 // K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t sl_desc(const void* smem_ptr) {
   const uint32_t addr = smem_u32(smem_ptr);
@@ -383,6 +405,13 @@ __device__ __forceinline__ bool sl_test(uint64_t* bar, uint32_t parity) {
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return done != 0;
+}
+
+// a smem stage is free again once the MMAs issued so far have read it - in every CTA that received it
+template <int CL>
+__device__ __forceinline__ void sl_release(uint64_t* bar) {
+  if (CL == 1) sl_commit(bar);
+  else sl_commit_mc(bar, (uint16_t)3);
 }
 
 // threshold of the accumulator domain, rounded up:  (tau2 + band2 - nq) * scale
@@ -551,7 +580,10 @@ __device__ __forceinline__ void sl_process(const float (&v)[64], int coff, SlRow
   if (m <= st.thr) sl_cold(v, m, coff, st, p);
 }
 
-template <int R>
+// CL = 2: CTA pairs (thread-block cluster) of the same bank split share every bank tile: each CTA fetches one of
+// the two 32 KB boxes and TMA multicasts it into both shared memories, halving the L2 reads and the TMA
+// requests per SM; a stage is recycled when the MMA warps of BOTH CTAs have released it.
+template <int R, int CL>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const SlParams p) {
   constexpr int STAGES = SlCfg<R>::STAGES;
@@ -577,11 +609,13 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int b_chunks = (p.ksteps > 4) ? 2 : 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     mbar_init(a_full, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], SL_SET_WARPS); }
     fence_barrier_init();
   }
+  const int crank = (CL == 2) ? sl_cluster_rank() : 0;
+  if (CL == 2) sl_cluster_sync();          // the peer's barriers exist before anything is multicast to them
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
                  "r"(512));
@@ -606,7 +640,8 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const int s = it % STAGES;
           sl_wait(&empty[s], ((it / STAGES) & 1) ^ 1, p.wait_mode);
           mbar_expect_tx(&full[s], SL_B_CHUNK);
-          sl_tma_load(smem_b + s * SL_B_CHUNK, &tm_b, c * 64, row, &full[s]);
+          if (CL == 1) sl_tma_load(smem_b + s * SL_B_CHUNK, &tm_b, c * 64, row, &full[s]);
+          else if ((it & 1) == crank) sl_tma_load_mc(smem_b + s * SL_B_CHUNK, &tm_b, c * 64, row, &full[s], (uint16_t)3);
         }
       }
     }
@@ -643,7 +678,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (!ready || pend_buf < 0) {
           if (pend_buf >= 0) {
             sl_commit(&tmem_full[pend_buf]);
-            if (pend_release) { sl_commit(&empty[pend_s0]); if (b_chunks == 2) sl_commit(&empty[pend_s1]); }
+            if (pend_release) { sl_release<CL>(&empty[pend_s0]); if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]); }
             pend_buf = -1;
           }
           if (r == 0) {
@@ -655,7 +690,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         sl_fence_after();
         if (pend_buf >= 0) {
           sl_commit(&tmem_full[pend_buf]);
-          if (pend_release) { sl_commit(&empty[pend_s0]); if (b_chunks == 2) sl_commit(&empty[pend_s1]); }
+          if (pend_release) { sl_release<CL>(&empty[pend_s0]); if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]); }
         }
         const long long tm1 = p.dbg ? clock64() : 0;
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * SL_N;
@@ -681,7 +716,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       if (pend_buf >= 0) {
         sl_commit(&tmem_full[pend_buf]);
-        if (pend_release) { sl_commit(&empty[pend_s0]); if (b_chunks == 2) sl_commit(&empty[pend_s1]); }
+        if (pend_release) { sl_release<CL>(&empty[pend_s0]); if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]); }
       }
     }
   } else {
@@ -806,6 +841,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+  if (CL == 2) sl_cluster_sync();          // the peer may still signal this CTA's barriers until it is done too
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1155,7 +1191,7 @@ static int sl_split(int64_t n_qgroups, int64_t n_tiles, int n_split) {
 }
 
 struct SlPlan {
-  int R, n_qgroups, ns, tiles_per_split, n_parts;
+  int R, CL, n_qgroups, ns, tiles_per_split, n_parts;   // n_qgroups: CTAs along the queries (even when CL = 2)
   int64_t n_tiles, qrows;
 };
 
@@ -1166,6 +1202,13 @@ static SlPlan sl_plan(int64_t n_queries, int64_t n_clips, int n_split) {
   pl.qrows = sl_qrows(n_queries);
   const int64_t qtiles = (n_queries + SL_M - 1) / SL_M;
   pl.n_qgroups = (int)((qtiles + pl.R - 1) / pl.R);
+  {
+    const char* env = getenv("VFR_SEL_CL");
+    // measured on B200 (18 944 queries x 6 M clips): the filter is bound by the MMA -> epilogue -> MMA hand-off
+    // chain, not by L2 / TMA, so the CTA-pair multicast is off by default (VFR_SEL_CL=2 turns it on)
+    pl.CL = (env && env[0] == '2' && pl.n_qgroups >= 2) ? 2 : 1;
+    if (pl.CL == 2) pl.n_qgroups = (pl.n_qgroups + 1) / 2 * 2;     // an odd group gets an idle partner CTA
+  }
   const int ns_req = sl_split(pl.n_qgroups, pl.n_tiles, n_split);
   pl.tiles_per_split = (int)((pl.n_tiles + ns_req - 1) / ns_req);
   pl.ns = (int)((pl.n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
@@ -1289,12 +1332,27 @@ extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const in
   rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad * (1 + (size_t)pl.n_parts), st);   // tau_g and tau_part: +inf
   if (rc) return rc;
   const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
-  if (pl.R == 2) {
-    VFR_CUDA(cudaFuncSetAttribute(sl_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SlCfg<2>::SMEM));
-    sl_filter_kernel<2><<<grid, SL_THREADS, SlCfg<2>::SMEM, st>>>(ma, mb, p);
-  } else {
-    VFR_CUDA(cudaFuncSetAttribute(sl_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SlCfg<1>::SMEM));
-    sl_filter_kernel<1><<<grid, SL_THREADS, SlCfg<1>::SMEM, st>>>(ma, mb, p);
+  {
+    void (*kern)(CUtensorMap, CUtensorMap, SlParams) = nullptr;
+    uint32_t smem_bytes = 0;
+    if (pl.R == 2 && pl.CL == 2) { kern = sl_filter_kernel<2, 2>; smem_bytes = SlCfg<2>::SMEM; }
+    else if (pl.R == 2) { kern = sl_filter_kernel<2, 1>; smem_bytes = SlCfg<2>::SMEM; }
+    else if (pl.CL == 2) { kern = sl_filter_kernel<1, 2>; smem_bytes = SlCfg<1>::SMEM; }
+    else { kern = sl_filter_kernel<1, 1>; smem_bytes = SlCfg<1>::SMEM; }
+    VFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(SL_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)pl.CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VFR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
   }
   rc = check_launch("sl_filter_kernel");
   if (rc) return rc;
