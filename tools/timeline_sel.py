@@ -25,3 +25,13 @@ for s in (0, 1):
     for v in range(20, 23):
         print("  visit %d: " % v + "  ".join("ew%d %d/%d/%d" % (w, d[1 + w, v, 1] - t0, d[1 + w, v, 2] - t0, d[1 + w, v, 3] - t0) for w in range(4 * s, 4 * s + 4)))
 print("steady state: %.0f cycles per job" % ((d[0, 200, 0] - d[0, 40, 0]) / 160.0))
+hold = (d[1:9, :128, 2] - d[1:9, :128, 1])
+print("hold (full_seen -> release) per epilogue warp over the last 128 visits: median / p90 / max")
+for w in range(8):
+    h = np.sort(hold[w])
+    print("  ew%d: %5d %5d %5d   stragglers(>1200): %3d  at visits mod 4: %s" % (w, h[64], h[115], h[-1], int((hold[w] > 1200).sum()),
+          np.bincount(np.nonzero(hold[w] > 1200)[0] % 4, minlength=4).tolist()))
+tail = (d[1:9, :128, 3] - d[1:9, :128, 2])
+print("tail (release -> done): median %d p90 %d max %d" % (np.median(tail), np.percentile(tail, 90), tail.max()))
+wait = (d[1:9, :128, 1] - d[1:9, :128, 0])
+print("wait for tmem_full: median %d p90 %d" % (np.median(wait), np.percentile(wait, 90)))

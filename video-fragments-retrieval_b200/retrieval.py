@@ -120,7 +120,13 @@ class MomentRetriever:
         self.host_s = torch.empty((mq, self.k), dtype=torch.float32).pin_memory()
         self.host_i = torch.empty((mq, self.k), dtype=torch.int64).pin_memory()
         # kernels launched per search step: gather + 20 LSTM steps + 2 fc + query pack + threshold init + score (filter) + finish (refine) (+ merge)
-        self.launches_per_step = 1 + self.seq_len + 2 + 1 + 1 + 1 + 1 + (1 if self.world > 1 else 0)
+        if text_engine == "tc":
+            # zero + len/scan/perm + gather + (join + step GEMM) x L + final join folded in L + fc
+            n_text = 1 + 3 + 1 + 2 * self.seq_len + 1
+        else:
+            n_text = 1 + self.seq_len + 2
+        # query pack + threshold init + score (filter) + finish (refine)
+        self.launches_per_step = n_text + 4 + (1 if self.world > 1 else 0)
 
     def score_only(self, n_queries):
         """K4 alone (query pack excluded) on the query embeddings left in ``q_emb`` by the previous
