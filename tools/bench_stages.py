@@ -72,6 +72,19 @@ if tr is not None:
         emit(stage="K6 ranking_loss fwd+bwd", shape=f"R={R_} rows x3, B={Bq} queries", us=t * 1e3, bound="latency")
     except Exception as e:
         emit(stage="K6 ranking_loss", error=str(e)[:200])
+# ---- one training step (BASELINE config 2): 3 visual batches + text + ranking loss + backward + Adam ----
+try:
+    tmodel = models.CALModel(visual_input_dim=2 * 4096 + 2, pretrained_emb=table).to(dev)
+    opt = torch.optim.Adam(filter(lambda q_: q_.requires_grad, tmodel.parameters()), lr=5e-4, weight_decay=5e-3)
+    batch = {"posit": torch.rand(R_, 8194, device=dev, generator=g), "intra": torch.rand(R_, 8194, device=dev, generator=g),
+             "inter": torch.rand(R_, 8194, device=dev, generator=g),
+             "lang": torch.randint(1, 10000, (Bq, 20), device=dev, generator=g), "maskp": maskp, "maskn": maskp}
+    tr2 = vmain.Trainer(device=dev)
+    t = timeit(lambda: tr2.train_epoch(tmodel, [batch], opt), n=5, warm=2)
+    emit(stage="training step (fwd + ranking loss + bwd + Adam)", shape=f"R={R_} rows x3 streams, B={Bq} queries", ms=t,
+         note="embedding backward re-runs the branch with stock torch ops (SURVEY 8(f) item 2 is next); reference CPU step 600-1000 ms")
+except Exception as e:
+    emit(stage="training step", error=str(e)[:300])
 # ---- K4 variants on the val shape and the long-video shape ----
 for name, nv, seg, Q in (("val", 1094, (6, 5), 4180), ("long", 1094, (30,), 4180)):
     rng = np.random.default_rng(5)
