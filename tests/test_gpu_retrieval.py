@@ -90,3 +90,59 @@ def test_sel_engine_equals_exact_engine_and_fixes_up_flagged_queries():
         assert (getattr(auto, "n_fixups", 0) > 0) == expect_fixups
         hs, hi = auto.search(tokens)
         assert torch.equal(hi, ei.cpu()) and torch.equal(hs.view(torch.int32), es.cpu().view(torch.int32))
+
+
+def test_sharded_rank_of_first_positive_equals_single_bank(golden):
+    """Exact R@k / median-rank inputs over a sharded bank: tau by all-reduce(min), counts by all-reduce(sum)
+    (here the reducers combine four emulated shards on one GPU) == the unsharded evaluation core."""
+    from vfr_b200 import evaluate as vev
+    from vfr_b200.retrieval import sharded_rank_first_positive
+    z, meta = golden("val_eval")
+    clips, vid_off = z["video_emb"], z["vid_off"]
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    videos = synth.make_videos(meta["seed"], meta["n_videos"], meta["feat_dim"], tuple(meta["seg_choices"]), tuple(meta["seg_probs"]))
+    queries = synth.make_queries(meta["seed"], videos, meta["n_queries"], meta["vocab"])
+    q_emb = torch.from_numpy(z["query_emb"]).to(DEV)
+    Q = q_emb.shape[0]
+    q_video = queries["video_idx"][:Q]
+    times = queries["times"][:Q]
+    want = vev.rank_first_positive(bank, q_emb, q_video, times, [0.5, 0.7])
+    V, P = bank.n_videos, 4
+    shards, v0s = [], []
+    for r in range(P):
+        a, b = shard_range(V, r, P)
+        c0, c1 = int(vid_off[a]), int(vid_off[b])
+        shards.append(ops.Bank(torch.from_numpy(clips[c0:c1]).to(DEV), vid_off[a:b + 1] - c0))
+        v0s.append(a)
+    # run the P ranks "in lockstep": every reduce call combines the tensors the P ranks pass at the same call site
+    import threading
+    barrier = threading.Barrier(P)
+    slots, results, lock = {}, [None] * P, threading.Lock()
+
+    def make_reduce(rank):
+        calls = [0]
+
+        def reduce(t, op):
+            key = calls[0]
+            calls[0] += 1
+            with lock:
+                slots.setdefault(key, []).append(t.clone())
+            barrier.wait()
+            parts = torch.stack(slots[key])
+            barrier.wait()
+            return parts.min(dim=0).values if op == "min" else parts.sum(dim=0)
+        return reduce
+
+    def work(rank):
+        torch.cuda.set_device(0)
+        results[rank] = sharded_rank_first_positive(shards[rank], v0s[rank], q_emb, q_video, bank.nseg_host[q_video], times,
+                                                    [0.5, 0.7], reduce=make_reduce(rank))
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(P)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for r in range(P):
+        rank, npos = results[r]
+        assert np.array_equal(rank.cpu().numpy(), want["rank"])
+        assert np.array_equal(npos.cpu().numpy(), want["npos"])

@@ -35,5 +35,26 @@ for engine in ("sel", "tc", "exact"):
     if rank == 0:
         print(f"engine={engine}: sharded({world}) == single bank: {bool(t.item())}")
     ok = ok and bool(t.item())
+# exact rank of the first positive over the sharded bank (tau all-reduce(min) + count all-reduce(sum), NCCL)
+from vfr_b200 import ops, evaluate as vev
+from vfr_b200.retrieval import sharded_rank_first_positive
+videos = synth.make_videos(3, 2000, 8)
+queries = synth.make_queries(3, videos, 400, 500)
+nseg = np.array([v["num_segments"] for v in videos])
+vo = np.concatenate([[0], np.cumsum(nseg)])
+g = torch.Generator(device=dev).manual_seed(7)
+bank_clips = torch.randn(int(vo[-1]), 100, device=dev, generator=g) * 0.3
+q_emb = torch.randn(400, 100, device=dev, generator=g) * 0.3
+full_bank = ops.Bank(bank_clips, vo)
+want = vev.rank_first_positive(full_bank, q_emb, queries["video_idx"], queries["times"], [0.5, 0.7])["rank"]
+a, b = shard_range(2000, rank, world)
+shard_bank = ops.Bank(bank_clips[int(vo[a]):int(vo[b])], vo[a:b + 1] - vo[a])
+got, _ = sharded_rank_first_positive(shard_bank, a, q_emb, queries["video_idx"], nseg[queries["video_idx"]], queries["times"], [0.5, 0.7])
+same = bool(np.array_equal(got.cpu().numpy(), want))
+t = torch.tensor([int(same)], device=dev)
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"sharded exact rank of the first positive ({world} shards, NCCL all-reduce) == single bank: {bool(t.item())}")
+ok = ok and bool(t.item())
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -231,3 +231,54 @@ class MomentRetriever:
 
     def d2h_bytes(self, Q):
         return Q * self.k * (4 + 8)
+
+
+# ---------------------------------------------------------------------------------------------------
+# exact rank of the first positive over a SHARDED bank: the metrics of
+# model/evaluate.py:67-80 need ranks far beyond any top-k, so the owner shard of a query's video computes
+# tau = its smallest positive score, one all-reduce(min) hands tau to every shard, every shard counts
+# score < tau (and the deterministic tie terms) over its own videos, one all-reduce(sum) adds the counts.
+# ---------------------------------------------------------------------------------------------------
+def _dist_reduce(group):
+    def reduce(t, op):
+        dist.all_reduce(t, op=dist.ReduceOp.MIN if op == "min" else dist.ReduceOp.SUM, group=group)
+        return t
+    return reduce
+
+
+def sharded_rank_first_positive(shard, v0, q_emb, q_video, q_nseg, times_list, iou_thresholds, inclusive=False,
+                                reduce=None, group=None):
+    """``shard``: ``ops.Bank`` of the contiguous video range starting at global video ``v0``; ``q_video`` int [Q]
+    GLOBAL index of every query's own video, ``q_nseg`` int [Q] its clip count, ``times_list`` the annotator
+    times.  ``reduce(tensor, "min" | "sum")`` defaults to ``torch.distributed.all_reduce`` over ``group``.
+    Returns int64 [Q, T] on the device: the 0-based rank of the first positive among ALL moments of ALL shards -
+    identical to ``evaluate.rank_first_positive(...)['rank']`` on the unsharded bank."""
+    if reduce is None:
+        reduce = _dist_reduce(group)
+    dev = shard.device
+    q_video = np.asarray(q_video, dtype=np.int64)
+    local = q_video - int(v0)                                    # index inside this shard (may fall outside)
+    mine = (local >= 0) & (local < shard.n_videos)
+    Q, T = len(q_video), len(iou_thresholds)
+    tau = torch.full((Q, T), float("inf"), dtype=torch.float32, device=dev)
+    own_eqb = torch.zeros((Q, T), dtype=torch.int64, device=dev)
+    npos = torch.zeros((Q, T), dtype=torch.int64, device=dev)
+    if mine.any():
+        idx = torch.as_tensor(np.nonzero(mine)[0], device=dev)
+        own = ops.score_own(shard, q_emb[idx].contiguous(), torch.as_tensor(local[mine].astype(np.int32), device=dev))
+        times = ops.pack_times([times_list[i] for i in np.nonzero(mine)[0]], dev)
+        tables = ops.threshold_tables(list(iou_thresholds), inclusive, dev)
+        nseg = torch.as_tensor(np.asarray(q_nseg)[mine].astype(np.int32), device=dev)
+        _, t_own, _, n_own, e_own = ops.gt_select(own, nseg, times, tables)
+        tau[idx] = t_own
+        own_eqb[idx] = e_own.to(torch.int64)
+        npos[idx] = n_own.to(torch.int64)
+    tau = reduce(tau, "min")
+    own_eqb = reduce(own_eqb, "sum")
+    npos = reduce(npos, "sum")
+    # tie-break term counts videos BEFORE the query's own one: the kernel compares shard-local indices
+    qv_local = torch.as_tensor(np.clip(local, -1, 2 ** 31 - 2).astype(np.int32), device=dev)
+    lt, eqb = ops.score_count(shard, q_emb, tau, qv_local)
+    lt = reduce(lt.contiguous(), "sum")
+    eqb = reduce(eqb.contiguous(), "sum")
+    return lt + eqb + own_eqb, npos
