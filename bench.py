@@ -5,7 +5,8 @@
 
 Workload (BASELINE.json configs[4]): a bank of 1,000,000 six-clip videos
 (6 M clip embeddings, D = 100, 21 M candidate moments) resident in HBM; the 100,000 queries arrive in
-batches of --batch queries.  One STEP = one batch of tokenised queries through the retrieval hot
+batches of --batch queries (default 37,888 = 2 x 148 query tiles: one CTA per SM walks the whole bank shard for
+two query tiles, so a query keeps a single candidate list).  One STEP = one batch of tokenised queries through the retrieval hot
 path: K3 query embedding (GloVe gather -> BiLSTM -> Linear) -> K4 fused distance / moment-mean /
 top-100 over the whole bank (-> all-gather + K7 merge when the bank is sharded over N GPUs).
 Strong scaling: the bank is fixed and split by contiguous video ranges over the ranks.
@@ -48,7 +49,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=18944, help="queries per step (148 query tiles of 128 = one per SM)")
+    ap.add_argument("--batch", type=int, default=37888, help="queries per step (296 query tiles of 128: one CTA of two tiles per SM, no bank split)")
     ap.add_argument("--engine", type=str, default="sel", choices=["sel", "tc", "tc_bf16", "exact"])
     ap.add_argument("--videos", type=int, default=N_VIDEOS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
