@@ -97,3 +97,33 @@ for name, nv, seg, Q in (("val", 1094, (6, 5), 4180), ("long", 1094, (30,), 4180
     t_sel = timeit(lambda: ops.score_topk_sel(bank, q, 100), n=3, warm=1)
     pairs = Q * bank.m_total
     emit(stage=f"K4 {name} eval", shape=f"{Q} queries x {nv} videos ({bank.m_total} moments)", ms_score_full_exact=t_full, pairs_per_s_full=pairs / t_full * 1e3, ms_topk_sel=t_sel, pairs_per_s_topk=pairs / t_sel * 1e3)
+
+# ---- the reference's own protocols end to end at the val shape (BASELINE config 1): iterators in, metric dicts out ----
+import random, time
+from torch.utils.data import DataLoader
+from vfr_b200 import evaluate as vev, evaluate_single as vsingle
+videos = synth.make_videos(123, 1094, 4096)
+queries = synth.make_queries(123, videos, 4180, 10000)
+ds = vdata.CustomDataset.__new__(vdata.CustomDataset)
+ds.validate = True
+ds.video_features = {v["name"]: v for v in videos}
+ds.num_segments_info = {v["name"]: v["num_segments"] for v in videos}
+ds.lang_features = {a: torch.from_numpy(queries["tokens"][i:i + 1]) for i, a in enumerate(queries["annot_id"])}
+annotations = {a: dict(video=videos[int(queries["video_idx"][i])]["name"], description="", times=queries["times"][i])
+               for i, a in enumerate(queries["annot_id"])}
+vit = DataLoader(ds, collate_fn=vdata.validate_collate, batch_sampler=vdata.VideoBatchSampler([v["name"] for v in videos], ds.num_segments_info))
+lit = DataLoader(ds, collate_fn=vdata.validate_collate, batch_sampler=vdata.LanguageBatchSampler(annotations, ds.num_segments_info, 6))
+model.engine = "exact"
+import io, contextlib
+for name, fn in (("evaluate.evaluate (corpus protocol: 4180 queries x 1094 videos)", lambda: vev.evaluate(model, vit, lit, annotations, dev, preliminary=0)),
+                 ("evaluate_single.evaluate (single-video protocol)", lambda: vsingle.evaluate(model, vit, lit, annotations, dev, ["model"], synth.make_prior([5, 6])))):
+    np.random.seed(123); random.seed(123)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m = fn()
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    emit(stage=name, seconds=dt, note="drop-in call with the reference's iterators (host-side DataLoader loops included); reference on 8 CPU threads: ~29 min (corpus), ~2.5 min (single) at this shape",
+         first_metrics={k: {kk: float(vv) for kk, vv in v.items()} for k, v in list(m.items())[:1]})
