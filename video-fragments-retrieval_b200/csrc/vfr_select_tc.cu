@@ -84,6 +84,8 @@ struct SlParams {
   int n_parts;
   unsigned* tau_g;           // [Qpad] k-th smallest d2~ published by any list of the query
   float* tau_part;           // [Qpad][n_parts] ceil(k / n_parts)-th smallest d2~ of each list (inf until compacted)
+  int tile_lo;               // first bank tile of this launch (the scan may be split into several launches)
+  int resume;                // != 0: the candidate lists continue from a previous launch
   int wait_mode;             // mbarrier wait flavour (see sl_wait)
   long long* dbg;            // optional timeline of CTA 0 (development aid): [9 roles][256 events][4]
   int32_t* flags;            // [Qpad] != 0: a candidate list overflowed / scales out of range (see vfr.h)
@@ -603,7 +605,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int qgroup = blockIdx.x % p.n_qgroups;
   const int split = blockIdx.x / p.n_qgroups;
-  const int tile_begin = split * p.tiles_per_split;
+  const int tile_begin = p.tile_lo + split * p.tiles_per_split;
   const int tile_end = min(tile_begin + p.tiles_per_split, p.n_tiles);
   const int n_my_tiles = max(tile_end - tile_begin, 0);
   const int b_chunks = (p.ksteps > 4) ? 2 : 1;
@@ -732,7 +734,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     st.q = (int64_t)qtile * SL_M + quarter * 32 + lane;
     const bool valid = st.q < p.n_queries;
     st.list = p.cand + ((int64_t)st.q * p.n_parts + part) * SL_CAP;
-    st.cnt = 0;
+    st.cnt = p.resume ? p.cand_cnt[st.q * p.n_parts + part] : 0;
     {
       const float4 qm = __ldg(p.qmeta + st.q);
       st.nq = qm.x; st.scale = qm.y; st.inv_scale = qm.z; st.band2 = qm.w;
@@ -1290,27 +1292,18 @@ extern "C" size_t vfr_sel_topk_bytes(int64_t n_queries, int64_t n_clips, int n_s
   return worst;
 }
 
-extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const int32_t* vid_off, const int64_t* mom_off,
-                            int64_t n_videos, int64_t n_clips, int n_max, int dim, void* query_packed,
-                            const float* queries, int64_t n_queries, int k, int64_t id_base, float* out_scores,
-                            int64_t* out_ids, void* workspace, int n_split, vfr_stream_t stream) {
-  VFR_REQUIRE(bank_packed && bank && vid_off && mom_off && query_packed && queries && out_scores && out_ids && workspace,
-              VFR_ERR_INVALID, "vfr_sel_topk: null pointer");
-  VFR_REQUIRE(n_videos > 0 && n_clips > 0 && n_queries > 0, VFR_ERR_INVALID, "vfr_sel_topk: empty bank or batch");
-  VFR_REQUIRE(n_clips < (int64_t(1) << 31) - SL_N && n_videos < (int64_t(1) << 31) - 1, VFR_ERR_UNSUPPORTED,
-              "vfr_sel_topk: bank shard too large");
-  VFR_REQUIRE(dim >= 1 && dim + 3 <= SL_ROW, VFR_ERR_UNSUPPORTED, "vfr_sel_topk: dim=%d must be <= %d", dim, SL_ROW - 3);
-  VFR_REQUIRE(n_max >= 1 && n_max <= VFR_MAX_SEG, VFR_ERR_UNSUPPORTED, "vfr_sel_topk: n_max=%d", n_max);
+namespace vfr {
+
+// everything the two stages share: the launch plan, the workspace carve-up, the per-query metadata
+static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k,
+                    void* workspace, int n_split) {
+  VFR_REQUIRE(n_clips > 0 && n_queries > 0, VFR_ERR_INVALID, "vfr_sel: empty bank or batch");
+  VFR_REQUIRE(n_clips < (int64_t(1) << 31) - SL_N, VFR_ERR_UNSUPPORTED, "vfr_sel: bank shard too large");
+  VFR_REQUIRE(dim >= 1 && dim + 3 <= SL_ROW, VFR_ERR_UNSUPPORTED, "vfr_sel: dim=%d must be <= %d", dim, SL_ROW - 3);
   VFR_REQUIRE(k >= 1 && k <= VFR_TOPK_MAX, VFR_ERR_UNSUPPORTED, "k=%d not in [1,%d]", k, VFR_TOPK_MAX);
-  const SlPlan pl = sl_plan(n_queries, n_clips, n_split);
-  const int64_t rows = pl.n_tiles * SL_N;
-  CUtensorMap ma, mb;
-  int rc = sl_make_map(&ma, query_packed, (uint64_t)pl.qrows, SL_M);
-  if (rc) return rc;
-  rc = sl_make_map(&mb, bank_packed, (uint64_t)rows, SL_N);
-  if (rc) return rc;
+  pl = sl_plan(n_queries, n_clips, n_split);
   __half* qp = reinterpret_cast<__half*>(query_packed);
-  SlParams p{};
+  p = SlParams{};
   p.qmeta = reinterpret_cast<const float4*>(qp + pl.qrows * SL_ROW);
   p.flags = reinterpret_cast<int32_t*>(const_cast<float4*>(p.qmeta) + pl.qrows);
   p.n_clips = n_clips;
@@ -1327,35 +1320,61 @@ extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const in
   p.cand = reinterpret_cast<unsigned long long*>(workspace);
   p.cand_cnt = reinterpret_cast<int32_t*>(p.cand + qpad * (size_t)pl.n_parts * SL_CAP);
   p.tau_g = reinterpret_cast<unsigned*>(p.cand_cnt + qpad * (size_t)pl.n_parts);
-  cudaStream_t st = (cudaStream_t)stream;
   p.tau_part = reinterpret_cast<float*>(p.tau_g + qpad);
-  rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad * (1 + (size_t)pl.n_parts), st);   // tau_g and tau_part: +inf
+  return VFR_OK;
+}
+
+// stage 1 over the bank tiles [tile_lo, tile_hi)
+static int sl_run_filter(const SlPlan& pl, SlParams p, const void* bank_packed, void* query_packed, int64_t tile_lo,
+                         int64_t tile_hi, int resume, cudaStream_t st) {
+  if (tile_hi < 0 || tile_hi > pl.n_tiles) tile_hi = pl.n_tiles;
+  VFR_REQUIRE(tile_lo >= 0 && tile_lo <= tile_hi, VFR_ERR_INVALID, "vfr_sel_filter: bad tile range");
+  CUtensorMap ma, mb;
+  int rc = sl_make_map(&ma, query_packed, (uint64_t)pl.qrows, SL_M);
   if (rc) return rc;
-  const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
-  {
-    void (*kern)(CUtensorMap, CUtensorMap, SlParams) = nullptr;
-    uint32_t smem_bytes = 0;
-    if (pl.R == 2 && pl.CL == 2) { kern = sl_filter_kernel<2, 2>; smem_bytes = SlCfg<2>::SMEM; }
-    else if (pl.R == 2) { kern = sl_filter_kernel<2, 1>; smem_bytes = SlCfg<2>::SMEM; }
-    else if (pl.CL == 2) { kern = sl_filter_kernel<1, 2>; smem_bytes = SlCfg<1>::SMEM; }
-    else { kern = sl_filter_kernel<1, 1>; smem_bytes = SlCfg<1>::SMEM; }
-    VFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(SL_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)pl.CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VFR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+  rc = sl_make_map(&mb, bank_packed, (uint64_t)(pl.n_tiles * SL_N), SL_N);
+  if (rc) return rc;
+  if (!resume) {
+    const size_t qpad = (size_t)pl.qrows;
+    rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad * (1 + (size_t)pl.n_parts), st);   // tau_g and tau_part: +inf
+    if (rc) return rc;
+    if (tile_lo == tile_hi) VFR_CUDA(cudaMemsetAsync(p.cand_cnt, 0, qpad * (size_t)pl.n_parts * sizeof(int32_t), st));
   }
-  rc = check_launch("sl_filter_kernel");
-  if (rc) return rc;
+  if (tile_lo == tile_hi) return VFR_OK;
+  p.tile_lo = (int)tile_lo;
+  p.n_tiles = (int)tile_hi;
+  p.tiles_per_split = (int)((tile_hi - tile_lo + pl.ns - 1) / pl.ns);
+  p.resume = resume;
+  const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
+  void (*kern)(CUtensorMap, CUtensorMap, SlParams) = nullptr;
+  uint32_t smem_bytes = 0;
+  if (pl.R == 2 && pl.CL == 2) { kern = sl_filter_kernel<2, 2>; smem_bytes = SlCfg<2>::SMEM; }
+  else if (pl.R == 2) { kern = sl_filter_kernel<2, 1>; smem_bytes = SlCfg<2>::SMEM; }
+  else if (pl.CL == 2) { kern = sl_filter_kernel<1, 2>; smem_bytes = SlCfg<1>::SMEM; }
+  else { kern = sl_filter_kernel<1, 1>; smem_bytes = SlCfg<1>::SMEM; }
+  VFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(SL_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)pl.CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VFR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+  return check_launch("sl_filter_kernel");
+}
+
+static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vid_off, const int64_t* mom_off,
+                         int64_t n_videos, int n_max, int dim, const float* queries, int64_t n_queries, int k,
+                         int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  VFR_REQUIRE(bank && vid_off && mom_off && queries && out_scores && out_ids, VFR_ERR_INVALID, "vfr_sel_refine: null pointer");
+  VFR_REQUIRE(n_videos > 0 && n_videos < (int64_t(1) << 31) - 1, VFR_ERR_UNSUPPORTED, "vfr_sel_refine: n_videos");
+  VFR_REQUIRE(n_max >= 1 && n_max <= VFR_MAX_SEG, VFR_ERR_UNSUPPORTED, "vfr_sel_refine: n_max=%d", n_max);
   RfParams r{};
   r.bank = bank;
   r.queries = queries;
@@ -1376,6 +1395,89 @@ extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const in
   r.out_ids = out_ids;
   sl_refine_kernel<<<(unsigned)n_queries, RF_THREADS, 0, st>>>(r);
   return check_launch("sl_refine_kernel");
+}
+
+// bound[q] = tau_g[q] + E_q : an upper bound of the EXACT k-th smallest squared clip distance of this shard
+__global__ void sl_bound_get_kernel(const unsigned* __restrict__ tau_g, const float4* __restrict__ qmeta, int64_t n,
+                                    float* __restrict__ bound) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) bound[q] = __fadd_ru(__uint_as_float(tau_g[q]), 0.5f * qmeta[q].w);
+}
+// a bound that holds for the k-th smallest of a LARGER bank (all shards) tightens this shard's threshold:
+// a clip can only matter if its exact d^2 <= bound, i.e. its d2~ <= bound + E = (bound - E) + 2E
+__global__ void sl_bound_put_kernel(unsigned* __restrict__ tau_g, const float4* __restrict__ qmeta, int64_t n,
+                                    const float* __restrict__ bound) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) {
+    const float t = fmaxf(__fsub_ru(bound[q], 0.5f * qmeta[q].w), 0.f);
+    if (t < __uint_as_float(tau_g[q])) tau_g[q] = __float_as_uint(t);
+  }
+}
+
+}  // namespace vfr
+
+extern "C" int64_t vfr_sel_tiles(int64_t n_clips) { return n_clips > 0 ? sl_tiles(n_clips) : 0; }
+
+extern "C" int vfr_sel_filter(const void* bank_packed, int64_t n_clips, int dim, void* query_packed, int64_t n_queries,
+                              int k, void* workspace, int n_split, int64_t tile_lo, int64_t tile_hi, int resume,
+                              vfr_stream_t stream) {
+  VFR_REQUIRE(bank_packed && query_packed && workspace, VFR_ERR_INVALID, "vfr_sel_filter: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  return sl_run_filter(pl, p, bank_packed, query_packed, tile_lo, tile_hi, resume, (cudaStream_t)stream);
+}
+
+extern "C" int vfr_sel_bound_get(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
+                                 int n_split, float* bound, vfr_stream_t stream) {
+  VFR_REQUIRE(query_packed && workspace && bound, VFR_ERR_INVALID, "vfr_sel_bound_get: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  sl_bound_get_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.tau_g, p.qmeta, n_queries, bound);
+  return check_launch("sl_bound_get_kernel");
+}
+
+extern "C" int vfr_sel_bound_put(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
+                                 int n_split, const float* bound, vfr_stream_t stream) {
+  VFR_REQUIRE(query_packed && workspace && bound, VFR_ERR_INVALID, "vfr_sel_bound_put: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  sl_bound_put_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.tau_g, p.qmeta, n_queries, bound);
+  return check_launch("sl_bound_put_kernel");
+}
+
+extern "C" int vfr_sel_refine(const float* bank, const int32_t* vid_off, const int64_t* mom_off, int64_t n_videos,
+                              int64_t n_clips, int n_max, int dim, void* query_packed, const float* queries,
+                              int64_t n_queries, int k, int64_t id_base, float* out_scores, int64_t* out_ids,
+                              void* workspace, int n_split, vfr_stream_t stream) {
+  VFR_REQUIRE(query_packed && workspace, VFR_ERR_INVALID, "vfr_sel_refine: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  return sl_run_refine(p, bank, vid_off, mom_off, n_videos, n_max, dim, queries, n_queries, k, id_base, out_scores,
+                       out_ids, (cudaStream_t)stream);
+}
+
+extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const int32_t* vid_off, const int64_t* mom_off,
+                            int64_t n_videos, int64_t n_clips, int n_max, int dim, void* query_packed,
+                            const float* queries, int64_t n_queries, int k, int64_t id_base, float* out_scores,
+                            int64_t* out_ids, void* workspace, int n_split, vfr_stream_t stream) {
+  VFR_REQUIRE(bank_packed && bank && vid_off && mom_off && query_packed && queries && out_scores && out_ids && workspace,
+              VFR_ERR_INVALID, "vfr_sel_topk: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  rc = sl_run_filter(pl, p, bank_packed, query_packed, 0, -1, 0, (cudaStream_t)stream);
+  if (rc) return rc;
+  return sl_run_refine(p, bank, vid_off, mom_off, n_videos, n_max, dim, queries, n_queries, k, id_base, out_scores,
+                       out_ids, (cudaStream_t)stream);
 }
 
 // flags of the last vfr_sel_topk on this packed query buffer: device pointer to int32 [n_queries]

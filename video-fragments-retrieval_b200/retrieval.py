@@ -109,6 +109,7 @@ class MomentRetriever:
         p.out_scores_dev, p.out_ids_dev = self.out_s.data_ptr(), self.out_i.data_ptr()
         p.n_split, p.max_queries = int(n_split), mq
         self.plan = p
+        self.sel_bound = torch.empty(mq, dtype=torch.float32, device=dev)
         if self.world > 1:
             self.gather_s = torch.empty((self.world, mq, self.k), dtype=torch.float32, device=dev)
             self.gather_i = torch.empty((self.world, mq, self.k), dtype=torch.int64, device=dev)
@@ -144,6 +145,32 @@ class MomentRetriever:
         else:
             _lib.call("vfr_score_topk", p.bank_packed, p.vid_off, p.mom_off, b.n_videos, b.n_max, b.dim, p.q_packed,
                       n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev, p.topk_ws, p.n_split, lib_stream)
+
+    def _sel_score_sharded(self, Q, stream, reduce_min=None):
+        """K4 of one shard when the bank is spread over several ranks.  A shard's local top-k only has to hold what
+        can reach the GLOBAL top-k: after a first slice of its bank every shard knows an upper bound of its own k-th
+        smallest clip distance; the minimum over the shards (ONE small all-reduce) bounds the global one, and the rest
+        of the scan filters with it - the hit / list work per shard then shrinks with the number of shards instead of
+        staying that of a full top-k search.  Exactness is untouched: nothing that could enter the merged top-k is
+        dropped (include/vfr.h)."""
+        p, b = self.plan, self.bank
+        n_clips = self.n_clips
+        qt, ws = self.q_tc.data_ptr(), self.topk_ws.data_ptr()
+        _lib.call("vfr_sel_query_pack", p.q_emb, Q, b.dim, p.bank_tc, n_clips, qt, stream)
+        tiles = _lib.load().vfr_sel_tiles(n_clips)
+        first = min(tiles, getattr(self, "sel_first_tiles", None) or max(32, tiles // 8))
+        _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, first, 0, stream)
+        if first < tiles:
+            bound = self.sel_bound[:Q]
+            _lib.call("vfr_sel_bound_get", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
+            if reduce_min is None:
+                dist.all_reduce(bound, op=dist.ReduceOp.MIN, group=self.group)
+            else:
+                bound = reduce_min(bound)
+            _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
+            _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, first, tiles, 1, stream)
+        _lib.call("vfr_sel_refine", p.bank_clips, p.vid_off, p.mom_off, b.n_videos, n_clips, b.n_max, b.dim, qt, p.q_emb, Q,
+                  self.k, p.id_base, self.out_s.data_ptr(), self.out_i.data_ptr(), ws, p.n_split, stream)
 
     def _sel_flags(self, Q):
         """int32 [Q] view of the per-query flags of the last filter + refine call (0 = guaranteed exact)."""
@@ -190,8 +217,11 @@ class MomentRetriever:
         gathered = self.q_gather[:self.world * per]
         dist.all_gather_into_tensor(gathered, mine, group=self.group)
         self.q_emb[:Q].copy_(gathered[:Q])
-        _lib.call("vfr_search_score_device", C.byref(self.plan), Q, self.k, self.out_s.data_ptr(), self.out_i.data_ptr(),
-                  stream)
+        if self.plan.engine == 4:
+            self._sel_score_sharded(Q, stream)
+        else:
+            _lib.call("vfr_search_score_device", C.byref(self.plan), Q, self.k, self.out_s.data_ptr(),
+                      self.out_i.data_ptr(), stream)
         self._sel_fixup(Q)
         gs, gi = self.gather_s[:, :Q].contiguous(), self.gather_i[:, :Q].contiguous()
         dist.all_gather_into_tensor(gs, self.out_s[:Q].contiguous(), group=self.group)
