@@ -137,8 +137,12 @@ int vfr_score_full_tc(const void* bank_packed, const float* bank, const int32_t*
  * vfr_sel_flags(query_packed, n_queries) -> device pointer to int32 [n_queries] written by the last
  * vfr_sel_query_pack / vfr_sel_topk on that buffer: 0 = result guaranteed exact; 1 = the query's or the
  * bank's magnitudes do not fit the fp16 operand scales, 2 / 3 = more candidates inside the error band than
- * the stage-1 lists / stage-2 buffer hold (mass duplicates).  Flagged queries must be re-run through
- * vfr_score_topk by the caller (vfr_b200.retrieval does). */
+ * the stage-1 lists / stage-2 buffer hold (mass duplicates); 4 = the scan started from a SAMPLED threshold
+ * (large banks: the j-th smallest distance of a strided sample of the bank, j chosen so that the bank
+ * holds k clips under it except with probability < 1e-10 for a bank in no particular order) and stage 2
+ * found fewer than k clips under it.  Flagged queries must be re-run through vfr_score_topk by the caller
+ * (vfr_b200.retrieval does): a flag costs time, never correctness.  VFR_SEL_SAMPLE=0 turns the sample
+ * pass off. */
 size_t vfr_sel_bank_bytes(int64_t n_clips);
 int vfr_sel_bank_pack(const float* bank, int64_t n_clips, int dim, void* packed, vfr_stream_t stream);
 size_t vfr_sel_query_bytes(int64_t n_queries);
@@ -153,7 +157,8 @@ const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries);
 /* The two stages separately, for a bank sharded over several GPUs.  Every shard's local top-k only has to contain
  * what can reach the GLOBAL top-k, so the shards exchange a bound half way: vfr_sel_filter over a first slice of
  * the shard's bank tiles (tiles of 256 clips, vfr_sel_tiles(n_clips) in total; resume = 0 starts fresh lists) ->
- * vfr_sel_bound_get (bound[q] = an upper bound of the exact k-th smallest squared clip distance of THIS shard) ->
+ * vfr_sel_bound_get (bound[q] = a CERTIFIED upper bound of the exact k-th smallest squared clip distance of THIS
+ * shard: from k keys really seen, never from the sampled threshold; +inf until a list has been compacted) ->
  * all-reduce(min) over the shards -> vfr_sel_bound_put -> vfr_sel_filter over the remaining tiles with
  * resume = 1 -> vfr_sel_refine.  vfr_sel_topk == filter(all tiles) + refine. */
 int64_t vfr_sel_tiles(int64_t n_clips);

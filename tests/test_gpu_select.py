@@ -207,3 +207,59 @@ def test_sel_cluster_multicast_variant(monkeypatch):
     for n_queries in (700, 300, 129):            # 3, 2 (odd -> padded) and 1 query groups of 256
         q = torch.from_numpy((rng.standard_normal((n_queries, 100), dtype=np.float32) * 0.3)).to(DEV)
         _assert_same_as_exact(bank, q, 100)
+
+
+def _sample_rank(k, sample_tiles, n_tiles):
+    """The rank j the sample pass uses (sl_sample_plan in vfr_select_tc.cu): smallest j with
+    P(Poisson(k * sampled clips / bank clips) >= j) < 1e-10."""
+    import math
+    x = k * 256.0 * sample_tiles / ((n_tiles - 1) * 256.0)
+    term, cdf = math.exp(-x), 0.0
+    for j in range(1, 17):
+        cdf += term
+        term *= x / j
+        if 1.0 - cdf < 1e-10:
+            return j
+    return None
+
+
+@pytest.mark.parametrize("n_queries", [300, 100])         # two query tiles per CTA / one (two lists per query)
+def test_sel_sampled_starting_threshold(monkeypatch, n_queries):
+    """Banks with >= 128 tiles per candidate list start the scan from a sampled threshold (a strided sample of the
+    bank, stage 2 verifies it): same bits as the exact engine, and as the engine without the sample pass."""
+    rng = np.random.default_rng(41)
+    clips, vid_off = _ragged_bank(rng, 30000, 100, (6, 5))
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    q = torch.from_numpy((rng.standard_normal((n_queries, 100), dtype=np.float32) * 0.3)).to(DEV)
+    for k in (1, 20, 100):
+        _assert_same_as_exact(bank, q, k, n_split=1)
+        with_sample = ops.score_topk_sel(bank, q, k, n_split=1)
+        monkeypatch.setenv("VFR_SEL_SAMPLE", "0")
+        without = ops.score_topk_sel(bank, q, k, n_split=1)
+        monkeypatch.delenv("VFR_SEL_SAMPLE")
+        assert torch.equal(with_sample[1], without[1]) and torch.equal(with_sample[0], without[0])
+
+
+def test_sel_wrong_sampled_threshold_is_flagged(monkeypatch):
+    """An adversarial bank: the only clips near the queries sit exactly in the tiles the sample pass reads, fewer of
+    them than k.  The sampled threshold then promises k clips the bank does not have; stage 2 must notice (flag 4,
+    the retriever re-runs such queries through the exact engine) - and without the sample pass the same call is
+    exact."""
+    rng = np.random.default_rng(42)
+    V, D, k, Q = 8000, 100, 20, 300
+    n_clips = V * 6
+    n_tiles = (n_clips + 255) // 256
+    assert n_tiles == 188
+    sample_tiles, stride = 8, (n_tiles - 1) // 8          # one list per query (n_split = 1, two query tiles per CTA)
+    j = _sample_rank(k, sample_tiles, n_tiles)
+    assert j is not None and j < 16 < k
+    centre = rng.standard_normal(D).astype(np.float32)
+    clips = (centre + 3.0 * rng.standard_normal((n_clips, D))).astype(np.float32)       # far from every query
+    planted = [t * stride * 256 + c * 64 + 5 for t in range(sample_tiles) for c in (0, 2)]   # 16 clips, 16 chunks
+    clips[planted] = centre + 0.02 * rng.standard_normal((len(planted), D)).astype(np.float32)
+    q = torch.from_numpy((centre + 0.01 * rng.standard_normal((Q, D))).astype(np.float32)).to(DEV)
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), np.arange(V + 1) * 6)
+    gs, gi, flags, _ = ops.score_topk_sel(bank, q, k, n_split=1, return_flags=True)
+    assert bool((flags == 4).all()), flags.unique()
+    monkeypatch.setenv("VFR_SEL_SAMPLE", "0")
+    _assert_same_as_exact(bank, q, k, n_split=1)

@@ -4,18 +4,19 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vfr_b200
 from vfr_b200 import ops
-V, Q, k = 1000000, 18944, int(os.environ.get("K", "1"))
+V, Q, k = int(os.environ.get("V", "1000000")), int(os.environ.get("Q", "18944")), int(os.environ.get("K", "1"))
 D = int(os.environ.get("D", "100"))
 g = torch.Generator(device="cuda").manual_seed(0)
 clips = ((torch.randn(V, 1, D, device="cuda", generator=g) + 0.6 * torch.randn(V, 6, D, device="cuda", generator=g)) * 0.05).reshape(-1, D)
 q = torch.randn(Q, D, device="cuda", generator=g) * 0.06
 bank = ops.Bank(clips, np.arange(V + 1) * 6)
 ops.score_topk_sel(bank, q, k)
-dbg = torch.zeros(9 * 256 * 4, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(9 * 256 * 4 + 8, dtype=torch.int64, device="cuda")
 os.environ["VFR_SEL_DBG"] = hex(dbg.data_ptr())
 ops.score_topk_sel(bank, q, k)
 torch.cuda.synchronize()
-d = dbg.cpu().numpy().reshape(9, 256, 4)
+cnt = dbg.cpu().numpy()[9 * 256 * 4:]
+d = dbg.cpu().numpy()[:9 * 256 * 4].reshape(9, 256, 4)
 t0 = d[0, 0, 0]
 print("MMA thread (job = tile*2 + r): wait_start wait_end issued(commit) | wait issue")
 for j in range(40, 48):
@@ -35,3 +36,7 @@ tail = (d[1:9, :128, 3] - d[1:9, :128, 2])
 print("tail (release -> done): median %d p90 %d max %d" % (np.median(tail), np.percentile(tail, 90), tail.max()))
 wait = (d[1:9, :128, 1] - d[1:9, :128, 0])
 print("wait for tmem_full: median %d p90 %d" % (np.median(wait), np.percentile(wait, 90)))
+n_cta = 148
+print("compaction, all CTAs: %d warp events, %d lists, %.0f clk per list, %.0f clk per event; per CTA %.2f ms if serialised (1.9 GHz)" % (
+    cnt[1], cnt[2], cnt[0] / max(cnt[2], 1), cnt[0] / max(cnt[1], 1), cnt[0] / n_cta / 1.9e6))
+print("  per list: load %.0f clk, select %.0f clk, write-back %.0f clk" % tuple(cnt[3 + i] / max(cnt[2], 1) for i in range(3)))

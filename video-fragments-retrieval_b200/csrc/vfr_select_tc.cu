@@ -82,12 +82,15 @@ struct SlParams {
   unsigned long long* cand;  // [Qpad][n_parts][SL_CAP]  (d2~ bits << 32 | clip id)
   int32_t* cand_cnt;         // [Qpad][n_parts]
   int n_parts;
-  unsigned* tau_g;           // [Qpad] k-th smallest d2~ published by any list of the query
+  unsigned* tau_g;           // [Qpad] the threshold the filter uses: min(tau_cert, the sampled starting threshold)
+  unsigned* tau_cert;        // [Qpad] CERTIFIED part of it: k-th smallest d2~ of keys really seen (or a bound put from outside)
+  int tile_stride;           // bank tile of scan position i = i * tile_stride (1; the sample pass strides over the bank)
+  int sample_j;              // sample pass: the starting threshold is the sample_j-th smallest sampled minimum
   float* tau_part;           // [Qpad][n_parts] ceil(k / n_parts)-th smallest d2~ of each list (inf until compacted)
   int tile_lo;               // first bank tile of this launch (the scan may be split into several launches)
   int resume;                // != 0: the candidate lists continue from a previous launch
   int wait_mode;             // mbarrier wait flavour (see sl_wait)
-  long long* dbg;            // optional timeline of CTA 0 (development aid): [9 roles][256 events][4]
+  long long* dbg;            // optional timeline of CTA 0 (development aid): [9 roles][256 events][4] + 8 counters
   int32_t* flags;            // [Qpad] != 0: a candidate list overflowed / scales out of range (see vfr.h)
 };
 
@@ -429,39 +432,44 @@ __device__ __forceinline__ float sl_threshold(float tau2, float band2, float nq,
 // the whole bank - far tighter than any single list's k-th, which only knows 1/P of the clips.
 constexpr int SL_SLOTS = SL_CAP / 32;   // keys per lane
 
-__device__ __forceinline__ unsigned sl_radix_kth(const unsigned (&w)[SL_SLOTS], unsigned candmask, int kk, int m) {
-  unsigned a = 0xffffffffu, o = 0u;
+// 32 x 32 bit transpose in registers: on return bit s of w[b] = bit b of the old w[s]
+__device__ __forceinline__ void sl_transpose32(unsigned (&w)[SL_SLOTS]) {
+  static_assert(SL_SLOTS == 32, "one key per lane and bit of the slot mask");
+  unsigned m = 0x0000ffffu;
 #pragma unroll
-  for (int s = 0; s < SL_SLOTS; ++s)
-    if ((candmask >> s) & 1u) { a &= w[s]; o |= w[s]; }
-  a = warp_and(a);
-  o = warp_or(o);
-  const unsigned diff = a ^ o;
-  if (diff == 0u) return a;
-  const int top = 31 - __clz(diff);
-  unsigned value = a & ~((2u << top) - 1u);
-  int bit = top;
-  for (; bit >= 0 && m > 1; --bit) {
-    unsigned ones = 0u;
+  for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
 #pragma unroll
-    for (int s = 0; s < SL_SLOTS; ++s) ones |= ((w[s] >> bit) & 1u) << s;
-    const int c0 = warp_sum_int(__popc(candmask & ~ones));
-    if (kk <= c0) { m = c0; candmask &= ~ones; }
-    else { kk -= c0; m -= c0; candmask &= ones; value |= 1u << bit; }
+    for (int k = 0; k < 32; ++k) {
+      if ((k & j) == 0) {
+        const unsigned t = ((w[k] >> j) ^ w[k + j]) & m;
+        w[k + j] ^= t;
+        w[k] ^= t << j;
+      }
+    }
   }
-  if (bit >= 0) {
-    unsigned mine = 0u;
+}
+
+// The ka-th and the kb-th smallest word (1-based, ka, kb <= number of valid slots) of a warp's 32 x 32 words in ONE
+// most-significant-bit-first radix descent over the TRANSPOSED words (tw[b] = bit b of this lane's 32 slots): per bit
+// two popcounts and one hardware warp reduction carrying both counts (each <= 1024 < 2^16).
+__device__ __forceinline__ void sl_radix_kth2(const unsigned (&tw)[SL_SLOTS], unsigned valid, int ka, int kb, unsigned& va,
+                                              unsigned& vb) {
+  unsigned ca = valid, cb = valid;
+  va = 0u;
+  vb = 0u;
 #pragma unroll
-    for (int s = 0; s < SL_SLOTS; ++s)
-      if ((candmask >> s) & 1u) mine = w[s];
-    const unsigned who = __ballot_sync(0xffffffffu, candmask != 0u);
-    value = __shfl_sync(0xffffffffu, mine, __ffs(who) - 1);
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned ones = tw[bit];
+    const unsigned za = ca & ~ones, zb = cb & ~ones;
+    const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)__popc(za) | ((unsigned)__popc(zb) << 16));
+    const int na = (int)(tot & 0xffffu), nb = (int)(tot >> 16);
+    if (ka <= na) ca = za; else { ka -= na; ca &= ones; va |= 1u << bit; }
+    if (kb <= nb) cb = zb; else { kb -= nb; cb &= ones; vb |= 1u << bit; }
   }
-  return value;
 }
 
 __device__ __noinline__ void sl_compact(unsigned long long* list, int& cnt, float& tau_own, float& tau_part, float tau_shared,
-                                        float band2, int k, int k_part, bool need, int lane) {
+                                        float band2, int k, int k_part, bool need, int lane, long long* dbg = nullptr) {
   unsigned mask = __ballot_sync(0xffffffffu, need);
   while (mask) {
     const int src = __ffs(mask) - 1;
@@ -473,31 +481,54 @@ __device__ __noinline__ void sl_compact(unsigned long long* list, int& cnt, floa
     const float b2 = __shfl_sync(0xffffffffu, band2, src);
     if (n <= k) continue;
     __syncwarp();
-    unsigned hi[SL_SLOTS], lo[SL_SLOTS];
-    unsigned candmask = 0u;
+    const long long c0 = dbg ? clock64() : 0;
+    unsigned kth_hi, kpart_hi;
+    {
+      // the d2~ words (high half of every key; every list owns 32 x 32 slots, slots >= n are masked), transposed
+      unsigned w[SL_SLOTS];
+      unsigned valid = 0u;
+      const unsigned* hp = reinterpret_cast<const unsigned*>(lp) + 1;
 #pragma unroll
-    for (int s = 0; s < SL_SLOTS; ++s) {
-      const int idx = (s << 5) | lane;
-      unsigned long long key = ~0ull;
-      if (idx < n) { key = lp[idx]; candmask |= 1u << s; }
-      hi[s] = (unsigned)(key >> 32);
-      lo[s] = (unsigned)key;
+      for (int s = 0; s < SL_SLOTS; ++s) w[s] = hp[2 * ((s << 5) | lane)];
+#pragma unroll
+      for (int s = 0; s < SL_SLOTS; ++s) {
+        if (((s << 5) | lane) < n) valid |= 1u << s;
+        else w[s] = 0xffffffffu;
+      }
+      long long c1 = 0;
+      if (dbg) c1 = clock64();
+      sl_transpose32(w);
+      sl_radix_kth2(w, valid, k, min(k_part, k), kth_hi, kpart_hi);
+      if (dbg && lane == 0) {
+        unsigned long long* d = reinterpret_cast<unsigned long long*>(dbg + 9 * 256 * 4);
+        atomicAdd(d + 3, (unsigned long long)(c1 - c0));
+        atomicAdd(d + 4, (unsigned long long)(clock64() - c1));
+      }
     }
-    const unsigned kth_hi = sl_radix_kth(hi, candmask, k, n);
     const float kth = __uint_as_float(kth_hi);
-    const float kpart = (k_part < k) ? __uint_as_float(sl_radix_kth(hi, candmask, k_part, n)) : kth;
+    const float kpart = __uint_as_float(kpart_hi);
     const unsigned keep_bits = __float_as_uint(__fadd_ru(fminf(kth, ts), b2));
     __syncwarp();
+    const long long c2 = dbg ? clock64() : 0;
+    // second read of the (cache-hot) keys: volatile asm keeps the 32 loads back to back, ahead of the in-place writes
+    unsigned long long key[SL_SLOTS];
+#pragma unroll
+    for (int s = 0; s < SL_SLOTS; ++s)
+      asm volatile("ld.global.u64 %0, [%1];" : "=l"(key[s]) : "l"(__cvta_generic_to_global(lp + ((s << 5) | lane))) : "memory");
     int base = 0;
 #pragma unroll
     for (int s = 0; s < SL_SLOTS; ++s) {
       const int idx = (s << 5) | lane;
-      const bool keep = idx < n && hi[s] <= keep_bits;
+      const bool keep = idx < n && (unsigned)(key[s] >> 32) <= keep_bits;
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) lp[base + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)hi[s] << 32) | lo[s];
+      if (keep) lp[base + __popc(bal & ((1u << lane) - 1u))] = key[s];
       base += __popc(bal);
     }
     __syncwarp();
+    if (dbg && lane == 0) {
+      unsigned long long* d = reinterpret_cast<unsigned long long*>(dbg + 9 * 256 * 4);
+      atomicAdd(d + 5, (unsigned long long)(clock64() - c2));
+    }
     if (lane == src) {
       cnt = base;
       tau_own = kth;
@@ -582,10 +613,29 @@ __device__ __forceinline__ void sl_process(const float (&v)[64], int coff, SlRow
   if (m <= st.thr) sl_cold(v, m, coff, st, p);
 }
 
+// Sample pass (MODE 1): the SL_J smallest 64-column minima of the row, kept sorted in registers
+constexpr int SL_J = 16;
+__device__ __forceinline__ void sl_sample(const float (&v)[64], float (&a)[SL_J]) {
+  float g[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float x = fmin3(v[8 * i], v[8 * i + 1], v[8 * i + 2]);
+    const float y = fmin3(v[8 * i + 3], v[8 * i + 4], v[8 * i + 5]);
+    g[i] = fmin3(x, y, fminf(v[8 * i + 6], v[8 * i + 7]));
+  }
+  float m = fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), fminf(g[6], g[7]));
+#pragma unroll
+  for (int i = 0; i < SL_J; ++i) {
+    const float lo = fminf(a[i], m);
+    m = fmaxf(a[i], m);
+    a[i] = lo;
+  }
+}
+
 // CL = 2: CTA pairs (thread-block cluster) of the same bank split share every bank tile: each CTA fetches one of
 // the two 32 KB boxes and TMA multicasts it into both shared memories, halving the L2 reads and the TMA
 // requests per SM; a stage is recycled when the MMA warps of BOTH CTAs have released it.
-template <int R, int CL>
+template <int R, int CL, int MODE>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const SlParams p) {
   constexpr int STAGES = SlCfg<R>::STAGES;
@@ -637,7 +687,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           sl_tma_load(smem_a + (r * 2 + c) * SL_A_CHUNK, &tm_a, c * 64, (qgroup * R + r) * SL_M, a_full);
       int it = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
-        const int row = (tile_begin + t) * SL_N;
+        const int row = (tile_begin + t) * p.tile_stride * SL_N;
         for (int c = 0; c < b_chunks; ++c, ++it) {
           const int s = it % STAGES;
           sl_wait(&empty[s], ((it / STAGES) & 1) ^ 1, p.wait_mode);
@@ -730,6 +780,50 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // R = 2: set s serves query tile s on every bank tile; R = 1: set s serves the tiles of parity s
     const int qtile = (R == 2) ? (qgroup * 2 + set) : qgroup;
     const int part = (R == 2) ? split : (split * 2 + set);
+    const int t_first = (R == 2) ? 0 : set;
+    const int t_step = (R == 2) ? 1 : 2;
+    if constexpr (MODE == 1) {
+      // ---- sample pass: no lists, only the sample_j-th smallest of the 64-column minima of a strided sample of
+      //      the bank.  It becomes the query's STARTING threshold (stage 2 checks that the bank really holds k
+      //      keys under it, see sl_refine_kernel), so the scan proper skips the phase in which everything passes ----
+      const int64_t q = (int64_t)qtile * SL_M + quarter * 32 + lane;
+      float a[SL_J];
+#pragma unroll
+      for (int i = 0; i < SL_J; ++i) a[i] = CUDART_INF_F;
+      int visit = 0;
+      for (int t = t_first; t < n_my_tiles; t += t_step, ++visit) {
+        sl_wait(&tmem_full[set], visit & 1, p.wait_mode);
+        sl_fence_after();
+        float va[64], vb[64];
+        sl_ld32(lane_addr, va, 0);
+        sl_ld32(lane_addr + 32, va, 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        sl_ld32(lane_addr + 64, vb, 0);
+        sl_ld32(lane_addr + 96, vb, 32);
+        sl_sample(va, a);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        sl_ld32(lane_addr + 128, va, 0);
+        sl_ld32(lane_addr + 160, va, 32);
+        sl_sample(vb, a);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        sl_ld32(lane_addr + 192, vb, 0);
+        sl_ld32(lane_addr + 224, vb, 32);
+        sl_sample(va, a);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        sl_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[set]);
+        sl_sample(vb, a);
+      }
+      float x = CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < SL_J; ++i)
+        if (i == p.sample_j - 1) x = a[i];
+      if (q < p.n_queries && x < CUDART_INF_F) {
+        const float4 qm = __ldg(p.qmeta + q);
+        tau_publish(p.tau_g + q, fmaxf(__fmaf_ru(x, qm.z, qm.x), 0.f));
+      }
+    } else {
     SlRow st;
     st.q = (int64_t)qtile * SL_M + quarter * 32 + lane;
     const bool valid = st.q < p.n_queries;
@@ -742,8 +836,6 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     st.tau_own = CUDART_INF_F;
     st.tau_use = valid ? CUDART_INF_F : -1.f;
     st.thr = valid ? CUDART_INF_F : -CUDART_INF_F;
-    const int t_first = (R == 2) ? 0 : set;
-    const int t_step = (R == 2) ? 1 : 2;
 
     int visit = 0;
     for (int t = t_first; t < n_my_tiles; t += t_step, ++visit) {
@@ -789,13 +881,15 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
 
       if (__any_sync(0xffffffffu, st.cnt > SL_CAP_HI)) {
+        const long long tc0 = p.dbg ? clock64() : 0;
+        const int n_need = p.dbg ? __popc(__ballot_sync(0xffffffffu, st.cnt > SL_CAP_HI)) : 0;
         const float before = st.tau_own;
         // (copies: taking the address of a member would push the whole per-thread state into local memory)
         int cnt = st.cnt;
         float tau_own = st.tau_own;
         float tau_part = CUDART_INF_F;
         const int k_part = (p.k + p.n_parts - 1) / p.n_parts;
-        sl_compact(st.list, cnt, tau_own, tau_part, st.tau_use, st.band2, p.k, k_part, cnt > SL_CAP_HI, lane);
+        sl_compact(st.list, cnt, tau_own, tau_part, st.tau_use, st.band2, p.k, k_part, cnt > SL_CAP_HI, lane, p.dbg);
         const bool over = cnt > SL_CAP_HI;
         if (__any_sync(0xffffffffu, over)) {
           // more than CAP_HI keys inside the band (mass duplicates): keep the list bounded and flag the query
@@ -817,10 +911,17 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             best = fminf(best, worst);
           }
           tau_publish(p.tau_g + st.q, best);
+          tau_publish(p.tau_cert + st.q, best);
           if (best < st.tau_use) {
             st.tau_use = best;
             st.thr = sl_threshold(best, st.band2, st.nq, st.scale);
           }
+        }
+        if (p.dbg && lane == 0) {   // all CTAs: {clocks spent compacting, warp events, lists compacted}
+          unsigned long long* d = reinterpret_cast<unsigned long long*>(p.dbg + 9 * 256 * 4);
+          atomicAdd(d, (unsigned long long)(clock64() - tc0));
+          atomicAdd(d + 1, 1ull);
+          atomicAdd(d + 2, (unsigned long long)n_need);
         }
       }
     }
@@ -833,9 +934,13 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       sl_compact(st.list, cnt, tau_own, dummy, st.tau_use, st.band2, p.k, p.k, cnt > p.k, lane);
       st.cnt = cnt;
       st.tau_own = tau_own;
-      if (st.tau_own < before) tau_publish(p.tau_g + st.q, st.tau_own);
+      if (st.tau_own < before) {
+        tau_publish(p.tau_g + st.q, st.tau_own);
+        tau_publish(p.tau_cert + st.q, st.tau_own);
+      }
     }
     p.cand_cnt[st.q * p.n_parts + part] = st.cnt;
+    }   // MODE == 0
   }
 
   sl_fence_before();
@@ -868,6 +973,7 @@ struct RfParams {
   const int32_t* cand_cnt;
   int n_parts;
   const unsigned* tau_g;
+  const unsigned* tau_cert;
   int32_t* flags;
   int k;
   int64_t id_base;
@@ -1003,6 +1109,11 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
     rf_block_sort(keys, n_sorted);
     const unsigned long long kth_key = keys[p.k - 1];
     if (kth_key != ~0ull) tau_fin = fminf(tau_pub, __uint_as_float((unsigned)(kth_key >> 32)));
+    // The filter ran under a SAMPLED threshold that no certified one undercut: it only holds if the bank really
+    // has k keys under it (all of them are in the lists then).  Otherwise the query is flagged for the exact engine.
+    if (tid == 0 && tau_pub < tau_fetch(p.tau_cert + q) &&
+        (kth_key == ~0ull || (unsigned)(kth_key >> 32) > __float_as_uint(tau_pub)) && p.flags[q] == 0)
+      p.flags[q] = 4;
   }
   const unsigned keep_bits = __float_as_uint(__fadd_ru(tau_fin, qm.w));
   // no moment scoring above this can be among the k best: the k closest clips are moments themselves
@@ -1286,7 +1397,7 @@ extern "C" size_t vfr_sel_topk_bytes(int64_t n_queries, int64_t n_clips, int n_s
     const SlPlan pl = sl_plan(qt == qtiles ? n_queries : qt * SL_M, n_clips, n_split);
     const size_t qpad = (size_t)pl.qrows;
     const size_t need = qpad * pl.n_parts * SL_CAP * sizeof(unsigned long long) + qpad * pl.n_parts * sizeof(int32_t) +
-                        qpad * sizeof(unsigned) + qpad * pl.n_parts * sizeof(float);
+                        2 * qpad * sizeof(unsigned) + qpad * pl.n_parts * sizeof(float);
     if (need > worst) worst = need;
   }
   return worst;
@@ -1320,8 +1431,66 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
   p.cand = reinterpret_cast<unsigned long long*>(workspace);
   p.cand_cnt = reinterpret_cast<int32_t*>(p.cand + qpad * (size_t)pl.n_parts * SL_CAP);
   p.tau_g = reinterpret_cast<unsigned*>(p.cand_cnt + qpad * (size_t)pl.n_parts);
-  p.tau_part = reinterpret_cast<float*>(p.tau_g + qpad);
+  p.tau_cert = p.tau_g + qpad;
+  p.tau_part = reinterpret_cast<float*>(p.tau_cert + qpad);
+  p.tile_stride = 1;
   return VFR_OK;
+}
+
+// Sample pass planning.  Every list draws `tiles` bank tiles (a strided sample of the whole bank, n_eff = 256 * tiles
+// clips) and takes the j-th smallest of its 64-column minima as the starting threshold.  The threshold is wrong only
+// if fewer than k of the bank's clips lie under it, i.e. if at least j of the bank's k - 1 closest clips fell into
+// the sample: P <= P(Poisson(k * n_eff / n_clips) >= j) for a bank in no particular order.  j is the smallest rank
+// that makes this < 1e-10 per list; a wrong threshold is detected by stage 2 (flag 4) and costs a rerun, never a
+// wrong result.  tiles = 0: no sample (bank too small to gain from it).
+struct SlSample { int tiles, stride, j; };
+static SlSample sl_sample_plan(const SlPlan& pl, int64_t n_clips, int k) {
+  SlSample sp{0, 1, 0};
+  { const char* e = getenv("VFR_SEL_SAMPLE"); if (e && e[0] == '0') return sp; }
+  const int lists = pl.ns * (pl.R == 2 ? 1 : 2);              // lists per query, each samples on its own
+  const int64_t per_list = pl.n_tiles / lists;
+  int tiles = 64;
+  while (tiles >= 8) {
+    const int64_t stride = (pl.n_tiles - 1) / ((int64_t)tiles * lists);   // never reaches the (padded) last tile
+    if (per_list >= 16 * tiles && stride >= 2) {
+      const double x = (double)k * 256.0 * tiles / (double)((pl.n_tiles - 1) * SL_N);
+      double term = exp(-x), cdf = 0.0;                      // P(Poisson(x) >= j) = 1 - sum_{i<j} e^-x x^i / i!
+      for (int j = 1; j <= SL_J; ++j) {
+        cdf += term;
+        term *= x / j;
+        if (1.0 - cdf < 1e-10) { sp.tiles = tiles; sp.stride = (int)stride; sp.j = j; return sp; }
+      }
+    }
+    tiles >>= 1;
+  }
+  return sp;
+}
+
+template <int MODE>
+static int sl_launch_filter(const SlPlan& pl, const SlParams& p, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
+  const int CL = (MODE == 1) ? 1 : pl.CL;
+  const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
+  void (*kern)(CUtensorMap, CUtensorMap, SlParams) = nullptr;
+  uint32_t smem_bytes = 0;
+  if (pl.R == 2 && CL == 2) { kern = sl_filter_kernel<2, 2, 0>; smem_bytes = SlCfg<2>::SMEM; }
+  else if (pl.R == 2) { kern = sl_filter_kernel<2, 1, MODE>; smem_bytes = SlCfg<2>::SMEM; }
+  else if (CL == 2) { kern = sl_filter_kernel<1, 2, 0>; smem_bytes = SlCfg<1>::SMEM; }
+  else { kern = sl_filter_kernel<1, 1, MODE>; smem_bytes = SlCfg<1>::SMEM; }
+  VFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(SL_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VFR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+  return check_launch(MODE == 1 ? "sl_filter_kernel (sample pass)" : "sl_filter_kernel");
 }
 
 // stage 1 over the bank tiles [tile_lo, tile_hi)
@@ -1336,37 +1505,28 @@ static int sl_run_filter(const SlPlan& pl, SlParams p, const void* bank_packed, 
   if (rc) return rc;
   if (!resume) {
     const size_t qpad = (size_t)pl.qrows;
-    rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad * (1 + (size_t)pl.n_parts), st);   // tau_g and tau_part: +inf
+    rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad * (2 + (size_t)pl.n_parts), st);   // tau_g, tau_cert, tau_part: +inf
     if (rc) return rc;
     if (tile_lo == tile_hi) VFR_CUDA(cudaMemsetAsync(p.cand_cnt, 0, qpad * (size_t)pl.n_parts * sizeof(int32_t), st));
+    // starting thresholds from a strided sample of the WHOLE bank (whatever slice this call scans)
+    const SlSample sp = sl_sample_plan(pl, p.n_clips, p.k);
+    if (sp.tiles > 0) {
+      SlParams ps = p;
+      ps.tile_lo = 0;
+      ps.tiles_per_split = sp.tiles * (pl.R == 2 ? 1 : 2);    // R = 1: the two sets of a CTA take alternate sample tiles
+      ps.n_tiles = ps.tiles_per_split * pl.ns;
+      ps.tile_stride = sp.stride;
+      ps.sample_j = sp.j;
+      rc = sl_launch_filter<1>(pl, ps, ma, mb, st);
+      if (rc) return rc;
+    }
   }
   if (tile_lo == tile_hi) return VFR_OK;
   p.tile_lo = (int)tile_lo;
   p.n_tiles = (int)tile_hi;
   p.tiles_per_split = (int)((tile_hi - tile_lo + pl.ns - 1) / pl.ns);
   p.resume = resume;
-  const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
-  void (*kern)(CUtensorMap, CUtensorMap, SlParams) = nullptr;
-  uint32_t smem_bytes = 0;
-  if (pl.R == 2 && pl.CL == 2) { kern = sl_filter_kernel<2, 2>; smem_bytes = SlCfg<2>::SMEM; }
-  else if (pl.R == 2) { kern = sl_filter_kernel<2, 1>; smem_bytes = SlCfg<2>::SMEM; }
-  else if (pl.CL == 2) { kern = sl_filter_kernel<1, 2>; smem_bytes = SlCfg<1>::SMEM; }
-  else { kern = sl_filter_kernel<1, 1>; smem_bytes = SlCfg<1>::SMEM; }
-  VFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(SL_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem_bytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)pl.CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VFR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
-  return check_launch("sl_filter_kernel");
+  return sl_launch_filter<0>(pl, p, ma, mb, st);
 }
 
 static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vid_off, const int64_t* mom_off,
@@ -1388,6 +1548,7 @@ static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vi
   r.cand_cnt = p.cand_cnt;
   r.n_parts = p.n_parts;
   r.tau_g = p.tau_g;
+  r.tau_cert = p.tau_cert;
   r.flags = p.flags;
   r.k = k;
   r.id_base = id_base;
@@ -1397,20 +1558,21 @@ static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vi
   return check_launch("sl_refine_kernel");
 }
 
-// bound[q] = tau_g[q] + E_q : an upper bound of the EXACT k-th smallest squared clip distance of this shard
-__global__ void sl_bound_get_kernel(const unsigned* __restrict__ tau_g, const float4* __restrict__ qmeta, int64_t n,
+// bound[q] = tau_cert[q] + E_q (certified thresholds only - a sampled one is a guess until stage 2) : an upper bound of the EXACT k-th smallest squared clip distance of this shard
+__global__ void sl_bound_get_kernel(const unsigned* __restrict__ tau_cert, const float4* __restrict__ qmeta, int64_t n,
                                     float* __restrict__ bound) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < n) bound[q] = __fadd_ru(__uint_as_float(tau_g[q]), 0.5f * qmeta[q].w);
+  if (q < n) bound[q] = __fadd_ru(__uint_as_float(tau_cert[q]), 0.5f * qmeta[q].w);
 }
 // a bound that holds for the k-th smallest of a LARGER bank (all shards) tightens this shard's threshold:
 // a clip can only matter if its exact d^2 <= bound, i.e. its d2~ <= bound + E = (bound - E) + 2E
-__global__ void sl_bound_put_kernel(unsigned* __restrict__ tau_g, const float4* __restrict__ qmeta, int64_t n,
-                                    const float* __restrict__ bound) {
+__global__ void sl_bound_put_kernel(unsigned* __restrict__ tau_g, unsigned* __restrict__ tau_cert,
+                                    const float4* __restrict__ qmeta, int64_t n, const float* __restrict__ bound) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) {
     const float t = fmaxf(__fsub_ru(bound[q], 0.5f * qmeta[q].w), 0.f);
     if (t < __uint_as_float(tau_g[q])) tau_g[q] = __float_as_uint(t);
+    if (t < __uint_as_float(tau_cert[q])) tau_cert[q] = __float_as_uint(t);
   }
 }
 
@@ -1436,7 +1598,7 @@ extern "C" int vfr_sel_bound_get(void* query_packed, int64_t n_queries, int64_t 
   SlParams p;
   int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
   if (rc) return rc;
-  sl_bound_get_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.tau_g, p.qmeta, n_queries, bound);
+  sl_bound_get_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.tau_cert, p.qmeta, n_queries, bound);
   return check_launch("sl_bound_get_kernel");
 }
 
@@ -1447,7 +1609,7 @@ extern "C" int vfr_sel_bound_put(void* query_packed, int64_t n_queries, int64_t 
   SlParams p;
   int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
   if (rc) return rc;
-  sl_bound_put_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.tau_g, p.qmeta, n_queries, bound);
+  sl_bound_put_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.tau_g, p.tau_cert, p.qmeta, n_queries, bound);
   return check_launch("sl_bound_put_kernel");
 }
 
