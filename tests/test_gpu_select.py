@@ -215,7 +215,7 @@ def _sample_rank(k, sample_tiles, n_tiles):
     import math
     x = k * 256.0 * sample_tiles / ((n_tiles - 1) * 256.0)
     term, cdf = math.exp(-x), 0.0
-    for j in range(1, 17):
+    for j in range(1, 33):
         cdf += term
         term *= x / j
         if 1.0 - cdf < 1e-10:

@@ -39,6 +39,7 @@
 // (set s = query tile s); with R = 1 the two sets take the bank tiles of even / odd parity.
 #include "vfr_common.cuh"
 #include "vfr_topk.cuh"
+#include <algorithm>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -85,6 +86,7 @@ struct SlParams {
   unsigned* tau_g;           // [Qpad] the threshold the filter uses: min(tau_cert, the sampled starting threshold)
   unsigned* tau_cert;        // [Qpad] CERTIFIED part of it: k-th smallest d2~ of keys really seen (or a bound put from outside)
   int tile_stride;           // bank tile of scan position i = i * tile_stride (1; the sample pass strides over the bank)
+  int cap_trig;              // list length that triggers the FIRST compaction of a list (<= SL_CAP_HI)
   int sample_j;              // sample pass: the starting threshold is the sample_j-th smallest sampled minimum
   float* tau_part;           // [Qpad][n_parts] ceil(k / n_parts)-th smallest d2~ of each list (inf until compacted)
   int tile_lo;               // first bank tile of this launch (the scan may be split into several launches)
@@ -614,7 +616,7 @@ __device__ __forceinline__ void sl_process(const float (&v)[64], int coff, SlRow
 }
 
 // Sample pass (MODE 1): the SL_J smallest 64-column minima of the row, kept sorted in registers
-constexpr int SL_J = 16;
+constexpr int SL_J = 32;
 __device__ __forceinline__ void sl_sample(const float (&v)[64], float (&a)[SL_J]) {
   float g[8];
 #pragma unroll
@@ -880,16 +882,19 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         d[0] = te0; d[1] = te1; d[2] = te2; d[3] = clock64();
       }
 
-      if (__any_sync(0xffffffffu, st.cnt > SL_CAP_HI)) {
+      // a list is compacted when it is full - and once EARLY (cap_trig keys): a list that starts from the sampled
+      // threshold would otherwise keep that loose threshold (and its hit rate) until it has filled up, if ever
+      const bool need = st.cnt > ((st.tau_own < CUDART_INF_F) ? SL_CAP_HI : p.cap_trig);
+      if (__any_sync(0xffffffffu, need)) {
         const long long tc0 = p.dbg ? clock64() : 0;
-        const int n_need = p.dbg ? __popc(__ballot_sync(0xffffffffu, st.cnt > SL_CAP_HI)) : 0;
+        const int n_need = p.dbg ? __popc(__ballot_sync(0xffffffffu, need)) : 0;
         const float before = st.tau_own;
         // (copies: taking the address of a member would push the whole per-thread state into local memory)
         int cnt = st.cnt;
         float tau_own = st.tau_own;
         float tau_part = CUDART_INF_F;
         const int k_part = (p.k + p.n_parts - 1) / p.n_parts;
-        sl_compact(st.list, cnt, tau_own, tau_part, st.tau_use, st.band2, p.k, k_part, cnt > SL_CAP_HI, lane, p.dbg);
+        sl_compact(st.list, cnt, tau_own, tau_part, st.tau_use, st.band2, p.k, k_part, need, lane, p.dbg);
         const bool over = cnt > SL_CAP_HI;
         if (__any_sync(0xffffffffu, over)) {
           // more than CAP_HI keys inside the band (mass duplicates): keep the list bounded and flag the query
@@ -1434,6 +1439,8 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
   p.tau_cert = p.tau_g + qpad;
   p.tau_part = reinterpret_cast<float*>(p.tau_cert + qpad);
   p.tile_stride = 1;
+  p.cap_trig = std::min(SL_CAP_HI, std::max(64, 6 * k));
+  { const char* e = getenv("VFR_SEL_TRIG"); if (e) p.cap_trig = std::min(SL_CAP_HI, std::max(k + 1, atoi(e))); }
   return VFR_OK;
 }
 
@@ -1449,10 +1456,13 @@ static SlSample sl_sample_plan(const SlPlan& pl, int64_t n_clips, int k) {
   { const char* e = getenv("VFR_SEL_SAMPLE"); if (e && e[0] == '0') return sp; }
   const int lists = pl.ns * (pl.R == 2 ? 1 : 2);              // lists per query, each samples on its own
   const int64_t per_list = pl.n_tiles / lists;
-  int tiles = 64;
+  int tiles = 64;                                              // more sample for larger k: 8 k tiles, 64 ... 512
+  while (tiles < 512 && tiles < 8 * k) tiles <<= 1;
+  { const char* e = getenv("VFR_SEL_SAMPLE_TILES"); if (e) tiles = std::max(8, atoi(e)); }
   while (tiles >= 8) {
     const int64_t stride = (pl.n_tiles - 1) / ((int64_t)tiles * lists);   // never reaches the (padded) last tile
-    if (per_list >= 16 * tiles && stride >= 2) {
+    // (the sample costs tiles / per_list of a scan: <= 1/32; the tighter the starting threshold, the fewer keys pass)
+    if ((per_list >= 32 * tiles || tiles == 8) && per_list >= 128 && stride >= 2) {
       const double x = (double)k * 256.0 * tiles / (double)((pl.n_tiles - 1) * SL_N);
       double term = exp(-x), cdf = 0.0;                      // P(Poisson(x) >= j) = 1 - sum_{i<j} e^-x x^i / i!
       for (int j = 1; j <= SL_J; ++j) {
