@@ -126,8 +126,14 @@ class MomentRetriever:
             n_text = 1 + 3 + 1 + 2 * self.seq_len + 1
         else:
             n_text = 1 + self.seq_len + 2
-        # query pack + threshold init + score (filter) + finish (refine)
-        self.launches_per_step = n_text + 4 + (1 if self.world > 1 else 0)
+        if self.engine == "sel" and self.world > 1:
+            # query pack + threshold init + sample pass + filter (first slice) + bound get / put + filter (rest) + refine + merge
+            n_k4 = 9
+        elif self.engine == "sel":
+            n_k4 = 5          # query pack + threshold init + sample pass + filter + refine
+        else:
+            n_k4 = 4 + (1 if self.world > 1 else 0)   # query pack + threshold init + score + finish (+ merge)
+        self.launches_per_step = n_text + n_k4
 
     def score_only(self, n_queries):
         """K4 alone (query pack excluded) on the query embeddings left in ``q_emb`` by the previous
