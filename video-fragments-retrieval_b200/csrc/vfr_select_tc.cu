@@ -87,6 +87,7 @@ struct SlParams {
   unsigned* tau_cert;        // [Qpad] CERTIFIED part of it: k-th smallest d2~ of keys really seen (or a bound put from outside)
   int tile_stride;           // bank tile of scan position i = i * tile_stride (1; the sample pass strides over the bank)
   int cap_trig;              // list length that triggers the FIRST compaction of a list (<= SL_CAP_HI)
+  int cap_step;              // later ones: this many keys above what the previous compaction kept
   int sample_j;              // sample pass: the starting threshold is the sample_j-th smallest sampled minimum
   float* tau_part;           // [Qpad][n_parts] ceil(k / n_parts)-th smallest d2~ of each list (inf until compacted)
   int tile_lo;               // first bank tile of this launch (the scan may be split into several launches)
@@ -552,8 +553,8 @@ struct SlCfg {
 struct SlRow {
   unsigned long long* list;
   int cnt;
-  float tau_own;     // k-th smallest d2~ of this list (inf until it has been compacted once)
-  float tau_use;     // min(tau_own, the query's shared tau): what the filter currently uses
+  int trig;          // list length that triggers the next compaction of this list
+  float tau_use;     // min(k-th smallest d2~ of this list at its last compaction, the query's shared tau): what the filter uses
   float thr;         // the same in the accumulator domain, band included
   float nq, inv_scale, scale, band2;   // the query's qmeta
   int64_t q;
@@ -835,7 +836,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const float4 qm = __ldg(p.qmeta + st.q);
       st.nq = qm.x; st.scale = qm.y; st.inv_scale = qm.z; st.band2 = qm.w;
     }
-    st.tau_own = CUDART_INF_F;
+    st.trig = p.cap_trig;
     st.tau_use = valid ? CUDART_INF_F : -1.f;
     st.thr = valid ? CUDART_INF_F : -CUDART_INF_F;
 
@@ -882,16 +883,17 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         d[0] = te0; d[1] = te1; d[2] = te2; d[3] = clock64();
       }
 
-      // a list is compacted when it is full - and once EARLY (cap_trig keys): a list that starts from the sampled
-      // threshold would otherwise keep that loose threshold (and its hit rate) until it has filled up, if ever
-      const bool need = st.cnt > ((st.tau_own < CUDART_INF_F) ? SL_CAP_HI : p.cap_trig);
+      // A list is compacted long before it is full: every compaction refreshes the list's threshold (the k-th
+      // smallest key seen so far), and a stale threshold costs hits - each one lengthens the hold of the TMEM
+      // buffer by ~450 cycles, a compaction ~10 k cycles.  The first one comes after cap_trig keys (the sampled
+      // starting threshold is loose), the following ones every cap_step keys above what the last one kept.
+      const bool need = st.cnt > st.trig;
       if (__any_sync(0xffffffffu, need)) {
         const long long tc0 = p.dbg ? clock64() : 0;
         const int n_need = p.dbg ? __popc(__ballot_sync(0xffffffffu, need)) : 0;
-        const float before = st.tau_own;
         // (copies: taking the address of a member would push the whole per-thread state into local memory)
         int cnt = st.cnt;
-        float tau_own = st.tau_own;
+        float tau_own = CUDART_INF_F;
         float tau_part = CUDART_INF_F;
         const int k_part = (p.k + p.n_parts - 1) / p.n_parts;
         sl_compact(st.list, cnt, tau_own, tau_part, st.tau_use, st.band2, p.k, k_part, need, lane, p.dbg);
@@ -903,10 +905,10 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           sl_compact(st.list, cnt, tau_own, dummy, st.tau_use, 0.f, p.k, p.k, over, lane);
           if (over) cnt = min(cnt, SL_CAP_HI);
         }
+        if (need) st.trig = min(SL_CAP_HI, cnt + p.cap_step);
         st.cnt = cnt;
-        st.tau_own = tau_own;
-        if (st.tau_own < before) {
-          float best = st.tau_own;
+        if (tau_own < CUDART_INF_F) {
+          float best = tau_own;
           if (p.n_parts > 1 && tau_part < CUDART_INF_F) {
             // publish this list's share and bound the query's k-th smallest by the largest share of all its lists
             volatile float* tp = p.tau_part + st.q * p.n_parts;
@@ -932,16 +934,14 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     // a list that ends with more than k keys still tightens the query's threshold for stage 2
     if (__any_sync(0xffffffffu, st.cnt > p.k)) {
-      const float before = st.tau_own;
       int cnt = st.cnt;
-      float tau_own = st.tau_own;
+      float tau_own = CUDART_INF_F;
       float dummy = CUDART_INF_F;
       sl_compact(st.list, cnt, tau_own, dummy, st.tau_use, st.band2, p.k, p.k, cnt > p.k, lane);
       st.cnt = cnt;
-      st.tau_own = tau_own;
-      if (st.tau_own < before) {
-        tau_publish(p.tau_g + st.q, st.tau_own);
-        tau_publish(p.tau_cert + st.q, st.tau_own);
+      if (tau_own < CUDART_INF_F) {
+        tau_publish(p.tau_g + st.q, tau_own);
+        tau_publish(p.tau_cert + st.q, tau_own);
       }
     }
     p.cand_cnt[st.q * p.n_parts + part] = st.cnt;
@@ -1439,8 +1439,10 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
   p.tau_cert = p.tau_g + qpad;
   p.tau_part = reinterpret_cast<float*>(p.tau_cert + qpad);
   p.tile_stride = 1;
-  p.cap_trig = std::min(SL_CAP_HI, std::max(64, 6 * k));
+  p.cap_trig = std::min(SL_CAP_HI, std::max(64, 2 * k));
+  p.cap_step = std::min(SL_CAP_HI, std::max(32, k));
   { const char* e = getenv("VFR_SEL_TRIG"); if (e) p.cap_trig = std::min(SL_CAP_HI, std::max(k + 1, atoi(e))); }
+  { const char* e = getenv("VFR_SEL_STEP"); if (e) p.cap_step = std::min(SL_CAP_HI, std::max(1, atoi(e))); }
   return VFR_OK;
 }
 
