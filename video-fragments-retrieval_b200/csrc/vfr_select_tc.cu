@@ -572,16 +572,33 @@ __device__ __forceinline__ void sl_append(SlRow& st, float x, int64_t clip, cons
 // LOP3, four independent chains); the usual case is ONE passing column, whose value is the minimum the hot path
 // already holds, so no dynamic register indexing is needed.  Several passing columns (start of the scan) go
 // through a local-memory copy.
-__device__ __forceinline__ void sl_cold(const float (&v)[64], float m, int coff, SlRow& st, const SlParams& p) {
-  unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+__device__ __forceinline__ void sl_cold(const float (&v)[64], float ma, float mb, float m, int coff, SlRow& st,
+                                        const SlParams& p) {
+  // (the mask of a 32-column half is only built if that half's minimum passes: the mask is most of a pass, and a
+  // pass is paid for with the hold time of the TMEM buffer)
+  unsigned lo = 0u, hi = 0u;
+  if (ma <= st.thr) {
+    unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    m0 |= (v[j] <= st.thr) ? (1u << j) : 0u;
-    m1 |= (v[16 + j] <= st.thr) ? (1u << (16 + j)) : 0u;
-    m2 |= (v[32 + j] <= st.thr) ? (1u << j) : 0u;
-    m3 |= (v[48 + j] <= st.thr) ? (1u << (16 + j)) : 0u;
+    for (int j = 0; j < 8; ++j) {
+      m0 |= (v[j] <= st.thr) ? (1u << j) : 0u;
+      m1 |= (v[8 + j] <= st.thr) ? (1u << (8 + j)) : 0u;
+      m2 |= (v[16 + j] <= st.thr) ? (1u << (16 + j)) : 0u;
+      m3 |= (v[24 + j] <= st.thr) ? (1u << (24 + j)) : 0u;
+    }
+    lo = (m0 | m1) | (m2 | m3);
   }
-  unsigned lo = m0 | m1, hi = m2 | m3;
+  if (mb <= st.thr) {
+    unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      m0 |= (v[32 + j] <= st.thr) ? (1u << j) : 0u;
+      m1 |= (v[40 + j] <= st.thr) ? (1u << (8 + j)) : 0u;
+      m2 |= (v[48 + j] <= st.thr) ? (1u << (16 + j)) : 0u;
+      m3 |= (v[56 + j] <= st.thr) ? (1u << (24 + j)) : 0u;
+    }
+    hi = (m0 | m1) | (m2 | m3);
+  }
   const int64_t c0 = st.clip0 + coff;
   if (__popc(lo) + __popc(hi) == 1) {
     const int idx = lo ? (__ffs(lo) - 1) : (31 + __ffs(hi));
@@ -612,8 +629,10 @@ __device__ __forceinline__ void sl_process(const float (&v)[64], int coff, SlRow
     const float b = fmin3(v[8 * i + 3], v[8 * i + 4], v[8 * i + 5]);
     g[i] = fmin3(a, b, fminf(v[8 * i + 6], v[8 * i + 7]));
   }
-  const float m = fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), fminf(g[6], g[7]));
-  if (m <= st.thr) sl_cold(v, m, coff, st, p);
+  const float ma = fmin3(g[0], g[1], fminf(g[2], g[3]));
+  const float mb = fmin3(g[4], g[5], fminf(g[6], g[7]));
+  const float m = fminf(ma, mb);
+  if (m <= st.thr) sl_cold(v, ma, mb, m, coff, st, p);
 }
 
 // Sample pass (MODE 1): the SL_J smallest 64-column minima of the row, kept sorted in registers
