@@ -888,13 +888,14 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       sl_ld32(lane_addr + 192, vb, 0);
       sl_ld32(lane_addr + 224, vb, 32);
-      sl_process(va, 128, st, p);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      // the whole accumulator has been read: hand the TMEM buffer back to the MMA warp
+      // the whole accumulator has been read: hand the TMEM buffer back to the MMA warp BEFORE the last two
+      // 64-column groups (both in registers) are looked at - their hits then cost no hold time
       sl_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[set]);
       const long long te2 = p.dbg ? clock64() : 0;
+      sl_process(va, 128, st, p);
       sl_process(vb, 192, st, p);
       const int visit0 = (n_my_tiles - t_first + t_step - 1) / t_step - 128;
       if (p.dbg && blockIdx.x == 0 && visit >= visit0 && lane == 0) {
