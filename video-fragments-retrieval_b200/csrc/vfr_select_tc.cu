@@ -903,10 +903,10 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         d[0] = te0; d[1] = te1; d[2] = te2; d[3] = clock64();
       }
 
-      // A list is compacted long before it is full: every compaction refreshes the list's threshold (the k-th
-      // smallest key seen so far), and a stale threshold costs hits - each one lengthens the hold of the TMEM
-      // buffer by ~450 cycles, a compaction ~10 k cycles.  The first one comes after cap_trig keys (the sampled
-      // starting threshold is loose), the following ones every cap_step keys above what the last one kept.
+      // Every compaction refreshes the list's threshold (the k-th smallest key seen so far); a stale threshold costs
+      // hits - each one in the first two 64-column groups lengthens the hold of the TMEM buffer by ~450 cycles - a
+      // compaction ~10 k cycles.  The first one comes after cap_trig keys (the sampled starting threshold is loose),
+      // the following ones cap_step keys above what the last one kept (default: when the list is full).
       const bool need = st.cnt > st.trig;
       if (__any_sync(0xffffffffu, need)) {
         const long long tc0 = p.dbg ? clock64() : 0;
@@ -1459,8 +1459,11 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
   p.tau_cert = p.tau_g + qpad;
   p.tau_part = reinterpret_cast<float*>(p.tau_cert + qpad);
   p.tile_stride = 1;
-  p.cap_trig = std::min(SL_CAP_HI, std::max(64, 2 * k));
-  p.cap_step = std::min(SL_CAP_HI, std::max(32, k));
+  // measured (37 888 queries, k = 100; whole 6 M-clip bank / one of 8 shards): first compaction after 3k keys, later
+  // ones only when the list is full: 52.3 / 9.9 ms; every k keys: 52.0 / 12.1 ms - a compaction stalls the CTA's
+  // pipeline for ~10 k cycles whatever the bank size, and a shard's scan is short
+  p.cap_trig = std::min(SL_CAP_HI, std::max(64, 3 * k));
+  p.cap_step = SL_CAP_HI;
   { const char* e = getenv("VFR_SEL_TRIG"); if (e) p.cap_trig = std::min(SL_CAP_HI, std::max(k + 1, atoi(e))); }
   { const char* e = getenv("VFR_SEL_STEP"); if (e) p.cap_step = std::min(SL_CAP_HI, std::max(1, atoi(e))); }
   return VFR_OK;
