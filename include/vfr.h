@@ -161,6 +161,22 @@ const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries);
  * shard: from k keys really seen, never from the sampled threshold; +inf until a list has been compacted) ->
  * all-reduce(min) over the shards -> vfr_sel_bound_put -> vfr_sel_filter over the remaining tiles with
  * resume = 1 -> vfr_sel_refine.  vfr_sel_topk == filter(all tiles) + refine. */
+/* A tighter protocol for large sharded banks (what vfr_b200.retrieval uses when every shard is big enough to sample):
+ * the shards pool their SAMPLES instead of their bounds.  vfr_sel_sample starts fresh lists and writes, per query and
+ * candidate list (vfr_sel_sample_lists of them), the 32 smallest sampled 64-clip minima as upper bounds of exact squared
+ * distances, ascending (+inf padded); *n_sampled = clips sampled per query (0: shard too small, use the protocol above).
+ * All-gather the 32 smallest per shard, take T[q] = the j-th smallest of the union with
+ * j = vfr_sel_sample_rank(k, total sampled, total clips) (0: no rank <= 32 is safe), vfr_sel_bound_put(T), vfr_sel_filter
+ * over ALL tiles with resume = 1, then CHECK the guess: vfr_sel_count_under(T) counts the shard's clips that are certainly
+ * within T; where the all-reduced (sum) count is < k the query must be treated as flagged (the sample promised k clips the
+ * bank does not have).  Then vfr_sel_refine.  Every shard then keeps ~k/P candidates instead of ~k. */
+int vfr_sel_sample_rank(int k, int64_t n_sampled, int64_t n_total);
+int vfr_sel_sample_lists(int64_t n_queries, int64_t n_clips, int n_split);
+int64_t vfr_sel_sample_clips(int64_t n_queries, int64_t n_clips, int k, int n_split);   /* what vfr_sel_sample will report */
+int vfr_sel_sample(const void* bank_packed, int64_t n_clips, int dim, void* query_packed, int64_t n_queries, int k,
+                   void* workspace, int n_split, float* out, int64_t* n_sampled, vfr_stream_t stream);
+int vfr_sel_count_under(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
+                        int n_split, const float* bound, int32_t* count, vfr_stream_t stream);
 int64_t vfr_sel_tiles(int64_t n_clips);
 int vfr_sel_filter(const void* bank_packed, int64_t n_clips, int dim, void* query_packed, int64_t n_queries, int k,
                    void* workspace, int n_split, int64_t tile_lo, int64_t tile_hi, int resume, vfr_stream_t stream);

@@ -148,13 +148,50 @@ def test_sharded_rank_of_first_positive_equals_single_bank(golden):
         assert np.array_equal(npos.cpu().numpy(), want["npos"])
 
 
-@pytest.mark.parametrize("first_tiles,k", [(None, 100), (3, 100), (1, 1), (5, 37)])
-def test_sel_sharded_bound_exchange_equals_single_bank(first_tiles, k):
-    """N-GPU K4 with the mid-scan bound exchange (every shard filters the rest of its bank with the minimum of all
-    shards' k-th-distance bounds): four emulated shards on one GPU, the all-reduce(min) replaced by a lockstep
-    reducer; the merged lists are bit-identical to the exact engine over the whole bank."""
+class _LockstepComm:
+    """The collectives of P emulated ranks (threads on one GPU): every call combines what the P ranks pass at the same
+    call site."""
+
+    def __init__(self, n_ranks):
+        import threading
+        self.n, self.barrier, self.lock, self.slots, self.log = n_ranks, threading.Barrier(n_ranks), threading.Lock(), {}, []
+
+    def rank_view(self, rank):
+        comm, calls = self, [0]
+
+        class View:
+            def _exchange(self, t, kind):
+                key = calls[0]
+                calls[0] += 1
+                with comm.lock:
+                    comm.slots.setdefault(key, {})[rank] = t.clone()
+                comm.barrier.wait()
+                parts = torch.stack([comm.slots[key][r] for r in range(comm.n)])
+                comm.barrier.wait()
+                if rank == 0:
+                    comm.log.append(kind)
+                return parts
+
+            def all_gather(self, t):
+                return self._exchange(t, "all_gather")
+
+            def all_reduce_sum(self, t):
+                return self._exchange(t, "sum").sum(dim=0).to(t.dtype)
+
+            def all_reduce_min(self, t):
+                return self._exchange(t, "min").min(dim=0).values
+        return View()
+
+
+@pytest.mark.parametrize("pool,first_tiles,k,n_videos", [(False, None, 100, 9000), (False, 3, 100, 9000), (False, 1, 1, 9000),
+                                                           (False, 5, 37, 9000), (True, None, 100, 120000),
+                                                           (True, None, 1, 120000), (True, None, 37, 120000)])
+def test_sel_sharded_protocols_equal_single_bank(pool, first_tiles, k, n_videos):
+    """N-GPU K4: the shards agree on a threshold - by pooling their samples (large shards: every shard then keeps ~k/P
+    candidates) or by exchanging a certified bound mid-scan.  Four emulated shards on one GPU, the collectives replaced
+    by a lockstep exchange; the merged lists are bit-identical to the exact engine over the whole bank."""
     import threading
-    sd, model, clips, tokens = _setup(seed=31, V=9000, Q=150)
+    sd, model, clips, tokens = _setup(seed=31, V=n_videos, Q=150)
     V, P = clips.shape[0] // 6, 4
     tok = torch.from_numpy(tokens).to(DEV)
     Q = tok.shape[0]
@@ -166,38 +203,35 @@ def test_sel_sharded_bound_exchange_equals_single_bank(first_tiles, k):
     for r in range(P):
         v0, v1 = shard_range(V, r, P)
         sh = MomentRetriever(model, torch.from_numpy(clips[v0 * 6:v1 * 6]).to(DEV), np.arange(v1 - v0 + 1) * 6,
-                             id_base=v0 * 21, max_queries=256, k=k, engine="sel", text_engine="tc")
+                             id_base=v0 * 21, max_queries=256, k=k, engine="sel", text_engine="tc", n_split=1 if pool else 0)
         sh.sel_first_tiles = first_tiles
+        sh.sel_pool_samples = pool
         sh.q_emb[:Q].copy_(q_emb)
         shards.append(sh)
-    barrier, slots, lock = threading.Barrier(P), [], threading.Lock()
+    comm = _LockstepComm(P)
     errors = []
-
-    def reduce_min(t):
-        with lock:
-            slots.append(t.clone())
-        barrier.wait()
-        out = torch.stack(slots[:P]).min(dim=0).values
-        barrier.wait()
-        return out
 
     def work(r):
         try:
             torch.cuda.set_device(0)
             stream = torch.cuda.current_stream().cuda_stream
-            shards[r]._sel_score_sharded(Q, stream, reduce_min=reduce_min)
+            shards[r]._sel_score_sharded(Q, stream, comm=comm.rank_view(r))
             shards[r]._sel_fixup(Q)
         except Exception as e:  # noqa: BLE001
             errors.append(e)
-            barrier.abort()
+            comm.barrier.abort()
     threads = [threading.Thread(target=work, args=(r,)) for r in range(P)]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
     assert not errors, errors
-    assert len(slots) == P                      # the exchange ran (first slice < whole shard)
+    # the protocol that was meant to run did run
+    assert comm.log == (["sum", "all_gather", "sum"] if pool else ["sum", "min"]), comm.log
     ms, mi = ops.topk_merge(torch.stack([sh.out_s[:Q] for sh in shards]), torch.stack([sh.out_i[:Q] for sh in shards]))
     assert torch.equal(mi, ei) and torch.equal(ms.view(torch.int32), es.view(torch.int32))
-    # the exchanged bound prunes: the shards together hold fewer candidate keys than four independent searches
     assert all(int((sh._sel_flags(Q) != 0).sum().item()) == 0 for sh in shards)
+    if pool:
+        # every shard kept only what can reach the global top-k: together about k candidates (plus the error band), not P k
+        kept = sum(int((sh.out_i[:Q] >= 0).sum().item()) for sh in shards)
+        assert kept >= Q * k

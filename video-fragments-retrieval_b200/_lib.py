@@ -70,6 +70,11 @@ PROTOTYPES = {
     "vfr_sel_topk": (_i, [_p, _p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
     "vfr_sel_flags": (_p, [_p, _l]),
     "vfr_sel_tiles": (_l, [_l]),
+    "vfr_sel_sample_rank": (_i, [_i, _l, _l]),
+    "vfr_sel_sample_lists": (_i, [_l, _l, _i]),
+    "vfr_sel_sample_clips": (_l, [_l, _l, _i, _i]),
+    "vfr_sel_sample": (_i, [_p, _l, _i, _p, _l, _i, _p, _i, _p, _p, _p]),
+    "vfr_sel_count_under": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p, _p]),
     "vfr_sel_filter": (_i, [_p, _l, _i, _p, _l, _i, _p, _i, _l, _l, _i, _p]),
     "vfr_sel_bound_get": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p]),
     "vfr_sel_bound_put": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p]),

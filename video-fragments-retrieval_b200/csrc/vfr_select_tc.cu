@@ -88,6 +88,7 @@ struct SlParams {
   int tile_stride;           // bank tile of scan position i = i * tile_stride (1; the sample pass strides over the bank)
   int cap_trig;              // list length that triggers the FIRST compaction of a list (<= SL_CAP_HI)
   int cap_step;              // later ones: this many keys above what the previous compaction kept
+  float* samp;               // sample pass, optional export: [Qpad][n_parts][SL_J] ascending upper bounds of EXACT d^2
   int sample_j;              // sample pass: the starting threshold is the sample_j-th smallest sampled minimum
   float* tau_part;           // [Qpad][n_parts] ceil(k / n_parts)-th smallest d2~ of each list (inf until compacted)
   int tile_lo;               // first bank tile of this launch (the scan may be split into several launches)
@@ -841,9 +842,17 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
       for (int i = 0; i < SL_J; ++i)
         if (i == p.sample_j - 1) x = a[i];
-      if (q < p.n_queries && x < CUDART_INF_F) {
+      if (q < p.n_queries) {
         const float4 qm = __ldg(p.qmeta + q);
-        tau_publish(p.tau_g + q, fmaxf(__fmaf_ru(x, qm.z, qm.x), 0.f));
+        if (x < CUDART_INF_F) tau_publish(p.tau_g + q, fmaxf(__fmaf_ru(x, qm.z, qm.x), 0.f));
+        if (p.samp) {
+          // for a bank sharded over several GPUs: the sampled minima as upper bounds of exact squared distances
+          // (d2~ + E), so that values of shards with different operand scales compare
+          float* out = p.samp + ((int64_t)q * p.n_parts + part) * SL_J;
+#pragma unroll
+          for (int i = 0; i < SL_J; ++i)
+            out[i] = (a[i] < CUDART_INF_F) ? __fadd_ru(fmaxf(__fmaf_ru(a[i], qm.z, qm.x), 0.f), 0.5f * qm.w) : CUDART_INF_F;
+        }
       }
     } else {
     SlRow st;
@@ -1422,7 +1431,7 @@ extern "C" size_t vfr_sel_topk_bytes(int64_t n_queries, int64_t n_clips, int n_s
     const SlPlan pl = sl_plan(qt == qtiles ? n_queries : qt * SL_M, n_clips, n_split);
     const size_t qpad = (size_t)pl.qrows;
     const size_t need = qpad * pl.n_parts * SL_CAP * sizeof(unsigned long long) + qpad * pl.n_parts * sizeof(int32_t) +
-                        2 * qpad * sizeof(unsigned) + qpad * pl.n_parts * sizeof(float);
+                        2 * qpad * sizeof(unsigned) + qpad * pl.n_parts * sizeof(float) + qpad * pl.n_parts * SL_J * sizeof(float);
     if (need > worst) worst = need;
   }
   return worst;
@@ -1458,6 +1467,7 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
   p.tau_g = reinterpret_cast<unsigned*>(p.cand_cnt + qpad * (size_t)pl.n_parts);
   p.tau_cert = p.tau_g + qpad;
   p.tau_part = reinterpret_cast<float*>(p.tau_cert + qpad);
+  p.samp = nullptr;   // (the export buffer lives behind tau_part: sl_samp_buffer)
   p.tile_stride = 1;
   // measured (37 888 queries, k = 100; whole 6 M-clip bank / one of 8 shards): first compaction after 3k keys, later
   // ones only when the list is full: 52.3 / 9.9 ms; every k keys: 52.0 / 12.1 ms - a compaction stalls the CTA's
@@ -1476,7 +1486,7 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
 // that makes this < 1e-10 per list; a wrong threshold is detected by stage 2 (flag 4) and costs a rerun, never a
 // wrong result.  tiles = 0: no sample (bank too small to gain from it).
 struct SlSample { int tiles, stride, j; };
-static SlSample sl_sample_plan(const SlPlan& pl, int64_t n_clips, int k) {
+static SlSample sl_sample_plan(const SlPlan& pl, int64_t n_clips, int k, bool need_rank = true) {
   SlSample sp{0, 1, 0};
   { const char* e = getenv("VFR_SEL_SAMPLE"); if (e && e[0] == '0') return sp; }
   const int lists = pl.ns * (pl.R == 2 ? 1 : 2);              // lists per query, each samples on its own
@@ -1488,6 +1498,7 @@ static SlSample sl_sample_plan(const SlPlan& pl, int64_t n_clips, int k) {
     const int64_t stride = (pl.n_tiles - 1) / ((int64_t)tiles * lists);   // never reaches the (padded) last tile
     // (the sample costs tiles / per_list of a scan: <= 1/32; the tighter the starting threshold, the fewer keys pass)
     if ((per_list >= 32 * tiles || tiles == 8) && per_list >= 128 && stride >= 2) {
+      if (!need_rank) { sp.tiles = tiles; sp.stride = (int)stride; sp.j = 0; return sp; }
       const double x = (double)k * 256.0 * tiles / (double)((pl.n_tiles - 1) * SL_N);
       double term = exp(-x), cdf = 0.0;                      // P(Poisson(x) >= j) = 1 - sum_{i<j} e^-x x^i / i!
       for (int j = 1; j <= SL_J; ++j) {
@@ -1528,6 +1539,20 @@ static int sl_launch_filter(const SlPlan& pl, const SlParams& p, const CUtensorM
   return check_launch(MODE == 1 ? "sl_filter_kernel (sample pass)" : "sl_filter_kernel");
 }
 
+static float* sl_samp_buffer(const SlPlan& pl, const SlParams& p) { return p.tau_part + (size_t)pl.qrows * pl.n_parts; }
+
+static int sl_launch_sample(const SlPlan& pl, const SlParams& p, const SlSample& sp, float* samp, const CUtensorMap& ma,
+                            const CUtensorMap& mb, cudaStream_t st) {
+  SlParams ps = p;
+  ps.tile_lo = 0;
+  ps.tiles_per_split = sp.tiles * (pl.R == 2 ? 1 : 2);    // R = 1: the two sets of a CTA take alternate sample tiles
+  ps.n_tiles = ps.tiles_per_split * pl.ns;
+  ps.tile_stride = sp.stride;
+  ps.sample_j = sp.j;
+  ps.samp = samp;
+  return sl_launch_filter<1>(pl, ps, ma, mb, st);
+}
+
 // stage 1 over the bank tiles [tile_lo, tile_hi)
 static int sl_run_filter(const SlPlan& pl, SlParams p, const void* bank_packed, void* query_packed, int64_t tile_lo,
                          int64_t tile_hi, int resume, cudaStream_t st) {
@@ -1546,13 +1571,7 @@ static int sl_run_filter(const SlPlan& pl, SlParams p, const void* bank_packed, 
     // starting thresholds from a strided sample of the WHOLE bank (whatever slice this call scans)
     const SlSample sp = sl_sample_plan(pl, p.n_clips, p.k);
     if (sp.tiles > 0) {
-      SlParams ps = p;
-      ps.tile_lo = 0;
-      ps.tiles_per_split = sp.tiles * (pl.R == 2 ? 1 : 2);    // R = 1: the two sets of a CTA take alternate sample tiles
-      ps.n_tiles = ps.tiles_per_split * pl.ns;
-      ps.tile_stride = sp.stride;
-      ps.sample_j = sp.j;
-      rc = sl_launch_filter<1>(pl, ps, ma, mb, st);
+      rc = sl_launch_sample(pl, p, sp, nullptr, ma, mb, st);
       if (rc) return rc;
     }
   }
@@ -1611,9 +1630,93 @@ __global__ void sl_bound_put_kernel(unsigned* __restrict__ tau_g, unsigned* __re
   }
 }
 
+// count[q] = number of retained keys with d2~ <= bound[q] - E_q, i.e. of clips whose EXACT squared distance is
+// certainly <= bound[q].  One warp per query.
+__global__ void sl_count_under_kernel(const unsigned long long* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+                                      int n_parts, const float4* __restrict__ qmeta, int64_t n,
+                                      const float* __restrict__ bound, int32_t* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n) return;
+  const float t = __fsub_rd(bound[q], 0.5f * qmeta[q].w);
+  int c = 0;
+  if (t >= 0.f) {
+    const unsigned tb = __float_as_uint(t);
+    for (int part = 0; part < n_parts; ++part) {
+      const int64_t li = q * n_parts + part;
+      const int m = min(cand_cnt[li], SL_CAP);
+      for (int i = lane; i < m; i += 32) c += ((unsigned)(cand[li * SL_CAP + i] >> 32) <= tb) ? 1 : 0;
+    }
+  }
+  c = warp_sum_int(c);
+  if (lane == 0) count[q] = c;
+}
+
 }  // namespace vfr
 
 extern "C" int64_t vfr_sel_tiles(int64_t n_clips) { return n_clips > 0 ? sl_tiles(n_clips) : 0; }
+
+extern "C" int vfr_sel_sample_rank(int k, int64_t n_sampled, int64_t n_total) {
+  if (k < 1 || n_sampled <= 0 || n_total <= 0) return 0;
+  const double x = (double)k * (double)n_sampled / (double)n_total;
+  double term = exp(-x), cdf = 0.0;
+  for (int j = 1; j <= SL_J; ++j) {
+    cdf += term;
+    term *= x / j;
+    if (1.0 - cdf < 1e-10) return j;
+  }
+  return 0;
+}
+
+extern "C" int vfr_sel_sample_lists(int64_t n_queries, int64_t n_clips, int n_split) {
+  if (n_queries <= 0 || n_clips <= 0) return 0;
+  return sl_plan(n_queries, n_clips, n_split).n_parts;
+}
+
+extern "C" int64_t vfr_sel_sample_clips(int64_t n_queries, int64_t n_clips, int k, int n_split) {
+  if (n_queries <= 0 || n_clips <= 0 || k < 1) return 0;
+  const SlPlan pl = sl_plan(n_queries, n_clips, n_split);
+  return (int64_t)sl_sample_plan(pl, n_clips, k, /*need_rank=*/false).tiles * pl.n_parts * SL_N;
+}
+
+extern "C" int vfr_sel_sample(const void* bank_packed, int64_t n_clips, int dim, void* query_packed, int64_t n_queries,
+                              int k, void* workspace, int n_split, float* out, int64_t* n_sampled, vfr_stream_t stream) {
+  VFR_REQUIRE(bank_packed && query_packed && workspace && out && n_sampled, VFR_ERR_INVALID, "vfr_sel_sample: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t qpad = (size_t)pl.qrows;
+  rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad * (2 + (size_t)pl.n_parts), st);   // fresh thresholds and lists
+  if (rc) return rc;
+  VFR_CUDA(cudaMemsetAsync(p.cand_cnt, 0, qpad * (size_t)pl.n_parts * sizeof(int32_t), st));
+  const SlSample sp = sl_sample_plan(pl, n_clips, k, /*need_rank=*/false);
+  *n_sampled = (int64_t)sp.tiles * pl.n_parts * SL_N;
+  if (sp.tiles == 0) return VFR_OK;
+  CUtensorMap ma, mb;
+  rc = sl_make_map(&ma, query_packed, (uint64_t)pl.qrows, SL_M);
+  if (rc) return rc;
+  rc = sl_make_map(&mb, bank_packed, (uint64_t)(pl.n_tiles * SL_N), SL_N);
+  if (rc) return rc;
+  float* samp = sl_samp_buffer(pl, p);
+  rc = sl_launch_sample(pl, p, sp, samp, ma, mb, st);
+  if (rc) return rc;
+  VFR_CUDA(cudaMemcpyAsync(out, samp, (size_t)n_queries * pl.n_parts * SL_J * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return VFR_OK;
+}
+
+extern "C" int vfr_sel_count_under(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
+                                   int n_split, const float* bound, int32_t* count, vfr_stream_t stream) {
+  VFR_REQUIRE(query_packed && workspace && bound && count, VFR_ERR_INVALID, "vfr_sel_count_under: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  sl_count_under_kernel<<<(unsigned)((n_queries + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p.cand, p.cand_cnt, p.n_parts, p.qmeta,
+                                                                                        n_queries, bound, count);
+  return check_launch("sl_count_under_kernel");
+}
 
 extern "C" int vfr_sel_filter(const void* bank_packed, int64_t n_clips, int dim, void* query_packed, int64_t n_queries,
                               int k, void* workspace, int n_split, int64_t tile_lo, int64_t tile_hi, int resume,

@@ -26,6 +26,26 @@ def shard_range(n_videos, rank, world):
     return (n_videos * rank) // world, (n_videos * (rank + 1)) // world
 
 
+class _DistComm:
+    """The collectives of the sharded search over torch.distributed (NCCL)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def all_gather(self, t):
+        out = torch.empty((dist.get_world_size(self.group),) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def all_reduce_sum(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_min(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return t
+
+
 class MomentRetriever:
 
     ENGINES = {"exact": 0, "tc": 3, "tc_bf16": 1, "sel": 4}
@@ -110,6 +130,8 @@ class MomentRetriever:
         p.n_split, p.max_queries = int(n_split), mq
         self.plan = p
         self.sel_bound = torch.empty(mq, dtype=torch.float32, device=dev)
+        self.sel_samp = torch.empty(0, dtype=torch.float32, device=dev)       # grown on first use (sharded search)
+        self.sel_count = torch.empty(mq, dtype=torch.int32, device=dev)
         if self.world > 1:
             self.gather_s = torch.empty((self.world, mq, self.k), dtype=torch.float32, device=dev)
             self.gather_i = torch.empty((self.world, mq, self.k), dtype=torch.int64, device=dev)
@@ -152,31 +174,73 @@ class MomentRetriever:
             _lib.call("vfr_score_topk", p.bank_packed, p.vid_off, p.mom_off, b.n_videos, b.n_max, b.dim, p.q_packed,
                       n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev, p.topk_ws, p.n_split, lib_stream)
 
-    def _sel_score_sharded(self, Q, stream, reduce_min=None):
+    def _sel_score_sharded(self, Q, stream, comm=None):
         """K4 of one shard when the bank is spread over several ranks.  A shard's local top-k only has to hold what
-        can reach the GLOBAL top-k: after a first slice of its bank every shard knows an upper bound of its own k-th
-        smallest clip distance; the minimum over the shards (ONE small all-reduce) bounds the global one, and the rest
-        of the scan filters with it - the hit / list work per shard then shrinks with the number of shards instead of
-        staying that of a full top-k search.  Exactness is untouched: nothing that could enter the merged top-k is
-        dropped (include/vfr.h)."""
+        can reach the GLOBAL top-k, so the shards agree on a threshold before the scan (include/vfr.h):
+
+        * large shards pool their SAMPLES: every shard's 32 smallest sampled distances are all-gathered, the j-th
+          smallest of the union (j from the pooled sample size: the bank holds k clips under it except with
+          probability < 1e-10) becomes every shard's starting bound; after the scan ONE all-reduce(sum) of per-query
+          counts verifies the guess (queries that fail are flagged and re-run through the exact engine).  Every shard
+          then keeps ~k/P candidates instead of ~k: its hit / list / re-scoring work shrinks with the shard.
+        * otherwise the shards exchange a certified bound half way through the scan (one all-reduce(min)).
+
+        ``comm`` replaces the NCCL collectives (tests emulate the ranks on one GPU)."""
         p, b = self.plan, self.bank
+        lib = _lib.load()
+        comm = comm or _DistComm(self.group)
         n_clips = self.n_clips
         qt, ws = self.q_tc.data_ptr(), self.topk_ws.data_ptr()
         _lib.call("vfr_sel_query_pack", p.q_emb, Q, b.dim, p.bank_tc, n_clips, qt, stream)
-        tiles = _lib.load().vfr_sel_tiles(n_clips)
-        first = min(tiles, getattr(self, "sel_first_tiles", None) or max(32, tiles // 8))
-        _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, first, 0, stream)
-        if first < tiles:
-            bound = self.sel_bound[:Q]
-            _lib.call("vfr_sel_bound_get", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
-            if reduce_min is None:
-                dist.all_reduce(bound, op=dist.ReduceOp.MIN, group=self.group)
-            else:
-                bound = reduce_min(bound)
+        tiles = lib.vfr_sel_tiles(n_clips)
+        rank_j = self._sel_global_rank(Q, comm)
+        if rank_j > 0:
+            lists = lib.vfr_sel_sample_lists(Q, n_clips, p.n_split)
+            if self.sel_samp.numel() < Q * lists * 32:
+                self.sel_samp = torch.empty(Q * lists * 32, dtype=torch.float32, device=self.q_emb.device)
+            samp = self.sel_samp[:Q * lists * 32]
+            n_s = C.c_int64(0)
+            _lib.call("vfr_sel_sample", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, samp.data_ptr(),
+                      C.byref(n_s), stream)
+            mine = samp.view(Q, lists * 32)
+            if lists > 1:
+                mine = torch.topk(mine, 32, dim=1, largest=False, sorted=True).values
+            pooled = comm.all_gather(mine.contiguous())                                  # [P, Q, 32]
+            bound = torch.kthvalue(pooled.permute(1, 0, 2).reshape(Q, -1), rank_j, dim=1).values.contiguous()
             _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
-            _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, first, tiles, 1, stream)
+            _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, tiles, 1, stream)
+            count = self.sel_count[:Q]
+            _lib.call("vfr_sel_count_under", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(),
+                      count.data_ptr(), stream)
+            count = comm.all_reduce_sum(count)
+            flags = self._sel_flags(Q)
+            flags[(count < self.k) & (flags == 0)] = 4
+        else:
+            first = min(tiles, getattr(self, "sel_first_tiles", None) or max(32, tiles // 8))
+            _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, first, 0, stream)
+            if first < tiles:
+                bound = self.sel_bound[:Q]
+                _lib.call("vfr_sel_bound_get", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
+                bound = comm.all_reduce_min(bound)
+                _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
+                _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, first, tiles, 1,
+                          stream)
         _lib.call("vfr_sel_refine", p.bank_clips, p.vid_off, p.mom_off, b.n_videos, n_clips, b.n_max, b.dim, qt, p.q_emb, Q,
                   self.k, p.id_base, self.out_s.data_ptr(), self.out_i.data_ptr(), ws, p.n_split, stream)
+
+    def _sel_global_rank(self, Q, comm):
+        """The rank j of the pooled-sample protocol for batches of Q queries (0: not applicable - some shard is too
+        small to sample, or no rank <= 32 is safe).  Depends on the shard sizes only: one tiny all-reduce per distinct
+        batch size, cached."""
+        cache = self.__dict__.setdefault("_sel_rank_cache", {})
+        if Q not in cache:
+            lib = _lib.load()
+            n_s = 0 if getattr(self, "sel_pool_samples", True) is False else \
+                lib.vfr_sel_sample_clips(Q, self.n_clips, self.k, self.plan.n_split)
+            t = torch.tensor([n_s, self.n_clips, 1 if n_s > 0 else 0, 1], dtype=torch.int64, device=self.q_emb.device)
+            tot_s, tot_c, n_ok, n_ranks = comm.all_reduce_sum(t).tolist()
+            cache[Q] = lib.vfr_sel_sample_rank(self.k, tot_s, tot_c) if n_ok == n_ranks else 0
+        return cache[Q]
 
     def _sel_flags(self, Q):
         """int32 [Q] view of the per-query flags of the last filter + refine call (0 = guaranteed exact)."""
