@@ -65,3 +65,50 @@ pack(b0); filt(b0); refine(b0)
 print(f"  breakdown of the one-call path: query pack {timeit(lambda: pack(b0)):.2f} ms | filter {timeit(lambda: filt(b0)):.2f} ms | refine {timeit(lambda: refine(b0)):.2f} ms")
 os.environ["VFR_SEL_SAMPLE"] = "0"
 print(f"  without the sample pass: filter {timeit(lambda: filt(b0)):.2f} ms")
+
+# pooled-sample protocol: T from the samples of ALL shards
+os.environ.pop("VFR_SEL_SAMPLE", None)
+import ctypes as C
+lists = lib.vfr_sel_sample_lists(Q, nc, 0)
+samp = torch.empty(Q * lists * 32, dtype=torch.float32, device="cuda")
+count = torch.empty(Q, dtype=torch.int32, device="cuda")
+n_s = C.c_int64(0)
+def sample(b):
+    _lib.call("vfr_sel_query_pack", q.data_ptr(), Q, D, b.sel().data_ptr(), nc, qp.data_ptr(), stream)
+    _lib.call("vfr_sel_sample", b.sel().data_ptr(), nc, D, qp.data_ptr(), Q, k, ws.data_ptr(), 0, samp.data_ptr(), C.byref(n_s), stream)
+pool = []
+for b in banks:
+    sample(b)
+    m = samp.view(Q, lists * 32)
+    pool.append((torch.topk(m, 32, dim=1, largest=False).values if lists > 1 else m).clone())
+j = lib.vfr_sel_sample_rank(k, n_s.value * P, nc * P)
+T = torch.kthvalue(torch.stack(pool).permute(1, 0, 2).reshape(Q, -1), j, dim=1).values.contiguous()
+ranks = sorted({max(1, -(-j // d)) for d in (1, 2, 4, 8)}, reverse=True)
+levels = torch.sort(torch.stack(pool).permute(1, 0, 2).reshape(Q, -1), dim=1).values[:, [r - 1 for r in ranks]].t().contiguous()
+counts = torch.empty((len(ranks), Q), dtype=torch.int32, device="cuda")
+def scan(b):
+    sample(b)
+    _lib.call("vfr_sel_bound_put", qp.data_ptr(), Q, nc, D, k, ws.data_ptr(), 0, T.data_ptr(), stream)
+    _lib.call("vfr_sel_filter", b.sel().data_ptr(), nc, D, qp.data_ptr(), Q, k, ws.data_ptr(), 0, 0, tiles, 1, stream)
+    for i in range(len(ranks)):
+        _lib.call("vfr_sel_count_under", qp.data_ptr(), Q, nc, D, k, ws.data_ptr(), 0, levels[i].data_ptr(), counts[i].data_ptr(), stream)
+tot4 = torch.zeros((len(ranks), Q), dtype=torch.int64, device="cuda")
+for b in banks:
+    scan(b); tot4 += counts
+ok = tot4 >= k
+best = ok.to(torch.int32).sum(dim=0).clamp_(min=1) - 1
+T2 = levels.gather(0, best.view(1, Q).to(torch.int64)).view(Q).contiguous()
+print("  tightest certified level per query (0 = rank j ... 3 = rank j/8):", torch.bincount(best, minlength=len(ranks)).tolist())
+def pooled(b):
+    scan(b)
+    _lib.call("vfr_sel_bound_put", qp.data_ptr(), Q, nc, D, k, ws.data_ptr(), 0, T2.data_ptr(), stream)
+    _lib.call("vfr_sel_count_under", qp.data_ptr(), Q, nc, D, k, ws.data_ptr(), 0, T2.data_ptr(), count.data_ptr(), stream)
+    refine(b)
+t_scan = timeit(lambda: scan(b0))
+t_pool = timeit(lambda: pooled(b0))
+print(f"  scan part {t_scan:.2f} ms")
+tot = torch.zeros(Q, dtype=torch.int64, device="cuda")
+for b in banks:
+    pooled(b); tot += count
+print(f"  pooled-sample protocol (j = {j}, {n_s.value} sampled clips per shard): {t_pool:.2f} ms per shard; "
+      f"queries whose global count check fails: {int((tot < k).sum())}; candidates kept by shard 0: {float(count.float().mean()):.1f} per query")

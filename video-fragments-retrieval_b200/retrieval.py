@@ -131,7 +131,7 @@ class MomentRetriever:
         self.plan = p
         self.sel_bound = torch.empty(mq, dtype=torch.float32, device=dev)
         self.sel_samp = torch.empty(0, dtype=torch.float32, device=dev)       # grown on first use (sharded search)
-        self.sel_count = torch.empty(mq, dtype=torch.int32, device=dev)
+        self.sel_count = torch.empty(4 * mq, dtype=torch.int32, device=dev)
         if self.world > 1:
             self.gather_s = torch.empty((self.world, mq, self.k), dtype=torch.float32, device=dev)
             self.gather_i = torch.empty((self.world, mq, self.k), dtype=torch.int64, device=dev)
@@ -206,15 +206,25 @@ class MomentRetriever:
             if lists > 1:
                 mine = torch.topk(mine, 32, dim=1, largest=False, sorted=True).values
             pooled = comm.all_gather(mine.contiguous())                                  # [P, Q, 32]
-            bound = torch.kthvalue(pooled.permute(1, 0, 2).reshape(Q, -1), rank_j, dim=1).values.contiguous()
-            _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
+            # candidate bounds: the pooled sample values of rank j (safe a priori), j/2, j/4, j/8 (tighter guesses)
+            ranks = sorted({max(1, -(-rank_j // d)) for d in (1, 2, 4, 8)}, reverse=True)
+            levels = torch.sort(pooled.permute(1, 0, 2).reshape(Q, -1), dim=1).values[:, [r - 1 for r in ranks]]
+            levels = levels.t().contiguous()                                              # [L, Q], loosest first
+            _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels[0].data_ptr(), stream)
             _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, tiles, 1, stream)
-            count = self.sel_count[:Q]
-            _lib.call("vfr_sel_count_under", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(),
-                      count.data_ptr(), stream)
-            count = comm.all_reduce_sum(count)
+            # how many clips are CERTAINLY within each bound, over all shards: the tightest bound that still holds k
+            # clips is a certified bound of the global k-th distance - every shard re-scores only what is under it
+            counts = self.sel_count[:len(ranks) * Q].view(len(ranks), Q)
+            for i in range(len(ranks)):
+                _lib.call("vfr_sel_count_under", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels[i].data_ptr(),
+                          counts[i].data_ptr(), stream)
+            counts = comm.all_reduce_sum(counts)
+            ok = counts >= self.k                                                         # [L, Q], monotone in L
             flags = self._sel_flags(Q)
-            flags[(count < self.k) & (flags == 0)] = 4
+            flags[(~ok[0]) & (flags == 0)] = 4                                            # the sample promised k clips that are not there
+            best = ok.to(torch.int32).sum(dim=0).clamp_(min=1) - 1                        # index of the tightest bound that holds
+            bound = levels.gather(0, best.view(1, Q).to(torch.int64)).view(Q).contiguous()
+            _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
         else:
             first = min(tiles, getattr(self, "sel_first_tiles", None) or max(32, tiles // 8))
             _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, first, 0, stream)
