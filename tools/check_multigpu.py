@@ -35,6 +35,25 @@ for engine in ("sel", "tc", "exact"):
     if rank == 0:
         print(f"engine={engine}: sharded({world}) == single bank: {bool(t.item())}")
     ok = ok and bool(t.item())
+# a bank large enough for the pooled-sample protocol (one list per query: n_split = 1)
+V2 = 400000
+clips2 = torch.from_numpy(synth.make_bank(5, V2, S, 100)).to(dev)
+v0, v1 = shard_range(V2, rank, world)
+shard = MomentRetriever(model, clips2[v0 * S:v1 * S], np.arange(v1 - v0 + 1) * S, id_base=v0 * 21, max_queries=Q, k=k,
+                        engine="sel", text_engine="tc", n_split=1)
+s, i = shard.search(tokens)
+s, i = s.clone(), i.clone()
+pooled_ran = shard._sel_rank_cache.get(Q, 0) > 0
+full = MomentRetriever(model, clips2, np.arange(V2 + 1) * S, max_queries=Q, k=k, engine="exact", text_engine="tc")
+full.world = 1
+fs, fi = full.search(tokens)
+same = torch.equal(s, fs) and torch.equal(i, fi) and pooled_ran
+t = torch.tensor([int(same)], device=dev)
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"engine=sel, pooled-sample protocol (ran: {pooled_ran}, fix-ups: {getattr(shard, 'n_fixups', 0)}): sharded({world}) == exact single bank: {bool(t.item())}")
+ok = ok and bool(t.item())
+del clips2, shard, full
 # exact rank of the first positive over the sharded bank (tau all-reduce(min) + count all-reduce(sum), NCCL)
 from vfr_b200 import ops, evaluate as vev
 from vfr_b200.retrieval import sharded_rank_first_positive
