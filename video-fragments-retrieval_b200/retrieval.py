@@ -149,13 +149,21 @@ class MomentRetriever:
         else:
             n_text = 1 + self.seq_len + 2
         if self.engine == "sel" and self.world > 1:
-            # query pack + threshold init + sample pass + filter (first slice) + bound get / put + filter (rest) + refine + merge
+            # bound exchange: query pack + threshold init + sample pass + filter (first slice) + bound get / put + filter
+            # (rest) + refine + merge; pooled samples (see launches_per_step): query pack + threshold init + sample pass +
+            # bound put + filter + 4 counts + bound put + refine + merge
             n_k4 = 9
         elif self.engine == "sel":
             n_k4 = 5          # query pack + threshold init + sample pass + filter + refine
         else:
             n_k4 = 4 + (1 if self.world > 1 else 0)   # query pack + threshold init + score + finish (+ merge)
-        self.launches_per_step = n_text + n_k4
+        self._launches_base = n_text + n_k4
+
+    @property
+    def launches_per_step(self):
+        """Kernels of this library launched per search step (the claim bench.py reports as gpu_launches)."""
+        pooled = any(j > 0 for j in self.__dict__.get("_sel_rank_cache", {}).values())
+        return self._launches_base + (3 if pooled else 0)
 
     def score_only(self, n_queries):
         """K4 alone (query pack excluded) on the query embeddings left in ``q_emb`` by the previous
