@@ -180,6 +180,42 @@ def test_sharded_topk_merge_equals_global():
     assert bool((ms[:, 1:] >= ms[:, :-1]).all())
 
 
+@pytest.mark.parametrize("P,k,n_valid", [(8, 100, 100), (8, 100, 7), (3, 37, 20), (2, 1, 1), (5, 128, 0)])
+def test_topk_merge_sorted_lists_padding_ties_and_unsorted_input(P, k, n_valid):
+    """K7 takes the no-sort path when every list arrives sorted (what the shards send: ascending (score, id), (inf, -1)
+    padding last) and sorts otherwise; both must equal a lexicographic (score, id) sort of all valid entries.  Scores are
+    drawn from a few values so that ties are broken by id."""
+    g = torch.Generator(device=DEV).manual_seed(P * 1000 + k)
+    Q = 257
+    scores = torch.randint(0, 12, (P, Q, k), device=DEV, generator=g).float() * 0.25
+    ids = torch.randperm(P * Q * k, device=DEV, generator=g).reshape(P, Q, k).to(torch.int64)
+    n_ok = torch.randint(0, n_valid + 1, (P, Q, 1), device=DEV, generator=g) if n_valid else torch.zeros((P, Q, 1), device=DEV, dtype=torch.int64)
+    pad = torch.arange(k, device=DEV).view(1, 1, k) >= n_ok
+    scores[pad] = float("inf")
+    ids[pad] = -1
+    # sort every list by (score, id): padding (inf, -1) must go last, so order by a key that maps -1 to +big
+    key_id = torch.where(ids < 0, torch.full_like(ids, 2 ** 62), ids)
+    order = torch.argsort(key_id, dim=2, stable=True)
+    scores, ids, key_id = scores.gather(2, order), ids.gather(2, order), key_id.gather(2, order)
+    order = torch.argsort(scores, dim=2, stable=True)
+    scores, ids = scores.gather(2, order).contiguous(), ids.gather(2, order).contiguous()
+
+    def reference(sc, idd):
+        fs = sc.permute(1, 0, 2).reshape(Q, P * k)
+        fi = idd.permute(1, 0, 2).reshape(Q, P * k)
+        ki = torch.where(fi < 0, torch.full_like(fi, 2 ** 62), fi)
+        o = torch.argsort(ki, dim=1, stable=True)
+        fs, fi = fs.gather(1, o), fi.gather(1, o)
+        o = torch.argsort(fs, dim=1, stable=True)
+        return fs.gather(1, o)[:, :k], fi.gather(1, o)[:, :k]
+    ws, wi = reference(scores, ids)
+    ms, mi = ops.topk_merge(scores, ids)
+    assert torch.equal(ms, ws) and torch.equal(mi, wi)
+    perm = torch.randperm(k, device=DEV, generator=g)                      # unsorted lists: the sorting path
+    ms, mi = ops.topk_merge(scores[:, :, perm].contiguous(), ids[:, :, perm].contiguous())
+    assert torch.equal(ms, ws) and torch.equal(mi, wi)
+
+
 def test_scores_vs_oracle_random_dims():
     # dims that are not a multiple of the 20-wide k chunk, ragged clip counts up to 32
     rng = np.random.default_rng(9)

@@ -438,6 +438,33 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const float* 
       ids[i] = INT64_MAX;
     }
   }
+  // The lists of a sharded search arrive sorted (ascending (score, id), padding last): then every key's place in the
+  // merged order is its own index plus, per other list, the number of keys before it (binary search) - no sort.
+  __syncthreads();
+  bool unsorted = false;
+  for (int i = threadIdx.x; i < total; i += MERGE_THREADS)
+    if (i % k != 0 && si_gt(SI{ss[i - 1], ids[i - 1]}, SI{ss[i], ids[i]})) unsorted = true;
+  if (!__syncthreads_or(unsorted)) {
+    for (int i = threadIdx.x; i < k; i += MERGE_THREADS) { out_scores[q * k + i] = CUDART_INF_F; out_ids[q * k + i] = -1; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += MERGE_THREADS) {
+      const SI me{ss[i], ids[i]};
+      if (me.id == INT64_MAX) continue;
+      const int pi = i / k;
+      int rank = i - pi * k;
+      for (int b = 0; b < n_parts && rank < k; ++b) {
+        if (b == pi) continue;
+        int lo = 0, hi = k;                      // first index of list b whose key is not before mine
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (si_gt(me, SI{ss[b * k + mid], ids[b * k + mid]})) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < k) { out_scores[q * k + rank] = __uint_as_float(me.s); out_ids[q * k + rank] = me.id; }
+    }
+    return;
+  }
   for (int size = 2; size <= n_pad; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();

@@ -216,7 +216,8 @@ class MomentRetriever:
             pooled = comm.all_gather(mine.contiguous())                                  # [P, Q, 32]
             # candidate bounds: the pooled sample values of rank j (safe a priori), j/2, j/4, j/8 (tighter guesses)
             ranks = sorted({max(1, -(-rank_j // d)) for d in (1, 2, 4, 8)}, reverse=True)
-            levels = torch.sort(pooled.permute(1, 0, 2).reshape(Q, -1), dim=1).values[:, [r - 1 for r in ranks]]
+            smallest = torch.topk(pooled.permute(1, 0, 2).reshape(Q, -1), rank_j, dim=1, largest=False, sorted=True).values
+            levels = smallest[:, [r - 1 for r in ranks]]
             levels = levels.t().contiguous()                                              # [L, Q], loosest first
             _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels[0].data_ptr(), stream)
             _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, tiles, 1, stream)
