@@ -871,7 +871,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int visit = 0;
     for (int t = t_first; t < n_my_tiles; t += t_step, ++visit) {
       st.clip0 = (int64_t)(tile_begin + t) * SL_N;
-      if ((visit & 3) == 0) {
+      if ((visit & 3) == 0 && (p.n_parts > 1 || visit == 0)) {
         // the other lists of this query (other bank splits / tile parities) may have tightened the threshold
         const float tg = tau_fetch(p.tau_g + st.q);
         if (tg < st.tau_use) {
