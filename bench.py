@@ -338,8 +338,8 @@ def run_ours(args):
         "bound": "tensor", "achieved": achieved_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved_tflops / pk["bf16_tflops_sustained"],
         # dram__bytes_read.sum + dram__bytes_write.sum of the sample pass + filter kernel, one `ncu --set full` capture of
-        # this workload (profiles/r1_v5_sl_filter_raw.csv: 0.046 + 2.566 GB; the packed bank is 1.54 GB)
-        "traffic": 2.612e9 if (args.engine == "sel" and world == 1 and args.batch == 37888 and args.videos == 1000000) else None,
+        # this workload (profiles/r1_v6_sl_filter_raw.csv: 0.046 + 2.522 GB; the packed bank is 1.54 GB)
+        "traffic": 2.568e9 if (args.engine == "sel" and world == 1 and args.batch == 37888 and args.videos == 1000000) else None,
         "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
         "ms_per_launch": k4, "algorithmic_flop_per_pair": flop_per_pair,
         "note": notes[args.engine],
