@@ -79,3 +79,72 @@ def test_shard_ranges_partition_the_bank():
     for n, w in ((10, 3), (1_000_000, 8), (7, 8), (1094, 4)):
         r = [shard_range(n, i, w) for i in range(w)]
         assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+def _pooled_worker(rank, world, port, ret):
+    """The pooled-sample threshold protocol of the sharded filter + refine search (retrieval._sel_score_sharded), its
+    host logic played with numpy: strided sample per shard -> 32 smallest per query -> all-gather -> j-th smallest of
+    the union (j from the library's own vfr_sel_sample_rank) -> per-shard counts -> all-reduce(sum) certificate."""
+    from vfr_b200 import _lib
+    from vfr_b200.retrieval import _DistComm
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = _DistComm()
+    Vb, Qn, k = 6000, 7, 5
+    clips = synth.make_bank(11, Vb, S, D)
+    qs = synth.make_query_embeddings(11, Qn, D)
+    v0, v1 = shard_range(Vb, rank, world)
+    mine = clips[v0 * S:v1 * S]
+    d2 = ((mine[None, :, :] - qs[:, None, :] + 1e-6) ** 2).sum(-1).astype(np.float32)        # [Q, shard clips]
+    sample = d2[:, ::16]                                                                      # strided sample
+    smallest = torch.from_numpy(np.sort(sample, axis=1)[:, :32].copy())
+    sizes = comm.all_reduce_sum(torch.tensor([sample.shape[1], d2.shape[1]], dtype=torch.int64)).tolist()
+    j = _lib.load().vfr_sel_sample_rank(k, sizes[0], sizes[1])
+    pooled = comm.all_gather(smallest)                                                        # [P, Q, 32]
+    ok = pooled.shape == (world, Qn, 32) and 1 <= j <= 32
+    bound = torch.kthvalue(pooled.permute(1, 0, 2).reshape(Qn, -1), j, dim=1).values
+    count = comm.all_reduce_sum(torch.from_numpy((d2 <= bound.numpy()[:, None]).sum(1).astype(np.int32)))
+    ok = ok and bool((count >= k).all())                       # the certificate holds on this (unordered) bank
+    # and then the bound covers the global k closest clips: every shard may drop what lies above it
+    full = ((clips[None, :, :] - qs[:, None, :] + 1e-6) ** 2).sum(-1).astype(np.float32)
+    kth = np.sort(full, axis=1)[:, k - 1]
+    ok = ok and bool((kth <= bound.numpy()).all())
+    mn = comm.all_reduce_min(torch.tensor([float(rank + 3)]))
+    ok = ok and float(mn.item()) == 3.0
+    t = torch.tensor([int(ok)])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_pooled_sample_bound_protocol():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pooled_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1
+
+
+def test_sample_rank_is_the_smallest_safe_rank():
+    """vfr_sel_sample_rank(k, sampled, total): the smallest j <= 32 with P(Poisson(k * sampled / total) >= j) < 1e-10
+    (0 if there is none) - checked against scipy's survival function."""
+    from scipy.stats import poisson
+    from vfr_b200 import _lib
+    lib = _lib.load()
+    for k, n_s, n in ((100, 16384 * 8, 6_000_000), (1, 16384, 6_000_000), (100, 131072, 6_000_000), (128, 4096, 48000),
+                      (10, 2048, 48128), (100, 500_000, 1_000_000)):
+        j = lib.vfr_sel_sample_rank(k, n_s, n)
+        x = k * n_s / n
+        if j == 0:
+            assert poisson.sf(31, x) >= 1e-10                  # not even rank 32 is safe
+        else:
+            assert 1 <= j <= 32 and poisson.sf(j - 1, x) < 1.01e-10
+            assert j == 1 or poisson.sf(j - 2, x) >= 0.99e-10
+    assert lib.vfr_sel_sample_rank(0, 10, 10) == 0 and lib.vfr_sel_sample_rank(5, 0, 10) == 0
+    assert lib.vfr_sel_tiles(257) == 2 and lib.vfr_sel_tiles(0) == 0

@@ -33,9 +33,10 @@ class _DistComm:
         self.group = group
 
     def all_gather(self, t):
-        out = torch.empty((dist.get_world_size(self.group),) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        world = dist.get_world_size(self.group)
+        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)   # concatenated form
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        return out.view((world,) + tuple(t.shape))
 
     def all_reduce_sum(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
