@@ -46,6 +46,8 @@ const char* vfr_last_error(void);
 int vfr_version(void);
 /* number of SMs of the current device (grid sizing), or negative error */
 int vfr_device_sms(void);
+/* kernels this library has launched in this process so far (what bench.py reports as gpu_launches) */
+int64_t vfr_launch_count(void);
 
 /* ---- K4 : query x clip distance -> moment means -> full / count / top-k --------------------
  * replaces model/evaluate.py:49-58 (and evaluate_single.py:48-53, main.py:148-157):
@@ -178,6 +180,38 @@ int vfr_sel_sample(const void* bank_packed, int64_t n_clips, int dim, void* quer
 int vfr_sel_count_under(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
                         int n_split, const float* bound, int32_t* count, vfr_stream_t stream);
 int64_t vfr_sel_tiles(int64_t n_clips);
+/* The shard-level glue of the pooled-sample protocol as kernels (no host round trip, no library ops):
+ *  vfr_sel_pool_levels   pooled fp32 [n_src, Q, width] (the all-gathered samples, +inf padded) -> levels fp32 [n_levels, Q],
+ *                        levels[l][q] = the ranks[l]-th smallest pooled value of query q (ranks: HOST int32 [n_levels <= 4],
+ *                        1-based, descending = loosest level first; n_src * width <= 1024);
+ *  vfr_sel_count_levels  count int32 [n_levels, Q] = the shard's clips certainly within each level (vfr_sel_count_under for
+ *                        all levels in one pass) - all-reduce(sum) them over the shards;
+ *  vfr_sel_pick_put      the tightest level whose all-reduced count is >= k becomes the certified bound (vfr_sel_bound_put);
+ *                        queries whose loosest level fails are flagged 4;
+ *  vfr_sel_refine_blocks vfr_sel_refine writing the QUERY-SLICE records of the exchange: queries are cut into slices of
+ *                        `per` (slice j belongs to rank j), record j = {ids int64 [per, k] | scores fp32 [per, k] | flags
+ *                        int32 [per]} at out_blocks + j * vfr_topk_block_bytes(per, k); per * (3k + 1) must be even.
+ *                        ONE all-to-all then hands every rank the P shard records of its own slice (vfr_topk_merge_blocks). */
+int vfr_sel_pool_levels(const float* pooled, int n_src, int64_t n_queries, int width, const int32_t* ranks, int n_levels,
+                        float* levels, vfr_stream_t stream);
+int vfr_sel_count_levels(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace, int n_split,
+                         const float* levels, int n_levels, int32_t* count, vfr_stream_t stream);
+int vfr_sel_pick_put(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace, int n_split,
+                     const float* levels, const int32_t* count, int n_levels, vfr_stream_t stream);
+size_t vfr_topk_block_bytes(int64_t per, int k);
+int vfr_sel_refine_blocks(const float* bank, const int32_t* vid_off, const int64_t* mom_off, int64_t n_videos, int64_t n_clips,
+                          int n_max, int dim, void* query_packed, const float* queries, int64_t n_queries, int k,
+                          int64_t id_base, int64_t per, void* out_blocks, void* workspace, int n_split, vfr_stream_t stream);
+/* K7 on the records of the query-slice exchange: merges the first n_rows queries of n_parts records of one slice into
+ * out_scores / out_ids [n_rows, k]; out_flags int32 [n_rows] = OR of the shards' flags, *n_flagged (DEVICE counter, may be
+ * NULL) += number of flagged queries. */
+int vfr_topk_merge_blocks(const void* blocks, int n_parts, int64_t per, int64_t n_rows, int k, float* out_scores,
+                          int64_t* out_ids, int32_t* out_flags, int64_t* n_flagged, vfr_stream_t stream);
+/* diagnostics of the last filter on this workspace (what bench.py reports next to the throughput): out = DEVICE
+ * int64 [8] = {sum of the candidate-list lengths, longest list, flagged queries, lists, warp-level compaction events,
+ * lists compacted, 0, 0}. */
+int vfr_sel_stats(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace, int n_split,
+                  int64_t* out, vfr_stream_t stream);
 int vfr_sel_filter(const void* bank_packed, int64_t n_clips, int dim, void* query_packed, int64_t n_queries, int k,
                    void* workspace, int n_split, int64_t tile_lo, int64_t tile_hi, int resume, vfr_stream_t stream);
 int vfr_sel_bound_get(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,

@@ -331,3 +331,106 @@ def ranking_loss(posit, intra, inter, lang, maskp, maskn, b=0.1, lamb=0.4, norma
         ci = cost(inter[maskp == i], i)
         loss = loss + torch.relu(cp - cn + b) + lamb * torch.relu(cp - ci + b)
     return loss, n
+
+
+# --------------------------------------------------------------------------------------------
+# f1 : Trainer.validate_epoch
+# --------------------------------------------------------------------------------------------
+def validate_epoch(video_embs, query_embs, query_video, query_times, size=250, iou_thresholds=(0.5, 0.7),
+                   atk=(1, 10, 100)):
+    """model/main.py:121-212 on already-embedded inputs: the corpus scoring core with the ``>=`` IoU rule (:161),
+    thresholds 0.0 ... 1.0 when ``size == -1`` (:138), 1-based rank (:170), stop after ``size`` queries (:187-188).
+    Returns ``(scalars, pr_curve)``: ``scalars`` = the three ``add_scalars`` groups written to the val writer
+    (CustomRecall / MedianRank / MeanReciprocalRank, :190-199), ``pr_curve`` = the returned dict (:201-212)."""
+    from collections import defaultdict
+    iou_thresholds = list(iou_thresholds)
+    custom = defaultdict(lambda: defaultdict(list))
+    recipr_rank, median_rank = defaultdict(list), defaultdict(list)
+    true_posit = defaultdict(lambda: defaultdict(lambda: 0))
+    total_relevant = defaultdict(lambda: 0)
+    thr_range = [i / 10 for i in range(11)] if size == -1 else iou_thresholds
+    moments = {n: generate_moments(n) for n in set(int(v.shape[0]) for v in video_embs)}
+    li = -1
+    for li in range(len(query_embs)):
+        distances = []
+        predicts = defaultdict(list)
+        for vi, v in enumerate(video_embs):
+            mom = moments[int(v.shape[0])]
+            distances.extend(moment_scores(v, query_embs[li], mom).tolist())
+            for thr in thr_range:
+                if vi == int(query_video[li]):
+                    predicts[thr].extend(gt_bits(query_times[li], mom, thr, inclusive=True).tolist())
+                else:
+                    predicts[thr].extend([0] * len(mom))
+        order = np.argsort(distances)
+        for thr in thr_range:
+            ranked = np.array(predicts[thr], dtype=int)[order]
+            rank = np.where(ranked == 1)[0][0] + 1
+            total_relevant[thr] += ranked.sum()
+            if thr in iou_thresholds:
+                median_rank[thr].append(rank)
+                recipr_rank[thr].append(1 / rank)
+            for k in atk:
+                if size == -1:
+                    true_posit[thr][k] += ranked[:k].sum()
+                if thr in iou_thresholds:
+                    custom[thr][k].append(int(rank <= k))
+        if li == size - 1:
+            break
+    scalars = {"CustomRecall": {}, "MedianRank": {}, "MeanReciprocalRank": {}}
+    for thr, values in custom.items():
+        scalars["CustomRecall"].update({f"{k}_IoU0{round(thr * 10)}": float(np.mean(v)) for k, v in values.items()})
+    scalars["MedianRank"] = {f"IoU0{round(t * 10)}": float(np.median(v)) for t, v in median_rank.items()}
+    scalars["MeanReciprocalRank"] = {f"IoU0{round(t * 10)}": float(np.mean(v)) for t, v in recipr_rank.items()}
+    pr_curve = defaultdict(lambda: defaultdict(list))
+    if size == -1:
+        for k in atk:
+            for thr in thr_range:
+                pr_curve["precision"][k].append(true_posit[thr][k] / (k * (li + 1)))
+                pr_curve["recall"][k].append(true_posit[thr][k] / total_relevant[thr])
+    return scalars, {key: dict(value) for key, value in dict(pr_curve).items()}
+
+
+# --------------------------------------------------------------------------------------------
+# f2 : one whole training step (four forwards, loss, backward, Adam)
+# --------------------------------------------------------------------------------------------
+def adam_update(param, grad, exp_avg, exp_avg_sq, step, lr=5e-4, weight_decay=5e-3, betas=(0.9, 0.999), eps=1e-8):
+    """torch.optim.Adam (the optimiser of model/main.py:358; torch 2.11 defaults: L2 weight decay folded into the
+    gradient, bias-corrected moments, eps added after the sqrt).  In-place on ``param`` / the two moments; ``step`` is the
+    1-based step count.  Third-party algorithm restated from its published form (Kingma & Ba 2015, PyTorch docs)."""
+    g = grad + weight_decay * param
+    exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+    exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    bias1, bias2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+    denom = exp_avg_sq.sqrt() / (bias2 ** 0.5) + eps
+    param.addcdiv_(exp_avg, denom, value=-lr / bias1)
+
+
+TRAINABLE = ("visual_fc.0.weight", "visual_fc.0.bias", "visual_fc.2.weight", "visual_fc.2.bias",
+             "lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0",
+             "lstm.weight_ih_l0_reverse", "lstm.weight_hh_l0_reverse", "lstm.bias_ih_l0_reverse", "lstm.bias_hh_l0_reverse",
+             "lang_fc.weight", "lang_fc.bias")
+
+
+def train_step(sd, batch, state, step, normalize_loss=False, b=0.1, lamb=0.4, lr=5e-4, weight_decay=5e-3):
+    """model/main.py:57-67 with dropout disabled: forwards of posit / intra / inter / lang, ``ranking_loss``,
+    backward (torch CPU autograd over the restated forwards), Adam.  ``sd``: dict of torch tensors (updated in place),
+    ``state``: dict name -> (exp_avg, exp_avg_sq) (created on first use).  Returns (loss, n_samples, mean grad norm) -
+    the grad norm is the mean of the per-parameter L2 norms, model/utils.py:85-92."""
+    leaves = {k: _t(sd[k]).clone().requires_grad_(True) for k in TRAINABLE}
+    full = dict(sd)
+    full.update(leaves)
+    embs = [visual_embed(full, batch[k]) for k in ("posit", "intra", "inter")]
+    lang = text_embed(full, batch["lang"])
+    loss, n = ranking_loss(embs[0], embs[1], embs[2], lang, batch["maskp"], batch["maskn"], b=b, lamb=lamb,
+                           normalize=normalize_loss)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in TRAINABLE])
+    gnorm = float(np.mean([g.norm().item() for g in grads]))
+    with torch.no_grad():
+        for k, g in zip(TRAINABLE, grads):
+            if k not in state:
+                state[k] = (torch.zeros_like(g), torch.zeros_like(g))
+            p = _t(sd[k])
+            adam_update(p, g, state[k][0], state[k][1], step, lr=lr, weight_decay=weight_decay)
+            sd[k] = p
+    return float(loss.item()), n, gnorm

@@ -28,24 +28,15 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/model"
 sys.path.insert(0, ROOT)
-sys.path.insert(0, REF)
 
-_h5 = types.ModuleType("h5py")
-sys.modules["h5py"] = _h5
-_mpl, _plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
-_plt.switch_backend = lambda *a, **k: None
-_mpl.pyplot = _plt
-sys.modules.setdefault("matplotlib", _mpl)
-sys.modules.setdefault("matplotlib.pyplot", _plt)
+sys.modules["h5py"] = _h5 = types.ModuleType("h5py")   # a stub even if a real h5py exists: case_pool installs a fake File
 
 import vfr_b200  # noqa: E402,F401
 from vfr_b200 import synth  # noqa: E402
+from oracle import ref_harness  # noqa: E402
 
-import data as rdata  # noqa: E402  (reference)
-import evaluate as reval  # noqa: E402
-import evaluate_single as rsingle  # noqa: E402
-import models as rmodels  # noqa: E402
-import utils as rutils  # noqa: E402
+_ref = ref_harness.load(REF)   # the reference itself, straight from /root/reference/model
+rdata, reval, rsingle, rmodels, rutils = _ref.data, _ref.evaluate, _ref.evaluate_single, _ref.models, _ref.utils
 from torch.utils.data import DataLoader  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -59,38 +50,16 @@ def _save(name, meta, **arrays):
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
-def _ref_model(sd, feat_dim, normalize_lang=False):
-    model = rmodels.CALModel(pretrained_emb=torch.from_numpy(sd["word_embedding.weight"]),
-                             visual_input_dim=2 * feat_dim + 2, emb_dim=rdata.EMBEDDING_DIM,
-                             normalize_lang=normalize_lang)
-    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
-    return model.eval()
+def _ref_model(sd, feat_dim, normalize_lang=False, dropout_rate=0.3):
+    return ref_harness.ref_model(_ref, sd, feat_dim, normalize_lang, dropout_rate)
 
 
 def _ref_dataset(videos, queries, validate=True):
-    ds = rdata.CustomDataset.__new__(rdata.CustomDataset)
-    ds.validate = validate
-    ds.video_features = {v["name"]: dict(segment_features=v["segment_features"],
-                                         context_features=v["context_features"],
-                                         num_segments=v["num_segments"]) for v in videos}
-    ds.num_segments_info = {v["name"]: v["num_segments"] for v in videos}
-    ds.lang_features = {a: torch.from_numpy(queries["tokens"][i:i + 1]).long()
-                        for i, a in enumerate(queries["annot_id"])}
-    annotations = {a: dict(video=videos[int(queries["video_idx"][i])]["name"], description="",
-                           times=queries["times"][i]) for i, a in enumerate(queries["annot_id"])}
-    return ds, annotations
+    return ref_harness.ref_dataset(_ref, videos, queries, validate)
 
 
 def _ref_iters(ds, videos, annotations, max_seg=None):
-    names = [v["name"] for v in videos]
-    vit = DataLoader(ds, shuffle=False, collate_fn=rdata.validate_collate,
-                     batch_sampler=rdata.VideoBatchSampler(names, ds.num_segments_info))
-    lsamp = rdata.LanguageBatchSampler(annotations, ds.num_segments_info)
-    if max_seg is not None:   # the reference caps its table at n<7 (data.py:386): inject
-        for n in range(7, max_seg + 1):
-            lsamp.moments[n] = rutils.generate_moments(n)
-    lit = DataLoader(ds, shuffle=False, collate_fn=rdata.validate_collate, batch_sampler=lsamp)
-    return vit, lit, lsamp.moments
+    return ref_harness.ref_iters(_ref, ds, videos, annotations, max_seg)
 
 
 def _metrics_json(m):
@@ -271,7 +240,165 @@ def case_train_step():
                              spread=4.0, batch_size=120, b=0.1, lamb=0.4), **out)
 
 
-CASES = dict(tiny_eval=case_tiny_eval, long_eval=case_long_eval, text=case_text, pool=case_pool,
+def _train_with_reference(model, ds, annotations, epochs, batch_size=120):
+    """Brief training with the reference's own ``Trainer.train_epoch`` (main.py:43-79), its real negative sampler
+    (data.py:249-337) and the optimiser of main.py:358, seeds as main.py:237-239."""
+    import torch.optim as optim
+    rmain = ref_harness.load(REF, with_main=True).main
+    random.seed(123); np.random.seed(123); torch.random.manual_seed(123)
+    it = DataLoader(ds, shuffle=False, collate_fn=rdata.custom_collate,
+                    batch_sampler=rdata.CustomBatchSampler(batch_size, annotations, ds.num_segments_info, same_length=True))
+    tr = rmain.Trainer(train_writer=ref_harness.NullWriter(), device="cpu", compute_grads=False)
+    opt = optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-3)
+    losses = [float(tr.train_epoch(model, it, opt)) for _ in range(epochs)]
+    model.eval()
+    return losses
+
+
+def _corpus_eval_arrays(model, vit, lit, annotations, queries, moments, thresholds=(0.5, 0.7)):
+    """Embeddings of every video / query and, per query, the rank of the first positive in the reference's own
+    ordering (the ops of evaluate.py:35,44,53-58,71,77)."""
+    with torch.no_grad():
+        vemb = [model(b["feature"]) for b in vit]
+        qemb = torch.cat([model(b["feature"], False, "cpu") for b in lit], dim=0)
+    vid_off = np.cumsum([0] + [int(v.shape[0]) for v in vemb]).astype(np.int64)
+    ranks = {t: [] for t in thresholds}
+    for q in range(qemb.shape[0]):
+        dist_all = []
+        gts = {t: [] for t in thresholds}
+        for vi, ve in enumerate(vemb):
+            n = ve.size(0)
+            dist = torch.nn.functional.pairwise_distance(ve, qemb[q:q + 1].repeat(n, 1))
+            for s, e in moments[n]:
+                dist_all.append(dist.index_select(0, torch.arange(s, e + 1)).mean().item())
+                for thr in gts:
+                    if vi == int(queries["video_idx"][q]):
+                        gts[thr].append(int((rutils.get_iou(queries["times"][q], s, e) > thr).sum() >= 2))
+                    else:
+                        gts[thr].append(0)
+        order = np.argsort(dist_all)
+        for thr in gts:
+            ranks[thr].append(int(np.where(np.array(gts[thr])[order] == 1)[0][0]))
+    return torch.cat(vemb).numpy(), vid_off, qemb.numpy(), {t: np.asarray(r) for t, r in ranks.items()}
+
+
+def case_val_trained():
+    """The val shape (1,094 videos x 4096-d, 21.9 k moments) with a model the reference's own Trainer has trained
+    for a few epochs on these queries, so that R@1 / R@10 / R@100 are NOT all zero (the untrained val_eval golden
+    only carries information in MR).  The 52 MB of trained weights are not committed: the file holds the
+    embeddings the trained reference model produced, the reference's metric dicts and its per-query ranks."""
+    seed, n_videos, n_queries, feat_dim, vocab, epochs = 123, 1094, 192, 4096, 2000, 20
+    videos = synth.make_videos(seed, n_videos, feat_dim)
+    queries = synth.make_queries(seed + 7, videos, n_queries, vocab)
+    sd = synth.make_state_dict(seed, feat_dim, vocab, spread=1.0)
+    model = _ref_model(sd, feat_dim)
+    ds_train, annotations = _ref_dataset(videos, queries, validate=False)
+    losses = _train_with_reference(model, ds_train, annotations, epochs)
+    ds, annotations = _ref_dataset(videos, queries)
+    vit, lit, moments = _ref_iters(ds, videos, annotations)
+    torch.random.manual_seed(123); random.seed(123); np.random.seed(123)
+    with redirect_stdout(io.StringIO()):
+        m_corpus = reval.evaluate(model, vit, lit, annotations, "cpu", preliminary=10 ** 9, model_types=["model", "chance"])
+    prior = synth.make_prior(sorted(set(v["num_segments"] for v in videos)))
+    torch.random.manual_seed(123); random.seed(123); np.random.seed(123)
+    with redirect_stdout(io.StringIO()):
+        m_single = rsingle.evaluate(model, vit, lit, annotations, "cpu", ["model", "chance", "prior"], prior)
+    vemb, vid_off, qemb, ranks = _corpus_eval_arrays(model, vit, lit, annotations, queries, moments)
+    meta = dict(seed=seed, query_seed=seed + 7, n_videos=n_videos, n_queries=n_queries, feat_dim=feat_dim, vocab=vocab,
+                spread=1.0, epochs=epochs, train_losses=losses, seg_choices=[6, 5], seg_probs=[0.83, 0.17],
+                metrics_corpus=_metrics_json(m_corpus), metrics_single=_metrics_json(m_single))
+    _save("val_trained", meta, video_emb=vemb, vid_off=vid_off, query_emb=qemb, rank_05=ranks[0.5], rank_07=ranks[0.7])
+
+
+MID = dict(seed=71, n_videos=200, n_queries=160, feat_dim=256, vocab=300, hidden=128, epochs=30)
+
+
+def _mid_setup(train=True):
+    c = MID
+    videos = synth.make_videos(c["seed"], c["n_videos"], c["feat_dim"])
+    queries = synth.make_queries(c["seed"], videos, c["n_queries"], c["vocab"])
+    sd = synth.make_state_dict(c["seed"], c["feat_dim"], c["vocab"], hidden=c["hidden"], spread=1.0)
+    model = _ref_model(sd, c["feat_dim"])
+    losses = []
+    if train:
+        ds_train, annotations = _ref_dataset(videos, queries, validate=False)
+        losses = _train_with_reference(model, ds_train, annotations, c["epochs"])
+    return videos, queries, model, losses
+
+
+def case_mid_trained():
+    """A mid-size corpus (200 videos, 4,0xx moments) with a briefly TRAINED reference model whose weights ARE
+    committed (hidden_size 128 keeps them at ~2 MB): pins the full drop-in calls - ``evaluate.evaluate``,
+    ``evaluate_single.evaluate`` and ``Trainer.validate_epoch`` (main.py:121-212, both the ``size=250`` scalars and
+    the ``size=-1`` precision/recall curves) - on a model with informative R@k."""
+    rmain = ref_harness.load(REF, with_main=True).main
+    videos, queries, model, losses = _mid_setup()
+    ds, annotations = _ref_dataset(videos, queries)
+    vit, lit, moments = _ref_iters(ds, videos, annotations)
+    torch.random.manual_seed(123); random.seed(123); np.random.seed(123)
+    with redirect_stdout(io.StringIO()):
+        m_corpus = reval.evaluate(model, vit, lit, annotations, "cpu", preliminary=10 ** 9, model_types=["model", "chance"])
+    prior = synth.make_prior(sorted(set(v["num_segments"] for v in videos)))
+    torch.random.manual_seed(123); random.seed(123); np.random.seed(123)
+    with redirect_stdout(io.StringIO()):
+        m_single = rsingle.evaluate(model, vit, lit, annotations, "cpu", ["model", "chance", "prior"], prior)
+    validate = {}
+    for tag, size in (("size250", 250), ("size100", 100), ("all", -1)):
+        w = ref_harness.NullWriter()
+        tr = rmain.Trainer(val_writer=w, device="cpu")
+        tr.global_step = 7
+        with redirect_stdout(io.StringIO()):
+            pr = tr.validate_epoch(model, vit, lit, annotations, size=size)
+        validate[tag] = dict(pr_curve={k: {str(kk): [float(x) for x in vv] for kk, vv in v.items()} for k, v in pr.items()},
+                             scalars=[[name, vals, step] for name, vals, step in w.scalar_groups], figures=w.figures)
+    vemb, vid_off, qemb, ranks = _corpus_eval_arrays(model, vit, lit, annotations, queries, moments)
+    weights = {f"w:{k}": v.detach().numpy() for k, v in model.state_dict().items()}
+    meta = dict(MID, spread=1.0, train_losses=losses, metrics_corpus=_metrics_json(m_corpus),
+                metrics_single=_metrics_json(m_single), validate=validate, seg_choices=[6, 5], seg_probs=[0.83, 0.17])
+    _save("mid_trained", meta, video_emb=vemb, vid_off=vid_off, query_emb=qemb, rank_05=ranks[0.5], rank_07=ranks[0.7],
+          **weights)
+
+
+def case_train_full_step():
+    """Whole training steps of the reference (main.py:57-67: four forwards, ranking loss, backward, Adam lr 5e-4 /
+    wd 5e-3 of main.py:358) from the untrained mid-size model with dropout disabled (``dropout_rate=0``: the only
+    RNG-coupled op of a step).  Stores the batches (one epoch of the 160 queries = 2) the reference's sampler produced, the loss and
+    the mean gradient norm (utils.py:85-92) of every step and the weights after the first and after the last step."""
+    import torch.optim as optim
+    rmain = ref_harness.load(REF, with_main=True).main
+    c = MID
+    videos = synth.make_videos(c["seed"], c["n_videos"], c["feat_dim"])
+    queries = synth.make_queries(c["seed"], videos, c["n_queries"], c["vocab"])
+    sd = synth.make_state_dict(c["seed"], c["feat_dim"], c["vocab"], hidden=c["hidden"], spread=1.0)
+    out = {}
+    for norm in (False, True):
+        model = _ref_model(sd, c["feat_dim"], dropout_rate=0.0)
+        ds, annotations = _ref_dataset(videos, queries, validate=False)
+        random.seed(123); np.random.seed(123); torch.random.manual_seed(123)
+        it = DataLoader(ds, shuffle=False, collate_fn=rdata.custom_collate,
+                        batch_sampler=rdata.CustomBatchSampler(120, annotations, ds.num_segments_info, same_length=True))
+        batches = [b for b in it][:3]
+        w = ref_harness.NullWriter()
+        tr = rmain.Trainer(train_writer=w, device="cpu", compute_grads=True, normalize_loss=norm)
+        opt = optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-3)
+        tag = f"norm{int(norm)}"
+        for step, batch in enumerate(batches):
+            if not norm:
+                for k in ("posit", "intra", "inter", "lang", "maskp", "maskn"):
+                    out[f"b{step}_{k}"] = batch[k].numpy()
+            epoch_loss = tr.train_epoch(model, [batch], opt)
+            out[f"{tag}_s{step}_epoch_loss"] = np.asarray(epoch_loss, dtype=np.float64)
+            if step in (0, len(batches) - 1):
+                for k, v in model.state_dict().items():
+                    # (normalize_loss=True: the two output projections only - the file stays small)
+                    if k != "word_embedding.weight" and (not norm or (step > 0 and k.startswith(("lang_fc", "visual_fc.2")))):
+                        out[f"{tag}_s{step}_w:{k}"] = v.detach().numpy().copy()
+        out[f"{tag}_logged"] = np.asarray([v for _, v, _ in w.scalars], dtype=np.float64)   # loss/n, grad_norm per step
+    _save("train_full_step", dict(MID, spread=1.0, lr=5e-4, weight_decay=5e-3, steps=len(batches), batch_size=120), **out)
+
+
+CASES = dict(val_trained=case_val_trained, mid_trained=case_mid_trained, train_full_step=case_train_full_step,
+             tiny_eval=case_tiny_eval, long_eval=case_long_eval, text=case_text, pool=case_pool,
              train_step=case_train_step, val_eval=case_val_eval)
 
 if __name__ == "__main__":

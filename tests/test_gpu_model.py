@@ -249,3 +249,89 @@ def test_validate_epoch_matches_oracle(golden):
         np.testing.assert_allclose(pr["recall"][k], [tp[t][k] / rel[t] for t in thr_range])
     assert tr.last_validation["median_rank"][0.5] == ranks[0.5]
     assert tr.last_validation["median_rank"][0.7] == ranks[0.7]
+
+
+# ---- a TRAINED reference model (informative R@k): the drop-in protocols against what the reference returned ----------
+def _trained(golden, case):
+    z, meta = golden(case)
+    videos = synth.make_videos(meta["seed"], meta["n_videos"], meta["feat_dim"], tuple(meta["seg_choices"]),
+                               tuple(meta["seg_probs"]))
+    queries = synth.make_queries(meta.get("query_seed", meta["seed"]), videos, meta["n_queries"], meta["vocab"])
+    return z, meta, videos, queries
+
+
+def _trained_model(z, meta):
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    m = models.CALModel(visual_input_dim=2 * meta["feat_dim"] + 2, pretrained_emb=sd["word_embedding.weight"],
+                        hidden_size=meta["hidden"])
+    m.load_state_dict(sd)
+    return m.to(DEV).eval()
+
+
+def _plain(m):
+    return {k: {kk: float(vv) for kk, vv in v.items()} for k, v in m.items()}
+
+
+def test_trained_model_evaluate_drop_in_matches_reference(golden):
+    """evaluate.evaluate / evaluate_single.evaluate on a briefly trained model (R@1 = 21.9, R@10 = 60.6, R@100 = 91.9 in
+    the reference's own run): iterators in, metric dicts out, equal to the reference's dicts."""
+    z, meta, videos, queries = _trained(golden, "mid_trained")
+    assert meta["metrics_corpus"]["model, IoU=0.5"]["R@1"] > 0
+    model = _trained_model(z, meta)
+    ds, annotations = _dataset(videos, queries)
+    vit, lit = _iters(ds, videos, annotations)
+    torch.random.manual_seed(123); random.seed(123); np.random.seed(123)
+    m = vev.evaluate(model, vit, lit, annotations, DEV, preliminary=0, model_types=["model", "chance"])
+    assert _plain(m) == meta["metrics_corpus"]
+    prior = synth.make_prior(sorted(set(v["num_segments"] for v in videos)))
+    random.seed(123)
+    m = vsingle.evaluate(model, vit, lit, annotations, DEV, ["model", "chance", "prior"], prior)
+    assert _plain(m) == meta["metrics_single"]
+    # stage by stage: embeddings and the rank of the first positive of every query
+    feats = torch.from_numpy(np.concatenate([synth.clip_features(v) for v in videos])).to(DEV)
+    with torch.no_grad():
+        vemb = model(feats)
+        qemb = model(torch.from_numpy(queries["tokens"]).to(DEV), False, DEV)
+    _close(vemb.cpu().numpy(), z["video_emb"], 1e-5)
+    _close(qemb.cpu().numpy(), z["query_emb"], 1e-5)
+
+
+@pytest.mark.parametrize("tag,size", [("size250", 250), ("size100", 100), ("all", -1)])
+def test_validate_epoch_matches_reference_golden(golden, tag, size):
+    """Trainer.validate_epoch against the reference's own validate_epoch (model/main.py:121-212) run by
+    oracle/gen_golden.py with recording writers: the CustomRecall / MedianRank / MeanReciprocalRank scalar groups and
+    the returned precision / recall curves."""
+    from oracle.ref_harness import NullWriter
+    z, meta, videos, queries = _trained(golden, "mid_trained")
+    model = _trained_model(z, meta)
+    ds, annotations = _dataset(videos, queries)
+    vit, lit = _iters(ds, videos, annotations)
+    w = NullWriter()
+    tr = vmain.Trainer(val_writer=w, device=DEV)
+    tr.global_step = 7
+    pr = tr.validate_epoch(model, vit, lit, annotations, size=size)
+    ref = meta["validate"][tag]
+    assert [[n, v, s] for n, v, s in w.scalar_groups] == ref["scalars"]
+    assert {k: {str(kk): [float(x) for x in vv] for kk, vv in v.items()} for k, v in pr.items()} == ref["pr_curve"]
+
+
+def test_val_shape_trained_embeddings_metrics_match_reference(golden):
+    """The val shape (1,094 videos, 21.9 k moments, 192 queries) with the embeddings of a trained reference model:
+    R@1 / R@10 / R@100 / MR dicts equal to the reference's, per-query ranks equal off ties."""
+    z, meta, videos, queries = _trained(golden, "val_trained")
+    want = meta["metrics_corpus"]
+    assert want["model, IoU=0.5"]["R@1"] > 0 and want["model, IoU=0.5"]["R@100"] > 30
+    bank = ops.Bank(torch.from_numpy(z["video_emb"]).to(DEV), z["vid_off"])
+    q_emb = torch.from_numpy(z["query_emb"]).to(DEV)
+    np.random.seed(123)
+    m = vev.evaluate_embedded(bank, q_emb, queries["video_idx"], queries["times"], preliminary=0,
+                              model_types=("model", "chance"), verbose=False)
+    assert _plain(m) == want
+    res = vev.rank_first_positive(bank, q_emb, queries["video_idx"], queries["times"], [0.5, 0.7])
+    for ti, key in enumerate(("rank_05", "rank_07")):
+        ours, ref = res["rank"][:, ti], z[key]
+        assert (ours == ref).mean() > 0.97 and np.abs(ours - ref).max() <= 3      # the reference's argsort is unstable on ties
+    prior = synth.make_prior(sorted(set(v["num_segments"] for v in videos)))
+    random.seed(123)
+    m = vsingle.evaluate_embedded(bank, q_emb, queries["video_idx"], queries["times"], ("model", "chance", "prior"), prior)
+    assert _plain(m) == meta["metrics_single"]

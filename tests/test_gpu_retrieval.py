@@ -172,8 +172,20 @@ class _LockstepComm:
                     comm.log.append(kind)
                 return parts
 
-            def all_gather(self, t):
-                return self._exchange(t, "all_gather")
+            def all_gather(self, t, out=None):
+                parts = self._exchange(t, "all_gather")
+                if out is None:
+                    return parts
+                out.view(parts.shape).copy_(parts)
+                return out.view(parts.shape)
+
+            def all_to_all(self, send, out=None):
+                parts = self._exchange(send, "all_to_all")          # [P (src), P (dst), n]
+                res = parts[:, rank].contiguous()
+                if out is None:
+                    return res
+                out.copy_(res)
+                return out
 
             def all_reduce_sum(self, t):
                 return self._exchange(t, "sum").sum(dim=0).to(t.dtype)
@@ -235,3 +247,97 @@ def test_sel_sharded_protocols_equal_single_bank(pool, first_tiles, k, n_videos)
         # every shard kept only what can reach the global top-k: together about k candidates (plus the error band), not P k
         kept = sum(int((sh.out_i[:Q] >= 0).sum().item()) for sh in shards)
         assert kept >= Q * k
+
+
+def _run_ranks(P, fn):
+    import threading
+    comm = _LockstepComm(P)
+    errors, results = [], [None] * P
+
+    def work(r):
+        try:
+            torch.cuda.set_device(0)
+            results[r] = fn(r, comm.rank_view(r))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            comm.barrier.abort()
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(P)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    return results, comm
+
+
+@pytest.mark.parametrize("n_videos,Q,k,bounds", [
+    (120000, 150, 100, None),                 # pooled samples, equal shards
+    (120000, 151, 37, None),                  # odd batch: the last slice is short
+    (9000, 70, 10, None),                     # shards too small to sample: bound exchange
+    (9000, 150, 100, [0, 300, 700, 8000, 9000]),   # UNEVEN shards: some finish their tiles before the exchange
+    (120000, 3, 5, None),                     # fewer queries than ranks: empty slices
+])
+def test_sharded_search_step_by_query_slice_equals_single_bank(n_videos, Q, k, bounds):
+    """The whole P-rank step (K3 by slice -> all-gather -> K4 with the shard threshold protocol -> all-to-all of the
+    query-slice records -> K7 -> flags gather) on four emulated ranks: every rank returns its slice, and the slices
+    put together are bit-identical to the exact engine over the whole bank.  No collective is skipped by any rank,
+    whatever its shard size (the exchange log is the same list on every rank by construction of the lockstep comm)."""
+    sd, model, clips, tokens = _setup(seed=33, V=n_videos, Q=Q)
+    V, P = clips.shape[0] // 6, 4
+    tok = torch.from_numpy(tokens).to(DEV)
+    exact = MomentRetriever(model, torch.from_numpy(clips).to(DEV), np.arange(V + 1) * 6, max_queries=256, k=k,
+                            engine="exact", text_engine="tc")
+    es, ei = exact.search_device(tok)
+    es, ei = es.clone(), ei.clone()
+    bounds = bounds or [shard_range(V, r, P)[0] for r in range(P)] + [V]
+    shards = [None] * P
+
+    def step(r, comm):
+        v0, v1 = bounds[r], bounds[r + 1]
+        sh = MomentRetriever(model, torch.from_numpy(clips[v0 * 6:v1 * 6]).to(DEV), np.arange(v1 - v0 + 1) * 6,
+                             id_base=v0 * 21, max_queries=256, k=k, engine="sel", text_engine="tc", comm=comm, world=P, rank=r)
+        shards[r] = sh
+        s, i = sh.search_device(tok)
+        q0, q1 = sh.owned_range(Q)
+        # the host-buffer call returns the same slice
+        hs, hi = sh.search(tokens)
+        assert torch.equal(hs, s.cpu()) and torch.equal(hi, i.cpu())
+        return q0, q1, s.clone(), i.clone()
+    results, comm = _run_ranks(P, step)
+    rows = 0
+    for q0, q1, s, i in results:
+        assert s.shape[0] == q1 - q0
+        assert torch.equal(i, ei[q0:q1]) and torch.equal(s.view(torch.int32), es[q0:q1].view(torch.int32))
+        rows += q1 - q0
+    assert rows == Q
+    assert "all_to_all" in comm.log and sum(sh.n_fixups for sh in shards) == 0
+
+
+def test_sharded_search_flagged_queries_and_bad_tokens_are_handled_by_all_ranks_together():
+    """A bank the fp16 scales cannot hold flags every query on every shard: all ranks take the exact-engine rerun
+    together (same collectives everywhere) and still return the exact engine's bits; an out-of-range token id seen by
+    ONE rank raises IndexError on ALL ranks."""
+    sd, model, clips, tokens = _setup(seed=34, V=4000, Q=60)
+    V, P, k = clips.shape[0] // 6, 4, 20
+    tok = torch.from_numpy(tokens).to(DEV)
+    big = clips * np.float32(1e33)
+    exact = MomentRetriever(model, torch.from_numpy(big).to(DEV), np.arange(V + 1) * 6, max_queries=64, k=k, engine="exact",
+                            text_engine="tc")
+    es, ei = exact.search_device(tok)
+    es, ei = es.clone(), ei.clone()
+
+    def step(r, comm):
+        v0, v1 = shard_range(V, r, P)
+        sh = MomentRetriever(model, torch.from_numpy(big[v0 * 6:v1 * 6]).to(DEV), np.arange(v1 - v0 + 1) * 6,
+                             id_base=v0 * 21, max_queries=64, k=k, engine="sel", text_engine="tc", comm=comm, world=P, rank=r)
+        s, i = sh.search_device(tok)
+        q0, q1 = sh.owned_range(tok.shape[0])
+        assert sh.n_fixups == tok.shape[0]
+        assert torch.equal(i, ei[q0:q1]) and torch.equal(s.view(torch.int32), es[q0:q1].view(torch.int32))
+        bad = tokens.copy()
+        bad[1, 0] = 10 ** 6                      # row 1 lives in rank 0's slice only
+        with pytest.raises(IndexError):
+            sh.search(bad)
+        return True
+    results, _ = _run_ranks(P, step)
+    assert all(results)

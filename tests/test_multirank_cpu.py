@@ -148,3 +148,47 @@ def test_sample_rank_is_the_smallest_safe_rank():
             assert j == 1 or poisson.sf(j - 2, x) >= 0.99e-10
     assert lib.vfr_sel_sample_rank(0, 10, 10) == 0 and lib.vfr_sel_sample_rank(5, 0, 10) == 0
     assert lib.vfr_sel_tiles(257) == 2 and lib.vfr_sel_tiles(0) == 0
+
+
+def _a2a_worker(rank, world, port, ret):
+    """The query-slice exchange: rank r sends record j to rank j and ends up with the P records of slice r."""
+    from vfr_b200.retrieval import _DistComm, slice_rows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = _DistComm()
+    per, k = slice_rows(7, world), 3
+    blk = per * (k * 12 + 4)
+    send = torch.empty((world, blk), dtype=torch.uint8)
+    for j in range(world):
+        send[j] = (rank * 16 + j)                       # record (src = rank, dst = j)
+    recv = comm.all_to_all(send)
+    ok = all(bool((recv[j] == (j * 16 + rank)).all()) for j in range(world))
+    gathered = comm.all_gather(torch.tensor([rank, rank + 10], dtype=torch.int32), out=torch.empty(2 * world, dtype=torch.int32))
+    ok = ok and gathered.tolist() == [[r, r + 10] for r in range(world)]
+    t = torch.tensor([int(ok)])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_query_slice_all_to_all():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1
+
+
+def test_query_slices_partition_the_batch():
+    from vfr_b200.retrieval import slice_rows
+    for q, w in ((37888, 8), (37888, 2), (151, 4), (3, 4), (1, 8), (100000, 8)):
+        per = slice_rows(q, w)
+        assert per % 2 == 0 and per * w >= q and (per - 2) * w < q
+        rows = [(min(r * per, q), min((r + 1) * per, q)) for r in range(w)]
+        assert rows[0][0] == 0 and rows[-1][1] == q and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))

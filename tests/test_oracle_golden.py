@@ -134,3 +134,90 @@ def test_moments_and_iou_tables():
                     tab = utils.threshold_table(thr, inc)
                     ref = (orc.get_iou(times, s, e) >= thr) if inc else (orc.get_iou(times, s, e) > thr)
                     assert np.array_equal(tab[inter, union].astype(bool), ref)
+
+
+# ---- goldens of a TRAINED reference model (informative R@k), validate_epoch and whole training steps ------------
+def _trained_inputs(meta):
+    videos = synth.make_videos(meta["seed"], meta["n_videos"], meta["feat_dim"], tuple(meta["seg_choices"]),
+                               tuple(meta["seg_probs"]))
+    queries = synth.make_queries(meta.get("query_seed", meta["seed"]), videos, meta["n_queries"], meta["vocab"])
+    return videos, queries
+
+
+@pytest.mark.parametrize("case", ["val_trained", "mid_trained"])
+def test_trained_goldens_are_informative_and_match_the_oracle(golden, case):
+    z, meta = golden(case)
+    videos, queries = _trained_inputs(meta)
+    m = meta["metrics_corpus"]["model, IoU=0.5"]
+    assert m["R@1"] > 0 and m["R@10"] > m["R@1"] and m["R@100"] > m["R@10"]          # not the degenerate all-zero case
+    # ranks of the first positive from the vectorised restatement == the reference's own (ties aside: none here)
+    full = orc.score_matrix(z["video_emb"], z["vid_off"], z["query_emb"]).numpy()
+    mom_off = np.concatenate([[0], np.cumsum([n * (n + 1) // 2 for n in np.diff(z["vid_off"])])])
+    for thr, key in ((0.5, "rank_05"), (0.7, "rank_07")):
+        ranks = []
+        for q in range(full.shape[0]):
+            vi = int(queries["video_idx"][q])
+            gt = orc.gt_bits(queries["times"][q], orc.generate_moments(videos[vi]["num_segments"]), thr)
+            own = full[q, mom_off[vi]:mom_off[vi + 1]]
+            tau = own[gt == 1].min()
+            ranks.append(int((full[q] < tau).sum()))
+        ranks = np.asarray(ranks)
+        ref = z[key]
+        # equal wherever no other score ties with tau at fp32 resolution (the reference's argsort is unstable there)
+        assert (ranks == ref).mean() > 0.97 and np.abs(ranks - ref).max() <= 3
+        rec = {f"R@{k}": float(np.mean(ref < k) * 100) for k in (1, 10, 100)}
+        rec["MR"] = float(np.median(ref))
+        assert rec == meta["metrics_corpus"][f"model, IoU={thr}"]
+
+
+def test_mid_trained_full_protocols_match_reference(golden):
+    z, meta = golden("mid_trained")
+    videos, queries = _trained_inputs(meta)
+    vemb = _split(z)
+    np.random.seed(123)
+    metrics = orc.evaluate_corpus(vemb, z["query_emb"], queries["video_idx"], queries["times"], model_types=("model", "chance"))
+    assert {k: {kk: float(vv) for kk, vv in v.items()} for k, v in metrics.items()} == meta["metrics_corpus"]
+    prior = synth.make_prior(sorted(set(v["num_segments"] for v in videos)))
+    random.seed(123)
+    single = orc.evaluate_single(vemb, z["query_emb"], queries["video_idx"], queries["times"], prior,
+                                 model_types=("model", "chance", "prior"), py_random=random)
+    assert {k: {kk: float(vv) for kk, vv in v.items()} for k, v in single.items()} == meta["metrics_single"]
+    # the embeddings themselves, from the committed trained weights
+    sd = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+    feats = np.concatenate([synth.clip_features(v) for v in videos])
+    np.testing.assert_allclose(orc.visual_embed(sd, feats).numpy(), z["video_emb"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(orc.text_embed(sd, queries["tokens"]).numpy(), z["query_emb"], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("tag,size", [("size250", 250), ("size100", 100), ("all", -1)])
+def test_validate_epoch_matches_reference(golden, tag, size):
+    z, meta = golden("mid_trained")
+    videos, queries = _trained_inputs(meta)
+    scalars, pr = orc.validate_epoch(_split(z), z["query_emb"], queries["video_idx"], queries["times"], size=size)
+    ref = meta["validate"][tag]
+    ref_scalars = {name: vals for name, vals, _ in ref["scalars"]}
+    assert scalars == ref_scalars
+    assert {k: {str(kk): [float(x) for x in vv] for kk, vv in v.items()} for k, v in pr.items()} == ref["pr_curve"]
+    assert all(step == 7 for _, _, step in ref["scalars"])        # written at the trainer's global_step
+
+
+@pytest.mark.parametrize("norm", [0, 1])
+def test_whole_training_steps_match_reference(golden, norm):
+    """Four forwards + ranking loss + backward + Adam(lr 5e-4, wd 5e-3), dropout off: loss, mean grad norm and the
+    weights after every step against what the reference's Trainer.train_epoch produced."""
+    z, meta = golden("train_full_step")
+    sd = {k: torch.from_numpy(v) for k, v in
+          synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], hidden=meta["hidden"], spread=meta["spread"]).items()}
+    state = {}
+    logged = z[f"norm{norm}_logged"].reshape(-1, 2)
+    for step in range(meta["steps"]):
+        batch = {k: z[f"b{step}_{k}"] for k in ("posit", "intra", "inter", "lang", "maskp", "maskn")}
+        loss, n, gnorm = orc.train_step(sd, batch, state, step + 1, normalize_loss=bool(norm), lr=meta["lr"],
+                                        weight_decay=meta["weight_decay"])
+        np.testing.assert_allclose(loss / n, logged[step, 0], rtol=2e-5)
+        np.testing.assert_allclose(gnorm, logged[step, 1], rtol=2e-4)
+        np.testing.assert_allclose(loss / n, float(z[f"norm{norm}_s{step}_epoch_loss"]), rtol=2e-5)
+        for k in z.files:
+            pre = f"norm{norm}_s{step}_w:"
+            if k.startswith(pre):
+                np.testing.assert_allclose(sd[k[len(pre):]].numpy(), z[k], rtol=2e-4, atol=2e-6, err_msg=k)

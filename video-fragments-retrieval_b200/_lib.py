@@ -45,6 +45,7 @@ PROTOTYPES = {
     "vfr_last_error": (C.c_char_p, []),
     "vfr_version": (_i, []),
     "vfr_device_sms": (_i, []),
+    "vfr_launch_count": (_l, []),
     "vfr_bank_pack_bytes": (_z, [_l, _i, _i]),
     "vfr_bank_pack": (_i, [_p, _p, _l, _i, _i, _p, _p]),
     "vfr_query_pack_bytes": (_z, [_l, _i]),
@@ -70,6 +71,13 @@ PROTOTYPES = {
     "vfr_sel_topk": (_i, [_p, _p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
     "vfr_sel_flags": (_p, [_p, _l]),
     "vfr_sel_tiles": (_l, [_l]),
+    "vfr_sel_pool_levels": (_i, [_p, _i, _l, _i, _p, _i, _p, _p]),
+    "vfr_sel_count_levels": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _i, _p, _p]),
+    "vfr_sel_pick_put": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p, _i, _p]),
+    "vfr_topk_block_bytes": (_z, [_l, _i]),
+    "vfr_sel_refine_blocks": (_i, [_p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _l, _p, _p, _i, _p]),
+    "vfr_topk_merge_blocks": (_i, [_p, _i, _l, _l, _i, _p, _p, _p, _p, _p]),
+    "vfr_sel_stats": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p]),
     "vfr_sel_sample_rank": (_i, [_i, _l, _l]),
     "vfr_sel_sample_lists": (_i, [_l, _l, _i]),
     "vfr_sel_sample_clips": (_l, [_l, _l, _i, _i]),

@@ -1,10 +1,12 @@
 // Error plumbing and device queries of the libvfr C ABI.
 #include "vfr_common.cuh"
 #include <stdarg.h>
+#include <atomic>
 
 namespace vfr {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};   // kernels this library has launched (every launch goes through check_launch)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -19,10 +21,13 @@ int check_launch(const char* what) {
     set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
     return VFR_ERR_CUDA;
   }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return VFR_OK;
 }
 
 }  // namespace vfr
+
+extern "C" int64_t vfr_launch_count(void) { return (int64_t)vfr::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* vfr_last_error(void) { return vfr::g_err; }
 

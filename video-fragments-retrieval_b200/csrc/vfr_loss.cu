@@ -62,6 +62,8 @@ __global__ void loss_dist_kernel(const LossParams p) {
   for (int s = 0; s < 3; ++s) {
     if (w < p.rows[s]) {
       const int64_t i = p.mask[s][w];
+      // a row whose sample id is outside [0, n_samples) is never selected by the reference's `mask == i` (main.py:226-230)
+      if (i < 0 || i >= p.n_samples) { if (lane == 0) p.dist[s][w] = 0.f; return; }
       const float* xr = p.x[s] + (int64_t)w * p.dim;
       const float* lr = p.lang + i * p.dim;
       const float sx = p.normalize ? p.inv[s][w] : 1.f;
@@ -95,11 +97,14 @@ __global__ void loss_reduce_kernel(const LossParams p) {
       p.cost[s * B + i] = c[s];
     }
     const float h1 = c[0] - c[1] + p.b, h2 = c[0] - c[2] + p.b;
-    const float a1 = h1 > 0.f ? 1.f : 0.f, a2 = h2 > 0.f ? 1.f : 0.f;
+    // NaN (an empty run, diverged embeddings) must reach the loss as F.relu(nan) = nan does in the reference
+    // (main.py:231): fmaxf(nan, 0) would return 0 and hide the divergence
+    const float a1 = h1 > 0.f ? 1.f : (h1 != h1 ? h1 : 0.f), a2 = h2 > 0.f ? 1.f : (h2 != h2 ? h2 : 0.f);
     p.coef[0 * B + i] = __fdiv_rn(a1 + p.lamb * a2, (float)cnt[0]);
     p.coef[1 * B + i] = __fdiv_rn(-a1, (float)cnt[1]);
     p.coef[2 * B + i] = __fdiv_rn(-p.lamb * a2, (float)cnt[2]);
-    p.cost[3 * B + i] = fmaxf(h1, 0.f) + p.lamb * fmaxf(h2, 0.f);
+    const float r1 = h1 > 0.f ? h1 : (h1 != h1 ? h1 : 0.f), r2 = h2 > 0.f ? h2 : (h2 != h2 ? h2 : 0.f);
+    p.cost[3 * B + i] = r1 + p.lamb * r2;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -118,13 +123,17 @@ __global__ void loss_bwd_rows_kernel(const LossParams p) {
   for (int s = 0; s < 3; ++s) {
     if (w < p.rows[s]) {
       const int64_t i = p.mask[s][w];
+      float* gx = p.grad[s] + (int64_t)w * p.dim;
+      if (i < 0 || i >= p.n_samples) {       // row of no sample: no gradient (and no out-of-range access)
+        for (int k = lane; k < p.dim; k += 32) gx[k] = 0.f;
+        return;
+      }
       const float* xr = p.x[s] + (int64_t)w * p.dim;
       const float* lr = p.lang + i * p.dim;
       const float sx = p.normalize ? p.inv[s][w] : 1.f;
       const float sl = p.normalize ? p.inv[3][i] : 1.f;
       const float d = p.dist[s][w];
-      const float g = (d > 0.f) ? go * p.coef[s * B + i] / d : 0.f;   // dL/dd / d
-      float* gx = p.grad[s] + (int64_t)w * p.dim;
+      const float g = (d > 0.f || d != d) ? go * p.coef[s * B + i] / d : 0.f;   // dL/dd / d (NaN propagates)
       // u_k = g * (xhat_k - lhat_k + eps) is the gradient wrt xhat (and minus that wrt lhat)
       float dot = 0.f;   // sum_k u_k * xhat_k  (needed to back-propagate through the normalisation)
       for (int k = lane; k < p.dim; k += 32) {

@@ -416,11 +416,16 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_finish_kernel(const unsign
 struct SI { unsigned s; int64_t id; };
 __device__ __forceinline__ bool si_gt(const SI& a, const SI& b) { return a.s > b.s || (a.s == b.s && a.id > b.id); }
 
+// part pi of the input starts stride_s floats / stride_i int64s after part pi - 1 (flat [P, Q, k] arrays: Q k for both;
+// the blocked records of a sharded search: one record size for both, see vfr_topk_merge_blocks)
 __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const float* __restrict__ in_scores,
                                                                     const int64_t* __restrict__ in_ids, int n_parts,
-                                                                    int64_t n_queries, int k, int n_pad,
+                                                                    int64_t stride_s, int64_t stride_i, int k, int n_pad,
                                                                     float* __restrict__ out_scores,
-                                                                    int64_t* __restrict__ out_ids) {
+                                                                    int64_t* __restrict__ out_ids,
+                                                                    const int32_t* __restrict__ in_flags, int64_t stride_f,
+                                                                    int32_t* __restrict__ out_flags,
+                                                                    unsigned long long* __restrict__ n_flagged) {
   extern __shared__ __align__(16) unsigned char raw[];
   unsigned* ss = reinterpret_cast<unsigned*>(raw);                         // [n_pad]
   int64_t* ids = reinterpret_cast<int64_t*>(raw + (size_t)n_pad * 8);      // [n_pad] (8-B aligned)
@@ -429,14 +434,20 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const float* 
   for (int i = threadIdx.x; i < n_pad; i += MERGE_THREADS) {
     if (i < total) {
       const int pi = i / k, j = i % k;
-      const int64_t src = ((int64_t)pi * n_queries + q) * k + j;
-      const int64_t id = in_ids[src];
-      ss[i] = id < 0 ? 0xffffffffu : __float_as_uint(in_scores[src]);
+      const int64_t id = in_ids[(int64_t)pi * stride_i + q * k + j];
+      ss[i] = id < 0 ? 0xffffffffu : __float_as_uint(in_scores[(int64_t)pi * stride_s + q * k + j]);
       ids[i] = id < 0 ? INT64_MAX : id;
     } else {
       ss[i] = 0xffffffffu;
       ids[i] = INT64_MAX;
     }
+  }
+  if (in_flags && threadIdx.x == 0) {
+    // a query is only as good as its worst shard list: OR of the shards' filter + refine flags
+    int32_t f = 0;
+    for (int pi = 0; pi < n_parts; ++pi) f |= in_flags[(int64_t)pi * stride_f + q];
+    out_flags[q] = f;
+    if (f && n_flagged) atomicAdd(n_flagged, 1ull);
   }
   // The lists of a sharded search arrive sorted (ascending (score, id), padding last): then every key's place in the
   // merged order is its own index plus, per other list, the number of keys before it (binary search) - no sort.
@@ -716,6 +727,30 @@ extern "C" int vfr_topk_merge(const float* in_scores, const int64_t* in_ids, int
   const size_t smem = (size_t)n_pad * 16;
   VFR_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   topk_merge_kernel<<<(unsigned)n_queries, MERGE_THREADS, smem, (cudaStream_t)stream>>>(
-      in_scores, in_ids, n_parts, n_queries, k, n_pad, out_scores, out_ids);
+      in_scores, in_ids, n_parts, n_queries * k, n_queries * k, k, n_pad, out_scores, out_ids, nullptr, 0, nullptr, nullptr);
   return check_launch("topk_merge_kernel");
+}
+
+// K7 on the records of the query-slice exchange: `blocks` holds n_parts records (one per shard, as written by
+// vfr_sel_refine_blocks: {ids int64 [per, k] | scores fp32 [per, k] | flags int32 [per]}, vfr_topk_block_bytes(per, k)
+// bytes each) for the SAME slice of `per` queries; the first n_rows of them are merged.
+extern "C" int vfr_topk_merge_blocks(const void* blocks, int n_parts, int64_t per, int64_t n_rows, int k, float* out_scores,
+                                     int64_t* out_ids, int32_t* out_flags, int64_t* n_flagged, vfr_stream_t stream) {
+  VFR_REQUIRE(blocks && out_scores && out_ids && out_flags, VFR_ERR_INVALID, "vfr_topk_merge_blocks: null pointer");
+  VFR_REQUIRE(n_parts >= 1 && k >= 1 && per > 0 && n_rows >= 0 && n_rows <= per, VFR_ERR_INVALID, "vfr_topk_merge_blocks: bad shape");
+  const int total = n_parts * k;
+  VFR_REQUIRE(total <= 4096, VFR_ERR_UNSUPPORTED, "vfr_topk_merge_blocks: n_parts*k=%d > 4096", total);
+  const int64_t blk = per * ((int64_t)k * 12 + 4);
+  VFR_REQUIRE(blk % 8 == 0, VFR_ERR_INVALID, "vfr_topk_merge_blocks: per * (3k + 1) must be even");
+  if (n_rows == 0) return VFR_OK;
+  int n_pad = 2;
+  while (n_pad < total) n_pad <<= 1;
+  const size_t smem = (size_t)n_pad * 16;
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(blocks);
+  VFR_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_merge_kernel<<<(unsigned)n_rows, MERGE_THREADS, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float*>(base + per * k * 8), reinterpret_cast<const int64_t*>(base), n_parts, blk / 4, blk / 8, k,
+      n_pad, out_scores, out_ids, reinterpret_cast<const int32_t*>(base + per * k * 12), blk / 4, out_flags,
+      reinterpret_cast<unsigned long long*>(n_flagged));
+  return check_launch("topk_merge_kernel (blocks)");
 }

@@ -96,6 +96,7 @@ struct SlParams {
   int wait_mode;             // mbarrier wait flavour (see sl_wait)
   long long* dbg;            // optional timeline of CTA 0 (development aid): [9 roles][256 events][4] + 8 counters
   int32_t* flags;            // [Qpad] != 0: a candidate list overflowed / scales out of range (see vfr.h)
+  unsigned long long* stats; // [2] {warp-level compaction events, lists compacted} since the lists were started (vfr_sel_stats)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -919,7 +920,8 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const bool need = st.cnt > st.trig;
       if (__any_sync(0xffffffffu, need)) {
         const long long tc0 = p.dbg ? clock64() : 0;
-        const int n_need = p.dbg ? __popc(__ballot_sync(0xffffffffu, need)) : 0;
+        const int n_need = __popc(__ballot_sync(0xffffffffu, need));
+        if (lane == 0) { atomicAdd(p.stats, 1ull); atomicAdd(p.stats + 1, (unsigned long long)n_need); }
         // (copies: taking the address of a member would push the whole per-thread state into local memory)
         int cnt = st.cnt;
         float tau_own = CUDART_INF_F;
@@ -1013,6 +1015,12 @@ struct RfParams {
   int64_t id_base;
   float* out_scores;
   int64_t* out_ids;
+  // blocked output (sharded search, vfr_sel_refine_blocks): the queries are cut into slices of `per` (one per rank
+  // of the exchange); slice j is ONE contiguous record {ids int64 [per, k] | scores fp32 [per, k] | flags int32 [per]}
+  // at out_blocks + j * blk_bytes, so that a single all-to-all moves every rank's slice.  per = 0: flat [Q, k] arrays.
+  int64_t per;
+  int64_t blk_bytes;
+  unsigned char* out_blocks;
 };
 
 // exact fp32 distance of one (query, clip) pair: the arithmetic of score_kernel / score_own_kernel in
@@ -1262,6 +1270,19 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
   rf_merge_batch(keys, s_cnt, p.k, &s_cnt, &s_tau);
 
   // ---- 4. output: ascending (score, global moment id) ----
+  float* out_s;
+  int64_t* out_i;
+  if (p.per == 0) {
+    out_s = p.out_scores + q * p.k;
+    out_i = p.out_ids + q * p.k;
+  } else {
+    unsigned char* blk = p.out_blocks + (q / p.per) * p.blk_bytes;
+    const int64_t r = q % p.per;
+    out_i = reinterpret_cast<int64_t*>(blk) + r * p.k;
+    out_s = reinterpret_cast<float*>(blk + p.per * p.k * 8) + r * p.k;
+    // (flags 3 / 4 of this query were written by thread 0 of this CTA above, 1 / 2 by earlier kernels)
+    if (tid == 0) reinterpret_cast<int32_t*>(blk + p.per * p.k * 12)[r] = p.flags[q];
+  }
   for (int i = tid; i < p.k; i += RF_THREADS) {
     const unsigned long long key = keys[i];
     const bool ok = key != ~0ull;
@@ -1272,8 +1293,8 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
       score = __uint_as_float((unsigned)(key >> 32));
       id = p.id_base + __ldg(p.mom_off + uvid[low >> 10]) + (int64_t)(low & 1023u);
     }
-    p.out_scores[q * p.k + i] = score;
-    p.out_ids[q * p.k + i] = id;
+    out_s[i] = score;
+    out_i[i] = id;
   }
 }
 
@@ -1431,7 +1452,8 @@ extern "C" size_t vfr_sel_topk_bytes(int64_t n_queries, int64_t n_clips, int n_s
     const SlPlan pl = sl_plan(qt == qtiles ? n_queries : qt * SL_M, n_clips, n_split);
     const size_t qpad = (size_t)pl.qrows;
     const size_t need = qpad * pl.n_parts * SL_CAP * sizeof(unsigned long long) + qpad * pl.n_parts * sizeof(int32_t) +
-                        2 * qpad * sizeof(unsigned) + qpad * pl.n_parts * sizeof(float) + qpad * pl.n_parts * SL_J * sizeof(float);
+                        2 * qpad * sizeof(unsigned) + qpad * pl.n_parts * sizeof(float) + qpad * pl.n_parts * SL_J * sizeof(float) +
+                        8 * sizeof(unsigned long long);
     if (need > worst) worst = need;
   }
   return worst;
@@ -1468,6 +1490,7 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
   p.tau_cert = p.tau_g + qpad;
   p.tau_part = reinterpret_cast<float*>(p.tau_cert + qpad);
   p.samp = nullptr;   // (the export buffer lives behind tau_part: sl_samp_buffer)
+  p.stats = reinterpret_cast<unsigned long long*>(p.tau_part + qpad * (size_t)pl.n_parts * (1 + SL_J));
   p.tile_stride = 1;
   // measured (37 888 queries, k = 100; whole 6 M-clip bank / one of 8 shards): first compaction after 3k keys, later
   // ones only when the list is full: 52.3 / 9.9 ms; every k keys: 52.0 / 12.1 ms - a compaction stalls the CTA's
@@ -1567,6 +1590,7 @@ static int sl_run_filter(const SlPlan& pl, SlParams p, const void* bank_packed, 
     const size_t qpad = (size_t)pl.qrows;
     rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad * (2 + (size_t)pl.n_parts), st);   // tau_g, tau_cert, tau_part: +inf
     if (rc) return rc;
+    VFR_CUDA(cudaMemsetAsync(p.stats, 0, 8 * sizeof(unsigned long long), st));
     if (tile_lo == tile_hi) VFR_CUDA(cudaMemsetAsync(p.cand_cnt, 0, qpad * (size_t)pl.n_parts * sizeof(int32_t), st));
     // starting thresholds from a strided sample of the WHOLE bank (whatever slice this call scans)
     const SlSample sp = sl_sample_plan(pl, p.n_clips, p.k);
@@ -1585,8 +1609,11 @@ static int sl_run_filter(const SlPlan& pl, SlParams p, const void* bank_packed, 
 
 static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vid_off, const int64_t* mom_off,
                          int64_t n_videos, int n_max, int dim, const float* queries, int64_t n_queries, int k,
-                         int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st) {
-  VFR_REQUIRE(bank && vid_off && mom_off && queries && out_scores && out_ids, VFR_ERR_INVALID, "vfr_sel_refine: null pointer");
+                         int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st, int64_t per = 0,
+                         void* out_blocks = nullptr) {
+  VFR_REQUIRE(bank && vid_off && mom_off && queries && ((out_scores && out_ids) || (per > 0 && out_blocks)), VFR_ERR_INVALID,
+              "vfr_sel_refine: null pointer");
+  VFR_REQUIRE(per == 0 || (per * (3 * (int64_t)k + 1)) % 2 == 0, VFR_ERR_INVALID, "vfr_sel_refine_blocks: per * (3k + 1) must be even");
   VFR_REQUIRE(n_videos > 0 && n_videos < (int64_t(1) << 31) - 1, VFR_ERR_UNSUPPORTED, "vfr_sel_refine: n_videos");
   VFR_REQUIRE(n_max >= 1 && n_max <= VFR_MAX_SEG, VFR_ERR_UNSUPPORTED, "vfr_sel_refine: n_max=%d", n_max);
   RfParams r{};
@@ -1608,6 +1635,9 @@ static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vi
   r.id_base = id_base;
   r.out_scores = out_scores;
   r.out_ids = out_ids;
+  r.per = per;
+  r.blk_bytes = per * ((int64_t)k * 12 + 4);
+  r.out_blocks = reinterpret_cast<unsigned char*>(out_blocks);
   sl_refine_kernel<<<(unsigned)n_queries, RF_THREADS, 0, st>>>(r);
   return check_launch("sl_refine_kernel");
 }
@@ -1652,7 +1682,187 @@ __global__ void sl_count_under_kernel(const unsigned long long* __restrict__ can
   if (lane == 0) count[q] = c;
 }
 
+// out[0] = sum of the list lengths, out[1] = longest list, out[2] = flagged queries, out[3] = lists,
+// out[4] = warp-level compaction events, out[5] = lists compacted  (out zeroed by the caller)
+__global__ void sl_stats_kernel(const int32_t* __restrict__ cand_cnt, int n_parts, const int32_t* __restrict__ flags, int64_t n,
+                                const unsigned long long* __restrict__ stats, unsigned long long* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long tot = 0, mx = 0, fl = 0;
+  if (q < n) {
+    for (int part = 0; part < n_parts; ++part) {
+      const unsigned long long c = (unsigned long long)min(cand_cnt[q * n_parts + part], SL_CAP);
+      tot += c;
+      mx = c > mx ? c : mx;
+    }
+    fl = flags[q] != 0 ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    fl += __shfl_xor_sync(0xffffffffu, fl, o);
+    const unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = m2 > mx ? m2 : mx;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, tot);
+    atomicMax(out + 1, mx);
+    atomicAdd(out + 2, fl);
+  }
+  if (q == 0) { out[3] = (unsigned long long)n * n_parts; out[4] = stats[0]; out[5] = stats[1]; }
+}
+
+// ---- the shard-level glue of the pooled-sample protocol, one kernel each (was a chain of torch ops) ----------------
+// levels[l][q] = the ranks[l]-th smallest (1-based) of the n_src * width pooled sample values of query q
+// (pooled fp32 [n_src, Q, width], +inf padded).  One warp per query; rank by counting (ties by position).
+constexpr int PL_MAX = 1024;
+__global__ void __launch_bounds__(256) sl_pool_levels_kernel(const float* __restrict__ pooled, int n_src, int64_t n_queries,
+                                                             int width, int4 ranks, int n_levels, float* __restrict__ levels) {
+  __shared__ float vals[8][PL_MAX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * 8 + w;
+  if (q >= n_queries) return;
+  const int n = n_src * width;
+  for (int i = lane; i < n; i += 32) {
+    const int src = i / width, j = i - src * width;
+    vals[w][i] = pooled[((int64_t)src * n_queries + q) * width + j];
+  }
+  __syncwarp();
+  const int rk[4] = {ranks.x, ranks.y, ranks.z, ranks.w};
+  for (int i = lane; i < n; i += 32) {
+    const float v = vals[w][i];
+    int before = 0;
+    for (int j = 0; j < n; ++j) {
+      const float u = vals[w][j];
+      before += (u < v || (u == v && j < i)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (l < n_levels && before == rk[l] - 1) levels[(int64_t)l * n_queries + q] = v;
+  }
+}
+
+// count[l][q] = number of retained keys with d2~ <= levels[l][q] - E_q (clips CERTAINLY within that bound)
+__global__ void sl_count_levels_kernel(const unsigned long long* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+                                       int n_parts, const float4* __restrict__ qmeta, int64_t n, const float* __restrict__ levels,
+                                       int n_levels, int32_t* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n) return;
+  const float e = 0.5f * qmeta[q].w;
+  unsigned tb[4];
+  bool ok[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const float t = (l < n_levels) ? __fsub_rd(levels[(int64_t)l * n + q], e) : -1.f;
+    ok[l] = t >= 0.f;
+    tb[l] = __float_as_uint(fmaxf(t, 0.f));
+  }
+  int c[4] = {0, 0, 0, 0};
+  for (int part = 0; part < n_parts; ++part) {
+    const int64_t li = q * n_parts + part;
+    const int m = min(cand_cnt[li], SL_CAP);
+    for (int i = lane; i < m; i += 32) {
+      const unsigned key = (unsigned)(cand[li * SL_CAP + i] >> 32);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) c[l] += (ok[l] && key <= tb[l]) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int tot = warp_sum_int(c[l]);
+    if (lane == 0 && l < n_levels) count[(int64_t)l * n + q] = tot;
+  }
+}
+
+// after the all-reduce of the counts: the tightest level that still holds k clips over ALL shards is a certified bound
+// of the global k-th distance (levels are ordered loosest first, so ok is monotone); a query whose loosest level fails
+// was promised k clips the bank does not have -> flag 4.  The bound is put into tau_g / tau_cert like sl_bound_put.
+__global__ void sl_pick_put_kernel(const float* __restrict__ levels, const int32_t* __restrict__ count, int n_levels, int k,
+                                   unsigned* __restrict__ tau_g, unsigned* __restrict__ tau_cert, const float4* __restrict__ qmeta,
+                                   int32_t* __restrict__ flags, int64_t n) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int n_ok = 0;
+  for (int l = 0; l < n_levels; ++l) n_ok += (count[(int64_t)l * n + q] >= k) ? 1 : 0;
+  if (count[q] < k && flags[q] == 0) flags[q] = 4;
+  const float bound = levels[(int64_t)(max(n_ok, 1) - 1) * n + q];
+  const float t = fmaxf(__fsub_ru(bound, 0.5f * qmeta[q].w), 0.f);
+  if (t < __uint_as_float(tau_g[q])) tau_g[q] = __float_as_uint(t);
+  if (t < __uint_as_float(tau_cert[q])) tau_cert[q] = __float_as_uint(t);
+}
+
 }  // namespace vfr
+
+extern "C" int vfr_sel_pool_levels(const float* pooled, int n_src, int64_t n_queries, int width, const int32_t* ranks,
+                                   int n_levels, float* levels, vfr_stream_t stream) {
+  VFR_REQUIRE(pooled && ranks && levels, VFR_ERR_INVALID, "vfr_sel_pool_levels: null pointer");
+  VFR_REQUIRE(n_src >= 1 && width >= 1 && n_src * (int64_t)width <= PL_MAX && n_levels >= 1 && n_levels <= 4 && n_queries > 0,
+              VFR_ERR_UNSUPPORTED, "vfr_sel_pool_levels: %d x %d pooled values, %d levels", n_src, width, n_levels);
+  int4 rk = make_int4(0, 0, 0, 0);
+  int* rp = &rk.x;
+  for (int l = 0; l < n_levels; ++l) {
+    VFR_REQUIRE(ranks[l] >= 1 && ranks[l] <= n_src * width, VFR_ERR_INVALID, "vfr_sel_pool_levels: rank %d", ranks[l]);
+    rp[l] = ranks[l];
+  }
+  sl_pool_levels_kernel<<<(unsigned)((n_queries + 7) / 8), 256, 0, (cudaStream_t)stream>>>(pooled, n_src, n_queries, width, rk,
+                                                                                        n_levels, levels);
+  return check_launch("sl_pool_levels_kernel");
+}
+
+extern "C" int vfr_sel_count_levels(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
+                                    int n_split, const float* levels, int n_levels, int32_t* count, vfr_stream_t stream) {
+  VFR_REQUIRE(query_packed && workspace && levels && count && n_levels >= 1 && n_levels <= 4, VFR_ERR_INVALID,
+              "vfr_sel_count_levels: bad argument");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  sl_count_levels_kernel<<<(unsigned)((n_queries + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      p.cand, p.cand_cnt, p.n_parts, p.qmeta, n_queries, levels, n_levels, count);
+  return check_launch("sl_count_levels_kernel");
+}
+
+extern "C" int vfr_sel_pick_put(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
+                                int n_split, const float* levels, const int32_t* count, int n_levels, vfr_stream_t stream) {
+  VFR_REQUIRE(query_packed && workspace && levels && count && n_levels >= 1 && n_levels <= 4, VFR_ERR_INVALID,
+              "vfr_sel_pick_put: bad argument");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  sl_pick_put_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      levels, count, n_levels, k, p.tau_g, p.tau_cert, p.qmeta, p.flags, n_queries);
+  return check_launch("sl_pick_put_kernel");
+}
+
+extern "C" size_t vfr_topk_block_bytes(int64_t per, int k) { return (per > 0 && k > 0) ? (size_t)per * ((size_t)k * 12 + 4) : 0; }
+
+extern "C" int vfr_sel_refine_blocks(const float* bank, const int32_t* vid_off, const int64_t* mom_off, int64_t n_videos,
+                                     int64_t n_clips, int n_max, int dim, void* query_packed, const float* queries,
+                                     int64_t n_queries, int k, int64_t id_base, int64_t per, void* out_blocks, void* workspace,
+                                     int n_split, vfr_stream_t stream) {
+  VFR_REQUIRE(query_packed && workspace && out_blocks && per > 0, VFR_ERR_INVALID, "vfr_sel_refine_blocks: bad argument");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  return sl_run_refine(p, bank, vid_off, mom_off, n_videos, n_max, dim, queries, n_queries, k, id_base, nullptr, nullptr,
+                       (cudaStream_t)stream, per, out_blocks);
+}
+
+extern "C" int vfr_sel_stats(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,
+                             int n_split, int64_t* out, vfr_stream_t stream) {
+  VFR_REQUIRE(query_packed && workspace && out, VFR_ERR_INVALID, "vfr_sel_stats: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  VFR_CUDA(cudaMemsetAsync(out, 0, 8 * sizeof(int64_t), st));
+  sl_stats_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(p.cand_cnt, p.n_parts, p.flags, n_queries, p.stats,
+                                                                      reinterpret_cast<unsigned long long*>(out));
+  return check_launch("sl_stats_kernel");
+}
 
 extern "C" int64_t vfr_sel_tiles(int64_t n_clips) { return n_clips > 0 ? sl_tiles(n_clips) : 0; }
 
@@ -1691,6 +1901,7 @@ extern "C" int vfr_sel_sample(const void* bank_packed, int64_t n_clips, int dim,
   rc = launch_fill_u32(p.tau_g, 0x7f800000u, qpad * (2 + (size_t)pl.n_parts), st);   // fresh thresholds and lists
   if (rc) return rc;
   VFR_CUDA(cudaMemsetAsync(p.cand_cnt, 0, qpad * (size_t)pl.n_parts * sizeof(int32_t), st));
+  VFR_CUDA(cudaMemsetAsync(p.stats, 0, 8 * sizeof(unsigned long long), st));
   const SlSample sp = sl_sample_plan(pl, n_clips, k, /*need_rank=*/false);
   *n_sampled = (int64_t)sp.tiles * pl.n_parts * SL_N;
   if (sp.tiles == 0) return VFR_OK;

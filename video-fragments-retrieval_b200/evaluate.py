@@ -37,8 +37,10 @@ def get_metrics(recalls):
     return out
 
 
-def collect_embeddings(model, video_iterator, lang_iterator, device, rows_per_call=16384):
+def collect_embeddings(model, video_iterator, lang_iterator, device, rows_per_call=16384, bert=False):
     """Run the two embedding prologues of ``evaluate.py:33-35,42-44`` as batched calls.
+    ``bert`` is the flag ``Trainer.validate_epoch`` forwards to the model (main.py:146): the language batches then
+    hold float BERT-pooled features ``[1, 768]`` instead of token ids.
     Returns (Bank, names, q_emb [Q, D], q_video_names, q_annot_ids)."""
     feats, names, nseg = [], [], []
     for batch in video_iterator:
@@ -59,7 +61,7 @@ def collect_embeddings(model, video_iterator, lang_iterator, device, rows_per_ca
         q_names.append(batch["video"])
         q_annots.append(batch["annot_id"])
     with torch.no_grad():
-        q_emb = model(torch.cat(ids, dim=0).to(device), False, device)
+        q_emb = model(torch.cat(ids, dim=0).to(device), False, device, bert)
     return bank, names, q_emb.float().contiguous(), q_names, q_annots
 
 

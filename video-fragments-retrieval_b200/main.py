@@ -98,7 +98,8 @@ class Trainer:
         """main.py:121-212: ``>=`` IoU rule (:161), thresholds 0.0..1.0 when ``size == -1`` (:138),
         1-based rank (:170), CustomRecall / MedianRank / MRR scalars, precision/recall curves."""
         model.eval()
-        bank, names, q_emb, q_names, q_annots = collect_embeddings(model, video_iterator, lang_iterator, self.device)
+        bank, names, q_emb, q_names, q_annots = collect_embeddings(model, video_iterator, lang_iterator, self.device,
+                                                                      bert=self.bert)
         if size != -1:
             q_emb, q_names, q_annots = q_emb[:size], q_names[:size], q_annots[:size]
         index = {name: i for i, name in enumerate(names)}

@@ -7,6 +7,8 @@ import torch
 from . import _lib
 from .utils import MAX_SEGMENTS, threshold_table
 
+SEL_MAX_DIM = 125   # largest embedding dimension of the filter + refine engine (vfr_sel_*)
+
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
@@ -82,8 +84,8 @@ class Bank:
     def sel(self):
         """Packed fp16 operand of the filter + refine top-k (vfr_sel_topk); built lazily, cached."""
         if "_sel" not in self.__dict__:
-            if self.dim > 125:
-                raise _lib.VfrError("the filter + refine top-k holds embeddings of at most 125 dimensions")
+            if self.dim > SEL_MAX_DIM:
+                raise _lib.VfrError(f"the filter + refine top-k holds embeddings of at most {SEL_MAX_DIM} dimensions")
             n_clips = int(self.clips.shape[0])
             packed = torch.empty(_lib.load().vfr_sel_bank_bytes(n_clips), dtype=torch.uint8, device=self.device)
             _lib.call("vfr_sel_bank_pack", _ptr(self.clips), n_clips, self.dim, _ptr(packed), _stream())

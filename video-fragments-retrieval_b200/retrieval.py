@@ -7,11 +7,26 @@ The reference has no serving entry point - its corpus protocol is the python loo
 scores it against the bank with the fused top-k (K4) and returns the k best (score, moment id).
 
 Multi-GPU: the bank is partitioned by contiguous video ranges across the ranks of
-one NVSwitch box, queries are replicated, every rank computes its local top-k with GLOBAL moment ids
-and the per-rank lists are exchanged with ONE ``all_gather`` over NCCL/NVLink and merged (K7).
-Moment id = ``mom_off[video] + moment_index`` over the WHOLE corpus, so results do not depend on the
-number of ranks.
+one NVSwitch box; moment id = ``mom_off[video] + moment_index`` over the WHOLE corpus, so results do not
+depend on the number of ranks.  One step on P ranks (``search_device``):
+
+1. every rank embeds ITS SLICE of the query batch (K3 is data-parallel over queries), one all-gather
+   replicates the embeddings;
+2. every rank scores the whole batch against its bank shard (K4); with the filter + refine engine the
+   shards first agree on a threshold (pooled samples, ``_sel_score_sharded``) so that a shard keeps ~k/P
+   candidates;
+3. the refine stage writes its lists straight into QUERY-SLICE records (ids | scores | flags) and ONE
+   all-to-all hands rank r the P shard lists of slice r - 1/P of the bytes of an all-gather of ``[P, Q, k]``,
+   and every rank merges only its own Q/P queries (K7);
+4. rank r OWNS the results of slice r: ``search`` copies only that slice back to the host (and copied only
+   that slice of the token ids to the device).  ``owned_range(Q)`` gives the rows.
+
+The per-query flags of the filter + refine engine travel inside the records; a tiny all-gather makes every rank
+see all of them (plus the out-of-range-token flag of every rank's K3), so the rare exact-engine rerun and the
+``IndexError`` of a bad token are taken by all ranks together - no collective is ever guarded by a rank-local
+condition, and the only host synchronisation of a step is one event wait at its very end.
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -26,15 +41,23 @@ def shard_range(n_videos, rank, world):
     return (n_videos * rank) // world, (n_videos * (rank + 1)) // world
 
 
+def slice_rows(n_queries, world):
+    """Queries per rank of the query-slice exchange: ceil(Q / P), rounded up to an even count (the records hold
+    int64 ids behind fp32 scores and int32 flags: ``per * (3k + 1)`` must be even for 8-byte alignment)."""
+    per = (int(n_queries) + world - 1) // world
+    return per + (per & 1)
+
+
 class _DistComm:
-    """The collectives of the sharded search over torch.distributed (NCCL)."""
+    """The collectives of the sharded search over torch.distributed (NCCL; gloo in the CPU tests)."""
 
     def __init__(self, group=None):
         self.group = group
 
-    def all_gather(self, t):
+    def all_gather(self, t, out=None):
         world = dist.get_world_size(self.group)
-        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)   # concatenated form
+        if out is None:
+            out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)   # concatenated form
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out.view((world,) + tuple(t.shape))
 
@@ -46,26 +69,38 @@ class _DistComm:
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
         return t
 
+    def all_to_all(self, send, out=None):
+        """send [P, n] (row j goes to rank j) -> [P, n] (row j came from rank j)."""
+        if out is None:
+            out = torch.empty_like(send)
+        dist.all_to_all_single(out.view(-1), send.contiguous().view(-1), group=self.group)
+        return out
+
 
 class MomentRetriever:
 
     ENGINES = {"exact": 0, "tc": 3, "tc_bf16": 1, "sel": 4}
 
     def __init__(self, model, clips, vid_off, id_base=0, max_queries=4096, k=100, n_split=0, group=None,
-                 engine="auto", text_engine="auto"):
+                 engine="auto", text_engine="auto", comm=None, world=None, rank=None):
         """``model``: a ``CALModel`` (text branch used); ``clips`` fp32 [C_local, D] + ``vid_off`` =
         this rank's bank shard; ``id_base`` = global moment id of the shard's first moment.
         ``engine``: "exact" (fp32 CUDA-core scoring, bit-identical to the evaluation path), "tc"
         (tcgen05 split-bf16 scoring, fp32 scores within 1e-5), "tc_bf16" (plain bf16, 1e-2), or
         "sel" (filter + refine: one fp16 tcgen05 pass with a rigorous error band + exact fp32 re-scoring of the
         survivors; results bit-identical to "exact", any clip count per video), or "auto" = "sel" whenever
-        D <= 125."""
+        the embedding dimension fits the engine.
+        ``comm`` / ``world`` / ``rank`` replace torch.distributed (the tests emulate the ranks on one GPU)."""
         self.model = model
         self.bank = ops.Bank(clips, vid_off)
         self.k = int(k)
         self.max_queries = int(max_queries)
         self.group = group
-        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if world is None:
+            world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+            rank = dist.get_rank(group) if world > 1 else 0
+        self.world, self.rank = int(world), int(rank or 0)
+        self.comm = comm if comm is not None else (_DistComm(group) if self.world > 1 else None)
         dev = self.bank.device
         self.device = dev
         self.seq_len = 20
@@ -77,9 +112,11 @@ class MomentRetriever:
         fc_b = model.lang_fc.bias.detach().float().contiguous()
         H, E, D = model.hidden_size, table.shape[1], fc_w.shape[0]
         mq = self.max_queries
+        per = slice_rows(mq, self.world) if self.world > 1 else mq
         self._keep = [fwd, bwd, table, length, fc_w, fc_b]
         self.tokens_dev = torch.empty((mq, self.seq_len), dtype=torch.int64, device=dev)
-        self.q_emb = torch.empty((mq, D), dtype=torch.float32, device=dev)
+        # the all-gather of the query slices lands straight in q_emb: room for world * per rows
+        self.q_emb = torch.zeros((max(mq, per * self.world), D), dtype=torch.float32, device=dev)
         if text_engine == "auto":
             text_engine = "tc" if H % 4 == 0 else "exact"
         self.text_engine = text_engine
@@ -90,7 +127,7 @@ class MomentRetriever:
             self.text_tc = None
             self.text_ws = torch.empty(lib.vfr_text_embed_bytes(mq, self.seq_len, H, E) // 4, dtype=torch.float32, device=dev)
         if engine == "auto":
-            engine = "sel" if D <= 125 else "exact"
+            engine = "sel" if D <= ops.SEL_MAX_DIM else "exact"
         self.engine = engine
         eng = self.ENGINES[engine]
         if eng == 0:
@@ -132,134 +169,196 @@ class MomentRetriever:
         self.plan = p
         self.sel_bound = torch.empty(mq, dtype=torch.float32, device=dev)
         self.sel_samp = torch.empty(0, dtype=torch.float32, device=dev)       # grown on first use (sharded search)
+        self.sel_levels = torch.empty(4 * mq, dtype=torch.float32, device=dev)
         self.sel_count = torch.empty(4 * mq, dtype=torch.int32, device=dev)
+        self.sel_stats = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.n_fixups = 0
+        self.profile = False               # True: every stage of a sharded step is bracketed by CUDA events (stage_ms)
+        self._prof = {}
         if self.world > 1:
-            self.gather_s = torch.empty((self.world, mq, self.k), dtype=torch.float32, device=dev)
-            self.gather_i = torch.empty((self.world, mq, self.k), dtype=torch.int64, device=dev)
-            per = (mq + self.world - 1) // self.world
+            blk = lib.vfr_topk_block_bytes(per, self.k)
+            self.send_blocks = torch.empty((self.world, blk), dtype=torch.uint8, device=dev)
+            self.recv_blocks = torch.empty((self.world, blk), dtype=torch.uint8, device=dev)
+            self.slice_s = torch.empty((per, self.k), dtype=torch.float32, device=dev)
+            self.slice_i = torch.empty((per, self.k), dtype=torch.int64, device=dev)
+            # per-query flags of my slice + one trailing word: this rank's out-of-range-token flag (K3)
+            self.slice_flags = torch.zeros(per + 1, dtype=torch.int32, device=dev)
+            self.flags_all = torch.zeros(self.world * (per + 1), dtype=torch.int32, device=dev)
+            self.host_flags = torch.zeros(self.world * (per + 1), dtype=torch.int32).pin_memory()
+            self.flags_event = torch.cuda.Event()
             self.q_slice = torch.zeros((per, D), dtype=torch.float32, device=dev)
-            self.q_gather = torch.empty((self.world * per, D), dtype=torch.float32, device=dev)
-        # pinned staging for the host-buffer path
-        self.host_tokens = torch.empty((mq, self.seq_len), dtype=torch.int64).pin_memory()
-        self.host_s = torch.empty((mq, self.k), dtype=torch.float32).pin_memory()
-        self.host_i = torch.empty((mq, self.k), dtype=torch.int64).pin_memory()
-        # kernels launched per search step: gather + 20 LSTM steps + 2 fc + query pack + threshold init + score (filter) + finish (refine) (+ merge)
-        if text_engine == "tc":
-            # zero + len/scan/perm + gather + (join + step GEMM) x L + final join folded in L + fc
-            n_text = 1 + 3 + 1 + 2 * self.seq_len + 1
-        else:
-            n_text = 1 + self.seq_len + 2
-        if self.engine == "sel" and self.world > 1:
-            # bound exchange: query pack + threshold init + sample pass + filter (first slice) + bound get / put + filter
-            # (rest) + refine + merge; pooled samples (see launches_per_step): query pack + threshold init + sample pass +
-            # bound put + filter + 4 counts + bound put + refine + merge
-            n_k4 = 9
-        elif self.engine == "sel":
-            n_k4 = 5          # query pack + threshold init + sample pass + filter + refine
-        else:
-            n_k4 = 4 + (1 if self.world > 1 else 0)   # query pack + threshold init + score + finish (+ merge)
-        self._launches_base = n_text + n_k4
+            self.gather_s = self.gather_i = None           # (non-sel engines: allocated on first use)
+        # pinned staging for the host-buffer path (a rank only ever moves its own slice)
+        self.host_tokens = torch.empty((per, self.seq_len), dtype=torch.int64).pin_memory()
+        self.host_s = torch.empty((per, self.k), dtype=torch.float32).pin_memory()
+        self.host_i = torch.empty((per, self.k), dtype=torch.int64).pin_memory()
 
-    @property
-    def launches_per_step(self):
-        """Kernels of this library launched per search step (the claim bench.py reports as gpu_launches)."""
-        pooled = any(j > 0 for j in self.__dict__.get("_sel_rank_cache", {}).values())
-        return self._launches_base + (3 if pooled else 0)
+    # -- bookkeeping -------------------------------------------------------------------------------------
+    def owned_range(self, n_queries):
+        """Rows [q0, q1) of a batch of ``n_queries`` whose results this rank returns."""
+        if self.world == 1:
+            return 0, int(n_queries)
+        per = slice_rows(n_queries, self.world)
+        return min(self.rank * per, int(n_queries)), min((self.rank + 1) * per, int(n_queries))
+
+    @contextlib.contextmanager
+    def _stage(self, name):
+        if not self.profile:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self._prof.setdefault(name, []).append((a, b))
+
+    def stage_ms(self, reset=True):
+        """Mean milliseconds per stage of the profiled steps (``profile = True``), in first-seen order."""
+        torch.cuda.synchronize()
+        out = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in self._prof.items()}
+        if reset:
+            self._prof = {}
+        return out
+
+    def filter_stats(self, n_queries):
+        """Diagnostics of the last filter + refine call (engine "sel"): candidates kept per query, compactions, flags."""
+        if self.plan.engine != 4:
+            return None
+        p, b = self.plan, self.bank
+        _lib.call("vfr_sel_stats", self.q_tc.data_ptr(), n_queries, self.n_clips, b.dim, self.k, self.topk_ws.data_ptr(),
+                  p.n_split, self.sel_stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        tot, longest, flagged, lists, events, compacted = self.sel_stats[:6].tolist()
+        return dict(candidates_per_query=tot / n_queries, longest_list=longest, n_flagged=flagged, lists=lists,
+                    compactions_per_list=compacted / max(lists, 1), compaction_warp_events=events)
+
+    # -- the stages of a step -----------------------------------------------------------------------------
+    def embed_only(self, tokens_dev):
+        """K3 (+ the all-gather of the slices on P ranks): query embeddings of the batch -> ``q_emb[:Q]``."""
+        Q = tokens_dev.shape[0]
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.world == 1:
+            _lib.call("vfr_search_embed_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.q_emb.data_ptr(), stream)
+            return
+        per = slice_rows(Q, self.world)
+        q0, q1 = self.owned_range(Q)
+        mine = self.q_slice[:per]
+        with self._stage("k3_embed"):
+            if q1 > q0:
+                _lib.call("vfr_search_embed_device", C.byref(self.plan), tokens_dev[q0:q1].data_ptr(), q1 - q0,
+                          mine.data_ptr(), stream)
+        with self._stage("allgather_queries"):
+            self.comm.all_gather(mine, out=self.q_emb[:self.world * per])
 
     def score_only(self, n_queries):
-        """K4 alone (query pack excluded) on the query embeddings left in ``q_emb`` by the previous
-        search - used by bench.py to time the dominant kernel inside the steps."""
-        lib_stream = torch.cuda.current_stream().cuda_stream
+        """K4 alone on the query embeddings in ``q_emb`` (the dominant kernel; bench.py times it inside the steps).
+        On P ranks this is the shard's whole K4 including the threshold protocol's collectives."""
+        stream = torch.cuda.current_stream().cuda_stream
         b, p = self.bank, self.plan
-        if p.engine == 4:
+        if self.world > 1 and p.engine == 4:
+            self._sel_score_sharded(n_queries, stream, per=slice_rows(n_queries, self.world))
+        elif p.engine == 4:
+            _lib.call("vfr_sel_query_pack", p.q_emb, n_queries, b.dim, p.bank_tc, self.n_clips, p.q_tc, stream)
             _lib.call("vfr_sel_topk", p.bank_tc, p.bank_clips, p.vid_off, p.mom_off, b.n_videos, self.n_clips, b.n_max,
                       b.dim, p.q_tc, p.q_emb, n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev, p.topk_ws,
-                      p.n_split, lib_stream)
-        elif p.engine:
-            _lib.call("vfr_score_topk_tc", p.bank_tc, p.bank_clips, p.vid_off, p.mom_off, b.n_videos, p.uniform6, b.dim,
-                      p.engine, p.q_tc, p.q_emb, n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev,
-                      p.topk_ws, p.n_split, lib_stream)
+                      p.n_split, stream)
         else:
-            _lib.call("vfr_score_topk", p.bank_packed, p.vid_off, p.mom_off, b.n_videos, b.n_max, b.dim, p.q_packed,
-                      n_queries, self.k, p.id_base, p.out_scores_dev, p.out_ids_dev, p.topk_ws, p.n_split, lib_stream)
+            _lib.call("vfr_search_score_device", C.byref(p), n_queries, self.k, self.out_s.data_ptr(), self.out_i.data_ptr(),
+                      stream)
 
-    def _sel_score_sharded(self, Q, stream, comm=None):
+    def _sel_score_sharded(self, Q, stream, comm=None, per=0):
         """K4 of one shard when the bank is spread over several ranks.  A shard's local top-k only has to hold what
         can reach the GLOBAL top-k, so the shards agree on a threshold before the scan (include/vfr.h):
 
-        * large shards pool their SAMPLES: every shard's 32 smallest sampled distances are all-gathered, the j-th
+        * large shards pool their SAMPLES: every shard's smallest sampled distances are all-gathered, the j-th
           smallest of the union (j from the pooled sample size: the bank holds k clips under it except with
           probability < 1e-10) becomes every shard's starting bound; after the scan ONE all-reduce(sum) of per-query
-          counts verifies the guess (queries that fail are flagged and re-run through the exact engine).  Every shard
-          then keeps ~k/P candidates instead of ~k: its hit / list / re-scoring work shrinks with the shard.
-        * otherwise the shards exchange a certified bound half way through the scan (one all-reduce(min)).
+          counts verifies the guess (queries that fail are flagged and re-run through the exact engine) and picks the
+          tightest of four candidate bounds that still holds k clips.  Every shard then keeps ~k/P candidates instead
+          of ~k: its hit / list / re-scoring work shrinks with the shard.  Kernels only between the collectives
+          (``vfr_sel_pool_levels`` / ``count_levels`` / ``pick_put``).
+        * otherwise the shards exchange a certified bound part way through the scan (one all-reduce(min)).
 
-        ``comm`` replaces the NCCL collectives (tests emulate the ranks on one GPU)."""
+        ``per`` > 0: the refine stage writes the query-slice records of the all-to-all (``send_blocks``) instead of
+        the flat ``out_s`` / ``out_i``.  ``comm`` replaces the NCCL collectives (tests emulate the ranks on one GPU)."""
         p, b = self.plan, self.bank
         lib = _lib.load()
-        comm = comm or _DistComm(self.group)
+        comm = comm or self.comm
         n_clips = self.n_clips
         qt, ws = self.q_tc.data_ptr(), self.topk_ws.data_ptr()
-        _lib.call("vfr_sel_query_pack", p.q_emb, Q, b.dim, p.bank_tc, n_clips, qt, stream)
+        with self._stage("k4_query_pack"):
+            _lib.call("vfr_sel_query_pack", p.q_emb, Q, b.dim, p.bank_tc, n_clips, qt, stream)
         tiles = lib.vfr_sel_tiles(n_clips)
-        rank_j = self._sel_global_rank(Q, comm)
+        rank_j, n_src = self._sel_global_rank(Q, comm)
+        lists = lib.vfr_sel_sample_lists(Q, n_clips, p.n_split)
         if rank_j > 0:
-            lists = lib.vfr_sel_sample_lists(Q, n_clips, p.n_split)
-            if self.sel_samp.numel() < Q * lists * 32:
-                self.sel_samp = torch.empty(Q * lists * 32, dtype=torch.float32, device=self.q_emb.device)
-            samp = self.sel_samp[:Q * lists * 32]
+            width = lists * 32
+            if self.sel_samp.numel() < Q * width:
+                self.sel_samp = torch.empty(Q * width, dtype=torch.float32, device=self.q_emb.device)
+            samp = self.sel_samp[:Q * width].view(Q, width)
             n_s = C.c_int64(0)
-            _lib.call("vfr_sel_sample", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, samp.data_ptr(),
-                      C.byref(n_s), stream)
-            mine = samp.view(Q, lists * 32)
-            if lists > 1:
-                mine = torch.topk(mine, 32, dim=1, largest=False, sorted=True).values
-            pooled = comm.all_gather(mine.contiguous())                                  # [P, Q, 32]
+            with self._stage("k4_sample_pass"):
+                _lib.call("vfr_sel_sample", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, samp.data_ptr(),
+                          C.byref(n_s), stream)
+            with self._stage("allgather_samples"):
+                pooled = comm.all_gather(samp)                                               # [P, Q, width]
             # candidate bounds: the pooled sample values of rank j (safe a priori), j/2, j/4, j/8 (tighter guesses)
             ranks = sorted({max(1, -(-rank_j // d)) for d in (1, 2, 4, 8)}, reverse=True)
-            smallest = torch.topk(pooled.permute(1, 0, 2).reshape(Q, -1), rank_j, dim=1, largest=False, sorted=True).values
-            levels = smallest[:, [r - 1 for r in ranks]]
-            levels = levels.t().contiguous()                                              # [L, Q], loosest first
-            _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels[0].data_ptr(), stream)
-            _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, tiles, 1, stream)
+            L = len(ranks)
+            levels, counts = self.sel_levels[:L * Q], self.sel_count[:L * Q]
+            with self._stage("k4_levels"):
+                _lib.call("vfr_sel_pool_levels", pooled.data_ptr(), n_src, Q, width, (C.c_int32 * L)(*ranks), L,
+                          levels.data_ptr(), stream)
+                _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels.data_ptr(), stream)
+            with self._stage("k4_filter"):
+                _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, tiles, 1, stream)
             # how many clips are CERTAINLY within each bound, over all shards: the tightest bound that still holds k
             # clips is a certified bound of the global k-th distance - every shard re-scores only what is under it
-            counts = self.sel_count[:len(ranks) * Q].view(len(ranks), Q)
-            for i in range(len(ranks)):
-                _lib.call("vfr_sel_count_under", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels[i].data_ptr(),
-                          counts[i].data_ptr(), stream)
-            counts = comm.all_reduce_sum(counts)
-            ok = counts >= self.k                                                         # [L, Q], monotone in L
-            flags = self._sel_flags(Q)
-            flags[(~ok[0]) & (flags == 0)] = 4                                            # the sample promised k clips that are not there
-            best = ok.to(torch.int32).sum(dim=0).clamp_(min=1) - 1                        # index of the tightest bound that holds
-            bound = levels.gather(0, best.view(1, Q).to(torch.int64)).view(Q).contiguous()
-            _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
+            with self._stage("k4_count"):
+                _lib.call("vfr_sel_count_levels", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels.data_ptr(), L,
+                          counts.data_ptr(), stream)
+            with self._stage("allreduce_counts"):
+                counts = comm.all_reduce_sum(counts)
+            with self._stage("k4_pick"):
+                _lib.call("vfr_sel_pick_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels.data_ptr(),
+                          counts.data_ptr(), L, stream)
         else:
             first = min(tiles, getattr(self, "sel_first_tiles", None) or max(32, tiles // 8))
-            _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, first, 0, stream)
-            if first < tiles:
-                bound = self.sel_bound[:Q]
-                _lib.call("vfr_sel_bound_get", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
+            with self._stage("k4_filter"):
+                _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, first, 0, stream)
+            # EVERY rank takes part in the exchange, whatever its own tile count (a collective guarded by a rank-local
+            # condition would desynchronise NCCL on uneven shards): a shard that has already scanned all of its tiles
+            # contributes the certified bound of its whole bank and simply has nothing left to filter
+            bound = self.sel_bound[:Q]
+            _lib.call("vfr_sel_bound_get", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
+            with self._stage("allreduce_bound"):
                 bound = comm.all_reduce_min(bound)
-                _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
-                _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, first, tiles, 1,
-                          stream)
-        _lib.call("vfr_sel_refine", p.bank_clips, p.vid_off, p.mom_off, b.n_videos, n_clips, b.n_max, b.dim, qt, p.q_emb, Q,
-                  self.k, p.id_base, self.out_s.data_ptr(), self.out_i.data_ptr(), ws, p.n_split, stream)
+            _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, bound.data_ptr(), stream)
+            if first < tiles:
+                with self._stage("k4_filter"):
+                    _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, first, tiles, 1,
+                              stream)
+        with self._stage("k4_refine"):
+            if per > 0:
+                _lib.call("vfr_sel_refine_blocks", p.bank_clips, p.vid_off, p.mom_off, b.n_videos, n_clips, b.n_max, b.dim,
+                          qt, p.q_emb, Q, self.k, p.id_base, per, self.send_blocks.data_ptr(), ws, p.n_split, stream)
+            else:
+                _lib.call("vfr_sel_refine", p.bank_clips, p.vid_off, p.mom_off, b.n_videos, n_clips, b.n_max, b.dim, qt,
+                          p.q_emb, Q, self.k, p.id_base, self.out_s.data_ptr(), self.out_i.data_ptr(), ws, p.n_split, stream)
 
     def _sel_global_rank(self, Q, comm):
-        """The rank j of the pooled-sample protocol for batches of Q queries (0: not applicable - some shard is too
-        small to sample, or no rank <= 32 is safe).  Depends on the shard sizes only: one tiny all-reduce per distinct
-        batch size, cached."""
+        """(j, P): the rank j of the pooled-sample protocol for batches of Q queries (0: not applicable - some shard is
+        too small to sample, more pooled values than the level kernel holds, or no rank <= 32 is safe) and the number
+        of shards.  Depends on the shard sizes only: one tiny all-reduce per distinct batch size, cached."""
         cache = self.__dict__.setdefault("_sel_rank_cache", {})
         if Q not in cache:
             lib = _lib.load()
             n_s = 0 if getattr(self, "sel_pool_samples", True) is False else \
                 lib.vfr_sel_sample_clips(Q, self.n_clips, self.k, self.plan.n_split)
-            t = torch.tensor([n_s, self.n_clips, 1 if n_s > 0 else 0, 1], dtype=torch.int64, device=self.q_emb.device)
-            tot_s, tot_c, n_ok, n_ranks = comm.all_reduce_sum(t).tolist()
-            cache[Q] = lib.vfr_sel_sample_rank(self.k, tot_s, tot_c) if n_ok == n_ranks else 0
+            lists = lib.vfr_sel_sample_lists(Q, self.n_clips, self.plan.n_split)
+            t = torch.tensor([n_s, self.n_clips, 1 if n_s > 0 else 0, 1, lists], dtype=torch.int64, device=self.q_emb.device)
+            tot_s, tot_c, n_ok, n_ranks, tot_lists = comm.all_reduce_sum(t).tolist()
+            fits = tot_lists == lists * n_ranks and n_ranks * lists * 32 <= 1024     # same list count everywhere
+            cache[Q] = (lib.vfr_sel_sample_rank(self.k, tot_s, tot_c) if (n_ok == n_ranks and fits) else 0, int(n_ranks))
         return cache[Q]
 
     def _sel_flags(self, Q):
@@ -280,16 +379,15 @@ class MomentRetriever:
         s, i = ops.score_topk(self.bank, self.q_emb[:Q][idx].contiguous(), self.k, id_base=int(self.plan.id_base))
         self.out_s[:Q][idx] = s
         self.out_i[:Q][idx] = i
-        self.n_fixups = getattr(self, "n_fixups", 0) + int(idx.numel())
+        self.n_fixups += int(idx.numel())
 
     # -- device-resident step ---------------------------------------------------------------------
-    def search_device(self, tokens_dev):
-        """tokens int64 [Q, 20] on the device -> (scores fp32 [Q, k], ids int64 [Q, k]) on the device.
+    def search_device(self, tokens_dev, check=True):
+        """tokens int64 [Q, 20] on the device -> (scores fp32 [n, k], ids int64 [n, k]) on the device for the rows
+        ``owned_range(Q)`` of the batch (one GPU: the whole batch).
 
-        One GPU: K3 -> K4 in one C call.  N GPUs: every rank embeds its slice of the batch (K3 is
-        data-parallel over queries), ONE all-gather replicates the embeddings, every rank scores the
-        whole batch against its bank shard (K4), ONE all-gather exchanges the per-shard top-k lists,
-        K7 merges them."""
+        One GPU: K3 -> K4 in one C call.  P GPUs: see the module docstring.  ``check=False`` skips the end-of-step
+        wait on the flags (the caller then calls ``finish_step(Q)`` before it trusts the result)."""
         Q = tokens_dev.shape[0]
         stream = torch.cuda.current_stream().cuda_stream
         if self.world == 1:
@@ -297,37 +395,84 @@ class MomentRetriever:
                       self.out_i.data_ptr(), stream)
             self._sel_fixup(Q)
             return self.out_s[:Q], self.out_i[:Q]
-        rank = dist.get_rank(self.group)
-        per = (Q + self.world - 1) // self.world                      # queries embedded per rank
-        q0, q1 = min(rank * per, Q), min((rank + 1) * per, Q)
-        mine = self.q_slice[:per]
-        if q1 > q0:
-            _lib.call("vfr_search_embed_device", C.byref(self.plan), tokens_dev[q0:q1].data_ptr(), q1 - q0,
-                      mine.data_ptr(), stream)
-        gathered = self.q_gather[:self.world * per]
-        dist.all_gather_into_tensor(gathered, mine, group=self.group)
-        self.q_emb[:Q].copy_(gathered[:Q])
+        per = slice_rows(Q, self.world)
+        q0, q1 = self.owned_range(Q)
+        self.embed_only(tokens_dev)
         if self.plan.engine == 4:
-            self._sel_score_sharded(Q, stream)
+            self._sel_score_sharded(Q, stream, per=per)
+            blk = _lib.load().vfr_topk_block_bytes(per, self.k)
+            # (a batch smaller than max_queries has shorter records: always the dense [P, blk] prefix of the buffers)
+            send = self.send_blocks.view(-1)[:self.world * blk].view(self.world, blk)
+            recv = self.recv_blocks.view(-1)[:self.world * blk].view(self.world, blk)
+            with self._stage("alltoall_lists"):
+                self.comm.all_to_all(send, out=recv)
+            with self._stage("k7_merge"):
+                _lib.call("vfr_topk_merge_blocks", recv.data_ptr(), self.world, per, q1 - q0, self.k, self.slice_s.data_ptr(),
+                          self.slice_i.data_ptr(), self.slice_flags.data_ptr(), None, stream)
         else:
-            _lib.call("vfr_search_score_device", C.byref(self.plan), Q, self.k, self.out_s.data_ptr(),
-                      self.out_i.data_ptr(), stream)
-        self._sel_fixup(Q)
-        gs, gi = self.gather_s[:, :Q].contiguous(), self.gather_i[:, :Q].contiguous()
-        dist.all_gather_into_tensor(gs, self.out_s[:Q].contiguous(), group=self.group)
-        dist.all_gather_into_tensor(gi, self.out_i[:Q].contiguous(), group=self.group)
-        return ops.topk_merge(gs, gi)
+            # the other engines keep the flat exchange: all-gather of [P, Q, k] lists, K7 over the whole batch
+            _lib.call("vfr_search_score_device", C.byref(self.plan), Q, self.k, self.out_s.data_ptr(), self.out_i.data_ptr(),
+                      stream)
+            gs = self.comm.all_gather(self.out_s[:Q])
+            gi = self.comm.all_gather(self.out_i[:Q])
+            ms, mi = ops.topk_merge(gs, gi)
+            self.slice_s[:q1 - q0].copy_(ms[q0:q1])
+            self.slice_i[:q1 - q0].copy_(mi[q0:q1])
+            self.slice_flags[:per].zero_()
+        # flags of every slice + every rank's bad-token word -> all ranks (tiny), then to pinned host memory
+        with self._stage("allgather_flags"):
+            if q1 > q0:
+                self.slice_flags[per:per + 1].copy_(self.text_ws[:1].view(torch.int32))
+            else:
+                self.slice_flags[per:per + 1].zero_()            # an empty slice embedded nothing this step
+            self.comm.all_gather(self.slice_flags[:per + 1], out=self.flags_all[:self.world * (per + 1)])
+            self.host_flags[:self.world * (per + 1)].copy_(self.flags_all[:self.world * (per + 1)], non_blocking=True)
+            self.flags_event.record()
+        if check:
+            self.finish_step(Q)
+        return self.slice_s[:q1 - q0], self.slice_i[:q1 - q0]
+
+    def finish_step(self, n_queries):
+        """The end-of-step check of a sharded search (the step's only host wait): raises ``IndexError`` on ALL ranks
+        if any rank saw an out-of-range token id, and re-runs the queries some shard flagged through the exact
+        engine - every rank takes the same branch, because every rank looks at the same gathered flags."""
+        if self.world == 1:
+            return
+        per = slice_rows(n_queries, self.world)
+        self.flags_event.synchronize()
+        flags = self.host_flags[:self.world * (per + 1)].view(self.world, per + 1).numpy()
+        if flags[:, per].any():
+            raise IndexError("index out of range in self")
+        flat = flags[:, :per].reshape(-1)[:n_queries]
+        if flat.any():
+            self._sharded_fixup(n_queries, np.nonzero(flat)[0])
+
+    def _sharded_fixup(self, Q, idx):
+        """Exact-engine rerun of the flagged queries ``idx`` (global rows, identical on every rank) over every shard,
+        flat all-gather + K7, owners patch their slice."""
+        q0, q1 = self.owned_range(Q)
+        idx_t = torch.as_tensor(idx, device=self.q_emb.device)
+        s, i = ops.score_topk(self.bank, self.q_emb[:Q][idx_t].contiguous(), self.k, id_base=int(self.plan.id_base))
+        ms, mi = ops.topk_merge(self.comm.all_gather(s), self.comm.all_gather(i))
+        mine = torch.as_tensor(np.nonzero((idx >= q0) & (idx < q1))[0], device=self.q_emb.device)
+        if mine.numel():
+            rows = idx_t[mine] - q0
+            self.slice_s[rows] = ms[mine]
+            self.slice_i[rows] = mi[mine]
+        self.n_fixups += int(len(idx))
 
     # -- host-buffer step (the call a user makes) -------------------------------------------------------
     def search(self, tokens):
-        """tokens: int64 [Q, 20] HOST tensor/array -> (scores, ids) HOST tensors [Q, k]."""
+        """tokens: int64 [Q, 20] HOST tensor/array (the whole batch, on every rank) -> (scores, ids) HOST tensors
+        [n, k] for the rows ``owned_range(Q)`` (one GPU: all Q rows).  A rank copies only its own slice of the token ids
+        to the device and only its own slice of the results back."""
         tokens = torch.as_tensor(tokens, dtype=torch.int64)
         Q = tokens.shape[0]
         if Q > self.max_queries:
             raise ValueError(f"batch of {Q} queries exceeds max_queries={self.max_queries}")
-        self.host_tokens[:Q].copy_(tokens)
         stream = torch.cuda.current_stream().cuda_stream
         if self.world == 1:
+            self.host_tokens[:Q].copy_(tokens)
             _lib.call("vfr_search_host", C.byref(self.plan), self.host_tokens.data_ptr(), Q, self.k,
                       self.host_s.data_ptr(), self.host_i.data_ptr(), stream)
             if self.plan.engine == 4 and int((self._sel_flags(Q) != 0).any().item()):
@@ -335,22 +480,35 @@ class MomentRetriever:
                 self.host_s[:Q].copy_(self.out_s[:Q])
                 self.host_i[:Q].copy_(self.out_i[:Q])
                 torch.cuda.current_stream().synchronize()
-        else:
-            self.tokens_dev[:Q].copy_(self.host_tokens[:Q], non_blocking=True)
-            s, i = self.search_device(self.tokens_dev[:Q])
-            self.host_s[:Q].copy_(s, non_blocking=True)
-            self.host_i[:Q].copy_(i, non_blocking=True)
+            bad = int(self.text_ws[:4].view(torch.int32)[0].item())
+            if bad:
+                raise IndexError("index out of range in self")
+            return self.host_s[:Q], self.host_i[:Q]
+        q0, q1 = self.owned_range(Q)
+        n = q1 - q0
+        self.host_tokens[:n].copy_(tokens[q0:q1])
+        self.tokens_dev[q0:q1].copy_(self.host_tokens[:n], non_blocking=True)
+        s, i = self.search_device(self.tokens_dev[:Q], check=False)
+        self.host_s[:n].copy_(s, non_blocking=True)
+        self.host_i[:n].copy_(i, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        fixups = self.n_fixups
+        self.finish_step(Q)
+        if self.n_fixups != fixups:
+            self.host_s[:n].copy_(self.slice_s[:n], non_blocking=True)
+            self.host_i[:n].copy_(self.slice_i[:n], non_blocking=True)
             torch.cuda.current_stream().synchronize()
-        bad = int(self.text_ws[:4].view(torch.int32)[0].item())
-        if bad:
-            raise IndexError("index out of range in self")
-        return self.host_s[:Q], self.host_i[:Q]
+        return self.host_s[:n], self.host_i[:n]
 
     def h2d_bytes(self, Q):
+        """Host -> device bytes of one ``search`` step, summed over all ranks (every rank copies its slice of the ids)."""
         return Q * self.seq_len * 8
 
     def d2h_bytes(self, Q):
-        return Q * self.k * (4 + 8)
+        """Device -> host bytes of one ``search`` step, summed over all ranks: the result slices, and on P ranks the
+        gathered flag words every rank reads back."""
+        extra = 0 if self.world == 1 else self.world * self.world * (slice_rows(Q, self.world) + 1) * 4
+        return Q * self.k * (4 + 8) + extra
 
 
 # ---------------------------------------------------------------------------------------------------
