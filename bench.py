@@ -286,7 +286,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def workload_config(args, world):
@@ -626,7 +626,7 @@ def run_ours(args):
             "filter_stats": dict(stats or {}, n_fixups_value_steps=fixups_value, n_fixups_total=retr.n_fixups),
             "parity_check": parity, "cpu_baseline": cpu_baseline, "library_baseline": library, "checksum_top1": checksum,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     if parity is not None and not parity.get("ok"):

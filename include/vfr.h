@@ -132,11 +132,14 @@ int vfr_score_full_tc(const void* bank_packed, const float* bank, const int32_t*
  * accumulation in TMEM) whose rounding error is bounded rigorously per query; every clip inside the
  * bound of the k-th smallest squared distance survives.  Stage 2 re-scores all moments of the surviving
  * videos with the exact-fp32 arithmetic of vfr_score_topk and selects the k best by (score, moment id).
- * Any number of clips per video (<= 32), dim <= 125; the bank is packed by clip rows (no video padding).
- *   packed bank    vfr_sel_bank_bytes(n_clips)   <- vfr_sel_bank_pack (once per bank)
- *   packed queries vfr_sel_query_bytes(n_queries) <- vfr_sel_query_pack (per batch; reads the bank's scales)
+ * Any number of clips per video (<= 32), dim <= 1085; the bank is packed by clip rows (no video padding): rows of 128 fp16
+ * while dim + 3 <= 128 (query tiles resident in shared memory), rows of ceil((dim + 3) / 64) * 64 fp16 beyond that (BASELINE
+ * configs[2]: the 1024-d joint space) - there the kernel streams 64-column chunks of the query tiles AND the bank tile
+ * through the TMA ring and the two TMEM accumulators integrate over the chunks (same epilogue, same bits out).
+ *   packed bank    vfr_sel_bank_bytes(n_clips, dim)   <- vfr_sel_bank_pack (once per bank)
+ *   packed queries vfr_sel_query_bytes(n_queries, dim) <- vfr_sel_query_pack (per batch; reads the bank's scales)
  *   workspace      vfr_sel_topk_bytes(max n_queries, n_clips, n_split)
- * vfr_sel_flags(query_packed, n_queries) -> device pointer to int32 [n_queries] written by the last
+ * vfr_sel_flags(query_packed, n_queries, dim) -> device pointer to int32 [n_queries] written by the last
  * vfr_sel_query_pack / vfr_sel_topk on that buffer: 0 = result guaranteed exact; 1 = the query's or the
  * bank's magnitudes do not fit the fp16 operand scales, 2 / 3 = more candidates inside the error band than
  * the stage-1 lists / stage-2 buffer hold (mass duplicates); 4 = the scan started from a SAMPLED threshold
@@ -145,9 +148,9 @@ int vfr_score_full_tc(const void* bank_packed, const float* bank, const int32_t*
  * found fewer than k clips under it.  Flagged queries must be re-run through vfr_score_topk by the caller
  * (vfr_b200.retrieval does): a flag costs time, never correctness.  VFR_SEL_SAMPLE=0 turns the sample
  * pass off. */
-size_t vfr_sel_bank_bytes(int64_t n_clips);
+size_t vfr_sel_bank_bytes(int64_t n_clips, int dim);
 int vfr_sel_bank_pack(const float* bank, int64_t n_clips, int dim, void* packed, vfr_stream_t stream);
-size_t vfr_sel_query_bytes(int64_t n_queries);
+size_t vfr_sel_query_bytes(int64_t n_queries, int dim);
 int vfr_sel_query_pack(const float* queries, int64_t n_queries, int dim, const void* bank_packed,
                        int64_t n_clips, void* packed, vfr_stream_t stream);
 size_t vfr_sel_topk_bytes(int64_t n_queries, int64_t n_clips, int n_split);
@@ -155,7 +158,7 @@ int vfr_sel_topk(const void* bank_packed, const float* bank, const int32_t* vid_
                  int64_t n_videos, int64_t n_clips, int n_max, int dim, void* query_packed,
                  const float* queries, int64_t n_queries, int k, int64_t id_base, float* out_scores,
                  int64_t* out_ids, void* workspace, int n_split, vfr_stream_t stream);
-const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries);
+const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries, int dim);
 /* The two stages separately, for a bank sharded over several GPUs.  Every shard's local top-k only has to contain
  * what can reach the GLOBAL top-k, so the shards exchange a bound half way: vfr_sel_filter over a first slice of
  * the shard's bank tiles (tiles of 256 clips, vfr_sel_tiles(n_clips) in total; resume = 0 starts fresh lists) ->
@@ -173,8 +176,8 @@ const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries);
  * within T; where the all-reduced (sum) count is < k the query must be treated as flagged (the sample promised k clips the
  * bank does not have).  Then vfr_sel_refine.  Every shard then keeps ~k/P candidates instead of ~k. */
 int vfr_sel_sample_rank(int k, int64_t n_sampled, int64_t n_total);
-int vfr_sel_sample_lists(int64_t n_queries, int64_t n_clips, int n_split);
-int64_t vfr_sel_sample_clips(int64_t n_queries, int64_t n_clips, int k, int n_split);   /* what vfr_sel_sample will report */
+int vfr_sel_sample_lists(int64_t n_queries, int64_t n_clips, int n_split, int dim);
+int64_t vfr_sel_sample_clips(int64_t n_queries, int64_t n_clips, int k, int n_split, int dim);   /* what vfr_sel_sample will report */
 int vfr_sel_sample(const void* bank_packed, int64_t n_clips, int dim, void* query_packed, int64_t n_queries, int k,
                    void* workspace, int n_split, float* out, int64_t* n_sampled, vfr_stream_t stream);
 int vfr_sel_count_under(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace,

@@ -55,17 +55,17 @@ def test_sel_host_planning_functions_without_a_gpu():
     lib = _lib.load()
     clips_1m = 6_000_000
     # one list per query when a CTA serves two query tiles and the bank is not split; two (tile parities) otherwise
-    assert lib.vfr_sel_sample_lists(37888, clips_1m, 1) == 1
-    assert lib.vfr_sel_sample_lists(100, clips_1m, 1) == 2
-    assert lib.vfr_sel_sample_lists(300, clips_1m, 3) == 3
+    assert lib.vfr_sel_sample_lists(37888, clips_1m, 1, 100) == 1
+    assert lib.vfr_sel_sample_lists(100, clips_1m, 1, 100) == 2
+    assert lib.vfr_sel_sample_lists(300, clips_1m, 3, 100) == 3
     # the sample: whole tiles of 256 clips per list, more for larger k, at most 1/32 of a list's share of the bank,
     # none for banks below 128 tiles per list
     for k, want_tiles in ((1, 64), (10, 128), (100, 512)):
-        n = lib.vfr_sel_sample_clips(37888, clips_1m, k, 1)
+        n = lib.vfr_sel_sample_clips(37888, clips_1m, k, 1, 100)
         assert n == want_tiles * 256, (k, n)
-    assert lib.vfr_sel_sample_clips(37888, 750_000, 100, 1) == 64 * 256          # 2930 tiles: 1/32 rule
-    assert lib.vfr_sel_sample_clips(37888, 127 * 256, 100, 1) == 0
-    assert lib.vfr_sel_sample_clips(100, clips_1m, 100, 1) == 2 * 256 * 256     # two lists, 1/32 of 11 719 tiles each
+    assert lib.vfr_sel_sample_clips(37888, 750_000, 100, 1, 100) == 64 * 256          # 2930 tiles: 1/32 rule
+    assert lib.vfr_sel_sample_clips(37888, 127 * 256, 100, 1, 100) == 0
+    assert lib.vfr_sel_sample_clips(100, clips_1m, 100, 1, 100) == 2 * 256 * 256     # two lists, 1/32 of 11 719 tiles each
     # workspace: lists dominate (1024 keys of 8 bytes per query and list), grows with the batch
     small, large = lib.vfr_sel_topk_bytes(1000, clips_1m, 1), lib.vfr_sel_topk_bytes(37888, clips_1m, 1)
     assert 1000 * 1024 * 8 <= small < large and large >= 37888 * 1024 * 8

@@ -263,3 +263,62 @@ def test_sel_wrong_sampled_threshold_is_flagged(monkeypatch):
     assert bool((flags == 4).all()), flags.unique()
     monkeypatch.setenv("VFR_SEL_SAMPLE", "0")
     _assert_same_as_exact(bank, q, k, n_split=1)
+
+
+# ---- joint spaces wider than one 128-column row (BASELINE configs[2]: 1024-d): the K-streaming kernel ----------------
+@pytest.mark.parametrize("dim,n_videos,n_queries,k", [(126, 4000, 200, 50), (256, 6000, 300, 100), (509, 3000, 129, 100),
+                                                       (1024, 30000, 300, 100), (1085, 2000, 64, 10), (1024, 3000, 20, 1)])
+def test_sel_large_dims_equal_exact_engine(dim, n_videos, n_queries, k):
+    """D + 3 > 128: both operands are streamed in 64-column chunks and the TMEM accumulators integrate over the chunks.
+    Same bar as at D = 100: ids and score BITS of the exact-fp32 engine, no query flagged; the 30 000-video case is
+    large enough for the sampled starting threshold (n_split = 1)."""
+    rng = np.random.default_rng(dim)
+    clips, vid_off = _ragged_bank(rng, n_videos, dim, (6, 5), scale=0.25 / np.sqrt(dim / 100.0))
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    q = torch.from_numpy(rng.standard_normal((n_queries, dim), dtype=np.float32) * np.float32(0.25 / np.sqrt(dim / 100.0))).to(DEV)
+    _assert_same_as_exact(bank, q, k)
+    _assert_same_as_exact(bank, q, k, n_split=1, id_base=987654321012)
+
+
+@pytest.mark.parametrize("dim", [256, 1024])
+def test_sel_large_dims_near_duplicates_offsets_and_ties(dim):
+    rng = np.random.default_rng(dim + 1)
+    qs = (rng.standard_normal((40, dim), dtype=np.float32) * 0.1 + 1.0).astype(np.float32)      # common offset
+    near = np.repeat(qs, 6, axis=0) + 1e-3 * rng.standard_normal((240, dim), dtype=np.float32)
+    near[::7] = np.repeat(qs, 6, axis=0)[::7]                                                   # exact hits
+    other, _ = _ragged_bank(rng, 400, dim, (6,), scale=0.1)
+    other = (other + 1.0).astype(np.float32)
+    dup = np.tile(other[:60], (3, 1))
+    clips = np.concatenate([near, other, dup]).astype(np.float32)
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), np.arange(clips.shape[0] // 6 + 1) * 6)
+    _assert_same_as_exact(bank, torch.from_numpy(qs).to(DEV), 100)
+
+
+@pytest.mark.parametrize("dim", [256, 1024])
+def test_sel_error_bound_holds_large_dims(dim):
+    """The rigorous bound E of the fp16 pass at K = D + 3 up to 1027 (fp32 accumulation over up to 65 MMA steps):
+    every approximate d^2 read back from the stage-1 lists stays below E / 2 of the float64 value."""
+    rng = np.random.default_rng(21 + dim)
+    C, Q, k = 128, 128, 128
+    clips = (rng.standard_normal((C, dim)) * np.exp(rng.uniform(-3, 1, size=(C, 1))) / np.sqrt(dim / 100) + 0.5).astype(np.float32)
+    qs = (rng.standard_normal((Q, dim)) * np.exp(rng.uniform(-3, 1, size=(Q, 1))) / np.sqrt(dim / 100) + 0.5).astype(np.float32)
+    qs[:8] = np.abs(clips[:8])
+    clips[:8] = np.abs(clips[:8])
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), np.arange(C // 4 + 1) * 4)
+    gs, gi, flags, (qp, ws) = ops.score_topk_sel(bank, torch.from_numpy(qs).to(DEV), k, return_flags=True)
+    assert int(flags.abs().sum().item()) == 0
+    n_parts, qpad = 1, 512                                   # two query tiles per CTA, one list per query
+    pitch = (dim + 3 + 63) // 64 * 64
+    cand = ws[:qpad * n_parts * CAP * 8].view(torch.int64).view(qpad, n_parts, CAP).cpu().numpy()
+    cnt = ws[qpad * n_parts * CAP * 8:qpad * n_parts * (CAP * 8 + 4)].view(torch.int32).view(qpad, n_parts).cpu().numpy()
+    assert cnt[:Q].sum(axis=1).tolist() == [C] * Q
+    qmeta = qp[qpad * pitch * 2:qpad * pitch * 2 + qpad * 16].view(torch.float32).view(qpad, 4).cpu().numpy()
+    d2 = (((clips[None, :, :].astype(np.float64) - qs[:, None, :].astype(np.float64) + 1e-6) ** 2).sum(-1))
+    worst = 0.0
+    for qi in range(Q):
+        keys = cand[qi, 0, :cnt[qi, 0]]
+        ids = (keys & 0xffffffff).astype(np.int64)
+        approx = (keys >> 32).astype(np.uint32).view(np.float32).astype(np.float64)
+        assert sorted(ids.tolist()) == list(range(C))
+        worst = max(worst, float((np.abs(approx - d2[qi, ids]) / (qmeta[qi, 3] / 2)).max()))
+    assert worst < 0.5, worst

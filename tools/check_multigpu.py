@@ -1,4 +1,5 @@
-"""Run under torchrun on N GPUs: sharded retrieval (local top-k -> NCCL all-gather -> K7 merge) must equal
+"""Run under torchrun on N GPUs: sharded retrieval (K3 by query slice -> all-gather -> K4 per shard with the threshold
+protocol -> all-to-all of the query-slice records -> K7; every rank returns ITS slice of the batch) must equal the rows of
 the single-bank search computed on every rank from the full bank."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,10 +27,10 @@ for engine in ("sel", "tc", "exact"):
     s, i = shard.search(tokens)                      # host in, host out, all-gather + merge inside
     s, i = s.clone(), i.clone()
     full = MomentRetriever(model, clips, np.arange(V + 1) * S, max_queries=Q, k=k, engine=engine,
-                           text_engine="tc" if engine == "sel" else engine)
-    full.world = 1                                   # single-bank reference on every rank
+                           text_engine="tc" if engine == "sel" else engine, world=1, rank=0)   # single-bank reference on every rank
     fs, fi = full.search(tokens)
-    same = torch.equal(s, fs) and torch.equal(i, fi)
+    q0, q1 = shard.owned_range(Q)
+    same = torch.equal(s, fs[q0:q1]) and torch.equal(i, fi[q0:q1])
     t = torch.tensor([int(same)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -43,11 +44,11 @@ shard = MomentRetriever(model, clips2[v0 * S:v1 * S], np.arange(v1 - v0 + 1) * S
                         engine="sel", text_engine="tc", n_split=1)
 s, i = shard.search(tokens)
 s, i = s.clone(), i.clone()
-pooled_ran = shard._sel_rank_cache.get(Q, 0) > 0
-full = MomentRetriever(model, clips2, np.arange(V2 + 1) * S, max_queries=Q, k=k, engine="exact", text_engine="tc")
-full.world = 1
+pooled_ran = shard._sel_rank_cache.get(Q, (0, 0))[0] > 0
+full = MomentRetriever(model, clips2, np.arange(V2 + 1) * S, max_queries=Q, k=k, engine="exact", text_engine="tc", world=1, rank=0)
 fs, fi = full.search(tokens)
-same = torch.equal(s, fs) and torch.equal(i, fi) and pooled_ran
+q0, q1 = shard.owned_range(Q)
+same = torch.equal(s, fs[q0:q1]) and torch.equal(i, fi[q0:q1]) and pooled_ran
 t = torch.tensor([int(same)], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:

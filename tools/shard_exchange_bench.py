@@ -18,7 +18,7 @@ banks = [ops.Bank(clips[r * per * S:(r + 1) * per * S], np.arange(per + 1) * S) 
 nc = per * S
 tiles = lib.vfr_sel_tiles(nc)
 first = min(tiles, max(32, tiles // FRAC))
-qp = torch.empty(lib.vfr_sel_query_bytes(Q), dtype=torch.uint8, device="cuda")
+qp = torch.empty(lib.vfr_sel_query_bytes(Q, 100), dtype=torch.uint8, device="cuda")
 ws = torch.empty(lib.vfr_sel_topk_bytes(Q, nc, 0), dtype=torch.uint8, device="cuda")
 out_s = torch.empty((Q, k), dtype=torch.float32, device="cuda")
 out_i = torch.empty((Q, k), dtype=torch.int64, device="cuda")
@@ -69,7 +69,7 @@ print(f"  without the sample pass: filter {timeit(lambda: filt(b0)):.2f} ms")
 # pooled-sample protocol: T from the samples of ALL shards
 os.environ.pop("VFR_SEL_SAMPLE", None)
 import ctypes as C
-lists = lib.vfr_sel_sample_lists(Q, nc, 0)
+lists = lib.vfr_sel_sample_lists(Q, nc, 0, 100)
 samp = torch.empty(Q * lists * 32, dtype=torch.float32, device="cuda")
 count = torch.empty(Q, dtype=torch.int32, device="cuda")
 n_s = C.c_int64(0)

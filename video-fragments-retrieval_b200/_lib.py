@@ -63,13 +63,13 @@ PROTOTYPES = {
     "vfr_score_topk_tc_bytes": (_z, [_l, _l, _i]),
     "vfr_score_topk_tc": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
     "vfr_score_full_tc": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _l, _p, _l, _p]),
-    "vfr_sel_bank_bytes": (_z, [_l]),
+    "vfr_sel_bank_bytes": (_z, [_l, _i]),
     "vfr_sel_bank_pack": (_i, [_p, _l, _i, _p, _p]),
-    "vfr_sel_query_bytes": (_z, [_l]),
+    "vfr_sel_query_bytes": (_z, [_l, _i]),
     "vfr_sel_query_pack": (_i, [_p, _l, _i, _p, _l, _p, _p]),
     "vfr_sel_topk_bytes": (_z, [_l, _l, _i]),
     "vfr_sel_topk": (_i, [_p, _p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
-    "vfr_sel_flags": (_p, [_p, _l]),
+    "vfr_sel_flags": (_p, [_p, _l, _i]),
     "vfr_sel_tiles": (_l, [_l]),
     "vfr_sel_pool_levels": (_i, [_p, _i, _l, _i, _p, _i, _p, _p]),
     "vfr_sel_count_levels": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _i, _p, _p]),
@@ -79,8 +79,8 @@ PROTOTYPES = {
     "vfr_topk_merge_blocks": (_i, [_p, _i, _l, _l, _i, _p, _p, _p, _p, _p]),
     "vfr_sel_stats": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p]),
     "vfr_sel_sample_rank": (_i, [_i, _l, _l]),
-    "vfr_sel_sample_lists": (_i, [_l, _l, _i]),
-    "vfr_sel_sample_clips": (_l, [_l, _l, _i, _i]),
+    "vfr_sel_sample_lists": (_i, [_l, _l, _i, _i]),
+    "vfr_sel_sample_clips": (_l, [_l, _l, _i, _i, _i]),
     "vfr_sel_sample": (_i, [_p, _l, _i, _p, _l, _i, _p, _i, _p, _p, _p]),
     "vfr_sel_count_under": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p, _p]),
     "vfr_sel_filter": (_i, [_p, _l, _i, _p, _l, _i, _p, _i, _l, _l, _i, _p]),

@@ -49,7 +49,8 @@ namespace vfr {
 
 constexpr int SL_N = 256;                 // clip rows per bank tile (MMA N)
 constexpr int SL_M = 128;                 // query rows per MMA
-constexpr int SL_ROW = 128;               // fp16 columns per packed row (D + 3 <= 128)
+constexpr int SL_ROW = 128;               // fp16 columns per packed row when D + 3 <= 128 ...
+constexpr int SL_MAXROW = 1088;           // ... larger D: rows of ceil((D + 3) / 64) * 64 columns, D <= 1085 (K-streaming kernel)
 constexpr int SL_A_CHUNK = SL_M * 128;    // bytes of one [128 x 64 fp16] box
 constexpr int SL_B_CHUNK = SL_N * 128;    // bytes of one [256 x 64 fp16] box = 32 KB
 constexpr int SL_SET_WARPS = 4;           // one epilogue warp per TMEM lane quarter ...
@@ -66,8 +67,8 @@ struct SlBankMeta {          // written by the bank pack kernels, read by the qu
   int sb;                    // operand scale exponent of the bank
   int t;                     // exponent of the nv columns
   int pad[2];
-  double colsum[SL_ROW];     // column sums of the bank (pack-time scratch)
-  float center[SL_ROW];      // bank mean: both operands are centred on it (d^2 is translation invariant), which
+  double colsum[SL_MAXROW];  // column sums of the bank (pack-time scratch)
+  float center[SL_MAXROW];   // bank mean: both operands are centred on it (d^2 is translation invariant), which
                              // keeps |q'||v'| - and with it the error bound - small for embeddings with a common offset
 };
 
@@ -79,6 +80,7 @@ struct SlParams {
   int n_tiles;
   int tiles_per_split;
   int ksteps;                // 16-wide k steps (ceil((D+3)/16))
+  int n_chunks;              // 64-column chunks per packed row (K-streaming kernel, D + 3 > 128)
   int k;
   unsigned long long* cand;  // [Qpad][n_parts][SL_CAP]  (d2~ bits << 32 | clip id)
   int32_t* cand_cnt;         // [Qpad][n_parts]
@@ -106,16 +108,15 @@ __device__ __forceinline__ void atomic_max_pos(unsigned* dst, float v) { atomicM
 
 // column sums of the bank -> its mean (the centre)
 __global__ void sl_bank_colsum_kernel(const float* __restrict__ bank, int64_t n_clips, int dim, SlBankMeta* meta) {
-  const int k = threadIdx.x & (SL_ROW - 1);
-  const int r = threadIdx.x >> 7;                       // 256 threads = 2 rows x 128 columns
-  double s = 0.0;
-  if (k < dim)
-    for (int64_t c = (int64_t)blockIdx.x * 2 + r; c < n_clips; c += (int64_t)gridDim.x * 2) s += (double)bank[c * dim + k];
-  if (k < dim) atomicAdd(&meta->colsum[k], s);
+  for (int k = threadIdx.x; k < dim; k += blockDim.x) {   // a block walks a strided set of rows, coalesced over k
+    double s = 0.0;
+    for (int64_t c = blockIdx.x; c < n_clips; c += gridDim.x) s += (double)bank[c * dim + k];
+    atomicAdd(&meta->colsum[k], s);
+  }
 }
 __global__ void sl_bank_center_kernel(int64_t n_clips, int dim, SlBankMeta* meta) {
-  const int k = threadIdx.x;
-  meta->center[k] = (k < dim) ? (float)(meta->colsum[k] / (double)n_clips) : 0.f;
+  for (int k = threadIdx.x; k < SL_MAXROW; k += blockDim.x)
+    meta->center[k] = (k < dim) ? (float)(meta->colsum[k] / (double)n_clips) : 0.f;
 }
 
 // one warp per clip row: maxima the scales and the error bound are derived from (centred values)
@@ -178,21 +179,21 @@ __device__ __forceinline__ void split3_h(double x, __half& a, __half& b, __half&
 }
 
 // one warp per packed row (rows >= n_clips are padding: zero operands, nv = 2^15)
-__global__ void sl_bank_pack_kernel(const float* __restrict__ bank, int64_t n_clips, int64_t n_rows_pad, int dim,
+__global__ void sl_bank_pack_kernel(const float* __restrict__ bank, int64_t n_clips, int64_t n_rows_pad, int dim, int pitch,
                                     const SlBankMeta* __restrict__ meta, __half* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= n_rows_pad) return;
-  __half* row = out + c * SL_ROW;
+  __half* row = out + c * pitch;
   const __half zero = __float2half_rn(0.f);
   if (c >= n_clips) {
-    for (int k = lane; k < SL_ROW; k += 32) row[k] = (k == dim) ? __float2half_rn(32768.f) : zero;
+    for (int k = lane; k < pitch; k += 32) row[k] = (k == dim) ? __float2half_rn(32768.f) : zero;
     return;
   }
   const int sb = meta->sb, t = meta->t;
   const float* src = bank + c * dim;
   double ss = 0.0, sm = 0.0;
-  for (int k = lane; k < SL_ROW; k += 32) {
+  for (int k = lane; k < pitch; k += 32) {
     __half h = zero;
     if (k < dim) {
       const float x = __fsub_rn(src[k], meta->center[k]);
@@ -219,16 +220,16 @@ __global__ void sl_bank_pack_kernel(const float* __restrict__ bank, int64_t n_cl
 }
 
 // one warp per query row
-__global__ void sl_query_pack_kernel(const float* __restrict__ q, int64_t n_queries, int64_t n_rows_pad, int dim,
+__global__ void sl_query_pack_kernel(const float* __restrict__ q, int64_t n_queries, int64_t n_rows_pad, int dim, int pitch,
                                      const SlBankMeta* __restrict__ meta, __half* __restrict__ out,
                                      float4* __restrict__ qmeta, int32_t* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_rows_pad) return;
-  __half* row = out + r * SL_ROW;
+  __half* row = out + r * pitch;
   const __half zero = __float2half_rn(0.f);
   if (r >= n_queries) {
-    for (int k = lane; k < SL_ROW; k += 32) row[k] = zero;
+    for (int k = lane; k < pitch; k += 32) row[k] = zero;
     if (lane == 0) { qmeta[r] = make_float4(0.f, 1.f, 1.f, 0.f); flags[r] = 0; }
     return;
   }
@@ -255,7 +256,7 @@ __global__ void sl_query_pack_kernel(const float* __restrict__ q, int64_t n_quer
   if (!(ma < CUDART_INF_F) || !(ss < 1e300)) bad = 1;          // inf / nan in the query
   sq = min(sq, 14 - t);                                          // the nv multiplier 2^(sq+t) must fit fp16
   if (sq + t < -24 || sq + sb > 100 || sq + sb < -100) { bad = 1; sq = 0; }
-  for (int k = lane; k < SL_ROW; k += 32) {
+  for (int k = lane; k < pitch; k += 32) {
     __half h = zero;
     if (k < dim) h = __float2half_rn(scalbnf(__fsub_rn(src[k], meta->center[k]), sq));
     else if (k < dim + 3) h = bad ? zero : __float2half_rn(scalbnf(1.f, sq + t));
@@ -274,7 +275,8 @@ __global__ void sl_query_pack_kernel(const float* __restrict__ q, int64_t n_quer
     const double main_term = 1.05 * (1.0 / 1024.0) * (1.0 + 1.0 / 4096.0) * qn * 2.0 * vn;
     const double sub_term = 1.001 * ldexp(1.0, -25) * (ldexp((double)sa, -sb) + ldexp(2.0 * vsa, -sq));
     const double nv_term = ldexp(nvm, -30) + ldexp(1.0, t - sb - 24);
-    const double acc_term = ldexp(2.0 * qn * vn + nvm, -18);
+    // (2^-18 of the absolute sum covers K <= 128 with a factor 32 to spare; a longer contraction accumulates in more steps)
+    const double acc_term = ldexp(2.0 * qn * vn + nvm, -18) * fmax(1.0, (double)pitch / 128.0);
     const double key_term = ldexp(fabs(nq) + nvm + 2.0 * qn * vn, -21);
     const double ctr_term = ldexp((qn + vn) * (qn + vn), -22);   // fp32 rounding of the centring subtractions
     const double E = main_term + sub_term + nv_term + acc_term + key_term + ctr_term;
@@ -550,6 +552,11 @@ struct SlCfg {
   static constexpr int STAGES = (R == 1) ? 6 : 5;
   static constexpr uint32_t SMEM = R * 2 * SL_A_CHUNK + STAGES * SL_B_CHUNK + 1024 /*align*/ + 256 /*barriers*/;
 };
+// K-streaming variant (D + 3 > 128: the query tiles no longer fit in shared memory next to the ring): a stage holds one
+// 64-column chunk of BOTH query tiles and of the bank tile; the two accumulators integrate over all chunks
+constexpr int SL_BIG_STAGES = 3;
+constexpr int SL_BIG_STAGE = 2 * SL_A_CHUNK + SL_B_CHUNK;      // 64 KB
+constexpr uint32_t SL_BIG_SMEM = SL_BIG_STAGES * SL_BIG_STAGE + 1024 + 256;
 
 // per-thread state of the epilogue: one query row, one candidate list
 struct SlRow {
@@ -659,15 +666,20 @@ __device__ __forceinline__ void sl_sample(const float (&v)[64], float (&a)[SL_J]
 // CL = 2: CTA pairs (thread-block cluster) of the same bank split share every bank tile: each CTA fetches one of
 // the two 32 KB boxes and TMA multicasts it into both shared memories, halving the L2 reads and the TMA
 // requests per SM; a stage is recycled when the MMA warps of BOTH CTAs have released it.
-template <int R, int CL, int MODE>
+// BIG: the K-streaming variant for D + 3 > 128 (R = 2, CL = 1): every 64-column chunk of the two query tiles travels
+// through the ring together with the bank tile's chunk; a tile's two accumulators are committed after the last chunk
+// (no ping-pong - the epilogue's ~700-cycle read of a buffer is small against the >= 3 x 4 MMAs x 2 of a tile).
+template <int R, int CL, int MODE, bool BIG = false>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const SlParams p) {
-  constexpr int STAGES = SlCfg<R>::STAGES;
+  static_assert(!BIG || (R == 2 && CL == 1), "the K-streaming variant serves two query tiles per CTA, no cluster");
+  constexpr int STAGES = BIG ? SL_BIG_STAGES : SlCfg<R>::STAGES;
+  constexpr int STAGE_BYTES = BIG ? SL_BIG_STAGE : SL_B_CHUNK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                                   // [R][2 chunks]
-  uint8_t* smem_b = smem + R * 2 * SL_A_CHUNK;              // [STAGES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * SL_B_CHUNK);
+  uint8_t* smem_a = smem;                                   // [R][2 chunks]   (BIG: unused, the chunks live in the stages)
+  uint8_t* smem_b = BIG ? smem : smem + R * 2 * SL_A_CHUNK; // [STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * STAGE_BYTES);
   uint64_t* full = bars;                        // [STAGES]
   uint64_t* empty = bars + STAGES;              // [STAGES]
   uint64_t* a_full = bars + 2 * STAGES;         // [1]
@@ -704,6 +716,22 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     // ================= TMA producer =================
+    if (BIG) {
+      if (lane == 0 && n_my_tiles > 0) {
+        int it = 0;
+        for (int t = 0; t < n_my_tiles; ++t) {
+          const int row = (tile_begin + t) * p.tile_stride * SL_N;
+          for (int c = 0; c < p.n_chunks; ++c, ++it) {
+            const int s = it % STAGES;
+            sl_wait(&empty[s], ((it / STAGES) & 1) ^ 1, p.wait_mode);
+            uint8_t* st = smem_b + s * STAGE_BYTES;
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            for (int r = 0; r < R; ++r) sl_tma_load(st + r * SL_A_CHUNK, &tm_a, c * 64, (qgroup * R + r) * SL_M, &full[s]);
+            sl_tma_load(st + R * SL_A_CHUNK, &tm_b, c * 64, row, &full[s]);
+          }
+        }
+      }
+    } else
     if (lane == 0 && n_my_tiles > 0) {
       mbar_expect_tx(a_full, (uint32_t)(R * b_chunks) * SL_A_CHUNK);
       for (int r = 0; r < R; ++r)
@@ -723,6 +751,32 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
+    if (BIG) {
+      if (lane == 0 && n_my_tiles > 0) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(SL_N >> 3) << 17) | ((uint32_t)(SL_M >> 4) << 24);
+        int it = 0;
+        for (int t = 0; t < n_my_tiles; ++t) {
+          for (int r = 0; r < R; ++r) sl_wait(&tmem_empty[r], (t & 1) ^ 1, p.wait_mode);
+          sl_fence_after();
+          for (int c = 0; c < p.n_chunks; ++c, ++it) {
+            const int s = it % STAGES;
+            sl_wait(&full[s], (it / STAGES) & 1, p.wait_mode);
+            sl_fence_after();
+            uint8_t* st = smem_b + s * STAGE_BYTES;
+            const int ks = min(4, p.ksteps - 4 * c);
+            const uint64_t bdesc = sl_desc(st + R * SL_A_CHUNK);
+            for (int r = 0; r < R; ++r) {
+              const uint64_t adesc = sl_desc(st + r * SL_A_CHUNK);
+              const uint32_t d_tmem = tmem_base + (uint32_t)r * SL_N;
+              for (int k = 0; k < ks; ++k)
+                sl_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (c | k) ? 1u : 0u);
+            }
+            sl_commit(&empty[s]);                  // the stage is free once these MMAs have read it
+          }
+          for (int r = 0; r < R; ++r) sl_commit(&tmem_full[r]);
+        }
+      }
+    } else
     if (lane == 0 && n_my_tiles > 0) {
       // kind::f16, fp16 x fp16 -> fp32, K-major A and B, N = 256, M = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(SL_N >> 3) << 17) | ((uint32_t)(SL_M >> 4) << 24);
@@ -1098,7 +1152,7 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
   __shared__ int vids[RF_MAXC];
   __shared__ int uvid[RF_MAXC];
   __shared__ float dist[RF_DIST];
-  __shared__ float qrow[SL_ROW];
+  __shared__ float qrow[SL_MAXROW];
   __shared__ int warp_tot[RF_THREADS / 32];
   __shared__ int s_n, s_cnt;
   __shared__ float s_sq, s_tau;
@@ -1317,11 +1371,11 @@ static SlEncodeFn sl_get_encode() {
   return fn;
 }
 
-static int sl_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+static int sl_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows, int pitch) {
   SlEncodeFn enc = sl_get_encode();
   VFR_REQUIRE(enc, VFR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[2] = {(cuuint64_t)SL_ROW, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)SL_ROW * 2};
+  cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -1332,6 +1386,9 @@ static int sl_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32
 }
 
 static int64_t sl_tiles(int64_t n_clips) { return (n_clips + SL_N - 1) / SL_N; }
+// fp16 columns per packed row: 128 while D + 3 fits, then whole 64-column chunks
+static int sl_pitch(int dim) { return (dim + 3 <= SL_ROW) ? SL_ROW : (dim + 3 + 63) / 64 * 64; }
+static bool sl_dim_ok(int dim) { return dim >= 1 && dim + 3 <= SL_MAXROW; }
 static int64_t sl_qrows(int64_t n_queries) { return (n_queries + SL_QPAD - 1) / SL_QPAD * SL_QPAD; }
 
 // query tiles per CTA: two whenever that still fills the machine (halves the L2 -> SM bank traffic)
@@ -1361,11 +1418,15 @@ static int sl_split(int64_t n_qgroups, int64_t n_tiles, int n_split) {
 struct SlPlan {
   int R, CL, n_qgroups, ns, tiles_per_split, n_parts;   // n_qgroups: CTAs along the queries (even when CL = 2)
   int64_t n_tiles, qrows;
+  int pitch;      // fp16 columns per packed row
+  bool big;       // K-streaming kernel (pitch > 128)
 };
 
-static SlPlan sl_plan(int64_t n_queries, int64_t n_clips, int n_split) {
+static SlPlan sl_plan(int64_t n_queries, int64_t n_clips, int n_split, int dim = 100) {
   SlPlan pl;
-  pl.R = sl_rows(n_queries);
+  pl.pitch = sl_pitch(dim);
+  pl.big = pl.pitch > SL_ROW;
+  pl.R = pl.big ? 2 : sl_rows(n_queries);
   pl.n_tiles = sl_tiles(n_clips);
   pl.qrows = sl_qrows(n_queries);
   const int64_t qtiles = (n_queries + SL_M - 1) / SL_M;
@@ -1374,7 +1435,7 @@ static SlPlan sl_plan(int64_t n_queries, int64_t n_clips, int n_split) {
     const char* env = getenv("VFR_SEL_CL");
     // measured on B200 (18 944 queries x 6 M clips): the filter is bound by the MMA -> epilogue -> MMA hand-off
     // chain, not by L2 / TMA, so the CTA-pair multicast is off by default (VFR_SEL_CL=2 turns it on)
-    pl.CL = (env && env[0] == '2' && pl.n_qgroups >= 2) ? 2 : 1;
+    pl.CL = (env && env[0] == '2' && pl.n_qgroups >= 2 && !pl.big) ? 2 : 1;
     if (pl.CL == 2) pl.n_qgroups = (pl.n_qgroups + 1) / 2 * 2;     // an odd group gets an idle partner CTA
   }
   const int ns_req = sl_split(pl.n_qgroups, pl.n_tiles, n_split);
@@ -1388,26 +1449,27 @@ static SlPlan sl_plan(int64_t n_queries, int64_t n_clips, int n_split) {
 
 using namespace vfr;
 
-extern "C" size_t vfr_sel_bank_bytes(int64_t n_clips) {
-  if (n_clips <= 0) return 0;
-  return (size_t)sl_tiles(n_clips) * SL_N * SL_ROW * 2 + sizeof(SlBankMeta);
+extern "C" size_t vfr_sel_bank_bytes(int64_t n_clips, int dim) {
+  if (n_clips <= 0 || !sl_dim_ok(dim)) return 0;
+  return (size_t)sl_tiles(n_clips) * SL_N * sl_pitch(dim) * 2 + sizeof(SlBankMeta);
 }
 
 extern "C" int vfr_sel_bank_pack(const float* bank, int64_t n_clips, int dim, void* packed, vfr_stream_t stream) {
   VFR_REQUIRE(bank && packed, VFR_ERR_INVALID, "vfr_sel_bank_pack: null pointer");
   VFR_REQUIRE(n_clips > 0 && n_clips < (int64_t(1) << 31) - SL_N, VFR_ERR_UNSUPPORTED,
               "vfr_sel_bank_pack: n_clips=%lld out of range", (long long)n_clips);
-  VFR_REQUIRE(dim >= 1 && dim + 3 <= SL_ROW, VFR_ERR_UNSUPPORTED, "vfr_sel_bank_pack: dim=%d must be <= %d", dim, SL_ROW - 3);
+  VFR_REQUIRE(sl_dim_ok(dim), VFR_ERR_UNSUPPORTED, "vfr_sel_bank_pack: dim=%d must be <= %d", dim, SL_MAXROW - 3);
   const int64_t rows = sl_tiles(n_clips) * SL_N;
+  const int pitch = sl_pitch(dim);
   __half* out = reinterpret_cast<__half*>(packed);
-  SlBankMeta* meta = reinterpret_cast<SlBankMeta*>(out + rows * SL_ROW);
+  SlBankMeta* meta = reinterpret_cast<SlBankMeta*>(out + rows * pitch);
   cudaStream_t st = (cudaStream_t)stream;
   VFR_CUDA(cudaMemsetAsync(meta, 0, sizeof(SlBankMeta), st));
-  const int64_t sum_blocks = (n_clips + 1) / 2 < 148 * 8 ? (n_clips + 1) / 2 : 148 * 8;
+  const int64_t sum_blocks = n_clips < 148 * 8 ? n_clips : 148 * 8;
   sl_bank_colsum_kernel<<<(unsigned)sum_blocks, 256, 0, st>>>(bank, n_clips, dim, meta);
   int rc0 = check_launch("sl_bank_colsum_kernel");
   if (rc0) return rc0;
-  sl_bank_center_kernel<<<1, SL_ROW, 0, st>>>(n_clips, dim, meta);
+  sl_bank_center_kernel<<<1, 256, 0, st>>>(n_clips, dim, meta);
   rc0 = check_launch("sl_bank_center_kernel");
   if (rc0) return rc0;
   const int64_t stat_blocks = (n_clips + 7) / 8 < 148 * 16 ? (n_clips + 7) / 8 : 148 * 16;
@@ -1417,28 +1479,28 @@ extern "C" int vfr_sel_bank_pack(const float* bank, int64_t n_clips, int dim, vo
   sl_bank_scales_kernel<<<1, 1, 0, st>>>(meta);
   rc = check_launch("sl_bank_scales_kernel");
   if (rc) return rc;
-  sl_bank_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(bank, n_clips, rows, dim, meta, out);
+  sl_bank_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(bank, n_clips, rows, dim, pitch, meta, out);
   return check_launch("sl_bank_pack_kernel");
 }
 
-extern "C" size_t vfr_sel_query_bytes(int64_t n_queries) {
-  if (n_queries <= 0) return 0;
+extern "C" size_t vfr_sel_query_bytes(int64_t n_queries, int dim) {
+  if (n_queries <= 0 || !sl_dim_ok(dim)) return 0;
   const size_t rows = (size_t)sl_qrows(n_queries);
-  return rows * SL_ROW * 2 + rows * sizeof(float4) + rows * sizeof(int32_t);
+  return rows * sl_pitch(dim) * 2 + rows * sizeof(float4) + rows * sizeof(int32_t);
 }
 
 extern "C" int vfr_sel_query_pack(const float* queries, int64_t n_queries, int dim, const void* bank_packed,
                                   int64_t n_clips, void* packed, vfr_stream_t stream) {
   VFR_REQUIRE(queries && bank_packed && packed, VFR_ERR_INVALID, "vfr_sel_query_pack: null pointer");
-  VFR_REQUIRE(n_queries > 0 && n_clips > 0 && dim >= 1 && dim + 3 <= SL_ROW, VFR_ERR_UNSUPPORTED,
-              "vfr_sel_query_pack: bad shape");
+  VFR_REQUIRE(n_queries > 0 && n_clips > 0 && sl_dim_ok(dim), VFR_ERR_UNSUPPORTED, "vfr_sel_query_pack: bad shape");
   const int64_t rows = sl_qrows(n_queries);
+  const int pitch = sl_pitch(dim);
   const SlBankMeta* meta =
-      reinterpret_cast<const SlBankMeta*>(reinterpret_cast<const __half*>(bank_packed) + sl_tiles(n_clips) * SL_N * SL_ROW);
+      reinterpret_cast<const SlBankMeta*>(reinterpret_cast<const __half*>(bank_packed) + sl_tiles(n_clips) * SL_N * pitch);
   __half* out = reinterpret_cast<__half*>(packed);
-  float4* qmeta = reinterpret_cast<float4*>(out + rows * SL_ROW);
+  float4* qmeta = reinterpret_cast<float4*>(out + rows * pitch);
   int32_t* flags = reinterpret_cast<int32_t*>(qmeta + rows);
-  sl_query_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(queries, n_queries, rows, dim, meta,
+  sl_query_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(queries, n_queries, rows, dim, pitch, meta,
                                                                                      out, qmeta, flags);
   return check_launch("sl_query_pack_kernel");
 }
@@ -1449,6 +1511,7 @@ extern "C" size_t vfr_sel_topk_bytes(int64_t n_queries, int64_t n_clips, int n_s
   size_t worst = 0;
   const int64_t qtiles = (n_queries + SL_M - 1) / SL_M;
   for (int64_t qt = 1; qt <= qtiles; ++qt) {
+    // (the K-streaming kernel always serves two query tiles per CTA: lists per query <= the plan at D <= 125)
     const SlPlan pl = sl_plan(qt == qtiles ? n_queries : qt * SL_M, n_clips, n_split);
     const size_t qpad = (size_t)pl.qrows;
     const size_t need = qpad * pl.n_parts * SL_CAP * sizeof(unsigned long long) + qpad * pl.n_parts * sizeof(int32_t) +
@@ -1466,12 +1529,12 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
                     void* workspace, int n_split) {
   VFR_REQUIRE(n_clips > 0 && n_queries > 0, VFR_ERR_INVALID, "vfr_sel: empty bank or batch");
   VFR_REQUIRE(n_clips < (int64_t(1) << 31) - SL_N, VFR_ERR_UNSUPPORTED, "vfr_sel: bank shard too large");
-  VFR_REQUIRE(dim >= 1 && dim + 3 <= SL_ROW, VFR_ERR_UNSUPPORTED, "vfr_sel: dim=%d must be <= %d", dim, SL_ROW - 3);
+  VFR_REQUIRE(sl_dim_ok(dim), VFR_ERR_UNSUPPORTED, "vfr_sel: dim=%d must be <= %d", dim, SL_MAXROW - 3);
   VFR_REQUIRE(k >= 1 && k <= VFR_TOPK_MAX, VFR_ERR_UNSUPPORTED, "k=%d not in [1,%d]", k, VFR_TOPK_MAX);
-  pl = sl_plan(n_queries, n_clips, n_split);
+  pl = sl_plan(n_queries, n_clips, n_split, dim);
   __half* qp = reinterpret_cast<__half*>(query_packed);
   p = SlParams{};
-  p.qmeta = reinterpret_cast<const float4*>(qp + pl.qrows * SL_ROW);
+  p.qmeta = reinterpret_cast<const float4*>(qp + pl.qrows * pl.pitch);
   p.flags = reinterpret_cast<int32_t*>(const_cast<float4*>(p.qmeta) + pl.qrows);
   p.n_clips = n_clips;
   p.n_queries = n_queries;
@@ -1479,6 +1542,7 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
   p.n_tiles = (int)pl.n_tiles;
   p.tiles_per_split = pl.tiles_per_split;
   p.ksteps = (dim + 3 + 15) / 16;
+  p.n_chunks = pl.pitch / 64;
   p.k = k;
   p.n_parts = pl.n_parts;
   { const char* wm = getenv("VFR_SEL_WAIT"); p.wait_mode = wm ? atoi(wm) : 0; }
@@ -1541,7 +1605,8 @@ static int sl_launch_filter(const SlPlan& pl, const SlParams& p, const CUtensorM
   const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
   void (*kern)(CUtensorMap, CUtensorMap, SlParams) = nullptr;
   uint32_t smem_bytes = 0;
-  if (pl.R == 2 && CL == 2) { kern = sl_filter_kernel<2, 2, 0>; smem_bytes = SlCfg<2>::SMEM; }
+  if (pl.big) { kern = sl_filter_kernel<2, 1, MODE, true>; smem_bytes = SL_BIG_SMEM; }
+  else if (pl.R == 2 && CL == 2) { kern = sl_filter_kernel<2, 2, 0>; smem_bytes = SlCfg<2>::SMEM; }
   else if (pl.R == 2) { kern = sl_filter_kernel<2, 1, MODE>; smem_bytes = SlCfg<2>::SMEM; }
   else if (CL == 2) { kern = sl_filter_kernel<1, 2, 0>; smem_bytes = SlCfg<1>::SMEM; }
   else { kern = sl_filter_kernel<1, 1, MODE>; smem_bytes = SlCfg<1>::SMEM; }
@@ -1582,9 +1647,9 @@ static int sl_run_filter(const SlPlan& pl, SlParams p, const void* bank_packed, 
   if (tile_hi < 0 || tile_hi > pl.n_tiles) tile_hi = pl.n_tiles;
   VFR_REQUIRE(tile_lo >= 0 && tile_lo <= tile_hi, VFR_ERR_INVALID, "vfr_sel_filter: bad tile range");
   CUtensorMap ma, mb;
-  int rc = sl_make_map(&ma, query_packed, (uint64_t)pl.qrows, SL_M);
+  int rc = sl_make_map(&ma, query_packed, (uint64_t)pl.qrows, SL_M, pl.pitch);
   if (rc) return rc;
-  rc = sl_make_map(&mb, bank_packed, (uint64_t)(pl.n_tiles * SL_N), SL_N);
+  rc = sl_make_map(&mb, bank_packed, (uint64_t)(pl.n_tiles * SL_N), SL_N, pl.pitch);
   if (rc) return rc;
   if (!resume) {
     const size_t qpad = (size_t)pl.qrows;
@@ -1878,14 +1943,14 @@ extern "C" int vfr_sel_sample_rank(int k, int64_t n_sampled, int64_t n_total) {
   return 0;
 }
 
-extern "C" int vfr_sel_sample_lists(int64_t n_queries, int64_t n_clips, int n_split) {
-  if (n_queries <= 0 || n_clips <= 0) return 0;
-  return sl_plan(n_queries, n_clips, n_split).n_parts;
+extern "C" int vfr_sel_sample_lists(int64_t n_queries, int64_t n_clips, int n_split, int dim) {
+  if (n_queries <= 0 || n_clips <= 0 || !sl_dim_ok(dim)) return 0;
+  return sl_plan(n_queries, n_clips, n_split, dim).n_parts;
 }
 
-extern "C" int64_t vfr_sel_sample_clips(int64_t n_queries, int64_t n_clips, int k, int n_split) {
-  if (n_queries <= 0 || n_clips <= 0 || k < 1) return 0;
-  const SlPlan pl = sl_plan(n_queries, n_clips, n_split);
+extern "C" int64_t vfr_sel_sample_clips(int64_t n_queries, int64_t n_clips, int k, int n_split, int dim) {
+  if (n_queries <= 0 || n_clips <= 0 || k < 1 || !sl_dim_ok(dim)) return 0;
+  const SlPlan pl = sl_plan(n_queries, n_clips, n_split, dim);
   return (int64_t)sl_sample_plan(pl, n_clips, k, /*need_rank=*/false).tiles * pl.n_parts * SL_N;
 }
 
@@ -1906,9 +1971,9 @@ extern "C" int vfr_sel_sample(const void* bank_packed, int64_t n_clips, int dim,
   *n_sampled = (int64_t)sp.tiles * pl.n_parts * SL_N;
   if (sp.tiles == 0) return VFR_OK;
   CUtensorMap ma, mb;
-  rc = sl_make_map(&ma, query_packed, (uint64_t)pl.qrows, SL_M);
+  rc = sl_make_map(&ma, query_packed, (uint64_t)pl.qrows, SL_M, pl.pitch);
   if (rc) return rc;
-  rc = sl_make_map(&mb, bank_packed, (uint64_t)(pl.n_tiles * SL_N), SL_N);
+  rc = sl_make_map(&mb, bank_packed, (uint64_t)(pl.n_tiles * SL_N), SL_N, pl.pitch);
   if (rc) return rc;
   float* samp = sl_samp_buffer(pl, p);
   rc = sl_launch_sample(pl, p, sp, samp, ma, mb, st);
@@ -1993,9 +2058,9 @@ extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const in
 
 // flags of the last vfr_sel_topk on this packed query buffer: device pointer to int32 [n_queries]
 // (0 = exact result; 1 = operand scales out of fp16 range, 2 = candidate list overflow, 3 = refine overflow)
-extern "C" const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries) {
-  if (!query_packed || n_queries <= 0) return nullptr;
+extern "C" const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries, int dim) {
+  if (!query_packed || n_queries <= 0 || !sl_dim_ok(dim)) return nullptr;
   const int64_t rows = sl_qrows(n_queries);
   const __half* qp = reinterpret_cast<const __half*>(query_packed);
-  return reinterpret_cast<const int32_t*>(reinterpret_cast<const float4*>(qp + rows * SL_ROW) + rows);
+  return reinterpret_cast<const int32_t*>(reinterpret_cast<const float4*>(qp + rows * sl_pitch(dim)) + rows);
 }

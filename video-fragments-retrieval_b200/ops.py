@@ -7,7 +7,7 @@ import torch
 from . import _lib
 from .utils import MAX_SEGMENTS, threshold_table
 
-SEL_MAX_DIM = 125   # largest embedding dimension of the filter + refine engine (vfr_sel_*)
+SEL_MAX_DIM = 1085  # largest embedding dimension of the filter + refine engine (vfr_sel_*: rows of up to 1088 fp16)
 
 
 def _ptr(t):
@@ -87,7 +87,7 @@ class Bank:
             if self.dim > SEL_MAX_DIM:
                 raise _lib.VfrError(f"the filter + refine top-k holds embeddings of at most {SEL_MAX_DIM} dimensions")
             n_clips = int(self.clips.shape[0])
-            packed = torch.empty(_lib.load().vfr_sel_bank_bytes(n_clips), dtype=torch.uint8, device=self.device)
+            packed = torch.empty(_lib.load().vfr_sel_bank_bytes(n_clips, self.dim), dtype=torch.uint8, device=self.device)
             _lib.call("vfr_sel_bank_pack", _ptr(self.clips), n_clips, self.dim, _ptr(packed), _stream())
             self.__dict__["_sel"] = packed
         return self.__dict__["_sel"]
@@ -197,7 +197,7 @@ def score_topk_sel(bank, queries, k, id_base=0, n_split=0, return_flags=False):
     Q = q.shape[0]
     lib = _lib.load()
     n_clips = int(bank.clips.shape[0])
-    qp = torch.empty(lib.vfr_sel_query_bytes(Q), dtype=torch.uint8, device=bank.device)
+    qp = torch.empty(lib.vfr_sel_query_bytes(Q, bank.dim), dtype=torch.uint8, device=bank.device)
     _lib.call("vfr_sel_query_pack", _ptr(q), Q, bank.dim, _ptr(bank.sel()), n_clips, _ptr(qp), _stream())
     ws = torch.empty(lib.vfr_sel_topk_bytes(Q, n_clips, n_split), dtype=torch.uint8, device=bank.device)
     out_s = torch.empty((Q, k), dtype=torch.float32, device=bank.device)
@@ -207,7 +207,7 @@ def score_topk_sel(bank, queries, k, id_base=0, n_split=0, return_flags=False):
               n_split, _stream())
     if not return_flags:
         return out_s, out_i
-    off = lib.vfr_sel_flags(_ptr(qp), Q) - qp.data_ptr()
+    off = lib.vfr_sel_flags(_ptr(qp), Q, bank.dim) - qp.data_ptr()
     flags = qp[off:off + 4 * Q].view(torch.int32).clone()
     return out_s, out_i, flags, (qp, ws)
 

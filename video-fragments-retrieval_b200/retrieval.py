@@ -137,7 +137,7 @@ class MomentRetriever:
         elif eng == 4:
             self.n_clips = int(self.bank.clips.shape[0])
             self.q_packed = None
-            self.q_tc = torch.empty(lib.vfr_sel_query_bytes(mq), dtype=torch.uint8, device=dev)
+            self.q_tc = torch.empty(lib.vfr_sel_query_bytes(mq, D), dtype=torch.uint8, device=dev)
             self.topk_ws = torch.empty(lib.vfr_sel_topk_bytes(mq, self.n_clips, n_split), dtype=torch.uint8, device=dev)
         else:
             self.q_packed = None
@@ -289,7 +289,7 @@ class MomentRetriever:
             _lib.call("vfr_sel_query_pack", p.q_emb, Q, b.dim, p.bank_tc, n_clips, qt, stream)
         tiles = lib.vfr_sel_tiles(n_clips)
         rank_j, n_src = self._sel_global_rank(Q, comm)
-        lists = lib.vfr_sel_sample_lists(Q, n_clips, p.n_split)
+        lists = lib.vfr_sel_sample_lists(Q, n_clips, p.n_split, b.dim)
         if rank_j > 0:
             width = lists * 32
             if self.sel_samp.numel() < Q * width:
@@ -353,8 +353,8 @@ class MomentRetriever:
         if Q not in cache:
             lib = _lib.load()
             n_s = 0 if getattr(self, "sel_pool_samples", True) is False else \
-                lib.vfr_sel_sample_clips(Q, self.n_clips, self.k, self.plan.n_split)
-            lists = lib.vfr_sel_sample_lists(Q, self.n_clips, self.plan.n_split)
+                lib.vfr_sel_sample_clips(Q, self.n_clips, self.k, self.plan.n_split, self.bank.dim)
+            lists = lib.vfr_sel_sample_lists(Q, self.n_clips, self.plan.n_split, self.bank.dim)
             t = torch.tensor([n_s, self.n_clips, 1 if n_s > 0 else 0, 1, lists], dtype=torch.int64, device=self.q_emb.device)
             tot_s, tot_c, n_ok, n_ranks, tot_lists = comm.all_reduce_sum(t).tolist()
             fits = tot_lists == lists * n_ranks and n_ranks * lists * 32 <= 1024     # same list count everywhere
@@ -363,7 +363,7 @@ class MomentRetriever:
 
     def _sel_flags(self, Q):
         """int32 [Q] view of the per-query flags of the last filter + refine call (0 = guaranteed exact)."""
-        off = _lib.load().vfr_sel_flags(self.q_tc.data_ptr(), Q) - self.q_tc.data_ptr()
+        off = _lib.load().vfr_sel_flags(self.q_tc.data_ptr(), Q, self.bank.dim) - self.q_tc.data_ptr()
         return self.q_tc[off:off + 4 * Q].view(torch.int32)
 
     def _sel_fixup(self, Q):
