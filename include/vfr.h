@@ -159,6 +159,14 @@ int vfr_sel_topk(const void* bank_packed, const float* bank, const int32_t* vid_
                  const float* queries, int64_t n_queries, int k, int64_t id_base, float* out_scores,
                  int64_t* out_ids, void* workspace, int n_split, vfr_stream_t stream);
 const int32_t* vfr_sel_flags(const void* query_packed, int64_t n_queries, int dim);
+/* bf16 embedding path (BASELINE configs[2]): vfr_sel_topk with the bank's rows stored as bf16 [n_clips, dim] - stage 2 then
+ * reads half the bytes.  The packed operand must have been built (vfr_sel_bank_pack) from the same bf16-representable
+ * values, and the query rows are expected to be bf16-representable too; the scores are the exact engine's scores OF THOSE
+ * ROUNDED EMBEDDINGS bit for bit, i.e. within the stated 1e-2 of the fp32 embeddings' scores. */
+int vfr_sel_topk_b16(const void* bank_packed, const void* bank_b16, const int32_t* vid_off, const int64_t* mom_off,
+                     int64_t n_videos, int64_t n_clips, int n_max, int dim, void* query_packed, const float* queries,
+                     int64_t n_queries, int k, int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace,
+                     int n_split, vfr_stream_t stream);
 /* The two stages separately, for a bank sharded over several GPUs.  Every shard's local top-k only has to contain
  * what can reach the GLOBAL top-k, so the shards exchange a bound half way: vfr_sel_filter over a first slice of
  * the shard's bank tiles (tiles of 256 clips, vfr_sel_tiles(n_clips) in total; resume = 0 starts fresh lists) ->
@@ -262,6 +270,25 @@ int vfr_linear(const float* x, int64_t n_rows, int in_dim, int ldx, const float*
 int vfr_visual_embed(const float* x, int64_t n_rows, int in_dim, const float* w1, const float* b1, int hid,
                      const float* w2, const float* b2, int dim, float* hidden, float* out,
                      vfr_stream_t stream);
+
+/* K2 on tensor cores (csrc/vfr_visual_tc.cu): split-fp16 tcgen05 GEMMs (22 significand bits per operand, power-of-two
+ * operand scales computed on the device), bias / ReLU / tef columns fused into the epilogues; within 1e-5 of the fp32
+ * reference at K = 8194.  `packed` = vfr_visual_pack of (W1 [hid, 2F+2], b1, W2 [dim, hid], b2), once per weight update.
+ *  vfr_visual_embed_tc     x fp32 [n_rows, 2F+2] = the reference's assembled [segment | context | tef] rows -> out [n_rows, dim]
+ *  vfr_visual_embed_split  the SPLIT-WEIGHT form of model/data.py:204-213 + models.py:21-27: seg fp32 [n_clips, F] and ctx
+ *                          fp32 [n_videos, F] as K1 produces them, vid_off int32 [n_videos + 1] CSR clip offsets.  The
+ *                          8194-wide concat is never materialised; the context product is computed once per video and
+ *                          added per clip in the epilogue together with tef = (i/n, (i+1)/n) and the bias.
+ * workspace: vfr_visual_embed_tc_bytes(n_rows, n_videos, F, hid, dim, split). */
+size_t vfr_visual_pack_bytes(int feat_dim, int hid, int dim);
+int vfr_visual_pack(const float* w1, const float* b1, const float* w2, const float* b2, int feat_dim, int hid, int dim,
+                    void* packed, vfr_stream_t stream);
+size_t vfr_visual_embed_tc_bytes(int64_t n_rows, int64_t n_videos, int feat_dim, int hid, int dim, int split);
+int vfr_visual_embed_tc(const float* x, int64_t n_rows, int feat_dim, const void* packed, int hid, int dim, void* workspace,
+                        float* out, vfr_stream_t stream);
+int vfr_visual_embed_split(const float* seg, const float* ctx, const int32_t* vid_off, int64_t n_clips, int64_t n_videos,
+                           int feat_dim, const void* packed, int hid, int dim, void* workspace, float* out,
+                           vfr_stream_t stream);
 
 /* ---- K3 : query embedding (GloVe gather -> BiLSTM -> Linear) -----------------------------------
  * replaces model/models.py:33-48,61-66.  Weights of one direction are re-laid-out once per weight

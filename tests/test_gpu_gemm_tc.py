@@ -123,10 +123,14 @@ def test_visual_embed_tc_matches_reference_and_exact_path(golden):
     rng = np.random.default_rng(0)
     x = torch.from_numpy(rng.random((777, 2 * meta["feat_dim"] + 2), dtype=np.float32)).to(DEV)
     with torch.no_grad():
-        exact = model(x)
-        model.engine = "tc"
+        assert model.visual_engine == "tc"                     # the default K2 is the tcgen05 split-fp16 path
         got = model(x)
+        model.visual_engine = "exact"
+        exact = model(x)
+        model.visual_engine = "tc_bf16x3"
+        got3 = model(x)
     assert (got - exact).abs().max().item() <= 1e-5 * exact.abs().max().item()
+    assert (got3 - exact).abs().max().item() <= 1e-5 * exact.abs().max().item()
     # the reference's full-size rows: [L2-normalised segment | L2-normalised context | tef] (data.py:174-213)
     big = CALModelBig()
     seg = rng.random((1000, 4096), dtype=np.float32)
@@ -135,17 +139,28 @@ def test_visual_embed_tc_matches_reference_and_exact_path(golden):
     ctx /= np.linalg.norm(ctx, axis=1, keepdims=True) + 1e-5
     xb = torch.from_numpy(np.concatenate([seg, ctx, rng.random((1000, 2), dtype=np.float32)], axis=1)).to(DEV)
     with torch.no_grad():
+        g2 = big(xb)                                            # default: tcgen05 split-fp16
+        big.visual_engine = "exact"
         e2 = big(xb)
-        big.engine = "tc"
-        g2 = big(xb)
+        big.visual_engine = "tc_bf16x3"
+        g3 = big(xb)
         lin1, lin2 = big.visual_fc[0], big.visual_fc[2]
         want = torch.relu(xb.double() @ lin1.weight.double().t() + lin1.bias.double()) @ lin2.weight.double().t() + lin2.bias.double()
+        # the split-weight form on the same data: seg / ctx / CSR offsets in, no 8194-wide rows
+        vid_off = np.arange(0, 1001, 5)
+        ctx_v = ctx[::5]
+        xs = np.concatenate([seg, np.repeat(ctx_v, 5, axis=0), np.tile(np.stack([np.arange(5) / np.float32(5), (np.arange(5) + 1) / np.float32(5)], 1).astype(np.float32), (200, 1))], axis=1)
+        big.visual_engine = "tc"
+        g_split = big.embed_clips(torch.from_numpy(seg).to(DEV), torch.from_numpy(ctx_v).to(DEV), vid_off)
+        xs_t = torch.from_numpy(xs).to(DEV)
+        want_split = torch.relu(xs_t.double() @ lin1.weight.double().t() + lin1.bias.double()) @ lin2.weight.double().t() + lin2.bias.double()
     scale = want.abs().max().item()
-    # exact path: fp32 bar.  Tensor-core path: the 8194 all-positive products add their 2^-16 split-bf16 errors
-    # coherently and the second layer cancels ~100x, so the OPTIONAL tc engine is held to 5e-5 of the scale here
-    # (the default engine stays "exact"; at the text branch's shapes tc meets 1e-5)
+    # fp32 bar for the exact path AND for the default tensor-core path (22-bit split-fp16 operands); the round-1 split-bf16
+    # variant adds its 2^-16 errors coherently over 8194 all-positive products and is held to 5e-5
     assert (e2.double() - want).abs().max().item() <= 1e-5 * scale
-    assert (g2.double() - want).abs().max().item() <= 5e-5 * scale
+    assert (g2.double() - want).abs().max().item() <= 1e-5 * scale
+    assert (g3.double() - want).abs().max().item() <= 5e-5 * scale
+    assert (g_split.double() - want_split).abs().max().item() <= 1e-5 * want_split.abs().max().item()
 
 
 def CALModelBig():

@@ -335,3 +335,52 @@ def test_val_shape_trained_embeddings_metrics_match_reference(golden):
     random.seed(123)
     m = vsingle.evaluate_embedded(bank, q_emb, queries["video_idx"], queries["times"], ("model", "chance", "prior"), prior)
     assert _plain(m) == meta["metrics_single"]
+
+
+def test_feature_files_stream_through_pinned_staging_into_k1(golden, tmp_path, monkeypatch):
+    """Feature ingestion: the dataset's real constructor path on real files -
+    ``features_vgg19/vgg19_ft_<video>.npy`` as get_rgb_features.py writes them (data.py:164-166) and MCN's
+    ``fc7_subsample5_fps25_<video>.h5`` (data.py:145-148, through a stand-in h5py module: h5py is not installed) -
+    memory-mapped, staged in pinned buffers small enough to force several chunks and a video larger than a chunk, pooled
+    by K1; the result equals what the reference's own load_video_features produced from the same files (golden)."""
+    import sys
+    import types
+    z, meta = golden("pool")
+    monkeypatch.setitem(vdata.FEATURE_DIM, "vgg19", meta["feat_dim"])
+    (tmp_path / "features_vgg19").mkdir()
+    names = []
+    for i, (seed, nf) in enumerate(zip(meta["frame_seeds"], meta["n_frames"])):
+        np.save(tmp_path / "features_vgg19" / f"vgg19_ft_v{i}.npy", synth.make_frames(seed, nf, meta["feat_dim"]))
+        names.append(f"v{i}")
+    real_pool = vdata.pool_video_files
+    monkeypatch.setattr(vdata, "pool_video_files", lambda *a, **k: real_pool(*a, chunk_frames=140, **k))   # 151 > 140 frames
+    for pooling in ("avg", "max"):
+        ds = vdata.CustomDataset(names, {}, str(tmp_path), "vgg19", pooling=pooling, device=DEV)
+        for i, n in enumerate(names):
+            got = ds.video_features[n]
+            want_seg, want_ctx = z[f"{pooling}_v{i}_seg"], z[f"{pooling}_v{i}_ctx"]
+            assert got["num_segments"] == want_seg.shape[0] == ds.num_segments_info[n]
+            assert got["segment_features"].dtype == np.float64
+            _close(got["segment_features"], want_seg, 2e-6)
+            _close(got["context_features"], want_ctx, 2e-6)
+    store = {}
+    for i, (seed, nf) in enumerate(zip(meta["h5_seeds"], meta["h5_n_frames"])):
+        store[f"fc7_subsample5_fps25_h{i}.h5"] = synth.make_frames(seed, nf, meta["feat_dim"])
+
+    class FakeFile:
+        def __init__(self, path):
+            self.key = str(path).split("/")[-1]
+        def __enter__(self):
+            return self
+        def __exit__(self, *a):
+            return False
+        def __getitem__(self, k):
+            return store[self.key]
+    fake = types.ModuleType("h5py")
+    fake.File = FakeFile
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    h5names = [f"h{i}" for i in range(len(meta["h5_seeds"]))]
+    ds = vdata.CustomDataset(h5names, {}, str(tmp_path), "vgg19", prep=True, device=DEV)
+    for i, n in enumerate(h5names):
+        _close(ds.video_features[n]["segment_features"], z[f"h5_h{i}_seg"], 2e-6)
+        _close(ds.video_features[n]["context_features"], z[f"h5_h{i}_ctx"], 2e-6)

@@ -322,3 +322,29 @@ def test_sel_error_bound_holds_large_dims(dim):
         assert sorted(ids.tolist()) == list(range(C))
         worst = max(worst, float((np.abs(approx - d2[qi, ids]) / (qmeta[qi, 3] / 2)).max()))
     assert worst < 0.5, worst
+
+
+@pytest.mark.parametrize("dim,n_videos", [(100, 20000), (1024, 6000)])
+def test_bf16_embedding_path_tolerance(dim, n_videos):
+    """BASELINE configs[2]: embeddings stored in bf16 (bank rows AND queries), scored by the filter + refine engine whose
+    stage 2 reads the bf16 bank (vfr_sel_topk_b16).  (1) the scores are the exact engine's scores of the rounded
+    embeddings, bit for bit; (2) against the fp32 embeddings the scores stay within the stated 1e-2 relative tolerance
+    (observed ~1e-3 at D = 100, less at D = 1024), and the top-1 moment agrees wherever the fp32 top-2 gap exceeds it."""
+    rng = np.random.default_rng(77 + dim)
+    clips, vid_off = _ragged_bank(rng, n_videos, dim, (6, 5), scale=0.25 / np.sqrt(dim / 100.0))
+    q = rng.standard_normal((200, dim), dtype=np.float32) * np.float32(0.25 / np.sqrt(dim / 100.0))
+    clips_t, q_t = torch.from_numpy(clips).to(DEV), torch.from_numpy(q).to(DEV)
+    k = 50
+    fs, fi = ops.score_topk(ops.Bank(clips_t, vid_off), q_t, k)                               # fp32 embeddings
+    bank16 = ops.Bank(clips_t.to(torch.bfloat16), vid_off)                                    # values rounded to bf16
+    bs, bi, flags, _ = ops.score_topk_sel(bank16, q_t, k, return_flags=True, bf16=True)
+    assert int(flags.abs().sum().item()) == 0
+    es, ei = ops.score_topk(bank16, q_t.to(torch.bfloat16).float(), k)
+    assert torch.equal(bi, ei) and torch.equal(bs.view(torch.int32), es.view(torch.int32))
+    rel = ((bs - fs).abs() / fs).max().item()
+    assert rel < 1e-2, rel
+    gap = (fs[:, 1] - fs[:, 0]) / fs[:, 0]
+    clear = gap > 2e-2
+    assert bool((bi[clear, 0] == fi[clear, 0]).all())
+    with pytest.raises(_lib.VfrError):                                                        # an fp32 bank is refused
+        ops.score_topk_sel(ops.Bank(clips_t, vid_off), q_t, k, bf16=True)

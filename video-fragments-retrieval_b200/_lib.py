@@ -70,6 +70,7 @@ PROTOTYPES = {
     "vfr_sel_topk_bytes": (_z, [_l, _l, _i]),
     "vfr_sel_topk": (_i, [_p, _p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
     "vfr_sel_flags": (_p, [_p, _l, _i]),
+    "vfr_sel_topk_b16": (_i, [_p, _p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
     "vfr_sel_tiles": (_l, [_l]),
     "vfr_sel_pool_levels": (_i, [_p, _i, _l, _i, _p, _i, _p, _p]),
     "vfr_sel_count_levels": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _i, _p, _p]),
@@ -92,6 +93,11 @@ PROTOTYPES = {
     "vfr_single_metrics": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p]),
     "vfr_linear": (_i, [_p, _l, _i, _i, _p, _p, _i, _i, _p, _i, _p]),
     "vfr_visual_embed": (_i, [_p, _l, _i, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
+    "vfr_visual_pack_bytes": (_z, [_i, _i, _i]),
+    "vfr_visual_pack": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "vfr_visual_embed_tc_bytes": (_z, [_l, _l, _i, _i, _i, _i]),
+    "vfr_visual_embed_tc": (_i, [_p, _l, _i, _p, _i, _i, _p, _p, _p]),
+    "vfr_visual_embed_split": (_i, [_p, _p, _p, _l, _l, _i, _p, _i, _i, _p, _p, _p]),
     "vfr_lstm_pack_bytes": (_z, [_i, _i]),
     "vfr_lstm_pack": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "vfr_text_embed_bytes": (_z, [_l, _i, _i, _i]),

@@ -100,6 +100,9 @@ __device__ __forceinline__ void gt_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+constexpr uint32_t GT_FMT_BF16 = (1u << 7) | (1u << 10);
+constexpr uint32_t GT_FMT_F16 = 0u;
+
 // split an fp32 value into its bf16 hi / lo pair
 __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
@@ -110,15 +113,21 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
 //      called for 16 consecutive output columns n0..n0+15 of row m (m < M guaranteed, columns not).
 template <class Epi>
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __restrict__ m_limit, int k_chunks, int kp,
-               Epi epi) {
+gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __restrict__ m_limit, int k_chunks, int lo_a,
+               int lo_b, uint32_t fmt, int flush_chunks, float* __restrict__ flush_buf, int64_t flush_ld, Epi epi) {
   extern __shared__ uint8_t gt_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gt_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE);
   uint64_t* full = bars;
   uint64_t* empty = bars + GT_STAGES;
   uint64_t* acc_full = bars + 2 * GT_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  // K-segmented accumulation (flush_chunks > 0): the tensor core adds into its fp32 accumulator with truncation, a bias
+  // that grows with the number of accumulation steps (~1.5e-5 relative at K = 8192).  Every flush_chunks K-chunks the
+  // epilogue warps therefore drain the accumulator into an fp32 buffer (round-to-nearest adds) and the MMAs restart from
+  // zero; the fused epilogue functor sees the sum of the segments.
+  const int n_seg = (flush_chunks > 0) ? (k_chunks + flush_chunks - 1) / flush_chunks : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
@@ -132,6 +141,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
   if (threadIdx.x == 0) {
     for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
+    mbar_init(acc_empty, GT_THREADS / 32 - 2);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -153,17 +163,24 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
         const int kc = c * GT_BK;
         gt_tma_load(st + 0 * GT_A_SUB, ma, kc, m0, &full[s]);              // Ah rows m0..+127
         gt_tma_load(st + 1 * GT_A_SUB, ma, kc, m0 + 128, &full[s]);        // Ah rows m0+128..
-        gt_tma_load(st + 2 * GT_A_SUB, ma, kp + kc, m0, &full[s]);         // Al
-        gt_tma_load(st + 3 * GT_A_SUB, ma, kp + kc, m0 + 128, &full[s]);
+        gt_tma_load(st + 2 * GT_A_SUB, ma, lo_a + kc, m0, &full[s]);       // Al
+        gt_tma_load(st + 3 * GT_A_SUB, ma, lo_a + kc, m0 + 128, &full[s]);
         gt_tma_load(st + 4 * GT_A_SUB, mb, kc, n0, &full[s]);              // Bh
-        gt_tma_load(st + 4 * GT_A_SUB + GT_B_BOX, mb, kp + kc, n0, &full[s]);  // Bl
+        gt_tma_load(st + 4 * GT_A_SUB + GT_B_BOX, mb, lo_b + kc, n0, &full[s]);  // Bl
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GT_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // kind::f16: D = fp32; A / B formats from `fmt` (bits 7 / 10: 1 = bf16, 0 = fp16 - the split-fp16 operands)
+      const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(GT_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int seg = 0;
       for (int c = 0; c < k_chunks; ++c) {
         const int s = c % GT_STAGES;
+        const int cs = (flush_chunks > 0) ? c % flush_chunks : c;     // chunk index inside its accumulation segment
+        if (cs == 0 && c > 0) {                                       // the epilogue has drained the previous segment
+          gt_wait(acc_empty, (seg - 1) & 1, 32);
+          gt_fence_after();
+        }
         gt_wait(&full[s], (c / GT_STAGES) & 1, 32);
         gt_fence_after();
         uint8_t* st = smem + s * GT_STAGE;
@@ -174,27 +191,52 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
           const uint32_t d = tmem_base + (uint32_t)sub * 256;
 #pragma unroll
           for (int k = 0; k < GT_BK / 16; ++k) {
-            gt_mma(d, ah + 2 * k, bh + 2 * k, idesc, (c | k) ? 1u : 0u);
+            gt_mma(d, ah + 2 * k, bh + 2 * k, idesc, (cs | k) ? 1u : 0u);
             gt_mma(d, al + 2 * k, bh + 2 * k, idesc, 1u);
             gt_mma(d, ah + 2 * k, bl + 2 * k, idesc, 1u);
           }
         }
         gt_commit(&empty[s]);
+        if (c == k_chunks - 1 || (flush_chunks > 0 && cs == flush_chunks - 1)) {
+          gt_commit(acc_full);
+          ++seg;
+        }
       }
-      gt_commit(acc_full);
     }
   } else {
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int sub = ew >> 2;
     const int m = m0 + sub * 128 + quarter * 32 + lane;
-    gt_wait(acc_full, 0, 256);
-    gt_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)sub * 256;
-    for (int c = 0; c < GT_BN / 16; ++c) {
-      float v[16];
-      gt_ld16(taddr + c * 16, v);
-      if (m < M) epi(z, m, n0 + c * 16, v);
+    for (int f = 0; f < n_seg; ++f) {
+      gt_wait(acc_full, f & 1, 256);
+      gt_fence_after();
+      const bool last = f == n_seg - 1;
+      for (int c = 0; c < GT_BN / 16; ++c) {
+        float v[16];
+        gt_ld16(taddr + c * 16, v);
+        if (n_seg > 1 && m < M) {
+          float4* pb = reinterpret_cast<float4*>(flush_buf + (int64_t)m * flush_ld + n0 + c * 16);
+          if (f > 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 o = pb[j];
+              v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+            }
+          }
+          if (!last) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pb[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        if (last && m < M) epi(z, m, n0 + c * 16, v);
+      }
+      if (!last) {                       // the accumulator has been read: the MMAs of the next segment may overwrite it
+        gt_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
     }
   }
   gt_fence_before();
@@ -220,14 +262,16 @@ static inline GtEncodeFn gt_encode_fn() {
 }
 
 // packed operand [rows, ld_elems] bf16 (ld_elems >= 2*kp); box = [32 k] x [box_rows]; rows beyond `rows` read as 0
-static inline int gt_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
+static inline int gt_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t ld_elems, uint32_t box_rows,
+                              bool f16 = false) {
   GtEncodeFn enc = gt_encode_fn();
   VFR_REQUIRE(enc, VFR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)ld_elems, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * 2};
   cuuint32_t box[2] = {GT_BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                   gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VFR_REQUIRE(r == CUDA_SUCCESS, VFR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -236,24 +280,36 @@ static inline int gt_make_map(CUtensorMap* map, const void* base, uint64_t rows,
 
 static inline int gt_kp(int k) { return (k + GT_BK - 1) / GT_BK * GT_BK; }
 
-// A: packed [M, lda] (lda >= 2*kp), B: packed [N, ldb]; batch <= 2 problems with identical shapes
+// A: packed [M, lda] (lda >= 2*kp), B: packed [N, ldb]; batch <= 2 problems with identical shapes.
+// lo_a / lo_b (default kp): column distance between the hi and the lo half of a row of A / B - a K-segment of a wider
+// packed operand is used by passing its first column's address, its own kp and the wide operand's hi -> lo distance.
+// f16: the operands are split-fp16 (pre-scaled by powers of two into fp16's range) instead of split-bf16.
 template <class Epi>
 static int launch_gemm_tc(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda,
-                          int64_t ldb, Epi epi, cudaStream_t st, const int* m_limit = nullptr) {
+                          int64_t ldb, Epi epi, cudaStream_t st, const int* m_limit = nullptr, bool f16 = false,
+                          int lo_a = 0, int lo_b = 0, int flush_k = 0, float* flush_buf = nullptr, int64_t flush_ld = 0) {
   if (M <= 0 || N <= 0 || kp <= 0) return VFR_OK;
-  VFR_REQUIRE(batch >= 1 && batch <= 2 && kp % GT_BK == 0 && lda >= 2 * kp && ldb >= 2 * kp && lda % 8 == 0 && ldb % 8 == 0,
+  if (lo_a == 0) lo_a = kp;
+  if (lo_b == 0) lo_b = kp;
+  VFR_REQUIRE(batch >= 1 && batch <= 2 && kp % GT_BK == 0 && lda >= lo_a + kp && ldb >= lo_b + kp && lda % 8 == 0 &&
+                  ldb % 8 == 0 && lo_a % 8 == 0 && lo_b % 8 == 0,
               VFR_ERR_INVALID, "launch_gemm_tc: bad operand layout");
   GemmTcMaps maps;
   for (int z = 0; z < batch; ++z) {
-    int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128);
+    int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16);
     if (rc) return rc;
-    rc = gt_make_map(&maps.b[z], b[z], (uint64_t)N, (uint64_t)ldb, GT_BN);
+    rc = gt_make_map(&maps.b[z], b[z], (uint64_t)N, (uint64_t)ldb, GT_BN, f16);
     if (rc) return rc;
   }
   if (batch == 1) { maps.a[1] = maps.a[0]; maps.b[1] = maps.b[0]; }
+  // K-segmented accumulation: flush_buf fp32 [>= M rows, flush_ld >= N rounded up to 256] (batch 1 only), 16-byte aligned rows
+  VFR_REQUIRE(!flush_buf || (batch == 1 && flush_k >= GT_BK && flush_k % GT_BK == 0 && flush_ld % 4 == 0 &&
+                             flush_ld >= (N + GT_BN - 1) / GT_BN * GT_BN),
+              VFR_ERR_INVALID, "launch_gemm_tc: bad flush buffer");
   VFR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
   dim3 grid((N + GT_BN - 1) / GT_BN, (M + GT_BM - 1) / GT_BM, batch);
-  gemm_tc_kernel<Epi><<<grid, GT_THREADS, GT_SMEM, st>>>(maps, M, m_limit, kp / GT_BK, kp, epi);
+  gemm_tc_kernel<Epi><<<grid, GT_THREADS, GT_SMEM, st>>>(maps, M, m_limit, kp / GT_BK, lo_a, lo_b, f16 ? GT_FMT_F16 : GT_FMT_BF16,
+                                                         flush_buf ? flush_k / GT_BK : 0, flush_buf, flush_ld, epi);
   return check_launch("gemm_tc_kernel");
 }
 

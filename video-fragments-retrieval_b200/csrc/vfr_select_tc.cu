@@ -41,6 +41,7 @@
 #include "vfr_topk.cuh"
 #include <algorithm>
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
 #include <stdlib.h>
@@ -1051,7 +1052,8 @@ constexpr int RF_BATCH = RF_KEYS - VFR_TOPK_MAX;
 constexpr int RF_DIST = 1024;      // clip distances per chunk of videos
 
 struct RfParams {
-  const float* bank;           // fp32 [C, dim]
+  const float* bank;           // fp32 [C, dim] ...
+  const __nv_bfloat16* bank_b16; // ... or (bf16 embedding path, BASELINE configs[2]) the bank stored as bf16 [C, dim]
   const float* queries;        // fp32 [Q, dim]
   const int32_t* vid_off;      // [V+1]
   const int64_t* mom_off;      // [V+1]
@@ -1081,6 +1083,42 @@ struct RfParams {
 // vfr_score.cu (direct-difference form, k strictly sequential).  The bank row is fetched in batches of
 // 32 floats (8 independent 128-bit loads in flight) because the rows of the candidates are scattered
 // over the whole bank: the loop is bound by DRAM latency, not by the 100 dependent FFMAs.
+// the same arithmetic on a bank row stored in bf16 (exactly representable in fp32: the result equals the fp32 engine's on
+// the rounded embeddings, bit for bit); 16 values per 256-bit of loads
+__device__ __forceinline__ float rf_distance_b16(const __nv_bfloat16* __restrict__ vr, const float* qr, float sq, int dim) {
+  float acc = 0.f, sv = 0.f;
+  int k0 = 0;
+  if ((reinterpret_cast<uintptr_t>(vr) & 15u) == 0) {
+    for (; k0 + 32 <= dim; k0 += 32) {
+      uint4 x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = __ldg(reinterpret_cast<const uint4*>(vr + k0) + j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned w[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
+          float d = __fsub_rn(lo, qr[k0 + 8 * j + 2 * i]);
+          acc = __fmaf_rn(d, d, acc);
+          sv = __fadd_rn(sv, lo);
+          d = __fsub_rn(hi, qr[k0 + 8 * j + 2 * i + 1]);
+          acc = __fmaf_rn(d, d, acc);
+          sv = __fadd_rn(sv, hi);
+        }
+      }
+    }
+  }
+  for (int k = k0; k < dim; ++k) {
+    const float x = __bfloat162float(vr[k]);
+    const float d = __fsub_rn(x, qr[k]);
+    acc = __fmaf_rn(d, d, acc);
+    sv = __fadd_rn(sv, x);
+  }
+  const float corr = __fmaf_rn(2.f * VFR_PAIRWISE_EPS, __fsub_rn(sv, sq), (float)dim * VFR_PAIRWISE_EPS * VFR_PAIRWISE_EPS);
+  return __fsqrt_rn(fmaxf(__fadd_rn(acc, corr), 0.f));
+}
+
 __device__ __forceinline__ float rf_distance(const float* __restrict__ vr, const float* qr, float sq, int dim) {
   float acc = 0.f, sv = 0.f;
   int k0 = 0;
@@ -1298,7 +1336,9 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
       const int v = uvid[v0 + vi];
       const int c0 = __ldg(p.vid_off + v);
       const int n = __ldg(p.vid_off + v + 1) - c0;
-      if (c < n) dist[idx] = rf_distance(p.bank + (int64_t)(c0 + c) * p.dim, qrow, sq, p.dim);
+      if (c < n)
+        dist[idx] = p.bank_b16 ? rf_distance_b16(p.bank_b16 + (int64_t)(c0 + c) * p.dim, qrow, sq, p.dim)
+                               : rf_distance(p.bank + (int64_t)(c0 + c) * p.dim, qrow, sq, p.dim);
     }
     __syncthreads();
     const float tau = fminf(s_tau, s_max);
@@ -1675,14 +1715,15 @@ static int sl_run_filter(const SlPlan& pl, SlParams p, const void* bank_packed, 
 static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vid_off, const int64_t* mom_off,
                          int64_t n_videos, int n_max, int dim, const float* queries, int64_t n_queries, int k,
                          int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st, int64_t per = 0,
-                         void* out_blocks = nullptr) {
+                         void* out_blocks = nullptr, bool bank_is_b16 = false) {
   VFR_REQUIRE(bank && vid_off && mom_off && queries && ((out_scores && out_ids) || (per > 0 && out_blocks)), VFR_ERR_INVALID,
               "vfr_sel_refine: null pointer");
   VFR_REQUIRE(per == 0 || (per * (3 * (int64_t)k + 1)) % 2 == 0, VFR_ERR_INVALID, "vfr_sel_refine_blocks: per * (3k + 1) must be even");
   VFR_REQUIRE(n_videos > 0 && n_videos < (int64_t(1) << 31) - 1, VFR_ERR_UNSUPPORTED, "vfr_sel_refine: n_videos");
   VFR_REQUIRE(n_max >= 1 && n_max <= VFR_MAX_SEG, VFR_ERR_UNSUPPORTED, "vfr_sel_refine: n_max=%d", n_max);
   RfParams r{};
-  r.bank = bank;
+  r.bank = bank_is_b16 ? nullptr : bank;
+  r.bank_b16 = bank_is_b16 ? reinterpret_cast<const __nv_bfloat16*>(bank) : nullptr;
   r.queries = queries;
   r.vid_off = vid_off;
   r.mom_off = mom_off;
@@ -2054,6 +2095,24 @@ extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const in
   if (rc) return rc;
   return sl_run_refine(p, bank, vid_off, mom_off, n_videos, n_max, dim, queries, n_queries, k, id_base, out_scores,
                        out_ids, (cudaStream_t)stream);
+}
+
+// bf16 embedding path: the bank's fp32 rows are replaced by a bf16 [C, dim] array (half the HBM of stage 2); the packed
+// fp16 operand must have been built from the same (bf16-representable) values.  Scores = the exact engine's on those values.
+extern "C" int vfr_sel_topk_b16(const void* bank_packed, const void* bank_b16, const int32_t* vid_off, const int64_t* mom_off,
+                                int64_t n_videos, int64_t n_clips, int n_max, int dim, void* query_packed,
+                                const float* queries, int64_t n_queries, int k, int64_t id_base, float* out_scores,
+                                int64_t* out_ids, void* workspace, int n_split, vfr_stream_t stream) {
+  VFR_REQUIRE(bank_packed && bank_b16 && vid_off && mom_off && query_packed && queries && out_scores && out_ids && workspace,
+              VFR_ERR_INVALID, "vfr_sel_topk_b16: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  rc = sl_run_filter(pl, p, bank_packed, query_packed, 0, -1, 0, (cudaStream_t)stream);
+  if (rc) return rc;
+  return sl_run_refine(p, reinterpret_cast<const float*>(bank_b16), vid_off, mom_off, n_videos, n_max, dim, queries, n_queries,
+                       k, id_base, out_scores, out_ids, (cudaStream_t)stream, 0, nullptr, true);
 }
 
 // flags of the last vfr_sel_topk on this packed query buffer: device pointer to int32 [n_queries]

@@ -67,6 +67,71 @@ def pool_videos(frame_arrays, pooling="avg", preprocessed=False, device="cuda", 
     return out
 
 
+def pool_video_files(readers, pooling="avg", preprocessed=False, device="cuda", chunk_frames=1 << 15):
+    """Feature ingestion: per-video frame files -> K1, streamed through PINNED host staging.
+
+    ``readers``: one callable per video returning its frames ``[F_v, dim]`` (``np.load(..., mmap_mode="r")`` for the
+    ``get_rgb_features.py`` ``.npy`` files of data.py:164-166, an h5py dataset for MCN's ``.h5`` files of :145-148 - the
+    array is copied ONCE, from the file mapping straight into the pinned buffer).  Two pinned buffers of
+    ``chunk_frames`` frames alternate: while the host fills one, the other one's host->device copy (its own stream) and
+    K1 run; the pooled outputs stay on the device until the end, so nothing in the loop waits for the GPU except the
+    reuse of a staging buffer.  Returns the same list of dicts as ``pool_videos``."""
+    mode = "h5" if preprocessed else pooling
+    if mode not in ops.POOL_MODES:
+        raise KeyError(pooling)
+    dev = torch.device(device)
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    pinned, staged, copied, freed = [None, None], [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+    results = []
+    pending = None                      # frames of the video that did not fit the previous chunk
+    it = iter(readers)
+    b, dim, done = 0, None, False
+    while not done:
+        counts, n = [], 0
+        if freed[b] is not None:
+            freed[b].synchronize()      # K1 of the chunk that used this staging buffer two rounds ago has finished
+        while True:
+            if pending is None:
+                try:
+                    arr = next(it)()
+                except StopIteration:
+                    done = True
+                    break
+                arr = arr.reshape(arr.shape[0], -1)
+            else:
+                arr, pending = pending, None
+            if dim is None:
+                dim = int(arr.shape[1])
+            if pinned[b] is None or (n == 0 and arr.shape[0] > pinned[b].shape[0]):
+                pinned[b] = torch.empty((max(chunk_frames, arr.shape[0]), dim), dtype=torch.float32).pin_memory()
+                staged[b] = torch.empty(pinned[b].shape, dtype=torch.float32, device=dev)
+            if n + arr.shape[0] > pinned[b].shape[0]:
+                pending = arr
+                break
+            np.copyto(pinned[b][n:n + arr.shape[0]].numpy(), arr, casting="same_kind")   # file mapping -> pinned, one copy
+            counts.append(int(arr.shape[0]))
+            n += int(arr.shape[0])
+        if n == 0:
+            break
+        with torch.cuda.stream(copy_stream):
+            staged[b][:n].copy_(pinned[b][:n], non_blocking=True)
+            copied[b].record(copy_stream)
+        main.wait_event(copied[b])
+        off = np.concatenate([[0], np.cumsum(counts)])
+        results.append(ops.segment_pool(staged[b][:n], off, mode, _WINDOW))
+        freed[b] = torch.cuda.Event()
+        freed[b].record(main)
+        b ^= 1
+    out = []
+    for seg, ctx, n_seg in results:
+        seg, ctx, n_seg = seg.cpu().numpy(), ctx.cpu().numpy(), n_seg.cpu().numpy()
+        for k in range(len(n_seg)):
+            m = int(n_seg[k])
+            out.append(dict(segment_features=seg[k, :m].astype(np.float64), context_features=ctx[k].copy(), num_segments=m))
+    return out
+
+
 class CustomDataset(Dataset):
     """Same constructor and item format as the reference's ``CustomDataset`` (data.py:121-246)."""
 
@@ -93,12 +158,15 @@ class CustomDataset(Dataset):
             import h5py  # only needed for MCN's released .h5 features (data.py:144-148)
             with h5py.File(Path(self.ft_directory).joinpath(f"fc7_subsample5_fps25_{video}.h5")) as f:
                 return np.array(f["features"])
-        arr = np.load(Path(self.ft_directory).joinpath(f"features_{self.ft_type}/{self.ft_type}_ft_{video}.npy"))
+        # memory-mapped: the frames are copied once, from the page cache into the pinned staging buffer
+        arr = np.load(Path(self.ft_directory).joinpath(f"features_{self.ft_type}/{self.ft_type}_ft_{video}.npy"), mmap_mode="r")
         return arr.reshape((arr.shape[0], FEATURE_DIM[self.ft_type]))
 
     def load_video_features(self, videos):
+        """data.py:142-188 for all videos: the frame files stream through pinned staging buffers into K1."""
         videos = list(videos)
-        pooled = pool_videos([self._read_frames(v) for v in videos], self.pooling, self.preprocessed, self.device)
+        pooled = pool_video_files([(lambda v=v: self._read_frames(v)) for v in videos], self.pooling, self.preprocessed,
+                                  self.device)
         for video, feats in zip(videos, pooled):
             self.video_features[video] = feats
             self.num_segments_info[video] = feats["num_segments"]

@@ -37,24 +37,51 @@ def get_metrics(recalls):
     return out
 
 
+def _pooled_features(model, video_iterator):
+    """(names, seg [C, F], ctx [V, F], vid_off) when the iterator is our ``VideoBatchSampler`` over our ``CustomDataset``
+    (whole videos, start_t = 0, end_t = n - 1) and the model has the split-weight K2; otherwise None (any other iterator
+    is consumed batch by batch exactly as the reference does)."""
+    from . import data as vdata
+    ds = getattr(video_iterator, "dataset", None)
+    sampler = getattr(video_iterator, "batch_sampler", None)
+    if not (isinstance(ds, vdata.CustomDataset) and type(sampler) is vdata.VideoBatchSampler and hasattr(model, "embed_clips")
+            and getattr(model, "visual_engine", None) == "tc" and type(ds).make_visual_features is vdata.CustomDataset.make_visual_features):
+        return None
+    names = list(sampler.videos)
+    feats = [ds.video_features[v] for v in names]
+    nseg = [int(f["num_segments"]) for f in feats]
+    seg = torch.from_numpy(np.concatenate([np.asarray(f["segment_features"])[:n] for f, n in zip(feats, nseg)]).astype(np.float32))
+    ctx = torch.from_numpy(np.stack([np.asarray(f["context_features"], dtype=np.float32).reshape(-1) for f in feats]))
+    return names, seg, ctx, np.concatenate([[0], np.cumsum(nseg)]).astype(np.int64)
+
+
 def collect_embeddings(model, video_iterator, lang_iterator, device, rows_per_call=16384, bert=False):
     """Run the two embedding prologues of ``evaluate.py:33-35,42-44`` as batched calls.
     ``bert`` is the flag ``Trainer.validate_epoch`` forwards to the model (main.py:146): the language batches then
     hold float BERT-pooled features ``[1, 768]`` instead of token ids.
     Returns (Bank, names, q_emb [Q, D], q_video_names, q_annot_ids)."""
-    feats, names, nseg = [], [], []
-    for batch in video_iterator:
-        f = batch["feature"]
-        feats.append(f)
-        names.append(batch["video"])
-        nseg.append(int(f.shape[0]))
-    vid_off = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int64)
-    allf = torch.cat(feats, dim=0)
-    embs = []
-    with torch.no_grad():
-        for r0 in range(0, allf.shape[0], rows_per_call):
-            embs.append(model(allf[r0:r0 + rows_per_call].to(device, non_blocking=True)))
-    bank = ops.Bank(torch.cat(embs, dim=0), vid_off)
+    pooled = _pooled_features(model, video_iterator)
+    if pooled is not None:
+        # our own dataset + sampler: the pooled K1 features go to the split-weight K2 as they are - no per-video
+        # DataLoader round trip, no [n, 2F+2] rows (data.py:204-213), context product once per video
+        names, seg, ctx, vid_off = pooled
+        with torch.no_grad():
+            emb = model.embed_clips(seg.to(device, non_blocking=True), ctx.to(device, non_blocking=True), vid_off)
+        bank = ops.Bank(emb, vid_off)
+    else:
+        feats, names, nseg = [], [], []
+        for batch in video_iterator:
+            f = batch["feature"]
+            feats.append(f)
+            names.append(batch["video"])
+            nseg.append(int(f.shape[0]))
+        vid_off = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int64)
+        allf = torch.cat(feats, dim=0)
+        embs = []
+        with torch.no_grad():
+            for r0 in range(0, allf.shape[0], rows_per_call):
+                embs.append(model(allf[r0:r0 + rows_per_call].to(device, non_blocking=True)))
+        bank = ops.Bank(torch.cat(embs, dim=0), vid_off)
     ids, q_names, q_annots = [], [], []
     for batch in lang_iterator:
         ids.append(batch["feature"])

@@ -87,9 +87,12 @@ class CALModel(nn.Module):
         self._packed = None   # (version key, packed fwd, packed bwd)
         self._packed_tc = None
         self._packed_vis = None
-        # "exact": fp32 CUDA-core GEMMs (default, parity-critical evaluation); "tc": tcgen05 split-bf16 GEMMs for both
-        # embedding branches (K2 and K3), fp32-accurate (<= 1e-5 of the embedding scale)
+        # text branch (K3): "exact" = fp32 CUDA-core kernels (default of forward(); the retriever uses "tc"), "tc" = tcgen05
+        # split-bf16 GEMMs, fp32-accurate (<= 1e-5 of the embedding scale)
         self.engine = "exact"
+        # visual branch (K2): "tc" (default) = tcgen05 split-fp16 GEMMs (22-bit operands: <= 1e-5 of the embedding scale at
+        # K = 8194, csrc/vfr_visual_tc.cu), "exact" = fp32 CUDA-core SGEMM, "tc_bf16x3" = the round-1 split-bf16 GEMMs (5e-5)
+        self.visual_engine = "tc"
 
     def init_hidden(self, batch_size, device):
         """Zero (h0, c0) of the BiLSTM (models.py:50-52); the kernels start from zeros implicitly."""
@@ -139,9 +142,32 @@ class CALModel(nn.Module):
         return self.lang_fc(hidden[0].transpose(0, 1).reshape(tokens.size(0), 2 * self.hidden_size))
 
     # -- visual branch -----------------------------------------------------------------------
+    def _packed_visual(self):
+        lin1, lin2 = self.visual_fc[0], self.visual_fc[2]
+        ps = (lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+        key = ("f16",) + tuple((p.data_ptr(), p._version) for p in ps)
+        if self._packed_vis is None or self._packed_vis[0] != key:
+            packed, shape = ops.visual_pack(*[p.detach() for p in ps])
+            self._packed_vis = (key, packed, shape)
+        return self._packed_vis[1], self._packed_vis[2]
+
+    def embed_clips(self, seg, ctx, vid_off):
+        """The split-weight form of ``make_visual_features`` + ``visual_fc`` (data.py:204-213, models.py:21-27): clip
+        embeddings fp32 [C, emb_dim] straight from what K1 produces - ``seg`` fp32 [C, F] (segment features of all
+        videos back to back), ``ctx`` fp32 [V, F] (one context feature per video), ``vid_off`` [V+1] clip offsets.
+        The [C, 2F+2] rows of the reference are never built; the context product is computed once per video.
+        Eval-mode semantics (no dropout), no autograd."""
+        if not seg.is_cuda:
+            raise RuntimeError("vfr_b200.CALModel runs on CUDA tensors only (no CPU fallback)")
+        packed, shape = self._packed_visual()
+        return ops.visual_embed_split(seg, ctx, vid_off, packed, shape)
+
     def _visual_forward_kernels(self, batch):
         lin1, lin2 = self.visual_fc[0], self.visual_fc[2]
-        if self.engine == "tc":
+        if self.visual_engine == "tc":
+            packed, shape = self._packed_visual()
+            return ops.visual_embed_tc(batch, packed, shape)
+        if self.visual_engine == "tc_bf16x3":
             # K2 on tensor cores: two split-bf16 tcgen05 GEMMs (fp32-accurate), bias + ReLU in the epilogue
             ps = (lin1.weight, lin2.weight)
             key = tuple((p.data_ptr(), p._version) for p in ps)

@@ -92,6 +92,15 @@ class Bank:
             self.__dict__["_sel"] = packed
         return self.__dict__["_sel"]
 
+    def clips_b16(self):
+        """bf16 copy of the clip embeddings (the bf16 embedding path); the bank must hold bf16-representable values."""
+        if "_b16" not in self.__dict__:
+            b16 = self.clips.to(torch.bfloat16)
+            if not torch.equal(b16.to(torch.float32), self.clips):
+                raise _lib.VfrError("the bf16 path needs a bank of bf16-representable embeddings: build it from clips.bfloat16()")
+            self.__dict__["_b16"] = b16.contiguous()
+        return self.__dict__["_b16"]
+
     @property
     def uniform6(self):
         return int(bool((self.nseg_host == 6).all()))
@@ -188,12 +197,16 @@ def score_topk_tc(bank, queries, k, id_base=0, n_split=0, n_terms=3):
     return out_s, out_i
 
 
-def score_topk_sel(bank, queries, k, id_base=0, n_split=0, return_flags=False):
+def score_topk_sel(bank, queries, k, id_base=0, n_split=0, return_flags=False, bf16=False):
     """Filter + refine path (one fp16 tensor-core pass + exact fp32 re-scoring of the survivors):
     (scores fp32 [Q, k], ids int64 [Q, k]) bit-identical to ``score_topk``.  ``flags`` int32 [Q] is 0 for
-    every query whose result is guaranteed exact (see include/vfr.h, vfr_sel_flags)."""
+    every query whose result is guaranteed exact (see include/vfr.h, vfr_sel_flags).
+    ``bf16=True``: the bf16 embedding path - ``bank`` must hold bf16-representable values (``Bank(clips.bfloat16(), ...)``),
+    the queries are rounded to bf16 and stage 2 reads a bf16 copy of the bank (``vfr_sel_topk_b16``)."""
     _need_cuda(queries)
     q = _f32c(queries)
+    if bf16:
+        q = q.to(torch.bfloat16).to(torch.float32).contiguous()
     Q = q.shape[0]
     lib = _lib.load()
     n_clips = int(bank.clips.shape[0])
@@ -202,9 +215,14 @@ def score_topk_sel(bank, queries, k, id_base=0, n_split=0, return_flags=False):
     ws = torch.empty(lib.vfr_sel_topk_bytes(Q, n_clips, n_split), dtype=torch.uint8, device=bank.device)
     out_s = torch.empty((Q, k), dtype=torch.float32, device=bank.device)
     out_i = torch.empty((Q, k), dtype=torch.int64, device=bank.device)
-    _lib.call("vfr_sel_topk", _ptr(bank.sel()), _ptr(bank.clips), _ptr(bank.vid_off), _ptr(bank.mom_off), bank.n_videos,
-              n_clips, bank.n_max, bank.dim, _ptr(qp), _ptr(q), Q, k, id_base, _ptr(out_s), _ptr(out_i), _ptr(ws),
-              n_split, _stream())
+    if bf16:
+        _lib.call("vfr_sel_topk_b16", _ptr(bank.sel()), _ptr(bank.clips_b16()), _ptr(bank.vid_off), _ptr(bank.mom_off),
+                  bank.n_videos, n_clips, bank.n_max, bank.dim, _ptr(qp), _ptr(q), Q, k, id_base, _ptr(out_s), _ptr(out_i),
+                  _ptr(ws), n_split, _stream())
+    else:
+        _lib.call("vfr_sel_topk", _ptr(bank.sel()), _ptr(bank.clips), _ptr(bank.vid_off), _ptr(bank.mom_off), bank.n_videos,
+                  n_clips, bank.n_max, bank.dim, _ptr(qp), _ptr(q), Q, k, id_base, _ptr(out_s), _ptr(out_i), _ptr(ws),
+                  n_split, _stream())
     if not return_flags:
         return out_s, out_i
     off = lib.vfr_sel_flags(_ptr(qp), Q, bank.dim) - qp.data_ptr()
@@ -306,6 +324,58 @@ def visual_embed(x, w1, b1, w2, b2, return_hidden=False):
         _lib.call("vfr_visual_embed", _ptr(x), n, x.shape[1], _ptr(w1), _ptr(b1), w1.shape[0], _ptr(w2), _ptr(b2),
                   w2.shape[0], _ptr(hidden), _ptr(out), _stream())
     return (out, hidden) if return_hidden else out
+
+
+def visual_pack(w1, b1, w2, b2):
+    """Pack the visual MLP for the tensor-core K2 (split-fp16 operands + the tef columns and biases in fp32)."""
+    _need_cuda(w1, b1, w2, b2)
+    w1, b1, w2, b2 = (_f32c(t) for t in (w1, b1, w2, b2))
+    hid, dim = w1.shape[0], w2.shape[0]
+    if (w1.shape[1] - 2) % 2 or w2.shape[1] != hid:
+        raise _lib.VfrError(f"visual MLP shapes {tuple(w1.shape)} / {tuple(w2.shape)} are not [hid, 2F+2] / [dim, hid]")
+    feat = (w1.shape[1] - 2) // 2
+    packed = torch.empty(_lib.load().vfr_visual_pack_bytes(feat, hid, dim), dtype=torch.uint8, device=w1.device)
+    _lib.call("vfr_visual_pack", _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), feat, hid, dim, _ptr(packed), _stream())
+    return packed, (feat, hid, dim)
+
+
+def visual_embed_tc(x, packed, shape, rows_per_call=32768):
+    """K2 on tensor cores, general form: x fp32 [N, 2F+2] (the reference's assembled rows) -> fp32 [N, dim]."""
+    _need_cuda(x, packed)
+    feat, hid, dim = shape
+    x = _f32c(x)
+    if x.dim() != 2 or x.shape[1] != 2 * feat + 2:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x.shape)} and ({2 * feat + 2}, {hid}))")
+    out = torch.empty((x.shape[0], dim), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    for r0 in range(0, x.shape[0], rows_per_call):
+        n = min(rows_per_call, x.shape[0] - r0)
+        ws = torch.empty(lib.vfr_visual_embed_tc_bytes(n, 0, feat, hid, dim, 0), dtype=torch.uint8, device=x.device)
+        _lib.call("vfr_visual_embed_tc", _ptr(x[r0:r0 + n]), n, feat, _ptr(packed), hid, dim, _ptr(ws), _ptr(out[r0:r0 + n]),
+                  _stream())
+    return out
+
+
+def visual_embed_split(seg, ctx, vid_off, packed, shape, videos_per_call=8192):
+    """K2 on tensor cores, split-weight form: seg fp32 [C, F] (clips of all videos back to back), ctx fp32 [V, F],
+    vid_off [V+1] CSR clip offsets -> fp32 [C, dim].  No [C, 2F+2] concat, context product once per video."""
+    _need_cuda(seg, ctx, packed)
+    feat, hid, dim = shape
+    seg, ctx = _f32c(seg), _f32c(ctx)
+    vo = np.asarray(vid_off, dtype=np.int64)
+    V = len(vo) - 1
+    if seg.shape[1] != feat or ctx.shape != (V, feat) or vo[0] != 0 or vo[-1] != seg.shape[0] or np.any(np.diff(vo) < 1):
+        raise ValueError("visual_embed_split: seg [C, F], ctx [V, F] and CSR vid_off [V+1] do not fit together")
+    out = torch.empty((seg.shape[0], dim), dtype=torch.float32, device=seg.device)
+    lib = _lib.load()
+    for v0 in range(0, V, videos_per_call):
+        v1 = min(V, v0 + videos_per_call)
+        c0, c1 = int(vo[v0]), int(vo[v1])
+        off = torch.from_numpy((vo[v0:v1 + 1] - c0).astype(np.int32)).to(seg.device)
+        ws = torch.empty(lib.vfr_visual_embed_tc_bytes(c1 - c0, v1 - v0, feat, hid, dim, 1), dtype=torch.uint8, device=seg.device)
+        _lib.call("vfr_visual_embed_split", _ptr(seg[c0:c1]), _ptr(ctx[v0:v1]), _ptr(off), c1 - c0, v1 - v0, feat, _ptr(packed),
+                  hid, dim, _ptr(ws), _ptr(out[c0:c1]), _stream())
+    return out
 
 
 def lstm_pack(w_ih, w_hh, b_ih, b_hh):
