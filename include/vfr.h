@@ -194,7 +194,8 @@ int64_t vfr_sel_tiles(int64_t n_clips);
 /* The shard-level glue of the pooled-sample protocol as kernels (no host round trip, no library ops):
  *  vfr_sel_pool_levels   pooled fp32 [n_src, Q, width] (the all-gathered samples, +inf padded) -> levels fp32 [n_levels, Q],
  *                        levels[l][q] = the ranks[l]-th smallest pooled value of query q (ranks: HOST int32 [n_levels <= 4],
- *                        1-based, descending = loosest level first; n_src * width <= 1024);
+ *                        1-based, descending = loosest level first; n_src * width <= 1024; sorted_runs != 0 asserts that
+ *                        every run of 32 values is ascending, as vfr_sel_sample exports them: a shortcut, same result);
  *  vfr_sel_count_levels  count int32 [n_levels, Q] = the shard's clips certainly within each level (vfr_sel_count_under for
  *                        all levels in one pass) - all-reduce(sum) them over the shards;
  *  vfr_sel_pick_put      the tightest level whose all-reduced count is >= k becomes the certified bound (vfr_sel_bound_put);
@@ -204,7 +205,7 @@ int64_t vfr_sel_tiles(int64_t n_clips);
  *                        int32 [per]} at out_blocks + j * vfr_topk_block_bytes(per, k); per * (3k + 1) must be even.
  *                        ONE all-to-all then hands every rank the P shard records of its own slice (vfr_topk_merge_blocks). */
 int vfr_sel_pool_levels(const float* pooled, int n_src, int64_t n_queries, int width, const int32_t* ranks, int n_levels,
-                        float* levels, vfr_stream_t stream);
+                        int sorted_runs, float* levels, vfr_stream_t stream);
 int vfr_sel_count_levels(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace, int n_split,
                          const float* levels, int n_levels, int32_t* count, vfr_stream_t stream);
 int vfr_sel_pick_put(void* query_packed, int64_t n_queries, int64_t n_clips, int dim, int k, void* workspace, int n_split,
@@ -356,6 +357,44 @@ int vfr_ranking_loss_bwd(const float* posit, const float* intra, const float* in
                          int rows_inter, int n_samples, int dim, int normalize, float b, float lamb,
                          void* workspace, const float* grad_out, float* grad_posit, float* grad_intra,
                          float* grad_inter, float* grad_lang, vfr_stream_t stream);
+
+/* ---- training step: forward-with-saved-activations, BACKWARD of both embedding branches, fused Adam ---------------
+ * replaces the autograd graph / library calls behind  loss.backward(); optimizer.step()  of model/main.py:57-67 (optimiser
+ * main.py:358, grad-norm logging utils.py:85-92); the ranking loss between them is K6.  fp32 on the CUDA cores: a training
+ * step (R ~ 120 clip rows x 3 streams, B ~ 87 queries) is bound by launch latency and the 20 sequential recurrent steps.
+ *
+ * Text branch (models.py:61-66, train mode has no dropout here): w_ih / w_hh / b_ih / b_hh and their gradients are HOST
+ * arrays of TWO device pointers {forward direction, reverse direction} in nn.LSTM's own layout ([4H, E], [4H, H], [4H],
+ * gate order i, f, g, o).  The forward keeps every activation in `workspace` (vfr_text_train_bytes) for the backward call;
+ * vfr_text_train_flag(workspace) -> DEVICE int32, 1 if a token id was outside [0, vocab).  d_length (fp32 [vocab], must be
+ * zeroed by the caller, accumulated into) is the gradient of the learnable word length (normalize_lang), else NULL. */
+size_t vfr_text_train_bytes(int n_queries, int seq_len, int hidden, int emb, int dim);
+int vfr_text_train_fwd(const int64_t* tokens, int n_queries, int seq_len, const float* table, int64_t vocab,
+                       const float* length_table, int emb, const float* const* w_ih, const float* const* w_hh,
+                       const float* const* b_ih, const float* const* b_hh, int hidden, const float* fc_w, const float* fc_b,
+                       int dim, void* workspace, float* out, vfr_stream_t stream);
+int vfr_text_train_bwd(const int64_t* tokens, int n_queries, int seq_len, int64_t vocab, int has_length, int emb,
+                       const float* const* w_ih, const float* const* w_hh, int hidden, const float* fc_w, int dim,
+                       void* workspace, const float* grad_out, float* const* d_w_ih, float* const* d_w_hh,
+                       float* const* d_b_ih, float* const* d_b_hh, float* d_fc_w, float* d_fc_b, float* d_length,
+                       vfr_stream_t stream);
+const int32_t* vfr_text_train_flag(const void* workspace);
+/* Visual branch (models.py:21-27): e = relu(x W1^T + b1) W2^T + b2.  vfr_visual_train_fwd is the forward for the ~120-row
+ * batches of a training step (split-K fp32 SGEMMs over all SMs; scratch vfr_visual_train_fwd_bytes) and keeps the post-ReLU
+ * hidden [n, hid]; vfr_visual_train_bwd takes x [n, in_dim], that hidden and dE [n, dim]; scratch fp32 [n, hid]; d_x optional. */
+size_t vfr_visual_train_fwd_bytes(int64_t n_rows, int hid, int dim);
+int vfr_visual_train_fwd(const float* x, int64_t n_rows, int in_dim, const float* w1, const float* b1, int hid, const float* w2,
+                         const float* b2, int dim, float* scratch, float* hidden, float* out, vfr_stream_t stream);
+int vfr_visual_train_bwd(const float* x, int64_t n_rows, int in_dim, const float* hidden, int hid, const float* w1,
+                         const float* w2, int dim, const float* grad_out, float* scratch, float* d_w1, float* d_b1,
+                         float* d_w2, float* d_b2, float* d_x, vfr_stream_t stream);
+/* torch.optim.Adam(lr, weight_decay) of main.py:358 for up to 24 tensors in ONE launch (L2 decay folded into the gradient,
+ * bias-corrected moments, eps after the sqrt); pointer arrays and numel are HOST arrays, step = 1-based count of this update.
+ * vfr_grad_norms: out fp32 [count] (DEVICE) = L2 norm of every gradient tensor (utils.py:85-92 logs their mean). */
+int vfr_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                  const int64_t* numel, int count, int64_t step, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, vfr_stream_t stream);
+int vfr_grad_norms(const float* const* grads, const int64_t* numel, int count, float* out, vfr_stream_t stream);
 
 /* ---- retrieval step: K3 -> K4 behind one call --------------------------------------------------
  * The serving form of model/evaluate.py:42-80: one batch of tokenised queries against the resident

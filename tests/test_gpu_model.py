@@ -384,3 +384,80 @@ def test_feature_files_stream_through_pinned_staging_into_k1(golden, tmp_path, m
     for i, n in enumerate(h5names):
         _close(ds.video_features[n]["segment_features"], z[f"h5_h{i}_seg"], 2e-6)
         _close(ds.video_features[n]["context_features"], z[f"h5_h{i}_ctx"], 2e-6)
+
+
+# ---- whole training steps on the hand-written kernels (forward with saved activations, backward, fused Adam) ------------
+@pytest.mark.parametrize("norm", [0, 1])
+def test_training_steps_match_reference_train_epoch(golden, norm):
+    """Trainer.train_epoch with our CALModel (dropout_rate = 0, as the golden was produced) and FusedAdam(lr 5e-4,
+    wd 5e-3) on the batches the reference's sampler produced: the logged loss / n and mean gradient norm of every step
+    and the weights after the first and the last step equal what the reference's Trainer + torch.optim.Adam produced."""
+    from oracle.ref_harness import NullWriter
+    z, meta = golden("train_full_step")
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], hidden=meta["hidden"], spread=meta["spread"])
+    model = models.CALModel(visual_input_dim=2 * meta["feat_dim"] + 2, pretrained_emb=torch.from_numpy(sd["word_embedding.weight"]),
+                            hidden_size=meta["hidden"], dropout_rate=0.0)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.to(DEV)
+    w = NullWriter()
+    tr = vmain.Trainer(train_writer=w, device=DEV, compute_grads=True, normalize_loss=bool(norm))
+    opt = vmain.FusedAdam(model.parameters(), lr=meta["lr"], weight_decay=meta["weight_decay"])
+    logged = z[f"norm{norm}_logged"].reshape(-1, 2)
+    for step in range(meta["steps"]):
+        batch = {k: torch.from_numpy(z[f"b{step}_{k}"]) for k in ("posit", "intra", "inter", "lang", "maskp", "maskn")}
+        epoch_loss = tr.train_epoch(model, [batch], opt)
+        np.testing.assert_allclose(epoch_loss, float(z[f"norm{norm}_s{step}_epoch_loss"]), rtol=2e-5)
+        got = dict((n, v) for n, v, s in w.scalars if s == step)
+        np.testing.assert_allclose(got["loss"], logged[step, 0], rtol=2e-5)
+        np.testing.assert_allclose(got["grad_norm"], logged[step, 1], rtol=2e-4)
+        state = model.state_dict()
+        for k in z.files:
+            pre = f"norm{norm}_s{step}_w:"
+            if k.startswith(pre):
+                # Adam's first steps move every weight by ~lr whatever the size of its gradient (m / sqrt(v) ~ +-1), so a
+                # gradient of ~1e-9 that differs in its last bits moves a weight visibly: the bar is a tenth of one
+                # update for the worst element and a thousandth on average
+                err = np.abs(state[k[len(pre):]].cpu().numpy().astype(np.float64) - z[k])
+                assert err.max() <= 0.1 * meta["lr"] and err.mean() <= 1e-3 * meta["lr"], (k, err.max(), err.mean())
+    assert tr.global_step == meta["steps"]
+
+
+def test_fused_adam_equals_torch_adam():
+    torch.manual_seed(5)
+    shapes = [(500, 514), (500,), (100, 500), (100,), (512, 100), (512, 128), (3,)] * 5           # 35 tensors: two launches
+    ours = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    a = vmain.FusedAdam(ours, lr=5e-4, weight_decay=5e-3)
+    b = torch.optim.Adam(ref, lr=5e-4, weight_decay=5e-3)
+    for it in range(4):
+        for p, q in zip(ours, ref):
+            g = torch.randn_like(p) * (10.0 ** (it - 2))
+            p.grad, q.grad = g.clone(), g.clone()
+        a.step()
+        b.step()
+    for p, q in zip(ours, ref):
+        assert (p - q).abs().max().item() <= 2e-6 * max(1.0, q.abs().max().item())
+    assert a.state[ours[0]]["step"] == 4
+
+
+def test_text_backward_with_learnable_length_matches_torch_autograd(golden):
+    """normalize_lang=True: gradients of the LSTM, lang_fc AND the learnable word length (models.py:36-38,62-64) from the
+    hand-written BPTT against torch autograd over the CPU restatement."""
+    _, meta = golden("text_nl1")
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], normalize_lang=True)
+    model = _model(sd, meta["feat_dim"], normalize_lang=True).train()
+    q = synth.make_queries(meta["seed"], synth.make_videos(meta["seed"], 4, meta["feat_dim"]), meta["n_queries"], meta["vocab"])
+    tok = torch.from_numpy(q["tokens"])
+    g = torch.Generator().manual_seed(3)
+    up = torch.randn(tok.shape[0], 100, generator=g)
+    out = model(tok.to(DEV), False, DEV)
+    out.backward(up.to(DEV))
+    cpu = {k: torch.from_numpy(v.copy()).requires_grad_(k != "word_embedding.weight") for k, v in sd.items()}
+    ref = orc.text_embed(cpu, q["tokens"], normalize_lang=True)
+    ref.backward(up)
+    _close(out.detach().cpu().numpy(), ref.detach().numpy(), 1e-5)
+    for name, p in model.named_parameters():
+        if name.startswith(("lstm", "lang_fc", "learnable_length")):
+            assert p.grad is not None, name
+            _close(p.grad.cpu().numpy(), cpu[name].grad.numpy(), 2e-4)
+    assert float(model.learnable_length.weight.grad[0].abs().sum()) == 0.0        # padding_idx row

@@ -72,7 +72,7 @@ PROTOTYPES = {
     "vfr_sel_flags": (_p, [_p, _l, _i]),
     "vfr_sel_topk_b16": (_i, [_p, _p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
     "vfr_sel_tiles": (_l, [_l]),
-    "vfr_sel_pool_levels": (_i, [_p, _i, _l, _i, _p, _i, _p, _p]),
+    "vfr_sel_pool_levels": (_i, [_p, _i, _l, _i, _p, _i, _i, _p, _p]),
     "vfr_sel_count_levels": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _i, _p, _p]),
     "vfr_sel_pick_put": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p, _i, _p]),
     "vfr_topk_block_bytes": (_z, [_l, _i]),
@@ -115,6 +115,15 @@ PROTOTYPES = {
     "vfr_ranking_loss_bytes": (_z, [_i, _i, _i, _i]),
     "vfr_ranking_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p]),
     "vfr_ranking_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "vfr_text_train_bytes": (_z, [_i, _i, _i, _i, _i]),
+    "vfr_text_train_fwd": (_i, [_p, _i, _i, _p, _l, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
+    "vfr_text_train_bwd": (_i, [_p, _i, _i, _l, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vfr_text_train_flag": (_p, [_p]),
+    "vfr_visual_train_fwd_bytes": (_z, [_l, _i, _i]),
+    "vfr_visual_train_fwd": (_i, [_p, _l, _i, _p, _p, _i, _p, _p, _i, _p, _p, _p, _p]),
+    "vfr_visual_train_bwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vfr_adam_step": (_i, [_p, _p, _p, _p, _p, _i, _l, _f, _f, _f, _f, _f, _p]),
+    "vfr_grad_norms": (_i, [_p, _p, _i, _p, _p]),
     "vfr_search_embed_device": (_i, [C.POINTER(SearchPlan), _p, _l, _p, _p]),
     "vfr_search_score_device": (_i, [C.POINTER(SearchPlan), _l, _i, _p, _p, _p]),
     "vfr_search_device": (_i, [C.POINTER(SearchPlan), _p, _l, _i, _p, _p, _p]),

@@ -20,9 +20,46 @@ from .evaluate import collect_embeddings, rank_first_positive
 
 
 def grad_norm(model):
-    """Mean per-parameter gradient L2 norm (reference model/utils.py:85-92)."""
-    norms = [p.grad.data.norm().item() for p in model.parameters() if p.grad is not None]
+    """Mean per-parameter gradient L2 norm (reference model/utils.py:85-92): one kernel over all gradient tensors and one
+    read-back instead of a ``.norm().item()`` round trip per parameter."""
+    grads = [p.grad.detach().float().contiguous() for p in model.parameters() if p.grad is not None]
+    norms = ops.grad_norms(grads).cpu().tolist()
     return sum(norms) / len(norms)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam(params, lr, weight_decay)`` as the reference configures it (main.py:358) on ONE kernel launch
+    per step for all parameter tensors (``vfr_adam_step``): L2 weight decay folded into the gradient, bias-corrected
+    moments, eps after the square root.  State layout (``step`` / ``exp_avg`` / ``exp_avg_sq`` per parameter) as torch's."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            for p in ps:
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+            by_step = {}
+            for p in ps:
+                by_step.setdefault(self.state[p]["step"], []).append(p)
+            for step, group_ps in by_step.items():
+                ops.adam_step([p.data for p in group_ps], [p.grad.contiguous() for p in group_ps],
+                              [self.state[p]["exp_avg"] for p in group_ps], [self.state[p]["exp_avg_sq"] for p in group_ps],
+                              step, lr=group["lr"], betas=group["betas"], eps=group["eps"], weight_decay=group["weight_decay"])
+        return loss
 
 
 class Trainer:

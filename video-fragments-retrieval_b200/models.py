@@ -7,13 +7,16 @@ Same constructor signature, same sub-module names (so the reference's ``state_di
 The ``nn`` modules are parameter containers only: the forward pass runs the hand-written kernels
 (K2 ``vfr_visual_embed``, K3 ``vfr_text_embed``) on CUDA tensors and raises on CPU tensors.
 
-Backward (training, SURVEY.md 8(f) item 2 - "next"): gradients of the two embedding branches are
-obtained by re-running the branch with stock torch CUDA ops inside ``backward`` (activation
-recompute); the ranking loss itself has hand-written forward AND backward kernels (K6).
+Training: when gradients are enabled the two branches run the training kernels of
+``csrc/vfr_train.cu`` - forward with saved activations, hand-written backward (visual MLP: three strided SGEMMs + the
+ReLU mask; text: BPTT over the 20 steps with the weight gradients of all steps in one GEMM per matrix) - no library
+GEMM / RNN call and no autograd graph inside a branch; the ranking loss has its own forward / backward kernels (K6).
+The only stock torch op of a step is the Dropout(0.3) of the visual output, kept so that the mask consumes the torch
+RNG exactly as the reference does (models.py:25).
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
+import torch.nn.functional as F  # noqa: F401  (BERT branch: a single Linear, models.py:58-59)
 
 from . import ops
 
@@ -25,41 +28,6 @@ def init_weights(m):
     if isinstance(m, nn.Linear):
         nn.init.uniform_(m.weight, -0.08, 0.08)
         nn.init.constant_(m.bias, 0)
-
-
-class _VisualEmbed(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
-        ctx.save_for_backward(x, w1, b1, w2, b2)
-        return ops.visual_embed(x, w1, b1, w2, b2)
-
-    @staticmethod
-    def backward(ctx, grad):
-        x, w1, b1, w2, b2 = ctx.saved_tensors
-        with torch.enable_grad():
-            leaves = [t.detach().requires_grad_(t.requires_grad) for t in (x, w1, b1, w2, b2)]
-            out = F.linear(torch.relu(F.linear(leaves[0].float(), leaves[1], leaves[2])), leaves[3], leaves[4])
-            need = [t for t in leaves if t.requires_grad]
-            grads = iter(torch.autograd.grad(out, need, grad))
-        return tuple(next(grads) if t.requires_grad else None for t in leaves)
-
-
-class _TextEmbed(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, model, tokens, *params):
-        ctx.model = model
-        ctx.tokens = tokens
-        return model._text_forward_kernels(tokens)
-
-    @staticmethod
-    def backward(ctx, grad):
-        model = ctx.model
-        with torch.enable_grad():
-            out = model._text_forward_torch(ctx.tokens)
-            params = [p for p in model._text_params()]
-            need = [p for p in params if p.requires_grad]
-            grads = iter(torch.autograd.grad(out, need, grad, allow_unused=True))
-        return (None, None) + tuple(next(grads) if p.requires_grad else None for p in params)
 
 
 class CALModel(nn.Module):
@@ -132,15 +100,6 @@ class CALModel(nn.Module):
         return ops.text_embed(tokens, self.word_embedding.weight.detach(), length, fwd, bwd, self.hidden_size,
                               self.lang_fc.weight.detach(), self.lang_fc.bias.detach())
 
-    def _text_forward_torch(self, tokens):
-        # stock-torch re-execution used only inside backward (activation recompute)
-        embedded = self.word_embedding(tokens)
-        if self.normalize_lang:
-            embedded = embedded.div(embedded.norm(dim=-1, keepdim=True) + 1e-5) * self.learnable_length(tokens)
-        with torch.backends.cudnn.flags(enabled=self.lstm.training):   # cuDNN RNN backward needs train mode
-            _, hidden = self.lstm(embedded)
-        return self.lang_fc(hidden[0].transpose(0, 1).reshape(tokens.size(0), 2 * self.hidden_size))
-
     # -- visual branch -----------------------------------------------------------------------
     def _packed_visual(self):
         lin1, lin2 = self.visual_fc[0], self.visual_fc[2]
@@ -188,7 +147,7 @@ class CALModel(nn.Module):
         if visual:
             lin1, lin2, drop = self.visual_fc[0], self.visual_fc[2], self.visual_fc[3]
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.visual_fc.parameters()):
-                out = _VisualEmbed.apply(batch, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+                out = ops.visual_embed_train(batch, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
             else:
                 out = self._visual_forward_kernels(batch)
             return drop(out)            # identity in eval mode; torch RNG mask in train mode (models.py:25)
@@ -198,5 +157,6 @@ class CALModel(nn.Module):
             return ops.linear(batch, self.lang_fc.weight, self.lang_fc.bias)
         params = self._text_params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _TextEmbed.apply(self, batch, *params)
+            length = self.learnable_length.weight if self.normalize_lang else None
+            return ops.text_embed_train(batch, self.word_embedding.weight.detach(), length, self.hidden_size, params[:10])
         return self._text_forward_kernels(batch)

@@ -1,6 +1,8 @@
 """Thin torch-tensor wrappers over the libvfr C ABI: argument checking, workspace allocation
 (torch owns device memory and streams - plumbing only) and pointer extraction.  Every function
 requires CUDA tensors and raises otherwise: there is no CPU path in the product."""
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -535,3 +537,123 @@ class _RankingLoss(torch.autograd.Function):
 def ranking_loss(posit, intra, inter, lang, maskp, maskn, n_samples, normalize=False, b=0.1, lamb=0.4):
     """K6 (reference model/main.py:214-232): differentiable scalar loss (a sum over samples)."""
     return _RankingLoss.apply(posit, intra, inter, lang, maskp, maskn, int(n_samples), normalize, b, lamb)
+
+
+# ---------------------------------------------------------------------------------------------
+# training step: hand-written forward-with-saved-activations / backward of both embedding branches, fused Adam
+# (csrc/vfr_train.cu; reference model/main.py:57-67,358 and model/utils.py:85-92)
+# ---------------------------------------------------------------------------------------------
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class _VisualTrain(torch.autograd.Function):
+    """e = relu(x W1^T + b1) W2^T + b2 with a hand-written backward (vfr_visual_train_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        _need_cuda(x, w1, b1, w2, b2)
+        x, w1, b1, w2, b2 = (_f32c(t) for t in (x, w1, b1, w2, b2))
+        if x.dim() != 2 or x.shape[1] != w1.shape[1]:
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x.shape)} and {tuple(w1.t().shape)})")
+        n, hid, dim = x.shape[0], w1.shape[0], w2.shape[0]
+        hidden = torch.empty((n, hid), dtype=torch.float32, device=x.device)
+        out = torch.empty((n, dim), dtype=torch.float32, device=x.device)
+        if n:
+            scratch = torch.empty(_lib.load().vfr_visual_train_fwd_bytes(n, hid, dim) // 4, dtype=torch.float32, device=x.device)
+            _lib.call("vfr_visual_train_fwd", _ptr(x), n, x.shape[1], _ptr(w1), _ptr(b1), hid, _ptr(w2), _ptr(b2), dim,
+                      _ptr(scratch), _ptr(hidden), _ptr(out), _stream())
+        ctx.save_for_backward(x, hidden, w1, w2)
+        ctx.need_dx = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, hidden, w1, w2 = ctx.saved_tensors
+        g = _f32c(grad)
+        n, hid, dim = x.shape[0], w1.shape[0], w2.shape[0]
+        dev = x.device
+        d_w1, d_b1 = torch.empty_like(w1), torch.empty(hid, dtype=torch.float32, device=dev)
+        d_w2, d_b2 = torch.empty_like(w2), torch.empty(dim, dtype=torch.float32, device=dev)
+        d_x = torch.empty_like(x) if ctx.need_dx else None
+        if n == 0:
+            return (d_x, d_w1.zero_(), d_b1.zero_(), d_w2.zero_(), d_b2.zero_())
+        scratch = torch.empty((n, hid), dtype=torch.float32, device=dev)
+        _lib.call("vfr_visual_train_bwd", _ptr(x), n, x.shape[1], _ptr(hidden), hid, _ptr(w1), _ptr(w2), dim, _ptr(g),
+                  _ptr(scratch), _ptr(d_w1), _ptr(d_b1), _ptr(d_w2), _ptr(d_b2), _ptr(d_x), _stream())
+        return d_x, d_w1, d_b1, d_w2, d_b2
+
+
+def visual_embed_train(x, w1, b1, w2, b2):
+    """Differentiable K2 for the training step (gradients to W1, b1, W2, b2 and, if asked for, x)."""
+    return _VisualTrain.apply(x, w1, b1, w2, b2)
+
+
+class _TextTrain(torch.autograd.Function):
+    """GloVe gather -> BiLSTM -> Linear with saved activations and a hand-written BPTT (vfr_text_train_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, tokens, table, length, hidden, *params):
+        # params: w_ih, w_hh, b_ih, b_hh (forward), the same four (reverse), fc_w, fc_b
+        _need_cuda(tokens, table, *params)
+        tokens = tokens.to(torch.int64).contiguous()
+        table = _f32c(table)
+        ps = [_f32c(p) for p in params]
+        lt = None if length is None else _f32c(length).reshape(-1)
+        B, T = tokens.shape
+        E, D = table.shape[1], ps[8].shape[0]
+        lib = _lib.load()
+        ws = torch.empty(lib.vfr_text_train_bytes(B, T, hidden, E, D), dtype=torch.uint8, device=tokens.device)
+        out = torch.empty((B, D), dtype=torch.float32, device=tokens.device)
+        w_ih, w_hh, b_ih, b_hh = ([ps[i], ps[4 + i]] for i in range(4))
+        _lib.call("vfr_text_train_fwd", _ptr(tokens), B, T, _ptr(table), table.shape[0], _ptr(lt), E, _ptr_array(w_ih),
+                  _ptr_array(w_hh), _ptr_array(b_ih), _ptr_array(b_hh), hidden, _ptr(ps[8]), _ptr(ps[9]), D, _ptr(ws), _ptr(out),
+                  _stream())
+        if int(ws[:4].view(torch.int32)[0].item()) != 0:
+            raise IndexError("index out of range in self")
+        ctx.save_for_backward(tokens, ws, *ps)
+        ctx.cfg = (hidden, E, D, table.shape[0], lt is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        tokens, ws, *ps = ctx.saved_tensors
+        hidden, E, D, vocab, has_length = ctx.cfg
+        B, T = tokens.shape
+        g = _f32c(grad)
+        grads = [torch.empty_like(p) for p in ps]
+        d_len = torch.zeros(vocab, dtype=torch.float32, device=tokens.device) if has_length else None
+        w_ih, w_hh = [ps[0], ps[4]], [ps[1], ps[5]]
+        _lib.call("vfr_text_train_bwd", _ptr(tokens), B, T, vocab, int(has_length), E, _ptr_array(w_ih), _ptr_array(w_hh), hidden,
+                  _ptr(ps[8]), D, _ptr(ws), _ptr(g), _ptr_array([grads[0], grads[4]]), _ptr_array([grads[1], grads[5]]),
+                  _ptr_array([grads[2], grads[6]]), _ptr_array([grads[3], grads[7]]), _ptr(grads[8]), _ptr(grads[9]),
+                  _ptr(d_len), _stream())
+        return (None, None, None if d_len is None else d_len.view(-1, 1), None, *grads)
+
+
+def text_embed_train(tokens, table, length, hidden, params):
+    """Differentiable K3 for the training step; ``params`` = the ten LSTM / lang_fc tensors in ``CALModel._text_params``
+    order, ``length`` = the learnable word-length table [vocab, 1] or None."""
+    return _TextTrain.apply(tokens, table, length, hidden, *params)
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """torch.optim.Adam's update for a list of fp32 CUDA tensors, 24 tensors per launch (vfr_adam_step)."""
+    _need_cuda(*params, *grads, *exp_avg, *exp_avg_sq)
+    for i in range(0, len(params), 24):
+        sl = slice(i, i + 24)
+        numel = (C.c_int64 * len(params[sl]))(*[p.numel() for p in params[sl]])
+        _lib.call("vfr_adam_step", _ptr_array(params[sl]), _ptr_array(grads[sl]), _ptr_array(exp_avg[sl]),
+                  _ptr_array(exp_avg_sq[sl]), numel, len(params[sl]), int(step), float(lr), float(betas[0]), float(betas[1]),
+                  float(eps), float(weight_decay), _stream())
+
+
+def grad_norms(grads):
+    """L2 norm of every tensor of ``grads`` -> fp32 [len(grads)] on the device (one launch per 24 tensors)."""
+    _need_cuda(*grads)
+    out = torch.empty(len(grads), dtype=torch.float32, device=grads[0].device)
+    for i in range(0, len(grads), 24):
+        sl = slice(i, i + 24)
+        numel = (C.c_int64 * len(grads[sl]))(*[g.numel() for g in grads[sl]])
+        _lib.call("vfr_grad_norms", _ptr_array(grads[sl]), numel, len(grads[sl]), _ptr(out[i:]), _stream())
+    return out

@@ -306,7 +306,7 @@ class MomentRetriever:
             L = len(ranks)
             levels, counts = self.sel_levels[:L * Q], self.sel_count[:L * Q]
             with self._stage("k4_levels"):
-                _lib.call("vfr_sel_pool_levels", pooled.data_ptr(), n_src, Q, width, (C.c_int32 * L)(*ranks), L,
+                _lib.call("vfr_sel_pool_levels", pooled.data_ptr(), n_src, Q, width, (C.c_int32 * L)(*ranks), L, 1,
                           levels.data_ptr(), stream)
                 _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels.data_ptr(), stream)
             with self._stage("k4_filter"):
