@@ -396,6 +396,23 @@ int vfr_adam_step(float* const* params, const float* const* grads, float* const*
                   float weight_decay, vfr_stream_t stream);
 int vfr_grad_norms(const float* const* grads, const int64_t* numel, int count, float* out, vfr_stream_t stream);
 
+/* ---- training-batch construction on the device, pooled-moment features -------------------------
+ * vfr_sample_negatives: the per-query draws of CustomBatchSampler.__iter__ (model/data.py:275-337) for ALL queries of an epoch
+ * in one launch: times int32 [Q, n_annot, 2] ((-1,-1) padded), q_video int32 [Q], nseg int32 [V] -> out int32 [Q, 8] =
+ * {video_pos, video_neg, start_t, end_t, start_tn, end_tn, status, 0}; status 1 = no intra-video candidate (the reference's
+ * random.choice([]) raises IndexError there), 2 = no other video long enough, 3 = no usable annotation.  Counter-based RNG:
+ * a pure function of (seed, epoch, query) - the reference's distributions, not its Mersenne-Twister stream.
+ * vfr_gather_clip_rows: out fp32 [n_rows, 2F+2] = [seg[vid_off[v] + c] | ctx[v] | (c/n, (c+1)/n)] for (v, c) = (row_video[r],
+ * row_clip[r]) - model/data.py:204-213 straight from the pooled features in HBM.
+ * vfr_moment_pool: out fp32 [M_total, F], row mom_off[v] + moment_index = the MEAN segment feature of that moment (shared-
+ * memory prefix sums per column): MCN-style pooled-moment features, an additional NON-reference scoring variant. */
+int vfr_sample_negatives(const int32_t* times, int n_annot, const int32_t* q_video, const int32_t* nseg, int64_t n_queries,
+                         int64_t n_videos, int same_length, uint64_t seed, uint64_t epoch, int32_t* out, vfr_stream_t stream);
+int vfr_gather_clip_rows(const float* seg, const float* ctx, const int32_t* vid_off, const int32_t* row_video,
+                         const int32_t* row_clip, int64_t n_rows, int feat_dim, float* out, vfr_stream_t stream);
+int vfr_moment_pool(const float* seg, const int32_t* vid_off, const int64_t* mom_off, int64_t n_videos, int n_max, int feat_dim,
+                    float* out, vfr_stream_t stream);
+
 /* ---- retrieval step: K3 -> K4 behind one call --------------------------------------------------
  * The serving form of model/evaluate.py:42-80: one batch of tokenised queries against the resident
  * bank.  All pointers inside the plan are DEVICE pointers supplied by the caller (weights as for

@@ -461,3 +461,117 @@ def test_text_backward_with_learnable_length_matches_torch_autograd(golden):
             assert p.grad is not None, name
             _close(p.grad.cpu().numpy(), cpu[name].grad.numpy(), 2e-4)
     assert float(model.learnable_length.weight.grad[0].abs().sum()) == 0.0        # padding_idx row
+
+
+# ---- training batches built on the device (negative sampling + row gather), pooled-moment features ---------------------
+@pytest.mark.parametrize("same_length", [True, False])
+def test_device_batch_sampler_draws_what_the_reference_sampler_may_draw(golden, same_length):
+    """DeviceBatchSampler against the reference's CustomBatchSampler semantics (data.py:275-337): every draw satisfies the
+    reference's constraints, the batches are cut by its rule, the gathered rows equal make_visual_features bit for bit,
+    the draws cover the admissible choices about uniformly, and a training epoch consumes the stream."""
+    _, meta = golden("train_step")
+    videos = synth.make_videos(meta["seed"], meta["n_videos"], meta["feat_dim"])
+    queries = synth.make_queries(meta["seed"], videos, meta["n_queries"], meta["vocab"])
+    sd = synth.make_state_dict(meta["seed"], meta["feat_dim"], meta["vocab"], spread=meta["spread"])
+    ds, annotations = _dataset(videos, queries, validate=False)
+    if same_length:      # a positive that fills its video has no same-length negative: the reference raises there (H6)
+        annotations = {a: v for a, v in annotations.items()
+                       if all(t[1] - t[0] + 1 < ds.num_segments_info[v["video"]] for t in v["times"])}
+    samp = vdata.DeviceBatchSampler(120, annotations, ds.num_segments_info, ds, same_length=same_length, seed=7, device=DEV)
+    names = samp.videos
+    seen_q, n_batches = 0, 0
+    intra_hist = {}
+    for epoch in range(3):
+        for batch in samp:
+            n_batches += 1
+            s = batch["samples"]
+            B = s.shape[0]
+            assert batch["lang"].shape == (B, 20) and int(batch["maskp"].max()) == B - 1
+            rows_p = int((s[:, 3] - s[:, 2] + 1).sum())
+            rows_n = int((s[:, 5] - s[:, 4] + 1).sum())
+            assert batch["posit"].shape == (rows_p, 2 * meta["feat_dim"] + 2) and batch["intra"].shape[0] == rows_n
+            assert batch["inter"].shape[0] == rows_p and batch["maskn"].shape[0] == rows_n
+            # the reference's cut rule: the batch closed at the first query that reached batch_size (or is the last one)
+            cum_p, cum_n = np.cumsum(s[:, 3] - s[:, 2] + 1), np.cumsum(s[:, 5] - s[:, 4] + 1)
+            assert (np.maximum(cum_p, cum_n)[:-1] < 120).all()
+            r = 0
+            for i in range(B):
+                vp, vn, st, en, sn, enn, status = (int(x) for x in s[i, :7])
+                info = annotations[samp.annot_ids[int(np.nonzero((samp.lang == batch["lang"][i]).all(dim=1).cpu().numpy())[0][0])]]
+                n = ds.num_segments_info[names[vp]]
+                assert status == 0 and [st, en] in [list(t) for t in info["times"]]
+                assert 0 <= sn <= enn < n and (sn, enn) != (st, en)
+                if same_length:
+                    assert enn - sn == en - st
+                else:
+                    assert [sn, enn] not in [list(t) for t in info["times"]]
+                assert vn != vp and ds.num_segments_info[names[vn]] >= en + 1
+                intra_hist.setdefault((n, st, en), {}).setdefault((sn, enn), 0)
+                intra_hist[(n, st, en)][(sn, enn)] += 1
+                want = ds.make_visual_features(names[vp], st, en)
+                assert torch.equal(batch["posit"][r:r + en - st + 1].cpu(), want)
+                assert torch.equal(batch["inter"][r:r + en - st + 1].cpu(), ds.make_visual_features(names[vn], st, en))
+                r += en - st + 1
+            seen_q += B
+    assert seen_q == 3 * len(annotations) and n_batches >= 3
+    # every admissible same-length negative of a frequent (video length, positive) class was drawn
+    if same_length:
+        (n, st, en), hist = max(intra_hist.items(), key=lambda kv: sum(kv[1].values()))
+        assert len(hist) == (n - (en - st)) - 1 and min(hist.values()) > 0
+    model = _model(sd, meta["feat_dim"]).train()
+    tr = vmain.Trainer(device=DEV, compute_grads=False)
+    loss = tr.train_epoch(model, samp, vmain.FusedAdam(model.parameters(), lr=5e-4, weight_decay=5e-3))
+    assert np.isfinite(loss) and tr.global_step >= 1
+
+
+def test_device_batch_sampler_raises_like_the_reference_on_a_full_video_positive(golden):
+    _, meta = golden("train_step")
+    videos = synth.make_videos(meta["seed"], 8, meta["feat_dim"])
+    queries = synth.make_queries(meta["seed"], videos, 6, meta["vocab"])
+    n0 = videos[int(queries["video_idx"][0])]["num_segments"]
+    queries["times"][0] = [[0, n0 - 1]] * 4                               # the positive fills the whole video
+    ds, annotations = _dataset(videos, queries, validate=False)
+    samp = vdata.DeviceBatchSampler(120, annotations, ds.num_segments_info, ds, same_length=True, device=DEV)
+    with pytest.raises(IndexError):
+        next(iter(samp))
+
+
+def test_moment_pool_prefix_sums_match_numpy():
+    """Pooled-moment features (MCN-style, non-reference variant): mean segment feature of all n (n + 1) / 2 moments."""
+    rng = np.random.default_rng(2)
+    nseg = rng.choice([1, 5, 6, 30, 32], size=40)
+    vid_off = np.concatenate([[0], np.cumsum(nseg)])
+    seg = rng.random((int(vid_off[-1]), 512), dtype=np.float32)
+    out, mom_off = ops.moment_pool(torch.from_numpy(seg).to(DEV), vid_off)
+    out = out.cpu().numpy()
+    assert mom_off[-1] == sum(n * (n + 1) // 2 for n in nseg) == out.shape[0]
+    for v in (0, 7, 23, 39):
+        n = int(nseg[v])
+        for m, (s, e) in enumerate(orc.generate_moments(n)):
+            want = seg[vid_off[v] + s:vid_off[v] + e + 1].astype(np.float64).mean(axis=0)
+            # (a difference of fp32 prefix sums: absolute error ~ 2^-24 x the prefix, up to n = 32 summands)
+            np.testing.assert_allclose(out[mom_off[v] + m], want, rtol=1e-5, atol=4e-6)
+
+
+def test_pooled_moment_variant_scores_match_a_torch_restatement(golden):
+    """The non-reference pooled-moment variant end to end: pooled features -> K2 -> one-row candidates -> distance ranking,
+    against the same computation spelled out with plain torch fp64 / fp32 on the CPU."""
+    z, meta = golden("tiny_eval")
+    videos, queries, sd = _inputs(meta)
+    model = _model(sd, meta["feat_dim"])
+    nseg = [v["num_segments"] for v in videos]
+    vid_off = np.concatenate([[0], np.cumsum(nseg)])
+    seg = np.concatenate([v["segment_features"] for v in videos]).astype(np.float32)
+    ctx = np.stack([v["context_features"] for v in videos]).astype(np.float32)
+    bank, mom_off = vev.pooled_moment_bank(model, torch.from_numpy(seg).to(DEV), torch.from_numpy(ctx).to(DEV), vid_off)
+    assert bank.n_videos == int(mom_off[-1]) == sum(n * (n + 1) // 2 for n in nseg)
+    q = torch.from_numpy(z["query_emb"][:8]).to(DEV)
+    got = ops.score_full(bank, q).cpu().numpy()                       # [8, M]: one "moment" per single-row video
+    rows = []
+    for v, n in enumerate(nseg):
+        for (s, e) in orc.generate_moments(n):
+            f = seg[vid_off[v] + s:vid_off[v] + e + 1].astype(np.float64).mean(0).astype(np.float32)
+            rows.append(np.concatenate([f, ctx[v], np.asarray([s / n, (e + 1) / n], dtype=np.float32)]))
+    emb = orc.visual_embed(sd, np.stack(rows)).numpy()
+    want = np.sqrt((((emb[None] - z["query_emb"][:8, None]) + 1e-6) ** 2).sum(-1))
+    assert np.abs(got - want).max() <= 2e-5 * want.max()

@@ -124,6 +124,9 @@ PROTOTYPES = {
     "vfr_visual_train_bwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vfr_adam_step": (_i, [_p, _p, _p, _p, _p, _i, _l, _f, _f, _f, _f, _f, _p]),
     "vfr_grad_norms": (_i, [_p, _p, _i, _p, _p]),
+    "vfr_sample_negatives": (_i, [_p, _i, _p, _p, _l, _l, _i, C.c_uint64, C.c_uint64, _p, _p]),
+    "vfr_gather_clip_rows": (_i, [_p, _p, _p, _p, _p, _l, _i, _p, _p]),
+    "vfr_moment_pool": (_i, [_p, _p, _p, _l, _i, _i, _p, _p]),
     "vfr_search_embed_device": (_i, [C.POINTER(SearchPlan), _p, _l, _p, _p]),
     "vfr_search_score_device": (_i, [C.POINTER(SearchPlan), _l, _i, _p, _p, _p]),
     "vfr_search_device": (_i, [C.POINTER(SearchPlan), _p, _l, _i, _p, _p, _p]),

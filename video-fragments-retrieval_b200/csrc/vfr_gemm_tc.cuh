@@ -114,7 +114,7 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
 template <class Epi>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __restrict__ m_limit, int k_chunks, int lo_a,
-               int lo_b, uint32_t fmt, int flush_chunks, float* __restrict__ flush_buf, int64_t flush_ld, Epi epi) {
+               int lo_b, uint32_t fmt, int flush_chunks, float* __restrict__ flush_buf, int64_t flush_ld, int N_all, Epi epi) {
   extern __shared__ uint8_t gt_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gt_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE);
@@ -172,7 +172,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
   } else if (warp == 1) {
     if (lane == 0) {
       // kind::f16: D = fp32; A / B formats from `fmt` (bits 7 / 10: 1 = bf16, 0 = fp16 - the split-fp16 operands)
-      const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(GT_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // (the last N tile of a matrix whose N is not a multiple of 256 issues narrower MMAs: N rounded up to 16 -
+      //  4H = 4000 gate rows leave 160 of the 16th tile's 256 columns)
+      const int n_mma = min(GT_BN, (N_all - n0 + 15) / 16 * 16);
+      const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int seg = 0;
       for (int c = 0; c < k_chunks; ++c) {
         const int s = c % GT_STAGES;
@@ -309,7 +312,7 @@ static int launch_gemm_tc(const void* const* a, const void* const* b, int batch,
   VFR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
   dim3 grid((N + GT_BN - 1) / GT_BN, (M + GT_BM - 1) / GT_BM, batch);
   gemm_tc_kernel<Epi><<<grid, GT_THREADS, GT_SMEM, st>>>(maps, M, m_limit, kp / GT_BK, lo_a, lo_b, f16 ? GT_FMT_F16 : GT_FMT_BF16,
-                                                         flush_buf ? flush_k / GT_BK : 0, flush_buf, flush_ld, epi);
+                                                         flush_buf ? flush_k / GT_BK : 0, flush_buf, flush_ld, N, epi);
   return check_launch("gemm_tc_kernel");
 }
 

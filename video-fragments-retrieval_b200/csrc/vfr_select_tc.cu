@@ -1080,6 +1080,9 @@ struct RfParams {
   int64_t per;
   int64_t blk_bytes;
   unsigned char* out_blocks;
+  int fast_max;      // candidates per query up to which the counting path is taken (VFR_RF_FAST overrides; 0 = never)
+  int final_max;
+  unsigned long long* dbg;   // optional (VFR_RF_DBG = device address): clocks per phase, summed over all queries
 };
 
 // exact fp32 distance of one (query, clip) pair: the arithmetic of score_kernel / score_own_kernel in
@@ -1194,11 +1197,17 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
   __shared__ int uvid[RF_MAXC];
   __shared__ float dist[RF_DIST];
   __shared__ float qrow[SL_MAXROW];
+  __shared__ int u_c0[RF_MAXC];               // first clip of the unique candidate videos ...
+  __shared__ unsigned char u_n[RF_MAXC];      // ... and their clip counts (no vid_off round trips in the scoring loops)
   __shared__ int warp_tot[RF_THREADS / 32];
   __shared__ int s_n, s_cnt;
   __shared__ float s_sq, s_tau;
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  long long tq = p.dbg ? clock64() : 0;
+  auto stamp = [&](int phase) {
+    if (p.dbg && tid == 0) { const long long now = clock64(); atomicAdd(p.dbg + phase, (unsigned long long)(now - tq)); tq = now; }
+  };
 
   // ---- 0. the query row and its sequential row sum ----
   for (int i = tid; i < p.dim; i += RF_THREADS) qrow[i] = p.queries[q * p.dim + i];
@@ -1206,7 +1215,7 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
   for (int i = tid; i < RF_MAXC; i += RF_THREADS) vids[i] = INT_MAX;
   for (int i = tid; i < VFR_TOPK_MAX; i += RF_THREADS) keys[i] = ~0ull;
   __syncthreads();
-  if (tid == 0) {
+  if (tid == RF_THREADS - 32) {     // (a 100-step dependent chain: on a warp the candidate gather below leaves idle)
     float s = 0.f;
     for (int k = 0; k < p.dim; ++k) s = __fadd_rn(s, qrow[k]);
     s_sq = s;
@@ -1224,7 +1233,7 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
   // FAST PATH (the usual case: ~k + band candidates): every ordering step below is a rank-by-counting pass over shared
   // memory - O(n^2 / 256) compares per thread, two block barriers - instead of a 256-thread bitonic sort with one barrier
   // per stage (36 - 55 stages each for the key sort, the video sort and the final top-k: most of this kernel's time)
-  const bool fast = total <= RF_FAST;
+  const bool fast = total <= p.fast_max;
   __shared__ unsigned long long s_kth;
   if (fast) {
     if (tid == 0) s_kth = ~0ull;
@@ -1279,6 +1288,7 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
         (kth_key == ~0ull || (unsigned)(kth_key >> 32) > __float_as_uint(tau_pub)) && p.flags[q] == 0)
       p.flags[q] = 4;
   }
+  stamp(0);
   const unsigned keep_bits = __float_as_uint(__fadd_ru(tau_fin, qm.w));
   // no moment scoring above this can be among the k best: the k closest clips are moments themselves
   const float s_max = (tau_fin < CUDART_INF_F) ? __fmul_ru(__fsqrt_ru(__fadd_ru(tau_fin, qm.w)), 1.00001f) : CUDART_INF_F;
@@ -1399,6 +1409,17 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
   __syncthreads();
   }   // !fast
 
+  for (int i = tid; i < min(n_unique, RF_MAXC); i += RF_THREADS) {
+    const int v = uvid[i];
+    if (uniform) { u_c0[i] = v * p.n_max; u_n[i] = (unsigned char)p.n_max; }
+    else {
+      const int c0 = __ldg(p.vid_off + v);
+      u_c0[i] = c0;
+      u_n[i] = (unsigned char)(__ldg(p.vid_off + v + 1) - c0);
+    }
+  }
+  __syncthreads();
+  stamp(1);
   // ---- 3. chunks of videos: exact clip distances, exact moment means, streaming top-k ----
   const int mom_max = num_moments(p.n_max);
   const int vch = max(1, min(RF_DIST / p.n_max, RF_BATCH / mom_max));
@@ -1409,19 +1430,18 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
     if (s_cnt + nv * mom_max > RF_BATCH) { rf_merge_batch(keys, s_cnt, p.k, &s_cnt, &s_tau); merged = true; }
     for (int idx = tid; idx < nv * p.n_max; idx += RF_THREADS) {
       const int vi = idx / p.n_max, c = idx - vi * p.n_max;
-      const int v = uvid[v0 + vi];
-      const int c0 = __ldg(p.vid_off + v);
-      const int n = __ldg(p.vid_off + v + 1) - c0;
+      const int c0 = u_c0[v0 + vi];
+      const int n = u_n[v0 + vi];
       if (c < n)
         dist[idx] = p.bank_b16 ? rf_distance_b16(p.bank_b16 + (int64_t)(c0 + c) * p.dim, qrow, sq, p.dim)
                                : rf_distance(p.bank + (int64_t)(c0 + c) * p.dim, qrow, sq, p.dim);
     }
     __syncthreads();
+    stamp(2);
     const float tau = fminf(s_tau, s_max);
     for (int idx = tid; idx < nv * p.n_max; idx += RF_THREADS) {
       const int vi = idx / p.n_max, s = idx - vi * p.n_max;
-      const int v = uvid[v0 + vi];
-      const int n = __ldg(p.vid_off + v + 1) - __ldg(p.vid_off + v);
+      const int n = u_n[v0 + vi];
       if (s < n) {
         float run = 0.f;
         for (int e = s; e < n; ++e) {
@@ -1436,8 +1456,9 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
       }
     }
     __syncthreads();
+    stamp(3);
   }
-  if (!merged && s_cnt <= RF_FINAL) {
+  if (!merged && s_cnt <= p.final_max) {
     // the k best of the <= RF_FINAL surviving moments by counting (keys are unique: (score, video, moment)); slot r of
     // keys[0, 128) - initialised to "empty" above and untouched since - receives the key of rank r
     const int m = s_cnt;
@@ -1452,6 +1473,8 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
     rf_merge_batch(keys, s_cnt, p.k, &s_cnt, &s_tau);
   }
 
+  stamp(4);
+  if (p.dbg && tid == 0) { atomicAdd(p.dbg + 6, (unsigned long long)n_unique); atomicAdd(p.dbg + 7, (unsigned long long)s_cnt); }
   // ---- 4. output: ascending (score, global moment id) ----
   float* out_s;
   int64_t* out_i;
@@ -1834,6 +1857,10 @@ static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vi
   r.per = per;
   r.blk_bytes = per * ((int64_t)k * 12 + 4);
   r.out_blocks = reinterpret_cast<unsigned char*>(out_blocks);
+  r.fast_max = RF_FAST;
+  r.final_max = RF_FINAL;
+  { const char* e = getenv("VFR_RF_DBG"); r.dbg = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+  { const char* e = getenv("VFR_RF_FAST"); if (e) { r.fast_max = std::min(RF_FAST, std::max(0, atoi(e))); if (r.fast_max == 0) r.final_max = -1; } }
   sl_refine_kernel<<<(unsigned)n_queries, RF_THREADS, 0, st>>>(r);
   return check_launch("sl_refine_kernel");
 }

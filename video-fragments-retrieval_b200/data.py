@@ -8,9 +8,12 @@
 * ``VideoBatchSampler`` / ``LanguageBatchSampler`` (data.py:359-409) - one video / one query per
   batch, ``.moments`` table read by ``evaluate``.
 
+* ``DeviceBatchSampler`` - the training-batch stream of ``CustomBatchSampler`` + ``custom_collate`` (data.py:249-356) built
+  ON THE DEVICE: negative sampling for a whole epoch in one kernel, rows gathered from the pooled features in HBM.
+
 Host-side string work is out of scope: the GloVe text-file parser
-``WordIndexer`` (data.py:33-118) and the random negative sampler ``CustomBatchSampler``
-(data.py:249-337) are meant to be reused from the reference unchanged; ``CustomDataset`` here
+``WordIndexer`` (data.py:33-118) is meant to be reused from the reference unchanged (as is its host sampler
+``CustomBatchSampler`` when the reference's exact Mersenne-Twister draw sequence matters); ``CustomDataset`` here
 accepts any object with the reference's ``items2tensor(list_of_token_lists, max_len)`` method.
 """
 import re
@@ -250,3 +253,80 @@ class LanguageBatchSampler(BatchSampler):
 
     def __len__(self):
         return len(self.annotations)
+
+
+class DeviceBatchSampler:
+    """Training batches of the reference's ``DataLoader(dataset, batch_sampler=CustomBatchSampler(...),
+    collate_fn=custom_collate)`` (data.py:249-356), built on the device.
+
+    Per epoch: one host permutation of the queries (``train=True``), ONE kernel draws every query's positive annotation,
+    intra-video negative and inter-video negative (``vfr_sample_negatives``: the reference's distributions from a
+    counter-based RNG - not its ``random`` stream), the batches are cut by the reference's rule (a batch closes when
+    ``max(posit rows, intra rows) >= batch_size``, :329-332) and every batch's ``posit`` / ``intra`` / ``inter`` rows are
+    gathered from the pooled features resident in HBM (``vfr_gather_clip_rows``).  Yields the collate's dict
+    ``{posit, intra, inter, lang, maskp, maskn}`` as DEVICE tensors: ``Trainer.train_epoch`` consumes it unchanged.
+    A query whose positive fills its whole video under ``same_length=True`` has no intra-video candidate; the reference
+    raises ``IndexError`` there (``random.choice([])``, :306) and so does this iterator."""
+
+    def __init__(self, batch_size, annotations, num_segments_info, dataset, train=True, drop_last=False, same_length=True,
+                 seed=123, device="cuda"):
+        self.batch_size, self.train, self.drop_last, self.same_length = int(batch_size), train, drop_last, same_length
+        self.seed, self.epoch, self.device = int(seed), 0, torch.device(device)
+        self.annot_ids = list(annotations.keys())
+        self.videos = list(num_segments_info.keys())
+        index = {v: i for i, v in enumerate(self.videos)}
+        feats = [dataset.video_features[v] for v in self.videos]
+        nseg = np.asarray([int(num_segments_info[v]) for v in self.videos], dtype=np.int64)
+        dev = self.device
+        self.seg = torch.from_numpy(np.concatenate([np.asarray(f["segment_features"])[:n] for f, n in zip(feats, nseg)]).astype(np.float32)).to(dev)
+        self.ctx = torch.from_numpy(np.stack([np.asarray(f["context_features"], dtype=np.float32).reshape(-1) for f in feats])).to(dev)
+        self.vid_off = torch.from_numpy(np.concatenate([[0], np.cumsum(nseg)]).astype(np.int32)).to(dev)
+        self.nseg = torch.from_numpy(nseg.astype(np.int32)).to(dev)
+        self.times = ops.pack_times([annotations[a]["times"] for a in self.annot_ids], dev)
+        self.q_video = torch.from_numpy(np.asarray([index[annotations[a]["video"]] for a in self.annot_ids], dtype=np.int32)).to(dev)
+        self.lang = torch.cat([dataset.lang_features[a] for a in self.annot_ids], dim=0).to(dev)
+        self._rng = np.random.default_rng(self.seed)
+
+    def __len__(self):
+        return len(self.annot_ids)
+
+    def __iter__(self):
+        Q = len(self.annot_ids)
+        order = self._rng.permutation(Q) if self.train else np.arange(Q)
+        samples = ops.sample_negatives(self.times, self.q_video, self.nseg, self.same_length, self.seed, self.epoch).cpu().numpy()
+        self.epoch += 1
+        if (samples[:, 6] == 1).any():
+            raise IndexError("Cannot choose from an empty sequence")          # random.choice([]) in the reference
+        if (samples[:, 6] != 0).any():
+            raise IndexError("no valid annotation / negative video for some query")
+        batch, posit_rows, intra_rows = [], 0, 0
+        for q in order:
+            batch.append(int(q))
+            posit_rows += int(samples[q, 3] - samples[q, 2] + 1)
+            intra_rows += int(samples[q, 5] - samples[q, 4] + 1)
+            if max(posit_rows, intra_rows) >= self.batch_size:
+                yield self._build(batch, samples)
+                batch, posit_rows, intra_rows = [], 0, 0
+        if batch and not self.drop_last:
+            yield self._build(batch, samples)
+
+    def _build(self, batch, samples):
+        dev = self.device
+        rows = {"posit": ([], []), "intra": ([], []), "inter": ([], [])}
+        maskp, maskn = [], []
+        for i, q in enumerate(batch):
+            vp, vn, st, en, sn, enn = (int(x) for x in samples[q, :6])
+            for name, v, a, b in (("posit", vp, st, en), ("intra", vp, sn, enn), ("inter", vn, st, en)):
+                rows[name][0].extend([v] * (b - a + 1))
+                rows[name][1].extend(range(a, b + 1))
+            maskp.extend([i] * (en - st + 1))
+            maskn.extend([i] * (enn - sn + 1))
+        out = {}
+        for name, (rv, rc) in rows.items():
+            out[name] = ops.gather_clip_rows(self.seg, self.ctx, self.vid_off, torch.tensor(rv, dtype=torch.int32, device=dev),
+                                             torch.tensor(rc, dtype=torch.int32, device=dev))
+        out["lang"] = self.lang[torch.tensor(batch, dtype=torch.int64, device=dev)]
+        out["maskp"] = torch.tensor(maskp, dtype=torch.int64, device=dev)
+        out["maskn"] = torch.tensor(maskn, dtype=torch.int64, device=dev)
+        out["samples"] = samples[batch]
+        return out

@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .utils import generate_moments as utils_generate_moments
 
 # The reference draws one permutation of all N moments per query from the global NumPy RNG
 # (evaluate.py:68) even when 'chance' is not requested.  Set True to reproduce that side effect.
@@ -190,3 +191,30 @@ def evaluate(model, video_iterator, lang_iterator, annotations, device, prelimin
     times_list = [annotations[a]["times"] for a in q_annots]
     print("\nEvaluation:")
     return evaluate_embedded(bank, q_emb, q_video, times_list, preliminary, model_types, iou_thresholds)
+
+
+# ---------------------------------------------------------------------------------------------------
+# pooled-moment scoring: an ADDITIONAL, NON-REFERENCE variant (north-star item (1))
+# ---------------------------------------------------------------------------------------------------
+def pooled_moment_bank(model, seg, ctx, vid_off):
+    """MCN-style candidates: every moment (s, e) of every video is ONE feature row - the mean of its segment features
+    (``vfr_moment_pool``: per-column prefix sums in shared memory) next to the video's context feature and the moment's
+    temporal endpoints ``(s / n, (e + 1) / n)`` - embedded by the visual MLP (K2).  The reference does NOT do this (it
+    embeds clips and averages clip DISTANCES, evaluate.py:53-58); the variant exists because BASELINE.json's north star
+    names it.  Returns a ``Bank`` whose "videos" have ONE row per moment, in ``generate_moments`` order, i.e. a bank of
+    single-row candidates: ``ops.score_topk*`` / ``score_full`` over it rank pooled moments by plain distance.
+    ``seg`` fp32 [C, F], ``ctx`` fp32 [V, F] on the device, ``vid_off`` [V+1]."""
+    vo = np.asarray(vid_off, dtype=np.int64)
+    nseg = np.diff(vo)
+    pooled, mom_off = ops.moment_pool(seg, vo)                           # [M, F]
+    rows_v, tef = [], []
+    for v, n in enumerate(nseg):
+        mom = utils_generate_moments(int(n))
+        rows_v.extend([v] * len(mom))
+        tef.extend([(s_ / n, (e_ + 1) / n) for s_, e_ in mom])
+    dev = seg.device
+    rows_v = torch.tensor(rows_v, dtype=torch.int64, device=dev)
+    x = torch.cat([pooled, ctx.float()[rows_v], torch.tensor(tef, dtype=torch.float32, device=dev)], dim=1)
+    with torch.no_grad():
+        emb = model(x)
+    return ops.Bank(emb, np.arange(emb.shape[0] + 1)), mom_off

@@ -386,7 +386,8 @@ def lstm_pack(w_ih, w_hh, b_ih, b_hh):
     H, E = w_hh.shape[1], w_ih.shape[1]
     nbytes = _lib.load().vfr_lstm_pack_bytes(H, E)
     packed = torch.empty(nbytes // 4, dtype=torch.float32, device=w_ih.device)
-    _lib.call("vfr_lstm_pack", _ptr(_f32c(w_ih)), _ptr(_f32c(w_hh)), _ptr(_f32c(b_ih)), _ptr(_f32c(b_hh)), H, E,
+    w_ih, w_hh, b_ih, b_hh = (_f32c(t) for t in (w_ih, w_hh, b_ih, b_hh))    # converted copies stay alive until the launch
+    _lib.call("vfr_lstm_pack", _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), H, E,
               _ptr(packed), _stream())
     return packed
 
@@ -657,3 +658,47 @@ def grad_norms(grads):
         numel = (C.c_int64 * len(grads[sl]))(*[g.numel() for g in grads[sl]])
         _lib.call("vfr_grad_norms", _ptr_array(grads[sl]), numel, len(grads[sl]), _ptr(out[i:]), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# training-batch construction on the device, pooled-moment features (csrc/vfr_sample.cu)
+# ---------------------------------------------------------------------------------------------
+def sample_negatives(times, q_video, nseg, same_length=True, seed=123, epoch=0):
+    """The draws of the reference's ``CustomBatchSampler.__iter__`` (data.py:275-337) for all queries at once.
+    ``times`` int32 [Q, A, 2], ``q_video`` int32 [Q], ``nseg`` int32 [V] (device) -> int32 [Q, 8]
+    {video_pos, video_neg, start_t, end_t, start_tn, end_tn, status, 0}."""
+    _need_cuda(times, q_video, nseg)
+    times = times.to(torch.int32).contiguous()
+    q_video = q_video.to(torch.int32).contiguous()          # (held in locals until the launch: see moment_pool)
+    nseg = nseg.to(torch.int32).contiguous()
+    out = torch.empty((times.shape[0], 8), dtype=torch.int32, device=times.device)
+    _lib.call("vfr_sample_negatives", _ptr(times), times.shape[1], _ptr(q_video), _ptr(nseg), times.shape[0], nseg.shape[0],
+              int(bool(same_length)), int(seed), int(epoch), _ptr(out), _stream())
+    return out
+
+
+def gather_clip_rows(seg, ctx, vid_off, row_video, row_clip):
+    """``[segment | context | tef]`` rows (data.py:204-213) of the (video, clip) pairs -> fp32 [R, 2F+2]."""
+    _need_cuda(seg, ctx, vid_off, row_video, row_clip)
+    feat = seg.shape[1]
+    out = torch.empty((row_video.shape[0], 2 * feat + 2), dtype=torch.float32, device=seg.device)
+    _lib.call("vfr_gather_clip_rows", _ptr(seg), _ptr(ctx), _ptr(vid_off), _ptr(row_video), _ptr(row_clip), row_video.shape[0], feat,
+              _ptr(out), _stream())
+    return out
+
+
+def moment_pool(seg, vid_off):
+    """MCN-style pooled-moment features (a NON-reference scoring variant): the mean segment feature of every candidate
+    moment of every video -> (fp32 [M_total, F], mom_off int64 [V+1]); row ``mom_off[v] + moment_index(n, s, e)``."""
+    _need_cuda(seg)
+    seg = _f32c(seg)
+    vo = np.asarray(vid_off, dtype=np.int64)
+    nseg = np.diff(vo)
+    if nseg.max() > MAX_SEGMENTS or seg.shape[1] % 4:
+        raise _lib.VfrError("moment_pool: at most 32 segments per video, feature dimension a multiple of 4")
+    mo = np.concatenate([[0], np.cumsum(nseg * (nseg + 1) // 2)]).astype(np.int64)
+    out = torch.empty((int(mo[-1]), seg.shape[1]), dtype=torch.float32, device=seg.device)
+    vo_d = torch.from_numpy(vo.astype(np.int32)).to(seg.device)        # (named: a temporary would be freed - and its block
+    mo_d = torch.from_numpy(mo).to(seg.device)                         #  reused by the next one - before the kernel runs)
+    _lib.call("vfr_moment_pool", _ptr(seg), _ptr(vo_d), _ptr(mo_d), len(nseg), int(nseg.max()), seg.shape[1], _ptr(out), _stream())
+    return out, mo
