@@ -1,0 +1,26 @@
+"""K3 (text embedding, tcgen05 path) timed alone, A/B over VFR_GEMM_PRE (software-pipelined LSTM epilogue on / off), same process."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import vfr_b200
+from vfr_b200 import models
+import bench
+
+dev = "cuda"
+model = bench.make_model(dev)
+model.engine = "tc"
+B = int(os.environ.get("B", "37888"))
+tok = torch.from_numpy(bench.make_tokens(B, 1000)).to(dev)
+def run(n=5):
+    with torch.no_grad():
+        for _ in range(2): model(tok, False, dev)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n): model(tok, False, dev)
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+for rep in range(2):
+    for mode in ("1", "0"):
+        os.environ["VFR_GEMM_PRE"] = mode
+        print(json.dumps(dict(B=B, VFR_GEMM_PRE=mode, ms=run())), flush=True)

@@ -12,6 +12,8 @@
 #include "vfr_common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include <type_traits>
 
 namespace vfr {
 
@@ -100,6 +102,29 @@ __device__ __forceinline__ void gt_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load split in two: issue (the registers are NOT valid yet) and wait (which also orders every later use of
+// the registers after the wait) - global loads of the epilogue can be put in flight between the two
+__device__ __forceinline__ void gt_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void gt_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+// an epilogue functor that declares `struct Pre` and `Pre prefetch(z, m, n0) const` gets its global operands of column
+// group c + 1 requested while group c is computed:  operator()(z, m, n0, v, pre)
+template <class E, class = void>
+struct gt_has_pre : std::false_type {};
+template <class E>
+struct gt_has_pre<E, std::void_t<typename E::Pre>> : std::true_type {};
+
 constexpr uint32_t GT_FMT_BF16 = (1u << 7) | (1u << 10);
 constexpr uint32_t GT_FMT_F16 = 0u;
 
@@ -114,7 +139,7 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
 template <class Epi>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __restrict__ m_limit, int k_chunks, int lo_a,
-               int lo_b, uint32_t fmt, int flush_chunks, float* __restrict__ flush_buf, int64_t flush_ld, int N_all, Epi epi) {
+               int lo_b, uint32_t fmt, int flush_chunks, float* __restrict__ flush_buf, int64_t flush_ld, int N_all, int pre_mode, Epi epi) {
   extern __shared__ uint8_t gt_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gt_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE);
@@ -212,6 +237,28 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
     const int sub = ew >> 2;
     const int m = m0 + sub * 128 + quarter * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)sub * 256;
+    bool piped = false;
+    if constexpr (gt_has_pre<Epi>::value) piped = pre_mode != 0;
+    if constexpr (gt_has_pre<Epi>::value) if (piped) {
+      // software-pipelined epilogue (single accumulation segment, opt-in: see gt_pre_mode): the functor's global operands
+      // of the next column group and the TMEM load of this one are in flight together
+      typename Epi::Pre cur{}, nxt{};
+      if (m < M) cur = epi.prefetch(z, m, n0);
+      gt_wait(acc_full, 0, 256);
+      gt_fence_after();
+      for (int c = 0; c < GT_BN / 16; ++c) {
+        uint32_t r[16];
+        gt_ld16_issue(taddr + c * 16, r);
+        if (c + 1 < GT_BN / 16 && m < M) nxt = epi.prefetch(z, m, n0 + (c + 1) * 16);
+        gt_ld16_wait(r);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        if (m < M) epi(z, m, n0 + c * 16, v, cur);
+        cur = nxt;
+      }
+    }
+    if (!piped)
     for (int f = 0; f < n_seg; ++f) {
       gt_wait(acc_full, f & 1, 256);
       gt_fence_after();
@@ -233,7 +280,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
             for (int j = 0; j < 4; ++j) pb[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         }
-        if (last && m < M) epi(z, m, n0 + c * 16, v);
+        if (last && m < M) {
+          if constexpr (gt_has_pre<Epi>::value) epi(z, m, n0 + c * 16, v, epi.prefetch(z, m, n0 + c * 16));
+          else epi(z, m, n0 + c * 16, v);
+        }
       }
       if (!last) {                       // the accumulator has been read: the MMAs of the next segment may overwrite it
         gt_fence_before();
@@ -281,6 +331,14 @@ static inline int gt_make_map(CUtensorMap* map, const void* base, uint64_t rows,
   return VFR_OK;
 }
 
+// VFR_GEMM_PRE=1 turns the software-pipelined epilogue ON.  Measured on B200 (tools/k3_ab.py, K3 of 37 888 queries, same
+// process): pipelined 35.2 - 36.4 ms, plain 34.35 ms - the epilogue warps already overlap one another's global loads, and
+// the extra live registers cost more than the hidden latency gains.  Off by default; kept for shapes with fewer warps.
+static inline int gt_pre_mode() {
+  const char* e = getenv("VFR_GEMM_PRE");
+  return e ? atoi(e) : 0;
+}
+
 static inline int gt_kp(int k) { return (k + GT_BK - 1) / GT_BK * GT_BK; }
 
 // A: packed [M, lda] (lda >= 2*kp), B: packed [N, ldb]; batch <= 2 problems with identical shapes.
@@ -312,7 +370,7 @@ static int launch_gemm_tc(const void* const* a, const void* const* b, int batch,
   VFR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
   dim3 grid((N + GT_BN - 1) / GT_BN, (M + GT_BM - 1) / GT_BM, batch);
   gemm_tc_kernel<Epi><<<grid, GT_THREADS, GT_SMEM, st>>>(maps, M, m_limit, kp / GT_BK, lo_a, lo_b, f16 ? GT_FMT_F16 : GT_FMT_BF16,
-                                                         flush_buf ? flush_k / GT_BK : 0, flush_buf, flush_ld, N, epi);
+                                                         flush_buf ? flush_k / GT_BK : 0, flush_buf, flush_ld, N, gt_pre_mode(), epi);
   return check_launch("gemm_tc_kernel");
 }
 

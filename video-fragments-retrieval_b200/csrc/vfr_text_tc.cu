@@ -220,6 +220,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 2.f * sigmoid_fast(2.f * x) - 1.f; }
 
+// (members indexed by the problem z are selected with ?: - a runtime index into a by-value kernel parameter makes the
+//  compiler copy the whole functor to LOCAL memory and fetch every pointer with an LDL in front of the loads it feeds:
+//  6 % of all warp samples of the step GEMM sat on that, ncu source page of round 2)
 struct EpiLstmTc {
   const float* bias[2];
   float* c[2];                 // [B, H] fp32
@@ -228,25 +231,37 @@ struct EpiLstmTc {
   int col0[2];
   int lo_off;
   int H;
-  __device__ __forceinline__ void operator()(int z, int m, int n0, const float (&v)[16]) const {
+  // operands of one 16-column group (4 hidden units x 4 gates) that live in global memory: requested one group ahead
+  struct Pre {
+    float4 c_prev;
+    float4 b[4];
+  };
+  __device__ __forceinline__ Pre prefetch(int z, int m, int n0) const {
+    Pre p;
+    const int j0 = n0 >> 2;
+    if (j0 >= H) { p.c_prev = make_float4(0.f, 0.f, 0.f, 0.f); p.b[0] = p.b[1] = p.b[2] = p.b[3] = p.c_prev; return p; }
+    p.c_prev = *reinterpret_cast<const float4*>((z ? c[1] : c[0]) + (int64_t)m * H + j0);      // (the cell arrays start zeroed)
+    const float4* bz = reinterpret_cast<const float4*>((z ? bias[1] : bias[0]) + n0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p.b[u] = __ldg(bz + u);
+    return p;
+  }
+  __device__ __forceinline__ void operator()(int z, int m, int n0, const float (&v)[16], const Pre& p) const {
     const int j0 = n0 >> 2;
     if (j0 >= H) return;
-    const float4* bz = reinterpret_cast<const float4*>(bias[z] + n0);
-    float4* cp = reinterpret_cast<float4*>(c[z] + (int64_t)m * H + j0);
-    const float4 c_prev = *cp;                   // (the cell arrays start zeroed)
-    const float cpv[4] = {c_prev.x, c_prev.y, c_prev.z, c_prev.w};
+    const float cpv[4] = {p.c_prev.x, p.c_prev.y, p.c_prev.z, p.c_prev.w};
     float cn[4];
     __nv_bfloat16 hh[4], hl[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float4 bb = __ldg(bz + u);
+      const float4 bb = p.b[u];
       const float gi = v[4 * u + 0] + bb.x, gf = v[4 * u + 1] + bb.y, gg = v[4 * u + 2] + bb.z, go = v[4 * u + 3] + bb.w;
       cn[u] = sigmoid_fast(gf) * cpv[u] + sigmoid_fast(gi) * tanh_fast(gg);
       const float h = sigmoid_fast(go) * tanh_fast(cn[u]);
       split2(h, hh[u], hl[u]);
     }
-    *cp = make_float4(cn[0], cn[1], cn[2], cn[3]);
-    __nv_bfloat16* o = dst[z] + (int64_t)m * ld + col0[z] + j0;
+    *reinterpret_cast<float4*>((z ? c[1] : c[0]) + (int64_t)m * H + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    __nv_bfloat16* o = (z ? dst[1] : dst[0]) + (int64_t)m * ld + (z ? col0[1] : col0[0]) + j0;
     *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
     *reinterpret_cast<uint2*>(o + lo_off) = make_uint2(pack_bf16x2(hl[0], hl[1]), pack_bf16x2(hl[2], hl[3]));
   }
