@@ -24,3 +24,18 @@ for rep in range(2):
     for mode in ("1", "0"):
         os.environ["VFR_GEMM_PRE"] = mode
         print(json.dumps(dict(B=B, VFR_GEMM_PRE=mode, ms=run())), flush=True)
+
+# where a tile's cycles go (VFR_GEMM_DBG: sums over all working tiles of every GEMM launched while it is set)
+dbg = torch.zeros(8, dtype=torch.int64, device=dev)
+os.environ["VFR_GEMM_PRE"] = "0"
+with torch.no_grad():
+    model(tok, False, dev)
+    torch.cuda.synchronize()
+    os.environ["VFR_GEMM_DBG"] = hex(dbg.data_ptr())
+    model(tok, False, dev)
+    torch.cuda.synchronize()
+os.environ.pop("VFR_GEMM_DBG")
+d = dbg.cpu().numpy().astype(np.float64)
+n = d[7]
+print("K3 of %d queries: %d working tiles; cycles per tile: set-up %.0f | wait for first operands %.0f | main loop %.0f | epilogue %.0f | whole tile %.0f" % (
+    B, n, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n))

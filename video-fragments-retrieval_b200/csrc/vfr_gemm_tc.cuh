@@ -139,7 +139,7 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
 template <class Epi>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __restrict__ m_limit, int k_chunks, int lo_a,
-               int lo_b, uint32_t fmt, int flush_chunks, float* __restrict__ flush_buf, int64_t flush_ld, int N_all, int pre_mode, Epi epi) {
+               int lo_b, uint32_t fmt, int flush_chunks, float* __restrict__ flush_buf, int64_t flush_ld, int N_all, int pre_mode, long long* __restrict__ dbg, Epi epi) {
   extern __shared__ uint8_t gt_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gt_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE);
@@ -157,6 +157,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
   const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * GT_BN;
+  // development aid (VFR_GEMM_DBG = device address of int64 [8]): cycles summed over all tiles that do work -
+  // 0 set-up (barriers, TMEM), 1 wait for the first operands, 2 main loop (first operands -> last MMA issued),
+  // 3 epilogue (accumulator complete -> last store, one epilogue warp), 4 whole tile, 7 number of tiles
+  const bool trace = dbg != nullptr;
+  long long t_a = 0, t_b = 0;
+  if (trace) t_a = clock64();
+  const long long t_begin = t_a;
   // rows of problem z that are live in this launch (device-side count: no host sync); a tile past it retires
   const int M = m_limit ? min(M_all, m_limit[z]) : M_all;
   if (m0 >= M) return;
@@ -177,6 +184,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
   __syncthreads();
   gt_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (trace && threadIdx.x == 32) { t_b = clock64(); atomicAdd(reinterpret_cast<unsigned long long*>(dbg), (unsigned long long)(t_b - t_a)); }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -211,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
         }
         gt_wait(&full[s], (c / GT_STAGES) & 1, 32);
         gt_fence_after();
+        if (trace && c == 0) { t_a = clock64(); atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 1), (unsigned long long)(t_a - t_b)); }
         uint8_t* st = smem + s * GT_STAGE;
         const uint64_t bh = gt_desc(st + 4 * GT_A_SUB), bl = gt_desc(st + 4 * GT_A_SUB + GT_B_BOX);
 #pragma unroll
@@ -230,6 +239,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
           ++seg;
         }
       }
+      if (trace) atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 2), (unsigned long long)(clock64() - t_a));
     }
   } else {
     const int ew = warp - 2;
@@ -262,6 +272,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
     for (int f = 0; f < n_seg; ++f) {
       gt_wait(acc_full, f & 1, 256);
       gt_fence_after();
+      if (trace && f == n_seg - 1 && threadIdx.x == 64) t_b = clock64();
       const bool last = f == n_seg - 1;
       for (int c = 0; c < GT_BN / 16; ++c) {
         float v[16];
@@ -292,8 +303,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTcMaps maps, int M_all, const int* __
       }
     }
   }
+  if (trace && threadIdx.x == 64) atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 3), (unsigned long long)(clock64() - t_b));
   gt_fence_before();
   __syncthreads();
+  if (trace && threadIdx.x == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 4), (unsigned long long)(clock64() - t_begin));
+    atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 7), 1ull);
+  }
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
@@ -339,7 +355,17 @@ static inline int gt_pre_mode() {
   return e ? atoi(e) : 0;
 }
 
+static inline long long* gt_dbg_ptr() {
+  const char* e = getenv("VFR_GEMM_DBG");
+  return e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+}
+
 static inline int gt_kp(int k) { return (k + GT_BK - 1) / GT_BK * GT_BK; }
+
+template <class Epi>
+static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda, int64_t ldb,
+                           Epi epi, cudaStream_t st, const int* m_limit, bool f16, int lo_a, int lo_b);
+static inline int g2_enabled();
 
 // A: packed [M, lda] (lda >= 2*kp), B: packed [N, ldb]; batch <= 2 problems with identical shapes.
 // lo_a / lo_b (default kp): column distance between the hi and the lo half of a row of A / B - a K-segment of a wider
@@ -355,6 +381,8 @@ static int launch_gemm_tc(const void* const* a, const void* const* b, int batch,
   VFR_REQUIRE(batch >= 1 && batch <= 2 && kp % GT_BK == 0 && lda >= lo_a + kp && ldb >= lo_b + kp && lda % 8 == 0 &&
                   ldb % 8 == 0 && lo_a % 8 == 0 && lo_b % 8 == 0,
               VFR_ERR_INVALID, "launch_gemm_tc: bad operand layout");
+  // the persistent CTA-pair kernel (vfr_gemm_tc2.cuh) serves everything but the K-segmented accumulation
+  if (!flush_buf && g2_enabled()) return launch_gemm_tc2(a, b, batch, M, N, kp, lda, ldb, epi, st, m_limit, f16, lo_a, lo_b);
   GemmTcMaps maps;
   for (int z = 0; z < batch; ++z) {
     int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16);
@@ -370,8 +398,10 @@ static int launch_gemm_tc(const void* const* a, const void* const* b, int batch,
   VFR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
   dim3 grid((N + GT_BN - 1) / GT_BN, (M + GT_BM - 1) / GT_BM, batch);
   gemm_tc_kernel<Epi><<<grid, GT_THREADS, GT_SMEM, st>>>(maps, M, m_limit, kp / GT_BK, lo_a, lo_b, f16 ? GT_FMT_F16 : GT_FMT_BF16,
-                                                         flush_buf ? flush_k / GT_BK : 0, flush_buf, flush_ld, N, gt_pre_mode(), epi);
+                                                         flush_buf ? flush_k / GT_BK : 0, flush_buf, flush_ld, N, gt_pre_mode(), gt_dbg_ptr(), epi);
   return check_launch("gemm_tc_kernel");
 }
 
 }  // namespace vfr
+
+#include "vfr_gemm_tc2.cuh"

@@ -1,0 +1,262 @@
+// The split-operand tensor-core GEMM of vfr_gemm_tc.cuh as a PERSISTENT CTA-PAIR kernel (tcgen05 cta_group::2):
+//   C[M,N] = A[M,K] * B[N,K]^T,  A.B^T ~= Ah.Bh^T + Al.Bh^T + Ah.Bl^T  (same packed operands, same epilogue functors).
+//
+// Why.  Measured over the 66 294 working tiles of a 37 888-query K3 (tools/k3_ab.py, round 2), a 256 x 256 tile of the
+// one-CTA kernel takes 108.9 k cycles for 55.3 k cycles of MMA: 29.4 k are the epilogue (LSTM cell, exposed: the tile's
+// accumulators fill all 512 TMEM columns, nothing can run under them), 17.9 k main-loop stalls on a 3-stage ring,
+// 4.3 k set-up + first-operand latency per tile, 2 k tear-down.  Here
+//  * two CTAs of a cluster (one TPC) share every tile: each holds 128 of the 256 rows, so a tile's accumulator is 256
+//    TMEM columns per CTA and the OTHER 256 columns take the next tile - the epilogue of tile i runs under the MMAs of
+//    tile i + 1 (8 epilogue warps per CTA, two per TMEM lane quarter, 128 columns each);
+//  * each CTA stages only its half of B (tcgen05.mma.cta_group::2 reads both halves), so a K chunk is 32 KB per CTA instead
+//    of 64 KB - 6 stages in the same shared memory, same bytes per MMA cycle;
+//  * CTAs are persistent (one pair per TPC, static round-robin over the tiles, N fastest so that the pairs working at the
+//    same time share the A rows in L2): barriers, TMEM and tensor-map fetches are set up once per kernel, and the ring
+//    never drains between tiles.
+// Protocol (as CUTLASS's 2-SM pipelines): the LEADER CTA (cluster rank 0) issues every MMA; both CTAs' TMA loads
+// (cta_group::2) complete on the leader's `full` barrier, which the leader's producer arms with the bytes of both;
+// tcgen05.commit multicasts `empty` (stage free) and `acc_full` (accumulator complete) to both CTAs; the epilogue warps of
+// both CTAs arrive on the leader's `acc_empty`.
+#pragma once
+#include "vfr_gemm_tc.cuh"
+#include <algorithm>
+
+namespace vfr {
+
+constexpr int G2_STAGES = 6;
+constexpr int G2_SUB = 128 * GT_BK * 2;                   // one [128 x 32] 16-bit box = 8 KB
+constexpr int G2_STAGE = 4 * G2_SUB;                      // Ah Al Bh Bl (this CTA's halves) = 32 KB
+constexpr uint32_t G2_SMEM = G2_STAGES * G2_STAGE + 1024 + 512;
+constexpr int G2_EPI_WARPS = GT_THREADS / 32 - 2;         // 8
+
+__device__ __forceinline__ uint32_t g2_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void g2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t g2_mapa(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void g2_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load of a CTA pair: data into THIS CTA's shared memory, completion bytes on the barrier at `bar_cluster_addr`
+// (the leader's)
+__device__ __forceinline__ void g2_tma_load(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void g2_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void g2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+struct G2Tile { int z, m0, n0, M; };
+
+template <class Epi>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, const int* __restrict__ m_limit, int k_chunks,
+                int lo_a, int lo_b, uint32_t fmt, int N_all, Epi epi) {
+  extern __shared__ uint8_t g2_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE);
+  uint64_t* full = bars;                       // [S]  (the leader's are used)
+  uint64_t* empty = bars + G2_STAGES;          // [S]  per CTA
+  uint64_t* acc_full = bars + 2 * G2_STAGES;   // [2]  per CTA
+  uint64_t* acc_empty = acc_full + 2;          // [2]  (the leader's are used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = g2_cta_rank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 2 * G2_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  g2_cluster_sync();                  // the peer's barriers exist before anything signals them
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  gt_fence_before();
+  __syncthreads();
+  gt_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile list: problems z = 0 .. batch-1 back to back, inside a problem N fastest; tile t of the list belongs to pair
+  // t mod (pairs).  Both CTAs of a pair (and all their warps) walk the same list.
+  const int n_tiles_n = (N_all + GT_BN - 1) / GT_BN;
+  int Mz[2], tiles_z[2];
+  int total = 0;
+  for (int z = 0; z < 2; ++z) {
+    Mz[z] = z < batch ? (m_limit ? min(M_all, m_limit[z]) : M_all) : 0;
+    tiles_z[z] = (Mz[z] + GT_BM - 1) / GT_BM * n_tiles_n;
+    total += tiles_z[z];
+  }
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  auto decode = [&](int t) {
+    G2Tile tl;
+    tl.z = t < tiles_z[0] ? 0 : 1;
+    const int r = t - (tl.z ? tiles_z[0] : 0);
+    tl.m0 = (r / n_tiles_n) * GT_BM;
+    tl.n0 = (r % n_tiles_n) * GT_BN;
+    tl.M = Mz[tl.z];
+    return tl;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs: own 128 rows of A, own half of the B rows) =================
+    if (lane == 0) {
+      uint32_t full_leader[G2_STAGES];
+      for (int s = 0; s < G2_STAGES; ++s) full_leader[s] = g2_mapa(&full[s], 0);
+      int it = 0;
+      for (int t = pair; t < total; t += n_pairs) {
+        const G2Tile tl = decode(t);
+        const CUtensorMap* ma = tl.z ? &maps.a[1] : &maps.a[0];
+        const CUtensorMap* mb = tl.z ? &maps.b[1] : &maps.b[0];
+        // the last N tile of a matrix issues narrower MMAs (N rounded up to 32); the pair splits THAT N in halves
+        const int n_mma = min(GT_BN, (N_all - tl.n0 + 31) / 32 * 32);
+        const int row_a = tl.m0 + (int)rank * 128, row_b = tl.n0 + (int)rank * (n_mma >> 1);
+        for (int c = 0; c < k_chunks; ++c, ++it) {
+          const int s = it % G2_STAGES;
+          gt_wait(&empty[s], ((it / G2_STAGES) & 1) ^ 1, 32);
+          uint8_t* st = smem + s * G2_STAGE;
+          if (leader) mbar_expect_tx(&full[s], 2 * G2_STAGE);
+          const int kc = c * GT_BK;
+          g2_tma_load(st + 0 * G2_SUB, ma, kc, row_a, full_leader[s]);          // Ah
+          g2_tma_load(st + 1 * G2_SUB, ma, lo_a + kc, row_a, full_leader[s]);   // Al
+          g2_tma_load(st + 2 * G2_SUB, mb, kc, row_b, full_leader[s]);          // Bh (this CTA's half of the N rows)
+          g2_tma_load(st + 3 * G2_SUB, mb, lo_b + kc, row_b, full_leader[s]);   // Bl
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (lane == 0 && leader) {
+      int it = 0, ti = 0;
+      for (int t = pair; t < total; t += n_pairs, ++ti) {
+        const G2Tile tl = decode(t);
+        const int n_mma = min(GT_BN, (N_all - tl.n0 + 31) / 32 * 32);
+        // kind::f16, D = fp32, M = 256 (the pair), N = n_mma
+        const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        const int buf = ti & 1;
+        gt_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 32);        // both CTAs' epilogues have drained this buffer
+        gt_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)buf * 256;
+        for (int c = 0; c < k_chunks; ++c, ++it) {
+          const int s = it % G2_STAGES;
+          gt_wait(&full[s], (it / G2_STAGES) & 1, 32);
+          gt_fence_after();
+          uint8_t* st = smem + s * G2_STAGE;
+          const uint64_t ah = gt_desc(st), al = gt_desc(st + G2_SUB), bh = gt_desc(st + 2 * G2_SUB), bl = gt_desc(st + 3 * G2_SUB);
+#pragma unroll
+          for (int k = 0; k < GT_BK / 16; ++k) {
+            g2_mma(d, ah + 2 * k, bh + 2 * k, idesc, (c | k) ? 1u : 0u);
+            g2_mma(d, al + 2 * k, bh + 2 * k, idesc, 1u);
+            g2_mma(d, ah + 2 * k, bl + 2 * k, idesc, 1u);
+          }
+          g2_commit_both(&empty[s]);               // the stage is free in BOTH CTAs once these MMAs have read it
+        }
+        g2_commit_both(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ================= epilogue: 8 warps per CTA, two per TMEM lane quarter (128 columns each) =================
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t acc_empty_leader[2] = {g2_mapa(&acc_empty[0], 0), g2_mapa(&acc_empty[1], 0)};
+    int ti = 0;
+    for (int t = pair; t < total; t += n_pairs, ++ti) {
+      const G2Tile tl = decode(t);
+      const int buf = ti & 1;
+      const int m = tl.m0 + (int)rank * 128 + quarter * 32 + lane;
+      gt_wait(&acc_full[buf], (ti >> 1) & 1, 128);
+      gt_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
+      for (int c = 0; c < 8; ++c) {
+        float v[16];
+        gt_ld16(taddr + c * 16, v);
+        if (m < tl.M) {
+          const int nn = tl.n0 + half * 128 + c * 16;
+          if constexpr (gt_has_pre<Epi>::value) epi(tl.z, m, nn, v, epi.prefetch(tl.z, m, nn));
+          else epi(tl.z, m, nn, v);
+        }
+      }
+      gt_fence_before();
+      __syncwarp();
+      if (lane == 0) g2_arrive_remote(acc_empty_leader[buf]);
+    }
+  }
+  gt_fence_before();
+  __syncthreads();
+  g2_cluster_sync();                  // the peer may still read this CTA's shared memory / signal its barriers
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// 0 = the one-CTA kernel, 1 = the CTA-pair kernel where it applies (default)
+static inline int g2_enabled() {
+  const char* e = getenv("VFR_GEMM2");
+  return e ? atoi(e) : 1;
+}
+
+template <class Epi>
+static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda, int64_t ldb,
+                           Epi epi, cudaStream_t st, const int* m_limit, bool f16, int lo_a, int lo_b) {
+  GemmTcMaps maps;
+  for (int z = 0; z < batch; ++z) {
+    int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16);
+    if (rc) return rc;
+    rc = gt_make_map(&maps.b[z], b[z], (uint64_t)N, (uint64_t)ldb, 128, f16);
+    if (rc) return rc;
+  }
+  if (batch == 1) { maps.a[1] = maps.a[0]; maps.b[1] = maps.b[0]; }
+  static int n_sms = 0;
+  if (!n_sms) {
+    int dev = 0;
+    VFR_CUDA(cudaGetDevice(&dev));
+    VFR_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int64_t tiles = (int64_t)batch * ((M + GT_BM - 1) / GT_BM) * ((N + GT_BN - 1) / GT_BN);
+  const int pairs = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / 2, tiles));
+  VFR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+  cfg.blockDim = dim3(GT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = G2_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VFR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<Epi>, maps, batch, M, m_limit, kp / GT_BK, lo_a, lo_b,
+                              f16 ? GT_FMT_F16 : GT_FMT_BF16, N, epi));
+  return check_launch("gemm_tc2_kernel");
+}
+
+}  // namespace vfr
