@@ -25,7 +25,7 @@ for rep in range(2):
         os.environ["VFR_GEMM_PRE"] = mode
         print(json.dumps(dict(B=B, VFR_GEMM_PRE=mode, ms=run())), flush=True)
 
-# where a tile's cycles go (VFR_GEMM_DBG: sums over all working tiles of every GEMM launched while it is set)
+# where the cycles go (VFR_GEMM_DBG: sums over every GEMM launched while it is set)
 dbg = torch.zeros(8, dtype=torch.int64, device=dev)
 os.environ["VFR_GEMM_PRE"] = "0"
 with torch.no_grad():
@@ -36,6 +36,13 @@ with torch.no_grad():
     torch.cuda.synchronize()
 os.environ.pop("VFR_GEMM_DBG")
 d = dbg.cpu().numpy().astype(np.float64)
-n = d[7]
-print("K3 of %d queries: %d working tiles; cycles per tile: set-up %.0f | wait for first operands %.0f | main loop %.0f | epilogue %.0f | whole tile %.0f" % (
-    B, n, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n))
+if os.environ.get("VFR_GEMM2", "1") != "0":
+    # CTA-pair kernel: sums over the leader CTAs of all launches (d[7] = pairs x launches, d[6] = tiles)
+    n = d[6]
+    print("K3 of %d queries, pair kernel: %d tiles over %d pair-launches; cycles per tile: MMA issuer loop %.0f (waits: free accumulator %.0f, operands %.0f) | "
+          "epilogue warp: wait for accumulator %.0f, work %.0f | producer waits for free stages %.0f" % (
+              B, n, d[7], d[2] / n, d[0] / n, d[1] / n, d[3] / n, d[4] / n, d[5] / n))
+else:
+    n = d[7]
+    print("K3 of %d queries: %d working tiles; cycles per tile: set-up %.0f | wait for first operands %.0f | main loop %.0f | epilogue %.0f | whole tile %.0f" % (
+        B, n, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n))

@@ -1,7 +1,7 @@
 // Split-bf16 tensor-core GEMM  C[M,N] = A[M,K] * B[N,K]^T  at fp32 accuracy (tcgen05 / TMEM / TMA).
 //
 // Each fp32 operand x is stored as a bf16 pair (hi = bf16(x), lo = bf16(x - hi)); a packed row is
-// [hi(0..Kp) | lo(0..Kp)] bf16, Kp = K rounded up to 32.  The product is accumulated in fp32 in TMEM as
+// [hi(0..Kp) | lo(0..Kp)] bf16, Kp = K rounded up to 64.  The product is accumulated in fp32 in TMEM as
 //     A.B^T ~= Ah.Bh^T + Al.Bh^T + Ah.Bl^T        (relative error ~2^-17 / sqrt(K) per dot product)
 // One CTA computes a 256 x 256 output tile as two 128-row accumulators (2 x 256 TMEM columns), so a
 // K-chunk of 32 needs (256 + 256) rows x (hi + lo) x 64 B = 64 KB of operands for 12 MMAs of
@@ -332,16 +332,17 @@ static inline GtEncodeFn gt_encode_fn() {
 
 // packed operand [rows, ld_elems] bf16 (ld_elems >= 2*kp); box = [32 k] x [box_rows]; rows beyond `rows` read as 0
 static inline int gt_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t ld_elems, uint32_t box_rows,
-                              bool f16 = false) {
+                              bool f16 = false, uint32_t box_k = GT_BK) {
   GtEncodeFn enc = gt_encode_fn();
   VFR_REQUIRE(enc, VFR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)ld_elems, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * 2};
-  cuuint32_t box[2] = {GT_BK, box_rows};
+  cuuint32_t box[2] = {box_k, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
                    gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_k * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VFR_REQUIRE(r == CUDA_SUCCESS, VFR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return VFR_OK;
@@ -360,7 +361,8 @@ static inline long long* gt_dbg_ptr() {
   return e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
 }
 
-static inline int gt_kp(int k) { return (k + GT_BK - 1) / GT_BK * GT_BK; }
+// packed operand width: K rounded up to 64 (one K chunk of the CTA-pair kernel; two of the one-CTA kernel)
+static inline int gt_kp(int k) { return (k + 63) / 64 * 64; }
 
 template <class Epi>
 static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda, int64_t ldb,
@@ -382,7 +384,7 @@ static int launch_gemm_tc(const void* const* a, const void* const* b, int batch,
                   ldb % 8 == 0 && lo_a % 8 == 0 && lo_b % 8 == 0,
               VFR_ERR_INVALID, "launch_gemm_tc: bad operand layout");
   // the persistent CTA-pair kernel (vfr_gemm_tc2.cuh) serves everything but the K-segmented accumulation
-  if (!flush_buf && g2_enabled()) return launch_gemm_tc2(a, b, batch, M, N, kp, lda, ldb, epi, st, m_limit, f16, lo_a, lo_b);
+  if (!flush_buf && kp % 64 == 0 && g2_enabled()) return launch_gemm_tc2(a, b, batch, M, N, kp, lda, ldb, epi, st, m_limit, f16, lo_a, lo_b);
   GemmTcMaps maps;
   for (int z = 0; z < batch; ++z) {
     int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16);

@@ -23,12 +23,27 @@
 
 namespace vfr {
 
-constexpr int G2_STAGES = 6;
-constexpr int G2_SUB = 128 * GT_BK * 2;                   // one [128 x 32] 16-bit box = 8 KB
-constexpr int G2_STAGE = 4 * G2_SUB;                      // Ah Al Bh Bl (this CTA's halves) = 32 KB
+// K chunks of 64 columns: rows of 128 B (SWIZZLE_128B), i.e. every row of a TMA box is one full L2 line.  With chunks of 32
+// (64-byte rows, 6 stages) the MMA issuer of a 37 888-query K3 step waited for operands 46 % of its time at only 25 B per
+// clock and SM (tools/k3_ab.py, round 2).
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 3;
+constexpr int G2_SUB = 128 * G2_BK * 2;                   // one [128 x 64] 16-bit box = 16 KB
+constexpr int G2_STAGE = 4 * G2_SUB;                      // Ah Al Bh Bl (this CTA's halves) = 64 KB
 constexpr uint32_t G2_SMEM = G2_STAGES * G2_STAGE + 1024 + 512;
 constexpr int G2_EPI_WARPS = GT_THREADS / 32 - 2;         // 8
 
+// K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t g2_desc(const void* smem_ptr) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ uint32_t g2_cta_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -78,7 +93,7 @@ struct G2Tile { int z, m0, n0, M; };
 template <class Epi>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, const int* __restrict__ m_limit, int k_chunks,
-                int lo_a, int lo_b, uint32_t fmt, int N_all, Epi epi) {
+                int lo_a, int lo_b, uint32_t fmt, int N_all, long long* __restrict__ dbg, Epi epi) {
   extern __shared__ uint8_t g2_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE);
@@ -91,6 +106,11 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = g2_cta_rank();
   const bool leader = rank == 0;
+  // development aid (VFR_GEMM_DBG = device address of int64 [8]), cycles summed over the LEADER CTAs of all pairs:
+  // 0 MMA issuer waiting for a free accumulator, 1 waiting for operands, 2 its whole tile loop, 3 epilogue warp 2 waiting
+  // for a complete accumulator, 4 its epilogue work, 5 producer waiting for free stages, 6 tiles, 7 pairs
+  const bool trace = dbg != nullptr && leader;
+  long long w0 = 0, w1 = 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -110,29 +130,25 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
   // tile list: problems z = 0 .. batch-1 back to back, inside a problem N fastest; tile t of the list belongs to pair
   // t mod (pairs).  Both CTAs of a pair (and all their warps) walk the same list.
   const int n_tiles_n = (N_all + GT_BN - 1) / GT_BN;
-  int Mz[2], tiles_z[2];
-  int total = 0;
-  for (int z = 0; z < 2; ++z) {
-    Mz[z] = z < batch ? (m_limit ? min(M_all, m_limit[z]) : M_all) : 0;
-    tiles_z[z] = (Mz[z] + GT_BM - 1) / GT_BM * n_tiles_n;
-    total += tiles_z[z];
-  }
+  const int M0 = m_limit ? min(M_all, m_limit[0]) : M_all;
+  const int M1 = batch > 1 ? (m_limit ? min(M_all, m_limit[1]) : M_all) : 0;
+  const int tiles0 = (M0 + GT_BM - 1) / GT_BM * n_tiles_n, tiles1 = (M1 + GT_BM - 1) / GT_BM * n_tiles_n;
+  const int total = tiles0 + tiles1;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   auto decode = [&](int t) {
     G2Tile tl;
-    tl.z = t < tiles_z[0] ? 0 : 1;
-    const int r = t - (tl.z ? tiles_z[0] : 0);
+    tl.z = t < tiles0 ? 0 : 1;
+    const int r = t - (tl.z ? tiles0 : 0);
     tl.m0 = (r / n_tiles_n) * GT_BM;
     tl.n0 = (r % n_tiles_n) * GT_BN;
-    tl.M = Mz[tl.z];
+    tl.M = tl.z ? M1 : M0;
     return tl;
   };
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs: own 128 rows of A, own half of the B rows) =================
     if (lane == 0) {
-      uint32_t full_leader[G2_STAGES];
-      for (int s = 0; s < G2_STAGES; ++s) full_leader[s] = g2_mapa(&full[s], 0);
+      const uint32_t full_leader0 = g2_mapa(&full[0], 0);     // (+ 8 s: no runtime-indexed local array)
       int it = 0;
       for (int t = pair; t < total; t += n_pairs) {
         const G2Tile tl = decode(t);
@@ -143,38 +159,43 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
         const int row_a = tl.m0 + (int)rank * 128, row_b = tl.n0 + (int)rank * (n_mma >> 1);
         for (int c = 0; c < k_chunks; ++c, ++it) {
           const int s = it % G2_STAGES;
-          gt_wait(&empty[s], ((it / G2_STAGES) & 1) ^ 1, 32);
+          if (trace) { const long long t0 = clock64(); gt_wait(&empty[s], ((it / G2_STAGES) & 1) ^ 1, 32); w0 += clock64() - t0; }
+          else gt_wait(&empty[s], ((it / G2_STAGES) & 1) ^ 1, 32);
           uint8_t* st = smem + s * G2_STAGE;
           if (leader) mbar_expect_tx(&full[s], 2 * G2_STAGE);
-          const int kc = c * GT_BK;
-          g2_tma_load(st + 0 * G2_SUB, ma, kc, row_a, full_leader[s]);          // Ah
-          g2_tma_load(st + 1 * G2_SUB, ma, lo_a + kc, row_a, full_leader[s]);   // Al
-          g2_tma_load(st + 2 * G2_SUB, mb, kc, row_b, full_leader[s]);          // Bh (this CTA's half of the N rows)
-          g2_tma_load(st + 3 * G2_SUB, mb, lo_b + kc, row_b, full_leader[s]);   // Bl
+          const int kc = c * G2_BK;
+          g2_tma_load(st + 0 * G2_SUB, ma, kc, row_a, full_leader0 + 8u * (uint32_t)s);          // Ah
+          g2_tma_load(st + 1 * G2_SUB, ma, lo_a + kc, row_a, full_leader0 + 8u * (uint32_t)s);   // Al
+          g2_tma_load(st + 2 * G2_SUB, mb, kc, row_b, full_leader0 + 8u * (uint32_t)s);          // Bh (this CTA's half of the N rows)
+          g2_tma_load(st + 3 * G2_SUB, mb, lo_b + kc, row_b, full_leader0 + 8u * (uint32_t)s);   // Bl
         }
       }
+      if (trace) atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 5), (unsigned long long)w0);
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (lane == 0 && leader) {
       int it = 0, ti = 0;
+      const long long t_loop = trace ? clock64() : 0;
       for (int t = pair; t < total; t += n_pairs, ++ti) {
         const G2Tile tl = decode(t);
         const int n_mma = min(GT_BN, (N_all - tl.n0 + 31) / 32 * 32);
         // kind::f16, D = fp32, M = 256 (the pair), N = n_mma
         const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
         const int buf = ti & 1;
-        gt_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 32);        // both CTAs' epilogues have drained this buffer
+        if (trace) { const long long t0 = clock64(); gt_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 32); w0 += clock64() - t0; }
+        else gt_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 32);   // both CTAs' epilogues have drained this buffer
         gt_fence_after();
         const uint32_t d = tmem_base + (uint32_t)buf * 256;
         for (int c = 0; c < k_chunks; ++c, ++it) {
           const int s = it % G2_STAGES;
-          gt_wait(&full[s], (it / G2_STAGES) & 1, 32);
+          if (trace) { const long long t0 = clock64(); gt_wait(&full[s], (it / G2_STAGES) & 1, 32); w1 += clock64() - t0; }
+          else gt_wait(&full[s], (it / G2_STAGES) & 1, 32);
           gt_fence_after();
           uint8_t* st = smem + s * G2_STAGE;
-          const uint64_t ah = gt_desc(st), al = gt_desc(st + G2_SUB), bh = gt_desc(st + 2 * G2_SUB), bl = gt_desc(st + 3 * G2_SUB);
+          const uint64_t ah = g2_desc(st), al = g2_desc(st + G2_SUB), bh = g2_desc(st + 2 * G2_SUB), bl = g2_desc(st + 3 * G2_SUB);
 #pragma unroll
-          for (int k = 0; k < GT_BK / 16; ++k) {
+          for (int k = 0; k < G2_BK / 16; ++k) {
             g2_mma(d, ah + 2 * k, bh + 2 * k, idesc, (c | k) ? 1u : 0u);
             g2_mma(d, al + 2 * k, bh + 2 * k, idesc, 1u);
             g2_mma(d, ah + 2 * k, bl + 2 * k, idesc, 1u);
@@ -183,17 +204,26 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
         }
         g2_commit_both(&acc_full[buf]);
       }
+      if (trace) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 0), (unsigned long long)w0);
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 1), (unsigned long long)w1);
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 2), (unsigned long long)(clock64() - t_loop));
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 6), (unsigned long long)ti);
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 7), 1ull);
+      }
     }
   } else {
     // ================= epilogue: 8 warps per CTA, two per TMEM lane quarter (128 columns each) =================
     const int quarter = warp & 3, half = (warp - 2) >> 2;
-    const uint32_t acc_empty_leader[2] = {g2_mapa(&acc_empty[0], 0), g2_mapa(&acc_empty[1], 0)};
+    const uint32_t acc_empty_leader0 = g2_mapa(&acc_empty[0], 0);
     int ti = 0;
     for (int t = pair; t < total; t += n_pairs, ++ti) {
       const G2Tile tl = decode(t);
       const int buf = ti & 1;
       const int m = tl.m0 + (int)rank * 128 + quarter * 32 + lane;
-      gt_wait(&acc_full[buf], (ti >> 1) & 1, 128);
+      long long t_e = 0;
+      if (trace && warp == 2) { const long long t0 = clock64(); gt_wait(&acc_full[buf], (ti >> 1) & 1, 128); t_e = clock64(); w0 += t_e - t0; }
+      else gt_wait(&acc_full[buf], (ti >> 1) & 1, 128);
       gt_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
       for (int c = 0; c < 8; ++c) {
@@ -207,7 +237,12 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
       }
       gt_fence_before();
       __syncwarp();
-      if (lane == 0) g2_arrive_remote(acc_empty_leader[buf]);
+      if (lane == 0) g2_arrive_remote(acc_empty_leader0 + 8u * (uint32_t)buf);
+      if (trace && warp == 2) w1 += clock64() - t_e;
+    }
+    if (trace && warp == 2 && lane == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 3), (unsigned long long)w0);
+      atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 4), (unsigned long long)w1);
     }
   }
   gt_fence_before();
@@ -227,9 +262,9 @@ static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch
                            Epi epi, cudaStream_t st, const int* m_limit, bool f16, int lo_a, int lo_b) {
   GemmTcMaps maps;
   for (int z = 0; z < batch; ++z) {
-    int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16);
+    int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16, G2_BK);
     if (rc) return rc;
-    rc = gt_make_map(&maps.b[z], b[z], (uint64_t)N, (uint64_t)ldb, 128, f16);
+    rc = gt_make_map(&maps.b[z], b[z], (uint64_t)N, (uint64_t)ldb, 128, f16, G2_BK);
     if (rc) return rc;
   }
   if (batch == 1) { maps.a[1] = maps.a[0]; maps.b[1] = maps.b[0]; }
@@ -254,8 +289,8 @@ static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VFR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<Epi>, maps, batch, M, m_limit, kp / GT_BK, lo_a, lo_b,
-                              f16 ? GT_FMT_F16 : GT_FMT_BF16, N, epi));
+  VFR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<Epi>, maps, batch, M, m_limit, kp / G2_BK, lo_a, lo_b,
+                              f16 ? GT_FMT_F16 : GT_FMT_BF16, N, gt_dbg_ptr(), epi));
   return check_launch("gemm_tc2_kernel");
 }
 

@@ -2,7 +2,7 @@
 // tcgen05 as a split-bf16 product (vfr_gemm_tc.cuh), fp32 accumulation and fp32 cell state.
 // Same contract as vfr_text_embed (reference model/models.py:33-48,61-66).
 //
-// Layout: per direction L slots [B][2*Kp] bf16, Kp = Hp + Ep (H, E rounded up to 32); slot t holds
+// Layout: per direction L slots [B][2*Kp] bf16, Kp = Hp + Ep (H, E rounded up to 64); slot t holds
 // the split operand [h_{t-1} | x_t] = (hi | lo), so one recurrent step is ONE GEMM against the packed
 // weights [W_hh | W_ih] (rows interleaved 4j+g) whose epilogue adds the bias, applies the LSTM cell and
 // writes h_t, already split into bf16 hi/lo, straight into slot t+1 (the last step writes into the

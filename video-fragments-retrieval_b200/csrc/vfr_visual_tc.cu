@@ -25,9 +25,9 @@ namespace vfr {
 
 struct VisDims {
   int F, hid, dim;
-  int Fp;         // F rounded up to 32
+  int Fp;         // F rounded up to 64
   int K1;         // 2 * Fp : packed K of layer 1 = [segment | context]
-  int Hp;         // hid rounded up to 32
+  int Hp;         // hid rounded up to 64
   int N1, N2;     // output rows of the packed weights, rounded up to 256
 };
 static VisDims vis_dims(int F, int hid, int dim) {
