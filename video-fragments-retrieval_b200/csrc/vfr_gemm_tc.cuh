@@ -366,7 +366,8 @@ static inline int gt_kp(int k) { return (k + 63) / 64 * 64; }
 
 template <class Epi>
 static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda, int64_t ldb,
-                           Epi epi, cudaStream_t st, const int* m_limit, bool f16, int lo_a, int lo_b);
+                           Epi epi, cudaStream_t st, const int* m_limit, bool f16, int lo_a, int lo_b, int seg_k,
+                           float* seg_buf, int64_t seg_ld);
 static inline int g2_enabled();
 
 // A: packed [M, lda] (lda >= 2*kp), B: packed [N, ldb]; batch <= 2 problems with identical shapes.
@@ -383,8 +384,15 @@ static int launch_gemm_tc(const void* const* a, const void* const* b, int batch,
   VFR_REQUIRE(batch >= 1 && batch <= 2 && kp % GT_BK == 0 && lda >= lo_a + kp && ldb >= lo_b + kp && lda % 8 == 0 &&
                   ldb % 8 == 0 && lo_a % 8 == 0 && lo_b % 8 == 0,
               VFR_ERR_INVALID, "launch_gemm_tc: bad operand layout");
-  // the persistent CTA-pair kernel (vfr_gemm_tc2.cuh) serves everything but the K-segmented accumulation
-  if (!flush_buf && kp % 64 == 0 && g2_enabled()) return launch_gemm_tc2(a, b, batch, M, N, kp, lda, ldb, epi, st, m_limit, f16, lo_a, lo_b);
+  // K-segmented accumulation: flush_buf fp32 [>= M rounded up to 256 rows, flush_ld = N rounded up to 256] (batch 1 only),
+  // 16-byte aligned (the CTA-pair kernel uses it tile by tile: 256 KB per 256 x 256 tile)
+  VFR_REQUIRE(!flush_buf || (batch == 1 && flush_k >= GT_BK && flush_k % GT_BK == 0 && flush_ld % 4 == 0 &&
+                             flush_ld >= (N + GT_BN - 1) / GT_BN * GT_BN),
+              VFR_ERR_INVALID, "launch_gemm_tc: bad flush buffer");
+  // the persistent CTA-pair kernel (vfr_gemm_tc2.cuh) serves every operand whose K is a whole number of its 64-column chunks
+  if (kp % 64 == 0 && (!flush_buf || flush_k % 64 == 0) && g2_enabled())
+    return launch_gemm_tc2(a, b, batch, M, N, kp, lda, ldb, epi, st, m_limit, f16, lo_a, lo_b, flush_buf ? flush_k : 0, flush_buf,
+                           flush_ld);
   GemmTcMaps maps;
   for (int z = 0; z < batch; ++z) {
     int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16);
@@ -393,10 +401,6 @@ static int launch_gemm_tc(const void* const* a, const void* const* b, int batch,
     if (rc) return rc;
   }
   if (batch == 1) { maps.a[1] = maps.a[0]; maps.b[1] = maps.b[0]; }
-  // K-segmented accumulation: flush_buf fp32 [>= M rows, flush_ld >= N rounded up to 256] (batch 1 only), 16-byte aligned rows
-  VFR_REQUIRE(!flush_buf || (batch == 1 && flush_k >= GT_BK && flush_k % GT_BK == 0 && flush_ld % 4 == 0 &&
-                             flush_ld >= (N + GT_BN - 1) / GT_BN * GT_BN),
-              VFR_ERR_INVALID, "launch_gemm_tc: bad flush buffer");
   VFR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
   dim3 grid((N + GT_BN - 1) / GT_BN, (M + GT_BM - 1) / GT_BM, batch);
   gemm_tc_kernel<Epi><<<grid, GT_THREADS, GT_SMEM, st>>>(maps, M, m_limit, kp / GT_BK, lo_a, lo_b, f16 ? GT_FMT_F16 : GT_FMT_BF16,

@@ -90,10 +90,15 @@ __device__ __forceinline__ void g2_commit_both(uint64_t* bar) {
 
 struct G2Tile { int z, m0, n0, M; };
 
-template <class Epi>
+// SEG: K-segmented accumulation (see gemm_tc_kernel) - every seg_chunks K chunks are one work item with its own TMEM
+// buffer; the epilogue warps add item f to the fp32 partial sums of the tile in seg_buf (round-to-nearest adds; each
+// thread re-reads only what it wrote itself) while the MMAs of item f + 1 fill the other buffer, and the fused epilogue
+// functor runs on the last item of a tile.  Batch 1 only.
+template <class Epi, bool SEG>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, const int* __restrict__ m_limit, int k_chunks,
-                int lo_a, int lo_b, uint32_t fmt, int N_all, long long* __restrict__ dbg, Epi epi) {
+                int lo_a, int lo_b, uint32_t fmt, int N_all, int seg_chunks, float* __restrict__ seg_buf, int64_t seg_ld,
+                long long* __restrict__ dbg, Epi epi) {
   extern __shared__ uint8_t g2_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE);
@@ -134,6 +139,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
   const int M1 = batch > 1 ? (m_limit ? min(M_all, m_limit[1]) : M_all) : 0;
   const int tiles0 = (M0 + GT_BM - 1) / GT_BM * n_tiles_n, tiles1 = (M1 + GT_BM - 1) / GT_BM * n_tiles_n;
   const int total = tiles0 + tiles1;
+  const int n_seg = SEG ? (k_chunks + seg_chunks - 1) / seg_chunks : 1;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   auto decode = [&](int t) {
     G2Tile tl;
@@ -177,32 +183,36 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
     if (lane == 0 && leader) {
       int it = 0, ti = 0;
       const long long t_loop = trace ? clock64() : 0;
-      for (int t = pair; t < total; t += n_pairs, ++ti) {
+      for (int t = pair; t < total; t += n_pairs) {
         const G2Tile tl = decode(t);
         const int n_mma = min(GT_BN, (N_all - tl.n0 + 31) / 32 * 32);
         // kind::f16, D = fp32, M = 256 (the pair), N = n_mma
         const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-        const int buf = ti & 1;
-        if (trace) { const long long t0 = clock64(); gt_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 32); w0 += clock64() - t0; }
-        else gt_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 32);   // both CTAs' epilogues have drained this buffer
-        gt_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)buf * 256;
-        for (int c = 0; c < k_chunks; ++c, ++it) {
-          const int s = it % G2_STAGES;
-          if (trace) { const long long t0 = clock64(); gt_wait(&full[s], (it / G2_STAGES) & 1, 32); w1 += clock64() - t0; }
-          else gt_wait(&full[s], (it / G2_STAGES) & 1, 32);
+        int c = 0;
+        for (int f = 0; f < n_seg; ++f, ++ti) {
+          const int buf = ti & 1;
+          if (trace) { const long long t0 = clock64(); gt_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 32); w0 += clock64() - t0; }
+          else gt_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 32);   // both CTAs' epilogues have drained this buffer
           gt_fence_after();
-          uint8_t* st = smem + s * G2_STAGE;
-          const uint64_t ah = g2_desc(st), al = g2_desc(st + G2_SUB), bh = g2_desc(st + 2 * G2_SUB), bl = g2_desc(st + 3 * G2_SUB);
+          const uint32_t d = tmem_base + (uint32_t)buf * 256;
+          const int c_end = SEG ? min(k_chunks, c + seg_chunks) : k_chunks;
+          for (bool first = true; c < c_end; ++c, ++it, first = false) {
+            const int s = it % G2_STAGES;
+            if (trace) { const long long t0 = clock64(); gt_wait(&full[s], (it / G2_STAGES) & 1, 32); w1 += clock64() - t0; }
+            else gt_wait(&full[s], (it / G2_STAGES) & 1, 32);
+            gt_fence_after();
+            uint8_t* st = smem + s * G2_STAGE;
+            const uint64_t ah = g2_desc(st), al = g2_desc(st + G2_SUB), bh = g2_desc(st + 2 * G2_SUB), bl = g2_desc(st + 3 * G2_SUB);
 #pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k) {
-            g2_mma(d, ah + 2 * k, bh + 2 * k, idesc, (c | k) ? 1u : 0u);
-            g2_mma(d, al + 2 * k, bh + 2 * k, idesc, 1u);
-            g2_mma(d, ah + 2 * k, bl + 2 * k, idesc, 1u);
+            for (int k = 0; k < G2_BK / 16; ++k) {
+              g2_mma(d, ah + 2 * k, bh + 2 * k, idesc, (!first || k) ? 1u : 0u);
+              g2_mma(d, al + 2 * k, bh + 2 * k, idesc, 1u);
+              g2_mma(d, ah + 2 * k, bl + 2 * k, idesc, 1u);
+            }
+            g2_commit_both(&empty[s]);             // the stage is free in BOTH CTAs once these MMAs have read it
           }
-          g2_commit_both(&empty[s]);               // the stage is free in BOTH CTAs once these MMAs have read it
+          g2_commit_both(&acc_full[buf]);
         }
-        g2_commit_both(&acc_full[buf]);
       }
       if (trace) {
         atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 0), (unsigned long long)w0);
@@ -217,28 +227,50 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const uint32_t acc_empty_leader0 = g2_mapa(&acc_empty[0], 0);
     int ti = 0;
-    for (int t = pair; t < total; t += n_pairs, ++ti) {
+    for (int t = pair; t < total; t += n_pairs) {
       const G2Tile tl = decode(t);
-      const int buf = ti & 1;
       const int m = tl.m0 + (int)rank * 128 + quarter * 32 + lane;
-      long long t_e = 0;
-      if (trace && warp == 2) { const long long t0 = clock64(); gt_wait(&acc_full[buf], (ti >> 1) & 1, 128); t_e = clock64(); w0 += t_e - t0; }
-      else gt_wait(&acc_full[buf], (ti >> 1) & 1, 128);
-      gt_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
-      for (int c = 0; c < 8; ++c) {
-        float v[16];
-        gt_ld16(taddr + c * 16, v);
-        if (m < tl.M) {
-          const int nn = tl.n0 + half * 128 + c * 16;
-          if constexpr (gt_has_pre<Epi>::value) epi(tl.z, m, nn, v, epi.prefetch(tl.z, m, nn));
-          else epi(tl.z, m, nn, v);
+      for (int f = 0; f < n_seg; ++f, ++ti) {
+        const int buf = ti & 1;
+        long long t_e = 0;
+        if (trace && warp == 2) { const long long t0 = clock64(); gt_wait(&acc_full[buf], (ti >> 1) & 1, 128); t_e = clock64(); w0 += t_e - t0; }
+        else gt_wait(&acc_full[buf], (ti >> 1) & 1, 128);
+        gt_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
+        const bool last = f == n_seg - 1;
+        for (int c = 0; c < 8; ++c) {
+          float v[16];
+          gt_ld16(taddr + c * 16, v);
+          if (m < tl.M) {
+            const int nn = tl.n0 + half * 128 + c * 16;
+            if constexpr (SEG) {
+              // (tile-major layout private to this kernel - a thread only re-reads what it wrote: the 32 lanes of a
+              //  warp access 512 contiguous bytes per instruction instead of 32 rows)
+              float4* pb = reinterpret_cast<float4*>(seg_buf) +
+                           ((((int64_t)t * 2 + rank) * G2_EPI_WARPS + (warp - 2)) * 8 + c) * 128 + lane;
+              if (f > 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 o = pb[32 * j];
+                  v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+                }
+              }
+              if (!last) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pb[32 * j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+            }
+            if (last) {
+              if constexpr (gt_has_pre<Epi>::value) epi(tl.z, m, nn, v, epi.prefetch(tl.z, m, nn));
+              else epi(tl.z, m, nn, v);
+            }
+          }
         }
+        gt_fence_before();
+        __syncwarp();
+        if (lane == 0) g2_arrive_remote(acc_empty_leader0 + 8u * (uint32_t)buf);
+        if (trace && warp == 2) w1 += clock64() - t_e;
       }
-      gt_fence_before();
-      __syncwarp();
-      if (lane == 0) g2_arrive_remote(acc_empty_leader0 + 8u * (uint32_t)buf);
-      if (trace && warp == 2) w1 += clock64() - t_e;
     }
     if (trace && warp == 2 && lane == 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 3), (unsigned long long)w0);
@@ -257,9 +289,31 @@ static inline int g2_enabled() {
   return e ? atoi(e) : 1;
 }
 
+template <class Epi, bool SEG>
+static int launch_gemm_tc2_impl(const GemmTcMaps& maps, int pairs, int batch, int M, int N, int kp, Epi epi, cudaStream_t st,
+                                const int* m_limit, bool f16, int lo_a, int lo_b, int seg_k, float* seg_buf, int64_t seg_ld) {
+  VFR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+  cfg.blockDim = dim3(GT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = G2_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VFR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<Epi, SEG>, maps, batch, M, m_limit, kp / G2_BK, lo_a, lo_b,
+                              f16 ? GT_FMT_F16 : GT_FMT_BF16, N, seg_k / G2_BK, seg_buf, seg_ld, gt_dbg_ptr(), epi));
+  return check_launch("gemm_tc2_kernel");
+}
+
 template <class Epi>
 static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda, int64_t ldb,
-                           Epi epi, cudaStream_t st, const int* m_limit, bool f16, int lo_a, int lo_b) {
+                           Epi epi, cudaStream_t st, const int* m_limit, bool f16, int lo_a, int lo_b, int seg_k,
+                           float* seg_buf, int64_t seg_ld) {
   GemmTcMaps maps;
   for (int z = 0; z < batch; ++z) {
     int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16, G2_BK);
@@ -276,22 +330,8 @@ static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch
   }
   const int64_t tiles = (int64_t)batch * ((M + GT_BM - 1) / GT_BM) * ((N + GT_BN - 1) / GT_BN);
   const int pairs = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / 2, tiles));
-  VFR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
-  cfg.blockDim = dim3(GT_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = G2_SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VFR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<Epi>, maps, batch, M, m_limit, kp / G2_BK, lo_a, lo_b,
-                              f16 ? GT_FMT_F16 : GT_FMT_BF16, N, gt_dbg_ptr(), epi));
-  return check_launch("gemm_tc2_kernel");
+  if (seg_buf) return launch_gemm_tc2_impl<Epi, true>(maps, pairs, batch, M, N, kp, epi, st, m_limit, f16, lo_a, lo_b, seg_k, seg_buf, seg_ld);
+  return launch_gemm_tc2_impl<Epi, false>(maps, pairs, batch, M, N, kp, epi, st, m_limit, f16, lo_a, lo_b, 0, nullptr, 0);
 }
 
 }  // namespace vfr

@@ -106,6 +106,63 @@ __global__ void vis_split_rows_kernel(const float* __restrict__ x, int64_t rows,
     dst[lo_off + c] = lo;
   }
 }
+// The activations' form: ONE pass over HBM.  A warp owns a row, finds the row's max |x| over up to two column windows
+// (the second sweep over the row hits L1 / L2), derives the ROW's exponent (max 2^e in [2^13, 2^14), stored in row_exp for
+// the GEMM epilogue) and writes the split-fp16 packed row.  Window w = columns [c0[w], c0[w] + k) of x -> packed columns
+// [k0[w], k0[w] + kp).  Replaces a per-tensor amax pass (403 MB at 1.1 TB/s = 0.37 ms of a 1.5 ms K2) + a split pass.
+__global__ void vis_split_rows_auto_kernel(const float* __restrict__ x, int64_t rows, int n_win, int c0a, int c0b, int k,
+                                           int64_t ldx, int k0a, int k0b, int kp, int64_t ldo, int lo_off,
+                                           int* __restrict__ row_exp, __half* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* row = x + r * ldx;
+  const bool vec = ((reinterpret_cast<uintptr_t>(row + c0a) | reinterpret_cast<uintptr_t>(row + c0b)) & 15) == 0 && (k & 3) == 0;
+  float m = 0.f;
+  for (int w = 0; w < n_win; ++w) {
+    const float* src = row + (w ? c0b : c0a);
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int c = lane; c < (k >> 2); c += 32) {
+        const float4 v = s4[c];
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      }
+    } else {
+      for (int c = lane; c < k; c += 32) m = fmaxf(m, fabsf(src[c]));
+    }
+  }
+  m = warp_max(m);
+  int ex = 0;
+  if (m > 0.f && m < CUDART_INF_F) ex = max(-100, min(100, 13 - ilogbf(m)));
+  if (lane == 0) row_exp[r] = ex;
+  for (int w = 0; w < n_win; ++w) {
+    const float* src = row + (w ? c0b : c0a);
+    __half* dst = out + r * ldo + (w ? k0b : k0a);
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int c = lane; c < (kp >> 2); c += 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * c < k) v = s4[c];
+        __half h[4], l[4];
+        split2h(scalbnf(v.x, ex), h[0], l[0]);
+        split2h(scalbnf(v.y, ex), h[1], l[1]);
+        split2h(scalbnf(v.z, ex), h[2], l[2]);
+        split2h(scalbnf(v.w, ex), h[3], l[3]);
+        *reinterpret_cast<uint2*>(dst + 4 * c) = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                                                            (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+        *reinterpret_cast<uint2*>(dst + lo_off + 4 * c) = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                                                                     (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+      }
+    } else {
+      for (int c = lane; c < kp; c += 32) {
+        __half hi, lo;
+        split2h(c < k ? scalbnf(src[c], ex) : 0.f, hi, lo);
+        dst[c] = hi;
+        dst[lo_off + c] = lo;
+      }
+    }
+  }
+}
 __global__ void vis_zero_rows_kernel(__half* __restrict__ out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = __float2half_rn(0.f);
@@ -138,7 +195,8 @@ __global__ void vis_clip_meta_kernel(const int32_t* __restrict__ vid_off, int64_
 struct EpiVis1 {
   float* hidden;            // [M, hid]
   int hid;
-  const int* ea;            // exponent of the A operand
+  const int* ea;            // exponent of the A operand: ea[m] when ea_row, else ea[0]
+  int ea_row;
   const int* ew;            // exponent of W1
   const float* b1;          // bias (used when add == nullptr)
   const float* add;         // optional per-VIDEO term [V, hid] (context product + bias), row = clip_vid[m]
@@ -148,7 +206,7 @@ struct EpiVis1 {
   const float* w1t;         // [hid, 2]
   unsigned* hmax;           // max of the hidden activations (bit pattern), may be null
   __device__ __forceinline__ void operator()(int, int m, int n0, const float (&v)[16]) const {
-    const float s = scalbnf(1.f, -(*ea + *ew));
+    const float s = scalbnf(1.f, -(ea[ea_row ? m : 0] + *ew));
     const float t0 = tef ? tef[m * tef_ld] : 0.f, t1 = tef ? tef[m * tef_ld + 1] : 0.f;
     const float* arow = add ? add + (int64_t)clip_vid[m] * hid : nullptr;
     float mx = 0.f;
@@ -174,11 +232,12 @@ struct EpiVisOut {
   float* out;
   int64_t ldo;
   int N;
-  const int* ea;
+  const int* ea;            // ea[m] when ea_row, else ea[0]
+  int ea_row;
   const int* ew;
   const float* bias;
   __device__ __forceinline__ void operator()(int, int m, int n0, const float (&v)[16]) const {
-    const float s = scalbnf(1.f, -(*ea + *ew));
+    const float s = scalbnf(1.f, -(ea[ea_row ? m : 0] + *ew));
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int n = n0 + j;
@@ -196,8 +255,10 @@ struct VisWs {
   float* cvec;       // [vids, hid]
   int32_t* clip_vid; // [rows]
   float2* tef;       // [rows]
-  unsigned* amax;    // [2] : input operand, hidden
-  int* exps;         // [2]
+  unsigned* amax;    // [2] : (unused), hidden
+  int* exps;         // [2] : (unused), hidden
+  int* row_exp;      // [rows] exponents of the clip rows
+  int* vid_exp;      // [vids] exponents of the context rows (split form)
   float* flush;      // [max(rows, vids), N1] fp32: K-segmented accumulation of the layer-1 GEMMs (vfr_gemm_tc.cuh)
   size_t bytes;
 };
@@ -224,7 +285,10 @@ static VisWs vis_ws(void* base, const VisDims& d, int64_t rows, int64_t vids, bo
   w.tef = reinterpret_cast<float2*>(take(split ? (size_t)rows * 8 : 0));
   w.amax = reinterpret_cast<unsigned*>(take(2 * sizeof(unsigned)));
   w.exps = reinterpret_cast<int*>(take(2 * sizeof(int)));
-  w.flush = reinterpret_cast<float*>(take((size_t)std::max(rows, split ? vids : (int64_t)0) * d.N1 * 4));
+  w.row_exp = reinterpret_cast<int*>(take((size_t)rows * 4));
+  w.vid_exp = reinterpret_cast<int*>(take(split ? (size_t)vids * 4 : 0));
+  // (whole 256-row tiles: the CTA-pair kernel keeps a tile's partial sums in a tile-major layout)
+  w.flush = reinterpret_cast<float*>(take((size_t)((std::max(rows, split ? vids : (int64_t)0) + 255) / 256 * 256) * d.N1 * 4));
   w.bytes = (size_t)(p - reinterpret_cast<uint8_t*>(base));
   return w;
 }
@@ -247,7 +311,7 @@ static int vis_layer2(const VisDims& d, const VisBlob& blob, const VisWs& w, int
   if (rc) return rc;
   const void* a[1] = {w.ah};
   const void* b[1] = {blob.w2};
-  EpiVisOut epi{out, d.dim, d.dim, w.exps + 1, blob.exps + 1, blob.b2};
+  EpiVisOut epi{out, d.dim, d.dim, w.exps + 1, 0, blob.exps + 1, blob.b2};
   return launch_gemm_tc(a, b, 1, (int)rows, d.dim, d.Hp, 2 * (int64_t)d.Hp, 2 * (int64_t)d.Hp, epi, st, nullptr, true);
 }
 
@@ -310,20 +374,14 @@ extern "C" int vfr_visual_embed_tc(const float* x, int64_t n_rows, int feat_dim,
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ldx = 2 * (int64_t)feat_dim + 2;
   VFR_CUDA(cudaMemsetAsync(w.amax, 0, 2 * sizeof(unsigned), st));
-  int rc = vis_amax(x, n_rows, 2 * feat_dim, ldx, w.amax, st);
-  if (rc) return rc;
-  vis_exp_kernel<<<1, 1, 0, st>>>(w.amax, w.exps);
-  rc = check_launch("vis_exp_kernel");
-  if (rc) return rc;
-  const unsigned g = (unsigned)((n_rows + 7) / 8);
-  vis_split_rows_kernel<<<g, 256, 0, st>>>(x, n_rows, 0, feat_dim, ldx, 0, d.Fp, 2 * (int64_t)d.K1, d.K1, w.exps, w.a1);
-  vis_split_rows_kernel<<<g, 256, 0, st>>>(x, n_rows, feat_dim, feat_dim, ldx, d.Fp, d.Fp, 2 * (int64_t)d.K1, d.K1, w.exps, w.a1);
-  rc = check_launch("vis_split_rows_kernel");
+  vis_split_rows_auto_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(x, n_rows, 2, 0, feat_dim, feat_dim, ldx, 0, d.Fp, d.Fp,
+                                                                           2 * (int64_t)d.K1, d.K1, w.row_exp, w.a1);
+  int rc = check_launch("vis_split_rows_auto_kernel");
   if (rc) return rc;
   {
     const void* a[1] = {w.a1};
     const void* b[1] = {blob.w1};
-    EpiVis1 epi{w.hidden, hid, w.exps, blob.exps, blob.b1, nullptr, nullptr, x + 2 * feat_dim, ldx, blob.w1t, w.amax + 1};
+    EpiVis1 epi{w.hidden, hid, w.row_exp, 1, blob.exps, blob.b1, nullptr, nullptr, x + 2 * feat_dim, ldx, blob.w1t, w.amax + 1};
     const int fk = vis_flush_k();
     rc = launch_gemm_tc(a, b, 1, (int)n_rows, hid, d.K1, 2 * (int64_t)d.K1, 2 * (int64_t)d.K1, epi, st, nullptr, true, 0, 0, fk,
                         fk ? w.flush : nullptr, d.N1);
@@ -344,27 +402,21 @@ extern "C" int vfr_visual_embed_split(const float* seg, const float* ctx, const 
   const VisWs w = vis_ws(workspace, d, n_clips, n_videos, true);
   cudaStream_t st = (cudaStream_t)stream;
   VFR_CUDA(cudaMemsetAsync(w.amax, 0, 2 * sizeof(unsigned), st));
-  int rc = vis_amax(seg, n_clips, feat_dim, feat_dim, w.amax, st);
-  if (rc) return rc;
-  rc = vis_amax(ctx, n_videos, feat_dim, feat_dim, w.amax, st);      // one exponent for both operands
-  if (rc) return rc;
-  vis_exp_kernel<<<1, 1, 0, st>>>(w.amax, w.exps);
-  rc = check_launch("vis_exp_kernel");
-  if (rc) return rc;
+  int rc;
   vis_clip_meta_kernel<<<(unsigned)((n_videos + 255) / 256), 256, 0, st>>>(vid_off, n_videos, w.clip_vid, w.tef);
   rc = check_launch("vis_clip_meta_kernel");
   if (rc) return rc;
-  vis_split_rows_kernel<<<(unsigned)((n_clips + 7) / 8), 256, 0, st>>>(seg, n_clips, 0, feat_dim, feat_dim, 0, d.Fp,
-                                                                       2 * (int64_t)d.Fp, d.Fp, w.exps, w.a1);
-  vis_split_rows_kernel<<<(unsigned)((n_videos + 7) / 8), 256, 0, st>>>(ctx, n_videos, 0, feat_dim, feat_dim, 0, d.Fp,
-                                                                        2 * (int64_t)d.Fp, d.Fp, w.exps, w.ac);
-  rc = check_launch("vis_split_rows_kernel");
+  vis_split_rows_auto_kernel<<<(unsigned)((n_clips + 7) / 8), 256, 0, st>>>(seg, n_clips, 1, 0, 0, feat_dim, feat_dim, 0, 0, d.Fp,
+                                                                            2 * (int64_t)d.Fp, d.Fp, w.row_exp, w.a1);
+  vis_split_rows_auto_kernel<<<(unsigned)((n_videos + 7) / 8), 256, 0, st>>>(ctx, n_videos, 1, 0, 0, feat_dim, feat_dim, 0, 0, d.Fp,
+                                                                             2 * (int64_t)d.Fp, d.Fp, w.vid_exp, w.ac);
+  rc = check_launch("vis_split_rows_auto_kernel");
   if (rc) return rc;
   {
     // once per VIDEO: cvec = ctx . W1[:, F:2F]^T + b1   (the K-segment [Fp, 2 Fp) of the packed W1)
     const void* a[1] = {w.ac};
     const void* b[1] = {blob.w1 + d.Fp};
-    EpiVisOut epi{w.cvec, hid, hid, w.exps, blob.exps, blob.b1};
+    EpiVisOut epi{w.cvec, hid, hid, w.vid_exp, 1, blob.exps, blob.b1};
     const int fk = vis_flush_k();
     rc = launch_gemm_tc(a, b, 1, (int)n_videos, hid, d.Fp, 2 * (int64_t)d.Fp, 2 * (int64_t)d.K1, epi, st, nullptr, true, d.Fp,
                         d.K1, fk, fk ? w.flush : nullptr, d.N1);
@@ -374,7 +426,7 @@ extern "C" int vfr_visual_embed_split(const float* seg, const float* ctx, const 
     // per clip: seg . W1[:, :F]^T + cvec[video] + tef . W1[:, 2F:]^T -> relu
     const void* a[1] = {w.a1};
     const void* b[1] = {blob.w1};
-    EpiVis1 epi{w.hidden, hid, w.exps, blob.exps, blob.b1, w.cvec, w.clip_vid, reinterpret_cast<const float*>(w.tef), 2,
+    EpiVis1 epi{w.hidden, hid, w.row_exp, 1, blob.exps, blob.b1, w.cvec, w.clip_vid, reinterpret_cast<const float*>(w.tef), 2,
                 blob.w1t, w.amax + 1};
     const int fk = vis_flush_k();
     rc = launch_gemm_tc(a, b, 1, (int)n_clips, hid, d.Fp, 2 * (int64_t)d.Fp, 2 * (int64_t)d.K1, epi, st, nullptr, true, d.Fp,
