@@ -23,3 +23,16 @@ with torch.no_grad():
         model.embed_clips(seg, ctx, vid_off)
     b.record(); torch.cuda.synchronize()
 print("V", V, "ms", a.elapsed_time(b) / 5)
+if os.environ.get("K2_DBG"):
+    # tile phases of the CTA-pair GEMMs of one call (sums over the three GEMMs; the clip GEMM dominates)
+    dbg = torch.zeros(8, dtype=torch.int64, device=dev)
+    os.environ["VFR_GEMM_DBG"] = hex(dbg.data_ptr())
+    with torch.no_grad():
+        model.embed_clips(seg, ctx, vid_off)
+    torch.cuda.synchronize()
+    os.environ.pop("VFR_GEMM_DBG")
+    d = dbg.cpu().numpy().astype(np.float64)
+    n = d[6]
+    print("work items %d over %d pair-launches; cycles per item: MMA issuer loop %.0f (waits: free accumulator %.0f, operands %.0f) | "
+          "epilogue warp: wait for accumulator %.0f, work %.0f | producer waits for free stages %.0f" % (
+              n, d[7], d[2] / n, d[0] / n, d[1] / n, d[3] / n, d[4] / n, d[5] / n))

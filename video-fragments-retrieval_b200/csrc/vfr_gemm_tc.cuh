@@ -125,6 +125,14 @@ struct gt_has_pre : std::false_type {};
 template <class E>
 struct gt_has_pre<E, std::void_t<typename E::Pre>> : std::true_type {};
 
+// an epilogue functor that declares `struct Row` and `Row row(z, m) const` gets its per-row operands (scales, gathered
+// pointers ...) computed once per tile row instead of once per 16-column group:  operator()(z, m, n0, v, row)
+// (CTA-pair kernel only)
+template <class E, class = void>
+struct gt_has_row : std::false_type {};
+template <class E>
+struct gt_has_row<E, std::void_t<typename E::Row>> : std::true_type {};
+
 constexpr uint32_t GT_FMT_BF16 = (1u << 7) | (1u << 10);
 constexpr uint32_t GT_FMT_F16 = 0u;
 

@@ -89,6 +89,11 @@ __device__ __forceinline__ void g2_commit_both(uint64_t* bar) {
 }
 
 struct G2Tile { int z, m0, n0, M; };
+struct G2NoRow {};
+template <class E, class = void>
+struct G2RowOf { using type = G2NoRow; };
+template <class E>
+struct G2RowOf<E, std::void_t<typename E::Row>> { using type = typename E::Row; };
 
 // SEG: K-segmented accumulation (see gemm_tc_kernel) - every seg_chunks K chunks are one work item with its own TMEM
 // buffer; the epilogue warps add item f to the fp32 partial sums of the tile in seg_buf (round-to-nearest adds; each
@@ -232,39 +237,61 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
       const int m = tl.m0 + (int)rank * 128 + quarter * 32 + lane;
       for (int f = 0; f < n_seg; ++f, ++ti) {
         const int buf = ti & 1;
+        // (SEG: tile-major fp32 partial sums private to this kernel - a thread only re-reads what it wrote, and the 32
+        //  lanes of a warp access 512 contiguous bytes per instruction.  They do not depend on the accumulator, so the
+        //  first two column groups are requested before the wait and the rest two groups ahead.)
+        float4* pb = nullptr;
+        float4 o[2][4];
+        const bool add_prev = SEG && f > 0 && m < tl.M;
+        if constexpr (SEG) {
+          pb = reinterpret_cast<float4*>(seg_buf) + (((int64_t)t * 2 + rank) * G2_EPI_WARPS + (warp - 2)) * 8 * 128 + lane;
+          if (add_prev) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { o[0][j] = pb[32 * j]; o[1][j] = pb[128 + 32 * j]; }
+          }
+        }
         long long t_e = 0;
         if (trace && warp == 2) { const long long t0 = clock64(); gt_wait(&acc_full[buf], (ti >> 1) & 1, 128); t_e = clock64(); w0 += t_e - t0; }
         else gt_wait(&acc_full[buf], (ti >> 1) & 1, 128);
         gt_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
         const bool last = f == n_seg - 1;
-        for (int c = 0; c < 8; ++c) {
+        typename G2RowOf<Epi>::type rowctx{};
+        if constexpr (gt_has_row<Epi>::value) if (last && m < tl.M) rowctx = epi.row(tl.z, m);
+        auto group = [&](int c, auto slot_c) {
+          constexpr int slot = decltype(slot_c)::value;
           float v[16];
           gt_ld16(taddr + c * 16, v);
           if (m < tl.M) {
             const int nn = tl.n0 + half * 128 + c * 16;
             if constexpr (SEG) {
-              // (tile-major layout private to this kernel - a thread only re-reads what it wrote: the 32 lanes of a
-              //  warp access 512 contiguous bytes per instruction instead of 32 rows)
-              float4* pb = reinterpret_cast<float4*>(seg_buf) +
-                           ((((int64_t)t * 2 + rank) * G2_EPI_WARPS + (warp - 2)) * 8 + c) * 128 + lane;
-              if (f > 0) {
+              if (add_prev) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float4 o = pb[32 * j];
-                  v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+                  const float4 q = o[slot][j];
+                  v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+                }
+                if (c + 2 < 8) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) o[slot][j] = pb[(c + 2) * 128 + 32 * j];
                 }
               }
               if (!last) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) pb[32 * j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 4; ++j) pb[c * 128 + 32 * j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               }
             }
             if (last) {
-              if constexpr (gt_has_pre<Epi>::value) epi(tl.z, m, nn, v, epi.prefetch(tl.z, m, nn));
+              if constexpr (gt_has_row<Epi>::value) epi(tl.z, m, nn, v, rowctx);
+              else if constexpr (gt_has_pre<Epi>::value) epi(tl.z, m, nn, v, epi.prefetch(tl.z, m, nn));
               else epi(tl.z, m, nn, v);
             }
           }
+        };
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          group(c, std::integral_constant<int, 0>{});
+          group(c + 1, std::integral_constant<int, 1>{});
         }
         gt_fence_before();
         __syncwarp();

@@ -205,21 +205,53 @@ struct EpiVis1 {
   int64_t tef_ld;
   const float* w1t;         // [hid, 2]
   unsigned* hmax;           // max of the hidden activations (bit pattern), may be null
-  __device__ __forceinline__ void operator()(int, int m, int n0, const float (&v)[16]) const {
-    const float s = scalbnf(1.f, -(ea[ea_row ? m : 0] + *ew));
-    const float t0 = tef ? tef[m * tef_ld] : 0.f, t1 = tef ? tef[m * tef_ld + 1] : 0.f;
-    const float* arow = add ? add + (int64_t)clip_vid[m] * hid : nullptr;
+  struct Row {              // what a row needs for all of its column groups
+    float s, t0, t1;
+    const float* arow;
+  };
+  __device__ __forceinline__ Row row(int, int m) const {
+    Row r;
+    r.s = scalbnf(1.f, -(ea[ea_row ? m : 0] + *ew));
+    r.t0 = tef ? tef[m * tef_ld] : 0.f;
+    r.t1 = tef ? tef[m * tef_ld + 1] : 0.f;
+    r.arow = add ? add + (int64_t)clip_vid[m] * hid : nullptr;
+    return r;
+  }
+  __device__ __forceinline__ void operator()(int z, int m, int n0, const float (&v)[16]) const { (*this)(z, m, n0, v, row(z, m)); }
+  __device__ __forceinline__ void operator()(int, int m, int n0, const float (&v)[16], const Row& rw) const {
+    const float s = rw.s, t0 = rw.t0, t1 = rw.t1;
+    const float* arow = rw.arow;
     float mx = 0.f;
+    if ((hid & 3) == 0) {
+      // 16-byte accesses (every array here is 16-byte aligned and hid % 4 == 0): a thread owns a row, so each access of a
+      // warp touches 32 rows - four columns per instruction instead of one
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int n = n0 + j;
-      if (n < hid) {
-        float x = __fmaf_rn(v[j], s, arow ? arow[n] : __ldg(b1 + n));
-        x = __fmaf_rn(t0, __ldg(w1t + 2 * n), x);
-        x = __fmaf_rn(t1, __ldg(w1t + 2 * n + 1), x);
-        x = fmaxf(x, 0.f);
-        hidden[(int64_t)m * hid + n] = x;
-        mx = fmaxf(mx, x);
+      for (int g = 0; g < 4; ++g) {
+        const int n = n0 + 4 * g;
+        if (n < hid) {
+          const float4 a = arow ? *reinterpret_cast<const float4*>(arow + n) : __ldg(reinterpret_cast<const float4*>(b1 + n));
+          const float4 wa = __ldg(reinterpret_cast<const float4*>(w1t + 2 * n)), wb = __ldg(reinterpret_cast<const float4*>(w1t + 2 * n + 4));
+          float4 x;
+          x.x = fmaxf(__fmaf_rn(t1, wa.y, __fmaf_rn(t0, wa.x, __fmaf_rn(v[4 * g + 0], s, a.x))), 0.f);
+          x.y = fmaxf(__fmaf_rn(t1, wa.w, __fmaf_rn(t0, wa.z, __fmaf_rn(v[4 * g + 1], s, a.y))), 0.f);
+          x.z = fmaxf(__fmaf_rn(t1, wb.y, __fmaf_rn(t0, wb.x, __fmaf_rn(v[4 * g + 2], s, a.z))), 0.f);
+          x.w = fmaxf(__fmaf_rn(t1, wb.w, __fmaf_rn(t0, wb.z, __fmaf_rn(v[4 * g + 3], s, a.w))), 0.f);
+          *reinterpret_cast<float4*>(hidden + (int64_t)m * hid + n) = x;
+          mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + j;
+        if (n < hid) {
+          float x = __fmaf_rn(v[j], s, arow ? arow[n] : __ldg(b1 + n));
+          x = __fmaf_rn(t0, __ldg(w1t + 2 * n), x);
+          x = __fmaf_rn(t1, __ldg(w1t + 2 * n + 1), x);
+          x = fmaxf(x, 0.f);
+          hidden[(int64_t)m * hid + n] = x;
+          mx = fmaxf(mx, x);
+        }
       }
     }
     // (a plain read first: the running maximum settles after a few tiles, and 768 k atomics on one address per 24 k rows
@@ -238,6 +270,19 @@ struct EpiVisOut {
   const float* bias;
   __device__ __forceinline__ void operator()(int, int m, int n0, const float (&v)[16]) const {
     const float s = scalbnf(1.f, -(ea[ea_row ? m : 0] + *ew));
+    if (((N | (int)ldo) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n0 + 4 * g;
+        if (n < N) {
+          const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(out + (int64_t)m * ldo + n) =
+              make_float4(__fmaf_rn(v[4 * g], s, b.x), __fmaf_rn(v[4 * g + 1], s, b.y), __fmaf_rn(v[4 * g + 2], s, b.z),
+                          __fmaf_rn(v[4 * g + 3], s, b.w));
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int n = n0 + j;
