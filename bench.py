@@ -286,7 +286,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, world):
@@ -650,14 +650,26 @@ def run_ours(args):
             "filter_stats": dict(stats or {}, n_fixups_value_steps=fixups_value, n_fixups_total=retr.n_fixups),
             "parity_check": parity, "cpu_baseline": cpu_baseline, "library_baseline": library, "checksum_top1": checksum,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     if parity is not None and not parity.get("ok"):
         sys.exit(3)
 
 
+_JSON_FD = 1
+
+
+def _emit(line):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print there (NCCL's version banner ...)
+    # goes to stderr
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
