@@ -670,10 +670,21 @@ __device__ __forceinline__ void sl_sample(const float (&v)[64], float (&a)[SL_J]
 // BIG: the K-streaming variant for D + 3 > 128 (R = 2, CL = 1): every 64-column chunk of the two query tiles travels
 // through the ring together with the bank tile's chunk; a tile's two accumulators are committed after the last chunk
 // (no ping-pong - the epilogue's ~700-cycle read of a buffer is small against the >= 3 x 4 MMAs x 2 of a tile).
-template <int R, int CL, int MODE, bool BIG = false>
+// NB = 4 (opt-in, VFR_SEL_NB=4; measured SLOWER): the 512 TMEM columns as FOUR accumulators of 128 columns, a job = one query
+// tile x one HALF of a bank tile (MMA N = 128).  The idea: a buffer's round trip - MMAs issued -> commit seen by the epilogue
+// (~550 cycles) -> its four warps have read it (~750 median, 1 200 p90) -> the issuer sees the release (~450) - is ~3 000
+// cycles, i.e. 1 500 per job with two buffers against 896 of MMA (tools/timeline_sel.py); four buffers would spread the same
+// latencies over four jobs in flight.  Measured on B200 (37 888 queries x 6 M clips, same box): the seven N = 128 MMAs of a
+// half job take ~855 cycles - as long as the seven N = 256 MMAs of a whole one (the A operand's 128 x 16 slice is re-read
+// per MMA; in isolation, with four repeating slices, N = 128 runs at its 64-cycle floor: tools/ubench_tc.cu) - so the scan
+// goes from 46 to 70 ms.  Kept as evidence that the N = 256 job is already the cheapest form of this loop.
+template <int R, int CL, int MODE, bool BIG = false, int NB = 2>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const SlParams p) {
   static_assert(!BIG || (R == 2 && CL == 1), "the K-streaming variant serves two query tiles per CTA, no cluster");
+  static_assert(NB == 2 || (NB == 4 && !BIG && CL == 1), "four accumulators: plain kernel only");
+  constexpr bool HALF = NB == 4;
+  constexpr int JOB_N = HALF ? SL_N / 2 : SL_N;       // accumulator columns of a job
   constexpr int STAGES = BIG ? SL_BIG_STAGES : SlCfg<R>::STAGES;
   constexpr int STAGE_BYTES = BIG ? SL_BIG_STAGE : SL_B_CHUNK;
   extern __shared__ uint8_t smem_raw[];
@@ -684,9 +695,9 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint64_t* full = bars;                        // [STAGES]
   uint64_t* empty = bars + STAGES;              // [STAGES]
   uint64_t* a_full = bars + 2 * STAGES;         // [1]
-  uint64_t* tmem_full = a_full + 1;             // [2]
-  uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_full = a_full + 1;             // [NB]
+  uint64_t* tmem_empty = tmem_full + 4;         // [NB]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -700,7 +711,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     mbar_init(a_full, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], SL_SET_WARPS); }
+    for (int b = 0; b < NB; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], SL_SET_WARPS); }
     fence_barrier_init();
   }
   const int crank = (CL == 2) ? sl_cluster_rank() : 0;
@@ -779,8 +790,8 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     } else
     if (lane == 0 && n_my_tiles > 0) {
-      // kind::f16, fp16 x fp16 -> fp32, K-major A and B, N = 256, M = 128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(SL_N >> 3) << 17) | ((uint32_t)(SL_M >> 4) << 24);
+      // kind::f16, fp16 x fp16 -> fp32, K-major A and B, N = 256 (128 with four accumulators), M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(JOB_N >> 3) << 17) | ((uint32_t)(SL_M >> 4) << 24);
       sl_wait(a_full, 0, p.wait_mode);
       sl_fence_after();
       // A barrier wait issued right after a tcgen05.commit stalls the thread ~250 cycles (until the MMAs ahead
@@ -790,19 +801,28 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int s0 = 0, s1 = 0, ph0 = 0, ph1 = 0;
       int pend_buf = -1, pend_s0 = 0, pend_s1 = 0;
       bool pend_release = false;
-      const int n_jobs = n_my_tiles * R;
+      constexpr int JPT = (HALF ? 2 : 1) * R;     // jobs per bank tile
+      const int n_jobs = n_my_tiles * JPT;
       for (int job = 0; job < n_jobs; ++job) {
-        const int r = (R == 2) ? (job & 1) : 0;
-        const int buf = job & 1;                   // R = 2: buffer = query tile; R = 1: buffer = tile parity
+        // two accumulators: buffer = query tile (R = 2) or tile parity (R = 1).  Four: a tile's jobs go (r0, h0), (r1, h0),
+        // (r0, h1), (r1, h1) - the sets get their work evenly spaced - on buffer 2 r + h; R = 1: tile parity s, 2 s + h.
+        int r, h, buf, use;
+        bool first, last;
+        if (HALF) {
+          if (R == 2) { const int j4 = job & 3; r = j4 & 1; h = j4 >> 1; buf = 2 * r + h; use = job >> 2; first = j4 == 0; last = j4 == 3; }
+          else { const int tt = job >> 1; r = 0; h = job & 1; buf = 2 * (tt & 1) + h; use = tt >> 1; first = h == 0; last = h == 1; }
+        } else {
+          r = (R == 2) ? (job & 1) : 0; h = 0; buf = job & 1; use = job >> 1; first = r == 0; last = r == R - 1;
+        }
         const long long tm0 = p.dbg ? clock64() : 0;
-        if (r == 0) {
+        if (first) {
           s0 = it % STAGES; ph0 = (it / STAGES) & 1;
           s1 = (it + 1) % STAGES; ph1 = ((it + 1) / STAGES) & 1;
           it += b_chunks;
         }
-        const uint32_t pe = ((job >> 1) & 1) ^ 1;
+        const uint32_t pe = (use & 1) ^ 1;
         bool ready = sl_test(&tmem_empty[buf], pe);
-        if (r == 0) {
+        if (first) {
           ready = ready && sl_test(&full[s0], ph0);
           if (b_chunks == 2) ready = ready && sl_test(&full[s1], ph1);
         }
@@ -812,7 +832,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (pend_release) { sl_release<CL>(&empty[pend_s0]); if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]); }
             pend_buf = -1;
           }
-          if (r == 0) {
+          if (first) {
             sl_wait(&full[s0], ph0, p.wait_mode);
             if (b_chunks == 2) sl_wait(&full[s1], ph1, p.wait_mode);
           }
@@ -824,12 +844,12 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (pend_release) { sl_release<CL>(&empty[pend_s0]); if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]); }
         }
         const long long tm1 = p.dbg ? clock64() : 0;
-        const uint32_t d_tmem = tmem_base + (uint32_t)buf * SL_N;
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * JOB_N;
         uint32_t accumulate = 0;
         for (int c = 0; c < b_chunks; ++c) {
           const int ks = (c == 0) ? min(p.ksteps, 4) : (p.ksteps - 4);
           const uint64_t adesc = sl_desc(smem_a + (r * 2 + c) * SL_A_CHUNK);
-          const uint64_t bdesc = sl_desc(smem_b + (c ? s1 : s0) * SL_B_CHUNK);
+          const uint64_t bdesc = sl_desc(smem_b + (c ? s1 : s0) * SL_B_CHUNK + h * (SL_B_CHUNK / 2));
           for (int k = 0; k < ks; ++k) {
             sl_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
             accumulate = 1;
@@ -838,7 +858,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         pend_buf = buf;
         pend_s0 = s0;
         pend_s1 = s1;
-        pend_release = (r == R - 1);
+        pend_release = last;
         const int job0 = n_jobs - 256;
         if (p.dbg && blockIdx.x == 0 && job >= job0) {
           long long* d = p.dbg + (0 * 256 + (job - job0)) * 4;
@@ -871,6 +891,28 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       for (int i = 0; i < SL_J; ++i) a[i] = CUDART_INF_F;
       int visit = 0;
       for (int t = t_first; t < n_my_tiles; t += t_step, ++visit) {
+        if constexpr (HALF) {
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            const int buf = 2 * set + h;
+            const uint32_t la = lane_addr + (uint32_t)h * JOB_N;
+            sl_wait(&tmem_full[buf], visit & 1, p.wait_mode);
+            sl_fence_after();
+            float va[64], vb[64];
+            sl_ld32(la, va, 0);
+            sl_ld32(la + 32, va, 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            sl_ld32(la + 64, vb, 0);
+            sl_ld32(la + 96, vb, 32);
+            sl_sample(va, a);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            sl_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            sl_sample(vb, a);
+          }
+          continue;
+        }
         sl_wait(&tmem_full[set], visit & 1, p.wait_mode);
         sl_fence_after();
         float va[64], vb[64];
@@ -935,6 +977,36 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           st.thr = sl_threshold(tg, st.band2, st.nq, st.scale);
         }
       }
+      if constexpr (HALF) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int buf = 2 * set + h;
+          const uint32_t la = lane_addr + (uint32_t)h * JOB_N;
+          const long long te0 = p.dbg ? clock64() : 0;
+          sl_wait(&tmem_full[buf], visit & 1, p.wait_mode);
+          sl_fence_after();
+          const long long te1 = p.dbg ? clock64() : 0;
+          float va[64], vb[64];
+          sl_ld32(la, va, 0);
+          sl_ld32(la + 32, va, 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          sl_ld32(la + 64, vb, 0);             // in flight while the first 64 columns are processed
+          sl_ld32(la + 96, vb, 32);
+          sl_process(va, h * JOB_N, st, p);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // the whole accumulator has been read: hand it back before the last 64 columns (in registers) are looked at
+          sl_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+          const long long te2 = p.dbg ? clock64() : 0;
+          sl_process(vb, h * JOB_N + 64, st, p);
+          const int visit0 = 2 * ((n_my_tiles - t_first + t_step - 1) / t_step) - 128;
+          if (p.dbg && blockIdx.x == 0 && 2 * visit + h >= visit0 && lane == 0) {
+            long long* d = p.dbg + ((1 + ew) * 256 + (2 * visit + h - visit0)) * 4;
+            d[0] = te0; d[1] = te1; d[2] = te2; d[3] = clock64();
+          }
+        }
+      } else {
       const long long te0 = p.dbg ? clock64() : 0;
       sl_wait(&tmem_full[set], visit & 1, p.wait_mode);
       sl_fence_after();
@@ -966,6 +1038,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (p.dbg && blockIdx.x == 0 && visit >= visit0 && lane == 0) {
         long long* d = p.dbg + ((1 + ew) * 256 + (visit - visit0)) * 4;
         d[0] = te0; d[1] = te1; d[2] = te2; d[3] = clock64();
+      }
       }
 
       // Every compaction refreshes the list's threshold (the k-th smallest key seen so far); a stale threshold costs
@@ -1757,11 +1830,13 @@ static int sl_launch_filter(const SlPlan& pl, const SlParams& p, const CUtensorM
   const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
   void (*kern)(CUtensorMap, CUtensorMap, SlParams) = nullptr;
   uint32_t smem_bytes = 0;
+  // accumulators per CTA: two of 256 columns (default); VFR_SEL_NB=4: four of 128 (measured slower, see the kernel)
+  static const int nb = [] { const char* e = getenv("VFR_SEL_NB"); return (e && atoi(e) == 4) ? 4 : 2; }();
   if (pl.big) { kern = sl_filter_kernel<2, 1, MODE, true>; smem_bytes = SL_BIG_SMEM; }
   else if (pl.R == 2 && CL == 2) { kern = sl_filter_kernel<2, 2, 0>; smem_bytes = SlCfg<2>::SMEM; }
-  else if (pl.R == 2) { kern = sl_filter_kernel<2, 1, MODE>; smem_bytes = SlCfg<2>::SMEM; }
+  else if (pl.R == 2) { kern = (nb == 4) ? sl_filter_kernel<2, 1, MODE, false, 4> : sl_filter_kernel<2, 1, MODE>; smem_bytes = SlCfg<2>::SMEM; }
   else if (CL == 2) { kern = sl_filter_kernel<1, 2, 0>; smem_bytes = SlCfg<1>::SMEM; }
-  else { kern = sl_filter_kernel<1, 1, MODE>; smem_bytes = SlCfg<1>::SMEM; }
+  else { kern = (nb == 4) ? sl_filter_kernel<1, 1, MODE, false, 4> : sl_filter_kernel<1, 1, MODE>; smem_bytes = SlCfg<1>::SMEM; }
   VFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
