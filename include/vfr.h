@@ -234,6 +234,12 @@ int vfr_sel_refine(const float* bank, const int32_t* vid_off, const int64_t* mom
                    int64_t n_clips, int n_max, int dim, void* query_packed, const float* queries, int64_t n_queries,
                    int k, int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, int n_split,
                    vfr_stream_t stream);
+/* vfr_sel_refine for the queries [q_begin, q_begin + q_count) only (rows q of out_scores / out_ids): finished rows can
+ * travel to the host while the rest is still being re-scored (what vfr_search_host does). */
+int vfr_sel_refine_range(const float* bank, const int32_t* vid_off, const int64_t* mom_off, int64_t n_videos,
+                         int64_t n_clips, int n_max, int dim, void* query_packed, const float* queries, int64_t n_queries,
+                         int k, int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, int n_split,
+                         int64_t q_begin, int64_t q_count, vfr_stream_t stream);
 
 /* ---- K5 : integer-exact temporal IoU, ground truth, rank statistics -------------------------
  * times int32 [Q, n_annot, 2] inclusive (start, end), absent annotators = (-1, -1);

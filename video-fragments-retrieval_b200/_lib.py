@@ -88,6 +88,7 @@ PROTOTYPES = {
     "vfr_sel_bound_get": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p]),
     "vfr_sel_bound_put": (_i, [_p, _l, _l, _i, _i, _p, _i, _p, _p]),
     "vfr_sel_refine": (_i, [_p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _p]),
+    "vfr_sel_refine_range": (_i, [_p, _p, _p, _l, _l, _i, _i, _p, _p, _l, _i, _l, _p, _p, _p, _i, _l, _l, _p]),
     "vfr_gt_select": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p, _p]),
     "vfr_rank_order": (_i, [_p, _i, _p, _l, _i, _p, _p]),
     "vfr_single_metrics": (_i, [_p, _i, _p, _p, _i, _p, _i, _l, _p, _p, _p, _p, _p]),

@@ -133,6 +133,14 @@ struct gt_has_row : std::false_type {};
 template <class E>
 struct gt_has_row<E, std::void_t<typename E::Row>> : std::true_type {};
 
+// an epilogue functor that declares `struct After` gets  after(z, m_warp, n0, lane)  called by ALL lanes of the warp after
+// every 16-column group of the final item (m_warp = the warp's first row; rows past M included) - warp-cooperative work
+// that follows from the group just written (CTA-pair kernel only)
+template <class E, class = void>
+struct gt_has_after : std::false_type {};
+template <class E>
+struct gt_has_after<E, std::void_t<typename E::After>> : std::true_type {};
+
 constexpr uint32_t GT_FMT_BF16 = (1u << 7) | (1u << 10);
 constexpr uint32_t GT_FMT_F16 = 0u;
 

@@ -91,6 +91,10 @@ __device__ __forceinline__ void g2_commit_both(uint64_t* bar) {
 struct G2Tile { int z, m0, n0, M; };
 struct G2NoRow {};
 template <class E, class = void>
+struct G2PreOf { using type = G2NoRow; };
+template <class E>
+struct G2PreOf<E, std::void_t<typename E::Pre>> { using type = typename E::Pre; };
+template <class E, class = void>
 struct G2RowOf { using type = G2NoRow; };
 template <class E>
 struct G2RowOf<E, std::void_t<typename E::Row>> { using type = typename E::Row; };
@@ -250,6 +254,14 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
             for (int j = 0; j < 4; ++j) { o[0][j] = pb[32 * j]; o[1][j] = pb[128 + 32 * j]; }
           }
         }
+        // (functors with a `Pre`: the global operands of all 8 column groups are in flight before the accumulator is)
+        typename G2PreOf<Epi>::type pre[8];
+        if constexpr (gt_has_pre<Epi>::value && !SEG) {
+          if (m < tl.M) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) pre[c] = epi.prefetch(tl.z, m, tl.n0 + half * 128 + c * 16);
+          }
+        }
         long long t_e = 0;
         if (trace && warp == 2) { const long long t0 = clock64(); gt_wait(&acc_full[buf], (ti >> 1) & 1, 128); t_e = clock64(); w0 += t_e - t0; }
         else gt_wait(&acc_full[buf], (ti >> 1) & 1, 128);
@@ -262,8 +274,8 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
           constexpr int slot = decltype(slot_c)::value;
           float v[16];
           gt_ld16(taddr + c * 16, v);
+          const int nn = tl.n0 + half * 128 + c * 16;
           if (m < tl.M) {
-            const int nn = tl.n0 + half * 128 + c * 16;
             if constexpr (SEG) {
               if (add_prev) {
 #pragma unroll
@@ -283,15 +295,25 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
             }
             if (last) {
               if constexpr (gt_has_row<Epi>::value) epi(tl.z, m, nn, v, rowctx);
+              else if constexpr (gt_has_pre<Epi>::value && !SEG) epi(tl.z, m, nn, v, pre[c]);
               else if constexpr (gt_has_pre<Epi>::value) epi(tl.z, m, nn, v, epi.prefetch(tl.z, m, nn));
               else epi(tl.z, m, nn, v);
             }
           }
+          if constexpr (gt_has_after<Epi>::value) if (last) epi.after(tl.z, m - lane, nn, lane);
         };
+        if constexpr (SEG) {
 #pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
-          group(c, std::integral_constant<int, 0>{});
-          group(c + 1, std::integral_constant<int, 1>{});
+          for (int c = 0; c < 8; c += 2) {
+            group(c, std::integral_constant<int, 0>{});
+            group(c + 1, std::integral_constant<int, 1>{});
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {          // (unrolled: pre[c] stays in registers)
+            group(c, std::integral_constant<int, 0>{});
+            group(c + 1, std::integral_constant<int, 1>{});
+          }
         }
         gt_fence_before();
         __syncwarp();

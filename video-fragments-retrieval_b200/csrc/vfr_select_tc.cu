@@ -1145,6 +1145,7 @@ struct RfParams {
   int32_t* flags;
   int k;
   int64_t id_base;
+  int64_t q0;                  // first query of this launch (the grid covers a query range)
   float* out_scores;
   int64_t* out_ids;
   // blocked output (sharded search, vfr_sel_refine_blocks): the queries are cut into slices of `per` (one per rank
@@ -1275,7 +1276,7 @@ __global__ void __launch_bounds__(RF_THREADS) sl_refine_kernel(const RfParams p)
   __shared__ int warp_tot[RF_THREADS / 32];
   __shared__ int s_n, s_cnt;
   __shared__ float s_sq, s_tau;
-  const int64_t q = blockIdx.x;
+  const int64_t q = p.q0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   long long tq = p.dbg ? clock64() : 0;
   auto stamp = [&](int phase) {
@@ -1902,7 +1903,7 @@ static int sl_run_filter(const SlPlan& pl, SlParams p, const void* bank_packed, 
 static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vid_off, const int64_t* mom_off,
                          int64_t n_videos, int n_max, int dim, const float* queries, int64_t n_queries, int k,
                          int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st, int64_t per = 0,
-                         void* out_blocks = nullptr, bool bank_is_b16 = false) {
+                         void* out_blocks = nullptr, bool bank_is_b16 = false, int64_t q_begin = 0, int64_t q_count = -1) {
   VFR_REQUIRE(bank && vid_off && mom_off && queries && ((out_scores && out_ids) || (per > 0 && out_blocks)), VFR_ERR_INVALID,
               "vfr_sel_refine: null pointer");
   VFR_REQUIRE(per == 0 || (per * (3 * (int64_t)k + 1)) % 2 == 0, VFR_ERR_INVALID, "vfr_sel_refine_blocks: per * (3k + 1) must be even");
@@ -1936,7 +1937,11 @@ static int sl_run_refine(const SlParams& p, const float* bank, const int32_t* vi
   r.final_max = RF_FINAL;
   { const char* e = getenv("VFR_RF_DBG"); r.dbg = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   { const char* e = getenv("VFR_RF_FAST"); if (e) { r.fast_max = std::min(RF_FAST, std::max(0, atoi(e))); if (r.fast_max == 0) r.final_max = -1; } }
-  sl_refine_kernel<<<(unsigned)n_queries, RF_THREADS, 0, st>>>(r);
+  if (q_count < 0) q_count = n_queries - q_begin;
+  VFR_REQUIRE(q_begin >= 0 && q_count >= 0 && q_begin + q_count <= n_queries, VFR_ERR_INVALID, "vfr_sel_refine: bad query range");
+  if (q_count == 0) return VFR_OK;
+  r.q0 = q_begin;
+  sl_refine_kernel<<<(unsigned)q_count, RF_THREADS, 0, st>>>(r);
   return check_launch("sl_refine_kernel");
 }
 
@@ -2298,6 +2303,21 @@ extern "C" int vfr_sel_refine(const float* bank, const int32_t* vid_off, const i
   if (rc) return rc;
   return sl_run_refine(p, bank, vid_off, mom_off, n_videos, n_max, dim, queries, n_queries, k, id_base, out_scores,
                        out_ids, (cudaStream_t)stream);
+}
+
+// stage 2 for the queries [q_begin, q_begin + q_count) only (rows q of out_scores / out_ids): lets a caller copy finished
+// rows to the host while the rest is still being re-scored (vfr_search_host)
+extern "C" int vfr_sel_refine_range(const float* bank, const int32_t* vid_off, const int64_t* mom_off, int64_t n_videos,
+                                    int64_t n_clips, int n_max, int dim, void* query_packed, const float* queries,
+                                    int64_t n_queries, int k, int64_t id_base, float* out_scores, int64_t* out_ids,
+                                    void* workspace, int n_split, int64_t q_begin, int64_t q_count, vfr_stream_t stream) {
+  VFR_REQUIRE(query_packed && workspace, VFR_ERR_INVALID, "vfr_sel_refine_range: null pointer");
+  SlPlan pl;
+  SlParams p;
+  int rc = sl_setup(pl, p, query_packed, n_queries, n_clips, dim, k, workspace, n_split);
+  if (rc) return rc;
+  return sl_run_refine(p, bank, vid_off, mom_off, n_videos, n_max, dim, queries, n_queries, k, id_base, out_scores,
+                       out_ids, (cudaStream_t)stream, 0, nullptr, false, q_begin, q_count);
 }
 
 extern "C" int vfr_sel_topk(const void* bank_packed, const float* bank, const int32_t* vid_off, const int64_t* mom_off,

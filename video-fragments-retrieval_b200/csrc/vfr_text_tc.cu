@@ -254,30 +254,52 @@ struct EpiLstmTc {
   int col0[2];
   int lo_off;
   int H;
-  // operands of one 16-column group (4 hidden units x 4 gates) that live in global memory: requested one group ahead
+  // Backward direction: the rows [*join_lo, *join_hi) consume their first real token at the NEXT step and start from the
+  // state the padding row (row 0) has reached (see TextOrder).  The warp that has just written row 0's 4 hidden units of a
+  // column group copies them into those rows (h hi / lo in the next slot, c) - what a copy kernel between two dependent
+  // GEMM launches did before (14 us per step, whatever the batch).  null: nothing joins.
+  const int* join_lo;
+  const int* join_hi;
+  struct After {};
+  __device__ __forceinline__ void after(int z, int m_warp, int n0, int lane) const {
+    if (z != 1 || m_warp != 0 || join_lo == nullptr) return;           // warp-uniform
+    const int j0 = n0 >> 2;
+    if (j0 >= H) return;
+    const int lo = max(*join_lo, 1), hi = *join_hi;
+    if (hi <= lo) return;
+    __syncwarp();                                                      // lane 0's stores of row 0 -> L2, then read from L2
+    const float4 cv = __ldcg(reinterpret_cast<const float4*>(c[1] + j0));
+    const __nv_bfloat16* o0 = dst[1] + col0[1] + j0;
+    const uint2 hv = __ldcg(reinterpret_cast<const uint2*>(o0)), lv = __ldcg(reinterpret_cast<const uint2*>(o0 + lo_off));
+    for (int r = lo + lane; r < hi; r += 32) {
+      *reinterpret_cast<float4*>(c[1] + (int64_t)r * H + j0) = cv;
+      __nv_bfloat16* o = dst[1] + (int64_t)r * ld + col0[1] + j0;
+      *reinterpret_cast<uint2*>(o) = hv;
+      *reinterpret_cast<uint2*>(o + lo_off) = lv;
+    }
+  }
+  // the operand of one 16-column group (4 hidden units x 4 gates) that comes from DRAM: the previous cell state.  The
+  // CTA-pair kernel requests all of a tile's groups BEFORE it waits for the accumulator (the biases are L1 hits).
   struct Pre {
     float4 c_prev;
-    float4 b[4];
   };
   __device__ __forceinline__ Pre prefetch(int z, int m, int n0) const {
     Pre p;
     const int j0 = n0 >> 2;
-    if (j0 >= H) { p.c_prev = make_float4(0.f, 0.f, 0.f, 0.f); p.b[0] = p.b[1] = p.b[2] = p.b[3] = p.c_prev; return p; }
+    if (j0 >= H) { p.c_prev = make_float4(0.f, 0.f, 0.f, 0.f); return p; }
     p.c_prev = *reinterpret_cast<const float4*>((z ? c[1] : c[0]) + (int64_t)m * H + j0);      // (the cell arrays start zeroed)
-    const float4* bz = reinterpret_cast<const float4*>((z ? bias[1] : bias[0]) + n0);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) p.b[u] = __ldg(bz + u);
     return p;
   }
   __device__ __forceinline__ void operator()(int z, int m, int n0, const float (&v)[16], const Pre& p) const {
     const int j0 = n0 >> 2;
     if (j0 >= H) return;
+    const float4* bz = reinterpret_cast<const float4*>((z ? bias[1] : bias[0]) + n0);
     const float cpv[4] = {p.c_prev.x, p.c_prev.y, p.c_prev.z, p.c_prev.w};
     float cn[4];
     __nv_bfloat16 hh[4], hl[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float4 bb = p.b[u];
+      const float4 bb = __ldg(bz + u);
       const float gi = v[4 * u + 0] + bb.x, gf = v[4 * u + 1] + bb.y, gg = v[4 * u + 2] + bb.z, go = v[4 * u + 3] + bb.w;
       cn[u] = sigmoid_fast(gf) * cpv[u] + sigmoid_fast(gi) * tanh_fast(gg);
       const float h = sigmoid_fast(go) * tanh_fast(cn[u]);
@@ -475,8 +497,11 @@ extern "C" int vfr_text_embed_tc(const int64_t* tokens, int64_t n_queries, int s
     if (rc) return rc;
   }
   const unsigned join_blocks = (unsigned)((Bp + 7) / 8);
+  // the CTA-pair GEMM copies the padding row's state into the joining rows from its epilogue (EpiLstmTc::after); the
+  // one-CTA kernel (VFR_GEMM2=0) keeps the copy kernel between the steps
+  const bool fused_join = g2_enabled() && d.Kp % 64 == 0;
   for (int t = 0; t < L; ++t) {
-    if (t > 0) {
+    if (t > 0 && !fused_join) {
       // rows whose first real token is consumed by backward step t join with the padding row's state
       tc_text_join_kernel<<<join_blocks, 256, 0, st>>>(o.n_active + (t - 1), o.n_active + t, 0,
                                                        slots[1] + (size_t)t * Bp * ld, ld, 0, d.Kp, d.Hp, c[1], hidden);
@@ -496,6 +521,8 @@ extern "C" int vfr_text_embed_tc(const int64_t* tokens, int64_t n_queries, int s
     epi.ld = last ? 2 * (int64_t)d.Kf : ld;
     epi.lo_off = last ? d.Kf : d.Kp;
     epi.H = hidden;
+    epi.join_lo = (fused_join && !last) ? o.n_active + t : nullptr;
+    epi.join_hi = (fused_join && !last) ? o.n_active + t + 1 : nullptr;
     rc = launch_gemm_tc(a, b, 2, (int)Bp, 4 * hidden, d.Kp, ld, ld, epi, st, o.limits + 2 * t);
     if (rc) return rc;
   }
