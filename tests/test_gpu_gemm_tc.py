@@ -167,3 +167,33 @@ def CALModelBig():
     torch.manual_seed(123)
     table = torch.randn(50, 100) * 0.4
     return models.CALModel(visual_input_dim=8194, pretrained_emb=table).to(DEV).eval()
+
+
+def test_visual_embed_tc_row_scales_and_unaligned_rows():
+    """K2's operand exponent is per ROW (found in the split pass): rows whose magnitudes differ by 1e6, an all-zero row
+    and a row count that is not a multiple of the 256-row tile each keep fp32 accuracy relative to THEIR OWN output;
+    the assembled [N, 8194] rows are only 8-byte aligned (8194 floats per row: the scalar branch of the split kernel),
+    the split-weight inputs 16-byte aligned (the vector branch)."""
+    big = CALModelBig()
+    rng = np.random.default_rng(5)
+    n_vid, n = 77, 5
+    seg = rng.random((n_vid * n, 4096), dtype=np.float32)
+    ctx = rng.random((n_vid, 4096), dtype=np.float32)
+    row_scale = (10.0 ** rng.uniform(-3, 3, size=(n_vid * n, 1))).astype(np.float32)
+    seg *= row_scale
+    seg[7] = 0.0
+    ctx *= (10.0 ** rng.uniform(-3, 3, size=(n_vid, 1))).astype(np.float32)
+    ctx[3] = 0.0
+    vid_off = np.arange(n_vid + 1) * n
+    tef = np.tile(np.stack([np.arange(n) / np.float32(n), (np.arange(n) + 1) / np.float32(n)], 1).astype(np.float32), (n_vid, 1))
+    x = torch.from_numpy(np.concatenate([seg, np.repeat(ctx, n, axis=0), tef], axis=1)).to(DEV)
+    lin1, lin2 = big.visual_fc[0], big.visual_fc[2]
+    with torch.no_grad():
+        hid = torch.relu(x.double() @ lin1.weight.double().t() + lin1.bias.double())
+        want = hid @ lin2.weight.double().t() + lin2.bias.double()
+        got_rows = big(x)
+        got_split = big.embed_clips(torch.from_numpy(seg).to(DEV), torch.from_numpy(ctx).to(DEV), vid_off)
+    # per-row bar: 1e-5 of what the row's own hidden activations can contribute to an output
+    row_bar = 1e-5 * (hid.abs() @ lin2.weight.double().abs().t()).max(dim=1, keepdim=True).values.clamp_min(1e-30)
+    assert bool(((got_rows.double() - want).abs() <= row_bar).all())
+    assert bool(((got_split.double() - want).abs() <= row_bar).all())

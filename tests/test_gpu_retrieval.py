@@ -52,6 +52,26 @@ def test_search_host_matches_oracle_and_device_path(engine):
         retr.search(bad)
 
 
+def test_search_host_large_batch_takes_the_chunked_copy_path():
+    """From 4 096 queries on vfr_search_host re-scores in query chunks and copies finished rows to the host on a second
+    stream: the host result equals the device-resident one, row for row (a batch that is not a multiple of the chunks)."""
+    sd, model, clips, _ = _setup(V=2000)
+    V = clips.shape[0] // 6
+    rng = np.random.default_rng(3)
+    Q = 4099
+    tokens = np.zeros((Q, 20), dtype=np.int64)
+    for r in range(Q):
+        n = 1 + int(rng.integers(0, 12))
+        tokens[r, :n] = rng.integers(1, 400, size=n)
+    retr = MomentRetriever(model, torch.from_numpy(clips).to(DEV), np.arange(V + 1) * 6, max_queries=Q, k=25, engine="sel",
+                           text_engine="tc")
+    for _ in range(2):                      # (second call: the copy stream and its events are reused)
+        s, i = retr.search(tokens)
+        sd_, id_ = retr.search_device(torch.from_numpy(tokens).to(DEV))
+        assert torch.equal(i, id_.cpu())
+        assert torch.equal(s.view(torch.int32), sd_.cpu().view(torch.int32))
+
+
 @pytest.mark.parametrize("engine", ["exact", "tc", "tc_bf16", "sel"])
 def test_sharded_search_equals_single_bank_search(engine):
     sd, model, clips, tokens = _setup(seed=22, V=1000)

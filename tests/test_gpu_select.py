@@ -348,3 +348,28 @@ def test_bf16_embedding_path_tolerance(dim, n_videos):
     assert bool((bi[clear, 0] == fi[clear, 0]).all())
     with pytest.raises(_lib.VfrError):                                                        # an fp32 bank is refused
         ops.score_topk_sel(ops.Bank(clips_t, vid_off), q_t, k, bf16=True)
+
+
+def test_refine_by_query_range_equals_whole_refine():
+    """vfr_sel_refine_range over consecutive query ranges (what vfr_search_host does to overlap the result copies with
+    stage 2) writes the same rows as ONE vfr_sel_refine - ragged ranges, an empty one, the last one short."""
+    rng = np.random.default_rng(11)
+    clips, vid_off = _ragged_bank(rng, 3000, 100, (5, 6))
+    bank = ops.Bank(torch.from_numpy(clips).to(DEV), vid_off)
+    Q, k = 301, 37
+    q = torch.from_numpy(rng.standard_normal((Q, 100), dtype=np.float32) * 0.25).to(DEV)
+    ws_s, ws_i, flags, (qp, ws) = ops.score_topk_sel(bank, q, k, return_flags=True)      # filter + whole refine
+    n_clips = int(bank.clips.shape[0])
+    out_s = torch.full((Q, k), -1.0, dtype=torch.float32, device=DEV)
+    out_i = torch.full((Q, k), -1, dtype=torch.int64, device=DEV)
+    stream = torch.cuda.current_stream().cuda_stream
+    for q0, n in ((0, 1), (1, 127), (128, 0), (128, 128), (256, 45)):
+        _lib.call("vfr_sel_refine_range", bank.clips.data_ptr(), bank.vid_off.data_ptr(), bank.mom_off.data_ptr(),
+                  bank.n_videos, n_clips, bank.n_max, bank.dim, qp.data_ptr(), q.data_ptr(), Q, k, 0, out_s.data_ptr(),
+                  out_i.data_ptr(), ws.data_ptr(), 0, q0, n, stream)
+    assert torch.equal(out_i, ws_i)
+    assert torch.equal(out_s.view(torch.int32), ws_s.view(torch.int32))
+    with pytest.raises(_lib.VfrError):
+        _lib.call("vfr_sel_refine_range", bank.clips.data_ptr(), bank.vid_off.data_ptr(), bank.mom_off.data_ptr(),
+                  bank.n_videos, n_clips, bank.n_max, bank.dim, qp.data_ptr(), q.data_ptr(), Q, k, 0, out_s.data_ptr(),
+                  out_i.data_ptr(), ws.data_ptr(), 0, 300, 2, stream)

@@ -191,7 +191,7 @@ __global__ void vis_clip_meta_kernel(const int32_t* __restrict__ vid_off, int64_
 }
 
 // ---- epilogues ---------------------------------------------------------------------------------------------------
-// layer 1: pre = acc 2^-(ea+ew) + add[row][n] (or b1[n]) + tef . w1t[n]  ->  relu  ->  hidden fp32; tracks max(hidden)
+// layer 1: pre = acc 2^-(ea+ew) + add[row][n] (or b1[n]) + tef . w1t[n]  ->  relu  ->  hidden fp32
 struct EpiVis1 {
   float* hidden;            // [M, hid]
   int hid;
@@ -204,7 +204,6 @@ struct EpiVis1 {
   const float* tef;         // [M, tef_ld] the two tef values of row m start at tef + m * tef_ld
   int64_t tef_ld;
   const float* w1t;         // [hid, 2]
-  unsigned* hmax;           // max of the hidden activations (bit pattern), may be null
   struct Row {              // what a row needs for all of its column groups
     float s, t0, t1;
     const float* arow;
@@ -221,7 +220,6 @@ struct EpiVis1 {
   __device__ __forceinline__ void operator()(int, int m, int n0, const float (&v)[16], const Row& rw) const {
     const float s = rw.s, t0 = rw.t0, t1 = rw.t1;
     const float* arow = rw.arow;
-    float mx = 0.f;
     if ((hid & 3) == 0) {
       // 16-byte accesses (every array here is 16-byte aligned and hid % 4 == 0): a thread owns a row, so each access of a
       // warp touches 32 rows - four columns per instruction instead of one
@@ -237,7 +235,6 @@ struct EpiVis1 {
           x.z = fmaxf(__fmaf_rn(t1, wb.y, __fmaf_rn(t0, wb.x, __fmaf_rn(v[4 * g + 2], s, a.z))), 0.f);
           x.w = fmaxf(__fmaf_rn(t1, wb.w, __fmaf_rn(t0, wb.z, __fmaf_rn(v[4 * g + 3], s, a.w))), 0.f);
           *reinterpret_cast<float4*>(hidden + (int64_t)m * hid + n) = x;
-          mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
         }
       }
     } else {
@@ -250,13 +247,9 @@ struct EpiVis1 {
           x = __fmaf_rn(t1, __ldg(w1t + 2 * n + 1), x);
           x = fmaxf(x, 0.f);
           hidden[(int64_t)m * hid + n] = x;
-          mx = fmaxf(mx, x);
         }
       }
     }
-    // (a plain read first: the running maximum settles after a few tiles, and 768 k atomics on one address per 24 k rows
-    //  cost more than the GEMM)
-    if (hmax && mx > __uint_as_float(*reinterpret_cast<volatile unsigned*>(hmax))) atomicMax(hmax, __float_as_uint(mx));
   }
 };
 // plain scaled output:  out = acc 2^-(ea+ew) + bias
@@ -300,9 +293,7 @@ struct VisWs {
   float* cvec;       // [vids, hid]
   int32_t* clip_vid; // [rows]
   float2* tef;       // [rows]
-  unsigned* amax;    // [2] : (unused), hidden
-  int* exps;         // [2] : (unused), hidden
-  int* row_exp;      // [rows] exponents of the clip rows
+  int* row_exp;      // [rows] exponents of the clip rows (layer 1), then of the hidden rows (layer 2)
   int* vid_exp;      // [vids] exponents of the context rows (split form)
   float* flush;      // [max(rows, vids), N1] fp32: K-segmented accumulation of the layer-1 GEMMs (vfr_gemm_tc.cuh)
   size_t bytes;
@@ -328,8 +319,6 @@ static VisWs vis_ws(void* base, const VisDims& d, int64_t rows, int64_t vids, bo
   w.cvec = reinterpret_cast<float*>(take(split ? (size_t)vids * d.hid * 4 : 0));
   w.clip_vid = reinterpret_cast<int32_t*>(take(split ? (size_t)rows * 4 : 0));
   w.tef = reinterpret_cast<float2*>(take(split ? (size_t)rows * 8 : 0));
-  w.amax = reinterpret_cast<unsigned*>(take(2 * sizeof(unsigned)));
-  w.exps = reinterpret_cast<int*>(take(2 * sizeof(int)));
   w.row_exp = reinterpret_cast<int*>(take((size_t)rows * 4));
   w.vid_exp = reinterpret_cast<int*>(take(split ? (size_t)vids * 4 : 0));
   // (whole 256-row tiles: the CTA-pair kernel keeps a tile's partial sums in a tile-major layout)
@@ -347,16 +336,14 @@ static int vis_amax(const float* x, int64_t rows, int cols, int64_t ld, unsigned
 
 // layer 2 shared by both forms: hidden fp32 [rows, hid] -> out [rows, dim]
 static int vis_layer2(const VisDims& d, const VisBlob& blob, const VisWs& w, int64_t rows, float* out, cudaStream_t st) {
-  vis_exp_kernel<<<1, 1, 0, st>>>(w.amax + 1, w.exps + 1);
-  int rc = check_launch("vis_exp_kernel");
-  if (rc) return rc;
-  vis_split_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.hidden, rows, 0, d.hid, d.hid, 0, d.Hp, 2 * (int64_t)d.Hp,
-                                                                    d.Hp, w.exps + 1, w.ah);
-  rc = check_launch("vis_split_rows_kernel");
+  // (per-row exponents again - the layer-1 exponents in row_exp are dead once its GEMM has run)
+  vis_split_rows_auto_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.hidden, rows, 1, 0, 0, d.hid, d.hid, 0, 0, d.Hp,
+                                                                         2 * (int64_t)d.Hp, d.Hp, w.row_exp, w.ah);
+  int rc = check_launch("vis_split_rows_auto_kernel");
   if (rc) return rc;
   const void* a[1] = {w.ah};
   const void* b[1] = {blob.w2};
-  EpiVisOut epi{out, d.dim, d.dim, w.exps + 1, 0, blob.exps + 1, blob.b2};
+  EpiVisOut epi{out, d.dim, d.dim, w.row_exp, 1, blob.exps + 1, blob.b2};
   return launch_gemm_tc(a, b, 1, (int)rows, d.dim, d.Hp, 2 * (int64_t)d.Hp, 2 * (int64_t)d.Hp, epi, st, nullptr, true);
 }
 
@@ -418,7 +405,6 @@ extern "C" int vfr_visual_embed_tc(const float* x, int64_t n_rows, int feat_dim,
   const VisWs w = vis_ws(workspace, d, n_rows, 1, false);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ldx = 2 * (int64_t)feat_dim + 2;
-  VFR_CUDA(cudaMemsetAsync(w.amax, 0, 2 * sizeof(unsigned), st));
   vis_split_rows_auto_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(x, n_rows, 2, 0, feat_dim, feat_dim, ldx, 0, d.Fp, d.Fp,
                                                                            2 * (int64_t)d.K1, d.K1, w.row_exp, w.a1);
   int rc = check_launch("vis_split_rows_auto_kernel");
@@ -426,7 +412,7 @@ extern "C" int vfr_visual_embed_tc(const float* x, int64_t n_rows, int feat_dim,
   {
     const void* a[1] = {w.a1};
     const void* b[1] = {blob.w1};
-    EpiVis1 epi{w.hidden, hid, w.row_exp, 1, blob.exps, blob.b1, nullptr, nullptr, x + 2 * feat_dim, ldx, blob.w1t, w.amax + 1};
+    EpiVis1 epi{w.hidden, hid, w.row_exp, 1, blob.exps, blob.b1, nullptr, nullptr, x + 2 * feat_dim, ldx, blob.w1t};
     const int fk = vis_flush_k();
     rc = launch_gemm_tc(a, b, 1, (int)n_rows, hid, d.K1, 2 * (int64_t)d.K1, 2 * (int64_t)d.K1, epi, st, nullptr, true, 0, 0, fk,
                         fk ? w.flush : nullptr, d.N1);
@@ -446,7 +432,6 @@ extern "C" int vfr_visual_embed_split(const float* seg, const float* ctx, const 
   const VisBlob blob = vis_blob(const_cast<void*>(packed), d);
   const VisWs w = vis_ws(workspace, d, n_clips, n_videos, true);
   cudaStream_t st = (cudaStream_t)stream;
-  VFR_CUDA(cudaMemsetAsync(w.amax, 0, 2 * sizeof(unsigned), st));
   int rc;
   vis_clip_meta_kernel<<<(unsigned)((n_videos + 255) / 256), 256, 0, st>>>(vid_off, n_videos, w.clip_vid, w.tef);
   rc = check_launch("vis_clip_meta_kernel");
@@ -472,7 +457,7 @@ extern "C" int vfr_visual_embed_split(const float* seg, const float* ctx, const 
     const void* a[1] = {w.a1};
     const void* b[1] = {blob.w1};
     EpiVis1 epi{w.hidden, hid, w.row_exp, 1, blob.exps, blob.b1, w.cvec, w.clip_vid, reinterpret_cast<const float*>(w.tef), 2,
-                blob.w1t, w.amax + 1};
+                blob.w1t};
     const int fk = vis_flush_k();
     rc = launch_gemm_tc(a, b, 1, (int)n_clips, hid, d.Fp, 2 * (int64_t)d.Fp, 2 * (int64_t)d.K1, epi, st, nullptr, true, d.Fp,
                         d.K1, fk, fk ? w.flush : nullptr, d.N1);
