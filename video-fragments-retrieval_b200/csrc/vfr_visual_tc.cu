@@ -118,6 +118,41 @@ __global__ void vis_split_rows_auto_kernel(const float* __restrict__ x, int64_t 
   if (r >= rows) return;
   const float* row = x + r * ldx;
   const bool vec = ((reinterpret_cast<uintptr_t>(row + c0a) | reinterpret_cast<uintptr_t>(row + c0b)) & 15) == 0 && (k & 3) == 0;
+  // one window of <= 4096 aligned columns (the split-weight form at F = 4096, the hidden layer): the row stays in
+  // registers between the two sweeps (32 float4 per lane) - one read of the row instead of two
+  if (vec && n_win == 1 && k <= 4096) {
+    const float4* s4 = reinterpret_cast<const float4*>(row + c0a);
+    const int n4 = k >> 2;
+    float4 v[32];
+    float m = 0.f;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const int c = u * 32 + lane;
+      v[u] = (c < n4) ? s4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+    }
+    m = warp_max(m);
+    int ex = 0;
+    if (m > 0.f && m < CUDART_INF_F) ex = max(-100, min(100, 13 - ilogbf(m)));
+    if (lane == 0) row_exp[r] = ex;
+    __half* dst = out + r * ldo + k0a;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const int c = u * 32 + lane;
+      if (4 * c < kp) {
+        __half h[4], l[4];
+        split2h(scalbnf(v[u].x, ex), h[0], l[0]);
+        split2h(scalbnf(v[u].y, ex), h[1], l[1]);
+        split2h(scalbnf(v[u].z, ex), h[2], l[2]);
+        split2h(scalbnf(v[u].w, ex), h[3], l[3]);
+        *reinterpret_cast<uint2*>(dst + 4 * c) = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                                                            (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+        *reinterpret_cast<uint2*>(dst + lo_off + 4 * c) = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                                                                     (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+      }
+    }
+    return;
+  }
   float m = 0.f;
   for (int w = 0; w < n_win; ++w) {
     const float* src = row + (w ? c0b : c0a);
