@@ -86,16 +86,21 @@ struct HostCopy {
   cudaEvent_t done = nullptr;
   bool ok = false;
 };
+// one set per device (a process may serve several GPUs); not for concurrent calls on the same device from several threads
 HostCopy& host_copy() {
-  static HostCopy hc = [] {
-    HostCopy h;
+  static HostCopy per_device[16];
+  static HostCopy none;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return none;
+  HostCopy& h = per_device[dev];
+  if (!h.stream) {
     bool ok = cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreateWithFlags(&h.ready[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming) == cudaSuccess;
     h.ok = ok;
-    return h;
-  }();
-  return hc;
+    if (!ok) cudaGetLastError();       // fall back to the plain path, do not leave a sticky-looking error behind
+  }
+  return h;
 }
 }  // namespace
 
