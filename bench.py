@@ -14,7 +14,8 @@ Strong scaling: the bank is fixed and split by contiguous video ranges over the 
 value      = batch * 21 M pairs / step time, inputs (token ids) already resident in HBM.
 e2e        = the same through the public host-buffer call (MomentRetriever.search): pinned host token ids in, host
              top-k lists out, copies inside the timed region (on N ranks every rank moves its own query slice).
-roofline   = the dominant kernel (K4) timed with CUDA events inside the steps; roofline_k3 = the same for K3.
+roofline   = the dominant kernel (K4) timed with CUDA events INSIDE the timed steps (an event between K3 and K4 of every
+             step); roofline_k3 = the same for K3.
 parity_check = OUTSIDE the timed regions: a subsample of the last step's results re-scored by the CPU oracle.
 filter_stats = candidates kept per query / compactions / flagged queries / exact-engine reruns of the last step.
 cpu_baseline / --impl reference = the UNMODIFIED reference (oracle/_ref, a verbatim copy of /root/reference/model made by
@@ -483,31 +484,22 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = lib.vfr_launch_count()
+    # (per step three event records on the stream: step start, K3 done, step end - the two dominant stages are timed
+    #  INSIDE the timed steps, in the clock / cache state the step really has)
+    marks = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     ev0.record()
     for i in range(args.steps):
-        retr.search_device(tokens_dev[args.warmup + i])
+        marks[i][0].record()
+        retr.search_device(tokens_dev[args.warmup + i], k3_done=marks[i][1])
+        marks[i][2].record()
     ev1.record()
     barrier()
     launches = lib.vfr_launch_count() - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop()
     fixups_value = retr.n_fixups
-
-    # ---- the two dominant stages alone, inside the same steps: K3 and K4 through their own entry points (on N ranks
-    #      these are the very functions the step runs, collectives of the threshold protocol included) ----
-    k3_ms, k4_ms = [], []
-    for i in range(args.steps):
-        retr.search_device(tokens_dev[args.warmup + i])        # keeps the step's cache/clock state
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record()
-        retr.embed_only(tokens_dev[args.warmup + i])
-        b.record()
-        retr.score_only(args.batch)
-        c.record()
-        torch.cuda.synchronize()
-        k3_ms.append(a.elapsed_time(b))
-        k4_ms.append(b.elapsed_time(c))
-    k3, k4 = max_over_ranks(float(np.mean(k3_ms))), max_over_ranks(float(np.mean(k4_ms)))
+    k3 = max_over_ranks(float(np.mean([m[0].elapsed_time(m[1]) for m in marks])))
+    k4 = max_over_ranks(float(np.mean([m[1].elapsed_time(m[2]) for m in marks])))
     stats = retr.filter_stats(args.batch)
     k4_parts = None
     if world == 1 and args.engine == "sel":

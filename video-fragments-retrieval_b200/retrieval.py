@@ -382,22 +382,32 @@ class MomentRetriever:
         self.n_fixups += int(idx.numel())
 
     # -- device-resident step ---------------------------------------------------------------------
-    def search_device(self, tokens_dev, check=True):
+    def search_device(self, tokens_dev, check=True, k3_done=None):
         """tokens int64 [Q, 20] on the device -> (scores fp32 [n, k], ids int64 [n, k]) on the device for the rows
         ``owned_range(Q)`` of the batch (one GPU: the whole batch).
 
         One GPU: K3 -> K4 in one C call.  P GPUs: see the module docstring.  ``check=False`` skips the end-of-step
-        wait on the flags (the caller then calls ``finish_step(Q)`` before it trusts the result)."""
+        wait on the flags (the caller then calls ``finish_step(Q)`` before it trusts the result).  ``k3_done``: a CUDA
+        event to record between K3 (+ the all-gather of the embeddings) and K4 (bench.py times the two inside its steps)."""
         Q = tokens_dev.shape[0]
         stream = torch.cuda.current_stream().cuda_stream
         if self.world == 1:
-            _lib.call("vfr_search_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.k, self.out_s.data_ptr(),
-                      self.out_i.data_ptr(), stream)
+            if k3_done is None:
+                _lib.call("vfr_search_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.k, self.out_s.data_ptr(),
+                          self.out_i.data_ptr(), stream)
+            else:
+                # the same two stages through their own entry points, with the caller's event between them
+                _lib.call("vfr_search_embed_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.q_emb.data_ptr(), stream)
+                k3_done.record()
+                _lib.call("vfr_search_score_device", C.byref(self.plan), Q, self.k, self.out_s.data_ptr(),
+                          self.out_i.data_ptr(), stream)
             self._sel_fixup(Q)
             return self.out_s[:Q], self.out_i[:Q]
         per = slice_rows(Q, self.world)
         q0, q1 = self.owned_range(Q)
         self.embed_only(tokens_dev)
+        if k3_done is not None:
+            k3_done.record()
         if self.plan.engine == 4:
             self._sel_score_sharded(Q, stream, per=per)
             blk = _lib.load().vfr_topk_block_bytes(per, self.k)
