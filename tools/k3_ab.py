@@ -1,4 +1,5 @@
-"""K3 (text embedding, tcgen05 path) timed alone, A/B over VFR_GEMM_PRE (software-pipelined LSTM epilogue on / off), same process."""
+"""K3 (text embedding, tcgen05 path) timed alone (B = queries, VFR_GEMM2=0 selects the one-CTA GEMM of round 1) and the
+tile-phase counters of its step GEMMs (VFR_GEMM_DBG)."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -20,10 +21,8 @@ def run(n=5):
         for _ in range(n): model(tok, False, dev)
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / n
-for rep in range(2):
-    for mode in ("1", "0"):
-        os.environ["VFR_GEMM_PRE"] = mode
-        print(json.dumps(dict(B=B, VFR_GEMM_PRE=mode, ms=run())), flush=True)
+for rep in range(4):
+    print(json.dumps(dict(B=B, gemm2=os.environ.get("VFR_GEMM2", "1"), ms=run())), flush=True)
 
 # where the cycles go (VFR_GEMM_DBG: sums over every GEMM launched while it is set)
 dbg = torch.zeros(8, dtype=torch.int64, device=dev)
