@@ -537,6 +537,8 @@ def run_ours(args):
     for i in range(args.warmup):
         retr.search(tokens_host[i])
     barrier()
+    if world > 1:
+        retr.trace_search = {}
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -545,6 +547,11 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+    e2e_host = None
+    if world > 1 and retr.trace_search:
+        n_tr = max(retr.trace_search.pop("steps", 1), 1)
+        e2e_host = {k: v / n_tr * 1e3 for k, v in retr.trace_search.items()}       # rank 0's host-side ms per step
+        retr.trace_search = None
     checksum = float(s[:, 0].double().sum().item())
     if world > 1:
         t = torch.tensor([checksum], dtype=torch.float64, device=device)
@@ -636,7 +643,8 @@ def run_ours(args):
             "e2e": {"value": pairs_per_step * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": retr.h2d_bytes(args.batch), "d2h_bytes_per_step": retr.d2h_bytes(args.batch),
                     "ms_per_step": e2e_ms / args.steps,
-                    "api": "MomentRetriever.search" + (" -> vfr_search_host" if world == 1 else " (every rank moves and owns its query slice)")},
+                    "api": "MomentRetriever.search" + (" -> vfr_search_host" if world == 1 else " (every rank moves and owns its query slice)"),
+                    "host_ms_per_step": e2e_host},
             "gpu_launches": int(launches), "gpu_launches_source": "vfr_launch_count() around the timed region (rank 0)",
             "roofline": roofline, "roofline_k3": roofline_k3, "comm": stage_ms,
             "filter_stats": dict(stats or {}, n_fixups_value_steps=fixups_value, n_fixups_total=retr.n_fixups),

@@ -29,6 +29,8 @@ condition, and the only host synchronisation of a step is one event wait at its 
 import contextlib
 import ctypes as C
 
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -174,6 +176,7 @@ class MomentRetriever:
         self.sel_stats = torch.zeros(8, dtype=torch.int64, device=dev)
         self.n_fixups = 0
         self.profile = False               # True: every stage of a sharded step is bracketed by CUDA events (stage_ms)
+        self.trace_search = None           # a dict: ``search`` adds the host-side seconds of its phases to it (P > 1)
         self._prof = {}
         if self.world > 1:
             blk = lib.vfr_topk_block_bytes(per, self.k)
@@ -496,14 +499,24 @@ class MomentRetriever:
             return self.host_s[:Q], self.host_i[:Q]
         q0, q1 = self.owned_range(Q)
         n = q1 - q0
+        tr = self.trace_search                      # optional host-side timeline of the step (seconds per phase, summed)
+        t0 = time.perf_counter() if tr is not None else 0.0
         self.host_tokens[:n].copy_(tokens[q0:q1])
         self.tokens_dev[q0:q1].copy_(self.host_tokens[:n], non_blocking=True)
+        t1 = time.perf_counter() if tr is not None else 0.0
         s, i = self.search_device(self.tokens_dev[:Q], check=False)
         self.host_s[:n].copy_(s, non_blocking=True)
         self.host_i[:n].copy_(i, non_blocking=True)
+        t2 = time.perf_counter() if tr is not None else 0.0
         torch.cuda.current_stream().synchronize()
+        t3 = time.perf_counter() if tr is not None else 0.0
         fixups = self.n_fixups
         self.finish_step(Q)
+        if tr is not None:
+            t4 = time.perf_counter()
+            for key, dt in (("stage_inputs", t1 - t0), ("issue_step", t2 - t1), ("wait_gpu", t3 - t2), ("finish", t4 - t3)):
+                tr[key] = tr.get(key, 0.0) + dt
+            tr["steps"] = tr.get("steps", 0) + 1
         if self.n_fixups != fixups:
             self.host_s[:n].copy_(self.slice_s[:n], non_blocking=True)
             self.host_i[:n].copy_(self.slice_i[:n], non_blocking=True)
