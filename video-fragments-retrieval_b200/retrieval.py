@@ -38,6 +38,11 @@ import torch.distributed as dist
 from . import _lib, ops
 
 
+def _mark(marks, name):
+    if marks and name in marks:
+        marks[name].record()
+
+
 def shard_range(n_videos, rank, world):
     """Contiguous video range [v0, v1) of ``rank``."""
     return (n_videos * rank) // world, (n_videos * (rank + 1)) // world
@@ -312,8 +317,10 @@ class MomentRetriever:
                 _lib.call("vfr_sel_pool_levels", pooled.data_ptr(), n_src, Q, width, (C.c_int32 * L)(*ranks), L, 1,
                           levels.data_ptr(), stream)
                 _lib.call("vfr_sel_bound_put", qt, Q, n_clips, b.dim, self.k, ws, p.n_split, levels.data_ptr(), stream)
+            _mark(getattr(self, "_marks", None), "scan_start")
             with self._stage("k4_filter"):
                 _lib.call("vfr_sel_filter", p.bank_tc, n_clips, b.dim, qt, Q, self.k, ws, p.n_split, 0, tiles, 1, stream)
+            _mark(getattr(self, "_marks", None), "scan_end")
             # how many clips are CERTAINLY within each bound, over all shards: the tightest bound that still holds k
             # clips is a certified bound of the global k-th distance - every shard re-scores only what is under it
             with self._stage("k4_count"):
@@ -385,34 +392,48 @@ class MomentRetriever:
         self.n_fixups += int(idx.numel())
 
     # -- device-resident step ---------------------------------------------------------------------
-    def search_device(self, tokens_dev, check=True, k3_done=None):
+    def search_device(self, tokens_dev, check=True, marks=None):
         """tokens int64 [Q, 20] on the device -> (scores fp32 [n, k], ids int64 [n, k]) on the device for the rows
         ``owned_range(Q)`` of the batch (one GPU: the whole batch).
 
         One GPU: K3 -> K4 in one C call.  P GPUs: see the module docstring.  ``check=False`` skips the end-of-step
-        wait on the flags (the caller then calls ``finish_step(Q)`` before it trusts the result).  ``k3_done``: a CUDA
-        event to record between K3 (+ the all-gather of the embeddings) and K4 (bench.py times the two inside its steps)."""
+        wait on the flags (the caller then calls ``finish_step(Q)`` before it trusts the result).  ``marks``: a dict of
+        CUDA events to record inside the step - ``k3_done`` (after K3 + the all-gather of the embeddings), ``scan_start`` /
+        ``scan_end`` (around the filter kernel's scan; one GPU: sample pass included) - bench.py times the stages inside
+        its steps with them."""
         Q = tokens_dev.shape[0]
         stream = torch.cuda.current_stream().cuda_stream
         if self.world == 1:
-            if k3_done is None:
+            if not marks:
                 _lib.call("vfr_search_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.k, self.out_s.data_ptr(),
                           self.out_i.data_ptr(), stream)
             else:
-                # the same two stages through their own entry points, with the caller's event between them
-                _lib.call("vfr_search_embed_device", C.byref(self.plan), tokens_dev.data_ptr(), Q, self.q_emb.data_ptr(), stream)
-                k3_done.record()
-                _lib.call("vfr_search_score_device", C.byref(self.plan), Q, self.k, self.out_s.data_ptr(),
-                          self.out_i.data_ptr(), stream)
+                # the same stages through their own entry points, with the caller's events between them
+                p, b = self.plan, self.bank
+                _lib.call("vfr_search_embed_device", C.byref(p), tokens_dev.data_ptr(), Q, self.q_emb.data_ptr(), stream)
+                _mark(marks, "k3_done")
+                if p.engine == 4:
+                    _lib.call("vfr_sel_query_pack", p.q_emb, Q, b.dim, p.bank_tc, self.n_clips, p.q_tc, stream)
+                    _mark(marks, "scan_start")
+                    _lib.call("vfr_sel_filter", p.bank_tc, self.n_clips, b.dim, p.q_tc, Q, self.k, p.topk_ws, p.n_split, 0, -1, 0,
+                              stream)
+                    _mark(marks, "scan_end")
+                    _lib.call("vfr_sel_refine", p.bank_clips, p.vid_off, p.mom_off, b.n_videos, self.n_clips, b.n_max, b.dim,
+                              p.q_tc, p.q_emb, Q, self.k, p.id_base, self.out_s.data_ptr(), self.out_i.data_ptr(), p.topk_ws,
+                              p.n_split, stream)
+                else:
+                    _lib.call("vfr_search_score_device", C.byref(p), Q, self.k, self.out_s.data_ptr(), self.out_i.data_ptr(),
+                              stream)
             self._sel_fixup(Q)
             return self.out_s[:Q], self.out_i[:Q]
         per = slice_rows(Q, self.world)
         q0, q1 = self.owned_range(Q)
         self.embed_only(tokens_dev)
-        if k3_done is not None:
-            k3_done.record()
+        _mark(marks, "k3_done")
+        self._marks = marks
         if self.plan.engine == 4:
             self._sel_score_sharded(Q, stream, per=per)
+            self._marks = None
             blk = _lib.load().vfr_topk_block_bytes(per, self.k)
             # (a batch smaller than max_queries has shorter records: always the dense [P, blk] prefix of the buffers)
             send = self.send_blocks.view(-1)[:self.world * blk].view(self.world, blk)
