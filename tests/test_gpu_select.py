@@ -373,3 +373,30 @@ def test_refine_by_query_range_equals_whole_refine():
         _lib.call("vfr_sel_refine_range", bank.clips.data_ptr(), bank.vid_off.data_ptr(), bank.mom_off.data_ptr(),
                   bank.n_videos, n_clips, bank.n_max, bank.dim, qp.data_ptr(), q.data_ptr(), Q, k, 0, out_s.data_ptr(),
                   out_i.data_ptr(), ws.data_ptr(), 0, 300, 2, stream)
+
+
+@pytest.mark.parametrize("n_src,width", [(8, 32), (3, 32), (2, 64), (1, 32), (16, 32)])
+def test_pool_levels_merge_equals_counting(n_src, width):
+    """The j-th smallest pooled sample values of every query: the 8-lane merge of the sorted runs (<= 8 runs), the
+    binary-search ranking (sorted runs, more than 8) and the plain counting kernel (sorted_runs = 0) agree, with ties
+    (quantised values) and +inf padding."""
+    import ctypes as C
+    rng = np.random.default_rng(n_src * 100 + width)
+    Q = 333
+    vals = np.round(rng.random((n_src, Q, width // 32, 32)).astype(np.float32) * 40) / 40      # many ties
+    n_valid = rng.integers(0, 33, size=(n_src, Q, width // 32, 1))
+    vals = np.where(np.arange(32).reshape(1, 1, 1, 32) < n_valid, vals, np.inf).astype(np.float32)
+    vals = np.sort(vals, axis=-1).reshape(n_src, Q, width)
+    pooled = torch.from_numpy(vals).to(DEV)
+    total = n_src * width
+    ranks = sorted({1, min(7, total), min(19, total), min(32, total)}, reverse=True)
+    L = len(ranks)
+    out = []
+    for sorted_runs in (1, 0):
+        lv = torch.full((L * Q,), -1.0, dtype=torch.float32, device=DEV)
+        _lib.call("vfr_sel_pool_levels", pooled.data_ptr(), n_src, Q, width, (C.c_int32 * L)(*ranks), L, sorted_runs,
+                  lv.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        out.append(lv.cpu().numpy().reshape(L, Q))
+    want = np.sort(vals.transpose(1, 0, 2).reshape(Q, total), axis=1)[:, [r - 1 for r in ranks]].T
+    np.testing.assert_array_equal(out[1], want)
+    np.testing.assert_array_equal(out[0], want)

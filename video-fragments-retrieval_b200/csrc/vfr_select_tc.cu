@@ -2070,6 +2070,54 @@ __global__ void __launch_bounds__(256) sl_pool_levels_kernel(const float* __rest
   }
 }
 
+// The same for <= 8 ascending runs of SL_J values per query (what the sample passes of <= 8 shards export): an 8-lane
+// group merges the runs head by head - lane s walks run s, a 3-step shuffle minimum on (value, run) picks the next
+// value in the order the counting kernel ranks by (ties by position) - and stops at the largest wanted rank.  Four
+// queries per warp; ~200 instructions per query instead of ~3 400 (0.28 -> 0.03 ms for 37 888 queries x 8 shards).
+__global__ void __launch_bounds__(256) sl_pool_levels_merge_kernel(const float* __restrict__ pooled, int n_src, int64_t n_queries,
+                                                                   int width, int4 ranks, int n_levels, float* __restrict__ levels) {
+  __shared__ float heads[32][8][SL_J + 1];
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = (threadIdx.x >> 3);      // grp: query slot of the block (0..31)
+  const int64_t q = (int64_t)blockIdx.x * 32 + grp;
+  const bool qv = q < n_queries;
+  const int runs_per_src = width / SL_J, n_runs = n_src * runs_per_src;
+  const bool mine = qv && sub < n_runs;
+  if (mine) {
+    const int src = sub / runs_per_src, j0 = (sub - src * runs_per_src) * SL_J;
+    const float4* run = reinterpret_cast<const float4*>(pooled + ((int64_t)src * n_queries + q) * width + j0);
+#pragma unroll
+    for (int i = 0; i < SL_J / 4; ++i) {
+      const float4 v = run[i];
+      heads[grp][sub][4 * i] = v.x; heads[grp][sub][4 * i + 1] = v.y; heads[grp][sub][4 * i + 2] = v.z; heads[grp][sub][4 * i + 3] = v.w;
+    }
+  }
+  __syncwarp();
+  const int rk[4] = {ranks.x, ranks.y, ranks.z, ranks.w};
+  int max_rank = 0;
+  for (int l = 0; l < n_levels; ++l) max_rank = max(max_rank, rk[l]);
+  int pos = 0;
+  float head = mine ? heads[grp][sub][0] : CUDART_INF_F;
+  for (int r = 1; r <= max_rank; ++r) {
+    float v = head;
+    int who = sub;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+      const int ow = __shfl_xor_sync(0xffffffffu, who, off);
+      if (ov < v || (ov == v && ow < who)) { v = ov; who = ow; }
+    }
+    if (sub == 0 && qv) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < n_levels && r == rk[l]) levels[(int64_t)l * n_queries + q] = v;
+    }
+    if (sub == who) {
+      ++pos;
+      head = (mine && pos < SL_J) ? heads[grp][sub][pos] : CUDART_INF_F;
+    }
+  }
+}
+
 // count[l][q] = number of retained keys with d2~ <= levels[l][q] - E_q (clips CERTAINLY within that bound)
 __global__ void sl_count_levels_kernel(const unsigned long long* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
                                        int n_parts, const float4* __restrict__ qmeta, int64_t n, const float* __restrict__ levels,
@@ -2134,6 +2182,11 @@ extern "C" int vfr_sel_pool_levels(const float* pooled, int n_src, int64_t n_que
     rp[l] = ranks[l];
   }
   // (width is a multiple of SL_J = 32 when the values come from vfr_sel_sample: runs of 32 ascending values)
+  if (sorted_runs && width % SL_J == 0 && n_src * (width / SL_J) <= 8 && (reinterpret_cast<uintptr_t>(pooled) & 15) == 0) {
+    sl_pool_levels_merge_kernel<<<(unsigned)((n_queries + 31) / 32), 256, 0, (cudaStream_t)stream>>>(pooled, n_src, n_queries, width,
+                                                                                                   rk, n_levels, levels);
+    return check_launch("sl_pool_levels_merge_kernel");
+  }
   sl_pool_levels_kernel<<<(unsigned)((n_queries + 7) / 8), 256, 0, (cudaStream_t)stream>>>(pooled, n_src, n_queries, width, rk,
                                                                                         n_levels, sorted_runs && width % SL_J == 0, levels);
   return check_launch("sl_pool_levels_kernel");
