@@ -380,10 +380,11 @@ static inline long long* gt_dbg_ptr() {
 // packed operand width: K rounded up to 64 (one K chunk of the CTA-pair kernel; two of the one-CTA kernel)
 static inline int gt_kp(int k) { return (k + 63) / 64 * 64; }
 
+struct G2Deps;
 template <class Epi>
 static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda, int64_t ldb,
                            Epi epi, cudaStream_t st, const int* m_limit, bool f16, int lo_a, int lo_b, int seg_k,
-                           float* seg_buf, int64_t seg_ld);
+                           float* seg_buf, int64_t seg_ld, const G2Deps* deps_in, bool overlap_prev);
 static inline int g2_enabled();
 
 // A: packed [M, lda] (lda >= 2*kp), B: packed [N, ldb]; batch <= 2 problems with identical shapes.
@@ -408,7 +409,7 @@ static int launch_gemm_tc(const void* const* a, const void* const* b, int batch,
   // the persistent CTA-pair kernel (vfr_gemm_tc2.cuh) serves every operand whose K is a whole number of its 64-column chunks
   if (kp % 64 == 0 && (!flush_buf || flush_k % 64 == 0) && g2_enabled())
     return launch_gemm_tc2(a, b, batch, M, N, kp, lda, ldb, epi, st, m_limit, f16, lo_a, lo_b, flush_buf ? flush_k : 0, flush_buf,
-                           flush_ld);
+                           flush_ld, nullptr, false);
   GemmTcMaps maps;
   for (int z = 0; z < batch; ++z) {
     int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16);

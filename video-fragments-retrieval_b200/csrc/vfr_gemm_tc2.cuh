@@ -89,6 +89,62 @@ __device__ __forceinline__ void g2_commit_both(uint64_t* bar) {
 }
 
 struct G2Tile { int z, m0, n0, M; };
+
+// Dependencies between CONSECUTIVE launches of the kernel that overlap in time (programmatic dependent launch: launch
+// t + 1 starts filling SMs as the CTAs of launch t exit, it does not wait for the whole grid).  Every epilogue warp of a
+// tile adds 1 to cur[z][row block] once its stores are visible; a tile of the next launch waits until the row block it
+// reads - and, per problem, the row block `src_block[z]` (-1: none) other rows of its operand are copied from - has
+// collected G2_DEP_DONE of them.  prev == nullptr: nothing to wait for.  cur == nullptr: nothing to publish.
+struct G2Deps {
+  const int* prev;         // [2][n_blocks] counters of the previous launch
+  int* cur;                // [2][n_blocks] counters of this launch (zero at launch)
+  const int* prev_limit;   // [2] row limits of the previous launch (row blocks at or past them had no tile there)
+  int n_blocks;
+  int src_block[2];
+  // cur[2 n_blocks] / prev[2 n_blocks]: one more counter, over ALL tiles of the launch - once the previous launch is seen
+  // complete a CTA stops looking at row blocks (an acquire load per tile is an L2 round trip in front of the TMA loads)
+};
+__device__ __forceinline__ int g2_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void g2_dep_wait_one(const int* p, int want) {
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0; g2_ld_acquire(p) < want; ++spin) {
+    __nanosleep(64);
+    if ((spin & 0xfff) == 0xfff) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("vfr: gemm_tc2 dependency wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+// rows of block `mb` of problem z (and of its copy source) written by the previous launch are visible after this
+__device__ __forceinline__ void g2_dep_wait(const G2Deps& d, int z, int mb, int n_tiles_n) {
+  if (d.prev == nullptr) return;
+  const int done = n_tiles_n * 2 * (GT_THREADS / 32 - 2);
+  const int* row = d.prev + z * d.n_blocks;
+  if (mb * GT_BM < d.prev_limit[z]) g2_dep_wait_one(row + mb, done);
+  const int sb = z ? d.src_block[1] : d.src_block[0];
+  if (sb >= 0 && sb != mb) g2_dep_wait_one(row + sb, done);
+  asm volatile("fence.proxy.async;" ::: "memory");       // what follows may be a TMA (async proxy) read of those rows
+}
+// has the previous launch finished altogether?  (sticky per thread: `all_done`)
+__device__ __forceinline__ bool g2_dep_all_done(const G2Deps& d, int n_tiles_n, bool& all_done) {
+  if (d.prev == nullptr || all_done) return true;
+  const int per_tile = 2 * (GT_THREADS / 32 - 2);
+  const int want = (((d.prev_limit[0] + GT_BM - 1) / GT_BM) + ((d.prev_limit[1] + GT_BM - 1) / GT_BM)) * n_tiles_n * per_tile;
+  if (g2_ld_acquire(d.prev + 2 * d.n_blocks) >= want) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    all_done = true;
+  }
+  return all_done;
+}
 struct G2NoRow {};
 template <class E, class = void>
 struct G2PreOf { using type = G2NoRow; };
@@ -107,7 +163,7 @@ template <class Epi, bool SEG>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, const int* __restrict__ m_limit, int k_chunks,
                 int lo_a, int lo_b, uint32_t fmt, int N_all, int seg_chunks, float* __restrict__ seg_buf, int64_t seg_ld,
-                long long* __restrict__ dbg, Epi epi) {
+                const G2Deps deps, long long* __restrict__ dbg, Epi epi) {
   extern __shared__ uint8_t g2_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE);
@@ -120,6 +176,8 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = g2_cta_rank();
   const bool leader = rank == 0;
+  // a dependent launch (if the host asked for one) may take this CTA's SM as soon as it exits
+  if (deps.cur != nullptr) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // development aid (VFR_GEMM_DBG = device address of int64 [8]), cycles summed over the LEADER CTAs of all pairs:
   // 0 MMA issuer waiting for a free accumulator, 1 waiting for operands, 2 its whole tile loop, 3 epilogue warp 2 waiting
   // for a complete accumulator, 4 its epilogue work, 5 producer waiting for free stages, 6 tiles, 7 pairs
@@ -165,6 +223,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
     if (lane == 0) {
       const uint32_t full_leader0 = g2_mapa(&full[0], 0);     // (+ 8 s: no runtime-indexed local array)
       int it = 0;
+      bool prev_done = false;
       for (int t = pair; t < total; t += n_pairs) {
         const G2Tile tl = decode(t);
         const CUtensorMap* ma = tl.z ? &maps.a[1] : &maps.a[0];
@@ -172,6 +231,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
         // the last N tile of a matrix issues narrower MMAs (N rounded up to 32); the pair splits THAT N in halves
         const int n_mma = min(GT_BN, (N_all - tl.n0 + 31) / 32 * 32);
         const int row_a = tl.m0 + (int)rank * 128, row_b = tl.n0 + (int)rank * (n_mma >> 1);
+        if (!g2_dep_all_done(deps, n_tiles_n, prev_done)) g2_dep_wait(deps, tl.z, tl.m0 / GT_BM, n_tiles_n);
         for (int c = 0; c < k_chunks; ++c, ++it) {
           const int s = it % G2_STAGES;
           if (trace) { const long long t0 = clock64(); gt_wait(&empty[s], ((it / G2_STAGES) & 1) ^ 1, 32); w0 += clock64() - t0; }
@@ -235,6 +295,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
     // ================= epilogue: 8 warps per CTA, two per TMEM lane quarter (128 columns each) =================
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const uint32_t acc_empty_leader0 = g2_mapa(&acc_empty[0], 0);
+    bool prev_done_e = false;
     int ti = 0;
     for (int t = pair; t < total; t += n_pairs) {
       const G2Tile tl = decode(t);
@@ -256,6 +317,10 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
         }
         // (functors with a `Pre`: the global operands of all 8 column groups are in flight before the accumulator is)
         typename G2PreOf<Epi>::type pre[8];
+        if (deps.prev != nullptr && f == 0 && !prev_done_e) {      // (this tile's global operands come from the previous launch too)
+          if (lane == 0 && !g2_dep_all_done(deps, n_tiles_n, prev_done_e)) g2_dep_wait(deps, tl.z, tl.m0 / GT_BM, n_tiles_n);
+          prev_done_e = __shfl_sync(0xffffffffu, prev_done_e ? 1 : 0, 0) != 0;
+        }
         if constexpr (gt_has_pre<Epi>::value && !SEG) {
           if (m < tl.M) {
 #pragma unroll
@@ -318,6 +383,16 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
         gt_fence_before();
         __syncwarp();
         if (lane == 0) g2_arrive_remote(acc_empty_leader0 + 8u * (uint32_t)buf);
+        if (deps.cur != nullptr && last) {
+          // this warp's part of the tile is written: visible to every later reader (generic and TMA) before the count
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(deps.cur + tl.z * deps.n_blocks + tl.m0 / GT_BM) : "memory");
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(deps.cur + 2 * deps.n_blocks) : "memory");
+          }
+        }
         if (trace && warp == 2) w1 += clock64() - t_e;
       }
     }
@@ -340,29 +415,37 @@ static inline int g2_enabled() {
 
 template <class Epi, bool SEG>
 static int launch_gemm_tc2_impl(const GemmTcMaps& maps, int pairs, int batch, int M, int N, int kp, Epi epi, cudaStream_t st,
-                                const int* m_limit, bool f16, int lo_a, int lo_b, int seg_k, float* seg_buf, int64_t seg_ld) {
+                                const int* m_limit, bool f16, int lo_a, int lo_b, int seg_k, float* seg_buf, int64_t seg_ld,
+                                const G2Deps& deps, bool overlap_prev) {
   VFR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<Epi, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
   cfg.blockDim = dim3(GT_THREADS, 1, 1);
   cfg.dynamicSmemBytes = G2_SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // overlap_prev: this launch may start while the previous kernel of the stream is still running (its CTAs wait for their
+  // operands through `deps`, the kernel never executes griddepcontrol.wait)
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = overlap_prev ? 2 : 1;
   VFR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<Epi, SEG>, maps, batch, M, m_limit, kp / G2_BK, lo_a, lo_b,
-                              f16 ? GT_FMT_F16 : GT_FMT_BF16, N, seg_k / G2_BK, seg_buf, seg_ld, gt_dbg_ptr(), epi));
+                              f16 ? GT_FMT_F16 : GT_FMT_BF16, N, seg_k / G2_BK, seg_buf, seg_ld, deps, gt_dbg_ptr(), epi));
   return check_launch("gemm_tc2_kernel");
 }
 
 template <class Epi>
 static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch, int M, int N, int kp, int64_t lda, int64_t ldb,
                            Epi epi, cudaStream_t st, const int* m_limit, bool f16, int lo_a, int lo_b, int seg_k,
-                           float* seg_buf, int64_t seg_ld) {
+                           float* seg_buf, int64_t seg_ld, const G2Deps* deps_in, bool overlap_prev) {
+  G2Deps deps{};
+  deps.src_block[0] = deps.src_block[1] = -1;
+  if (deps_in) deps = *deps_in;
   GemmTcMaps maps;
   for (int z = 0; z < batch; ++z) {
     int rc = gt_make_map(&maps.a[z], a[z], (uint64_t)M, (uint64_t)lda, 128, f16, G2_BK);
@@ -379,8 +462,8 @@ static int launch_gemm_tc2(const void* const* a, const void* const* b, int batch
   }
   const int64_t tiles = (int64_t)batch * ((M + GT_BM - 1) / GT_BM) * ((N + GT_BN - 1) / GT_BN);
   const int pairs = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / 2, tiles));
-  if (seg_buf) return launch_gemm_tc2_impl<Epi, true>(maps, pairs, batch, M, N, kp, epi, st, m_limit, f16, lo_a, lo_b, seg_k, seg_buf, seg_ld);
-  return launch_gemm_tc2_impl<Epi, false>(maps, pairs, batch, M, N, kp, epi, st, m_limit, f16, lo_a, lo_b, 0, nullptr, 0);
+  if (seg_buf) return launch_gemm_tc2_impl<Epi, true>(maps, pairs, batch, M, N, kp, epi, st, m_limit, f16, lo_a, lo_b, seg_k, seg_buf, seg_ld, deps, overlap_prev);
+  return launch_gemm_tc2_impl<Epi, false>(maps, pairs, batch, M, N, kp, epi, st, m_limit, f16, lo_a, lo_b, 0, nullptr, 0, deps, overlap_prev);
 }
 
 }  // namespace vfr
