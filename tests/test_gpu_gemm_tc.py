@@ -115,6 +115,28 @@ def test_text_embed_tc_padding_aware_rows(nl):
     assert torch.equal(shuffled, got)
 
 
+@pytest.mark.parametrize("n_queries", [1, 257, 700, 4737])
+def test_text_embed_tc_overlapped_step_launches_equal_serial_ones(n_queries, monkeypatch):
+    """The 20 step GEMMs of a batch of up to 20 000 rows overlap through programmatic dependent launch; a tile waits for
+    the row blocks of the previous step it reads through per-row-block counters (vfr_gemm_tc2.cuh, G2Deps).  The
+    embeddings must carry the same bits as with serial launches (VFR_K3_OVERLAP=0), every repetition."""
+    sd = synth.make_state_dict(11, 8, 900)
+    model = _model(sd, 8)
+    model.engine = "tc"
+    rng = np.random.default_rng(n_queries)
+    tok = np.zeros((n_queries, 20), dtype=np.int64)
+    lens = rng.integers(0, 21, size=n_queries)
+    for r in range(n_queries):
+        tok[r, :lens[r]] = rng.integers(1, 900, size=lens[r])
+    t = torch.from_numpy(tok).to(DEV)
+    with torch.no_grad():
+        monkeypatch.setenv("VFR_K3_OVERLAP", "0")
+        serial = model(t, False, DEV).clone()
+        monkeypatch.setenv("VFR_K3_OVERLAP", "1")
+        for _ in range(3):
+            assert torch.equal(model(t, False, DEV).view(torch.int32), serial.view(torch.int32))
+
+
 def test_visual_embed_tc_matches_reference_and_exact_path(golden):
     """K2 on tensor cores (engine "tc"): the reference's own visual embeddings within 1e-5 of their scale."""
     z, meta = golden("tiny_eval")

@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t tmem_ld<64>(uint32_t taddr) {
 template <int X>
 __global__ void __launch_bounds__(64 + 512, 1)
 ubench_kernel(int mode, int reader_warps, int ld_iters, int mma_n, int mma_count, int wait_every, long long* out_ld,
-              long long* out_mma, uint32_t* sink) {
+              long long* out_mma, uint32_t* sink, int chains = 2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -109,7 +109,16 @@ ubench_kernel(int mode, int reader_warps, int ld_iters, int mma_n, int mma_count
       const uint32_t idesc = (1u << 4) | ((wait_every & 1) ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // wait_every odd: bf16, even: fp16
       const uint64_t adesc = make_desc(smem), bdesc = make_desc(smem + 16384);
       const long long t0 = clock64();
-      for (int i = 0; i < mma_count; ++i) tc_mma(tmem_base + (uint32_t)((i & 1) * 256), adesc + (uint64_t)((i & 3) * 2), bdesc + (uint64_t)((i & 3) * 2), idesc, i > 1);
+      // `chains` accumulators in rotation: 1 = every MMA accumulates into the result of the one before it
+      if (chains == 2) for (int i = 0; i < mma_count; ++i) tc_mma(tmem_base + (uint32_t)((i & 1) * 256), adesc + (uint64_t)((i & 3) * 2), bdesc + (uint64_t)((i & 3) * 2), idesc, i > 1);
+      else {
+        // (no runtime division in the issuing thread: its instruction latency would bound the loop)
+        uint32_t c = 0;
+        for (int i = 0; i < mma_count; ++i) {
+          tc_mma(tmem_base + c * 128u, adesc + (uint64_t)((i & 3) * 2), bdesc + (uint64_t)((i & 3) * 2), idesc, i >= chains);
+          c = (c + 1 == (uint32_t)chains) ? 0u : c + 1;
+        }
+      }
       tc_commit(&bar);
       mbar_wait(&bar, 0);
       const long long t1 = clock64();
@@ -153,7 +162,7 @@ ubench_kernel(int mode, int reader_warps, int ld_iters, int mma_n, int mma_count
 }
 
 template <int X>
-static void run(int mode, int reader_warps, int ld_iters, int mma_n, int mma_count, int wait_every) {
+static void run(int mode, int reader_warps, int ld_iters, int mma_n, int mma_count, int wait_every, int chains = 2) {
   long long *d_ld, *d_mma;
   uint32_t* sink;
   cudaMalloc(&d_ld, 148 * 16 * sizeof(long long));
@@ -163,7 +172,7 @@ static void run(int mode, int reader_warps, int ld_iters, int mma_n, int mma_cou
   cudaMemset(d_mma, 0, 148 * sizeof(long long));
   const int smem = 64 * 1024;
   cudaFuncSetAttribute(ubench_kernel<X>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int rep = 0; rep < 2; ++rep) ubench_kernel<X><<<148, 64 + reader_warps * 32, smem>>>(mode, reader_warps, ld_iters, mma_n, mma_count, wait_every, d_ld, d_mma, sink);
+  for (int rep = 0; rep < 2; ++rep) ubench_kernel<X><<<148, 64 + reader_warps * 32, smem>>>(mode, reader_warps, ld_iters, mma_n, mma_count, wait_every, d_ld, d_mma, sink, chains);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(1); }
   std::vector<long long> ld(148 * 16), mma(148);
@@ -179,12 +188,19 @@ static void run(int mode, int reader_warps, int ld_iters, int mma_n, int mma_cou
     const double bytes = (double)reader_warps * ld_iters * X * 32 * 4;
     printf("  | ld: %lld cyc, %.1f B/clk/SM, %.2f cyc per x%d load per warp", ld_max, bytes / (double)ld_max, (double)ld_max / ld_iters, X);
   }
-  if (mode & 2) printf("  | mma N=%d: %.1f cyc per MMA (floor %.0f)", mma_n, (double)mma_max / mma_count, 128.0 * mma_n / 256.0);
+  if (mode & 2) printf("  | mma N=%d chains=%d: %.1f cyc per MMA (floor %.0f)", mma_n, chains, (double)mma_max / mma_count, 128.0 * mma_n / 256.0);
   printf("\n");
   cudaFree(d_ld); cudaFree(d_mma); cudaFree(sink);
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'd') {   // dependent accumulation: how long does an MMA take that accumulates into the previous one's result?
+    for (int n : {64, 96, 128, 256})
+      for (int chains : {1, 2, 3, 4})
+        if (n * chains <= 512 && !(chains == 2 && n > 128)) run<32>(2, 4, 0, n, 4000, 2, chains);
+    for (int chains : {1, 2, 4}) run<32>(3, 8, 4000, 128, 8000, 2, chains);
+    return 0;
+  }
   if (argc > 1) { run<32>(2, 4, 0, 256, 7, 1); for (int n : {128, 240, 256}) { run<32>(2, 4, 0, n, 4000, 1); run<32>(2, 4, 0, n, 4000, 2); } for (int readers : {8}) { run<32>(3, readers, 4000, 256, 8000, 1); run<32>(3, readers, 4000, 256, 8000, 2); } return 0; }
   for (int readers : {4, 8, 16}) {
     for (int we : {1, 2}) {

@@ -88,6 +88,64 @@ __device__ __forceinline__ void g2_commit_both(uint64_t* bar) {
                : "memory");
 }
 
+// One lane of a CONVERGED warp; deterministic (the same lane for the same mask every time), so the MMAs and the commits
+// that track them come from one thread.
+__device__ __forceinline__ bool g2_elect() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// The 12 MMAs of one 64-column K chunk (4 k steps x {Ah.Bh, Al.Bh, Ah.Bl}, in that order) as ONE asm block issued by the
+// elected lane of a converged warp.  Issued one by one from `if (lane == 0)` code, the compiler wraps every tcgen05.mma in an
+// ELECT / BRA.U.ANY loop and re-derives its descriptors (~15 instructions, ~120 cycles of issue per MMA - as long as the
+// MMA runs, so the issuer never gets ahead of the tensor pipe and every barrier wait of its own becomes a pipe bubble);
+// here the operands reach uniform registers once per chunk and the UTCHMMAs follow each other directly.
+// acc: does the first MMA accumulate?
+__device__ __forceinline__ void g2_mma_chunk(uint32_t d_tmem, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
+                                             uint32_t acc) {
+  static_assert(G2_BK == 64, "four k steps of 16 per chunk");
+  asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b64 ah1, al1, bh1, bl1, ah2, al2, bh2, bl2, ah3, al3, bh3, bl3;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.u64 ah1, %1, 2;\n"
+      "add.u64 al1, %2, 2;\n"
+      "add.u64 bh1, %3, 2;\n"
+      "add.u64 bl1, %4, 2;\n"
+      "add.u64 ah2, %1, 4;\n"
+      "add.u64 al2, %2, 4;\n"
+      "add.u64 bh2, %3, 4;\n"
+      "add.u64 bl2, %4, 4;\n"
+      "add.u64 ah3, %1, 6;\n"
+      "add.u64 al3, %2, 6;\n"
+      "add.u64 bh3, %3, 6;\n"
+      "add.u64 bl3, %4, 6;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %3, %5, p;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %2, %3, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %4, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah1, bh1, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], al1, bh1, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah1, bl1, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah2, bh2, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], al2, bh2, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah2, bl2, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah3, bh3, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], al3, bh3, %5, t;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah3, bl3, %5, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(ah), "l"(al), "l"(bh), "l"(bl), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 struct G2Tile { int z, m0, n0, M; };
 
 // Dependencies between CONSECUTIVE launches of the kernel that overlap in time (programmatic dependent launch: launch
@@ -249,7 +307,8 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
-    if (lane == 0 && leader) {
+    if (leader) {
+      // (the whole warp runs this loop converged; the tcgen05 instructions come from its elected lane - see g2_mma_chunk)
       int it = 0, ti = 0;
       const long long t_loop = trace ? clock64() : 0;
       for (int t = pair; t < total; t += n_pairs) {
@@ -272,18 +331,14 @@ gemm_tc2_kernel(const __grid_constant__ GemmTcMaps maps, int batch, int M_all, c
             gt_fence_after();
             uint8_t* st = smem + s * G2_STAGE;
             const uint64_t ah = g2_desc(st), al = g2_desc(st + G2_SUB), bh = g2_desc(st + 2 * G2_SUB), bl = g2_desc(st + 3 * G2_SUB);
-#pragma unroll
-            for (int k = 0; k < G2_BK / 16; ++k) {
-              g2_mma(d, ah + 2 * k, bh + 2 * k, idesc, (!first || k) ? 1u : 0u);
-              g2_mma(d, al + 2 * k, bh + 2 * k, idesc, 1u);
-              g2_mma(d, ah + 2 * k, bl + 2 * k, idesc, 1u);
-            }
-            g2_commit_both(&empty[s]);             // the stage is free in BOTH CTAs once these MMAs have read it
+            g2_mma_chunk(d, ah, al, bh, bl, idesc, first ? 0u : 1u);
+            if (g2_elect()) g2_commit_both(&empty[s]);             // the stage is free in BOTH CTAs once these MMAs have read it
           }
-          g2_commit_both(&acc_full[buf]);
+          if (g2_elect()) g2_commit_both(&acc_full[buf]);
+          __syncwarp();
         }
       }
-      if (trace) {
+      if (trace && lane == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 0), (unsigned long long)w0);
         atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 1), (unsigned long long)w1);
         atomicAdd(reinterpret_cast<unsigned long long*>(dbg + 2), (unsigned long long)(clock64() - t_loop));

@@ -56,6 +56,7 @@ constexpr int SL_A_CHUNK = SL_M * 128;    // bytes of one [128 x 64 fp16] box
 constexpr int SL_B_CHUNK = SL_N * 128;    // bytes of one [256 x 64 fp16] box = 32 KB
 constexpr int SL_SET_WARPS = 4;           // one epilogue warp per TMEM lane quarter ...
 constexpr int SL_THREADS = 64 + 2 * SL_SET_WARPS * 32;   // ... in two sets (one per TMEM buffer): 320 threads
+constexpr int SL_THREADS2 = SL_THREADS + 32;             // the two-issuer variant (NB = 5) has one more non-epilogue warp
 constexpr int SL_CAP = 1024;              // candidate slots per (query, part) list
 constexpr int SL_CAP_HI = SL_CAP - SL_N;  // a tile can append at most SL_N keys to a list
 constexpr int SL_QPAD = 512;              // packed query rows are padded to a multiple of this (R x 128 rows x CTA pair)
@@ -100,6 +101,7 @@ struct SlParams {
   long long* dbg;            // optional timeline of CTA 0 (development aid): [9 roles][256 events][4] + 8 counters
   int32_t* flags;            // [Qpad] != 0: a candidate list overflowed / scales out of range (see vfr.h)
   unsigned long long* stats; // [2] {warp-level compaction events, lists compacted} since the lists were started (vfr_sel_stats)
+  const uint32_t* qpack;     // the packed query rows themselves ([Qpad][128] fp16 as 64 words): the NB = 3 kernel keeps them in TMEM
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -313,6 +315,218 @@ __device__ __forceinline__ void sl_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// One lane of a CONVERGED warp (deterministic: the same lane for the same mask every time, so the MMAs and the commits
+// that track them come from one thread).  An issuer that runs as `if (lane == 0)` makes the compiler wrap every tcgen05.mma
+// in an ELECT / BRA.U.ANY loop with the operands moved by R2UR (~120 cycles of issue per MMA, measured: that - not the
+// tensor pipe - bounded jobs of N = 128); from a converged warp the UTCHMMAs issue back to back out of uniform registers.
+__device__ __forceinline__ bool sl_elect() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.mma from the elected lane of a converged warp, the election inside the asm block (no C++ branch: the operands stay
+// in uniform registers and consecutive UTCHMMAs are three instructions apart)
+__device__ __forceinline__ void sl_mma_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void sl_mma_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// N (1 ... 4) consecutive k steps of one 64-column chunk as ONE asm block from the elected lane of a converged warp: the
+// operands are moved to uniform registers once per block, the + 2 k (descriptors, 32-byte steps >> 4) / + 8 k (TMEM columns)
+// happen inside, and the UTCHMMAs follow each other directly.  acc: does the FIRST one accumulate?
+template <int N>
+__device__ __forceinline__ void sl_mma_block(uint32_t d_tmem, uint64_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if constexpr (N == 1) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+  }
+  else if constexpr (N == 2) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b64 a1, b1;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.u64 a1, %1, 2;\n"
+      "add.u64 b1, %2, 2;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+  }
+  else if constexpr (N == 3) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b64 a1, b1, a2, b2;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.u64 a1, %1, 2;\n"
+      "add.u64 b1, %2, 2;\n"
+      "add.u64 a2, %1, 4;\n"
+      "add.u64 b2, %2, 4;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+  }
+  else if constexpr (N == 4) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b64 a1, b1, a2, b2, a3, b3;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.u64 a1, %1, 2;\n"
+      "add.u64 b1, %2, 2;\n"
+      "add.u64 a2, %1, 4;\n"
+      "add.u64 b2, %2, 4;\n"
+      "add.u64 a3, %1, 6;\n"
+      "add.u64 b3, %2, 6;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+  }
+}
+template <int N>
+__device__ __forceinline__ void sl_mma_ts_block(uint32_t d_tmem, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if constexpr (N == 1) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+  }
+  else if constexpr (N == 2) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b32 a1;\n"
+      ".reg .b64 b1;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.u32 a1, %1, 8;\n"
+      "add.u64 b1, %2, 2;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+  }
+  else if constexpr (N == 3) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b32 a1, a2;\n"
+      ".reg .b64 b1, b2;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.u32 a1, %1, 8;\n"
+      "add.u64 b1, %2, 2;\n"
+      "add.u32 a2, %1, 16;\n"
+      "add.u64 b2, %2, 4;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+  }
+  else if constexpr (N == 4) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b32 a1, a2, a3;\n"
+      ".reg .b64 b1, b2, b3;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.u32 a1, %1, 8;\n"
+      "add.u64 b1, %2, 2;\n"
+      "add.u32 a2, %1, 16;\n"
+      "add.u64 b2, %2, 4;\n"
+      "add.u32 a3, %1, 24;\n"
+      "add.u64 b3, %2, 6;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, t;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+  }
+}
+// A operand in TMEM (lane = row, a 32-bit column = two consecutive K elements), B through its shared-memory descriptor
+__device__ __forceinline__ void sl_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void sl_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,"
+      "%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
 // the same load delivered to the same shared-memory offsets (data and mbarrier) of every CTA in `mask`
 __device__ __forceinline__ void sl_tma_load_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
   asm volatile(
@@ -346,6 +560,8 @@ __device__ __forceinline__ uint64_t sl_desc(const void* smem_ptr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// the upper word of sl_desc (it does not depend on the address)
+__host__ __device__ constexpr uint32_t sl_desc_hi() { return (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29); }
 __device__ __forceinline__ void sl_ld32(uint32_t taddr, float (&v)[64], int off) {
   uint32_t r[32];
   asm volatile(
@@ -558,6 +774,10 @@ struct SlCfg {
 constexpr int SL_BIG_STAGES = 3;
 constexpr int SL_BIG_STAGE = 2 * SL_A_CHUNK + SL_B_CHUNK;      // 64 KB
 constexpr uint32_t SL_BIG_SMEM = SL_BIG_STAGES * SL_BIG_STAGE + 1024 + 256;
+// NB = 3 (query tiles in TMEM): shared memory holds only the ring of bank tiles
+constexpr int SL_ATM_STAGES = 6;
+constexpr uint32_t SL_ATM_SMEM = SL_ATM_STAGES * SL_B_CHUNK + 1024 + 256;
+constexpr uint32_t SL_ATM_ACOL = 384;     // TMEM columns [384, 512): the two query tiles (64 columns = 128 fp16 each)
 
 // per-thread state of the epilogue: one query row, one candidate list
 struct SlRow {
@@ -670,27 +890,45 @@ __device__ __forceinline__ void sl_sample(const float (&v)[64], float (&a)[SL_J]
 // BIG: the K-streaming variant for D + 3 > 128 (R = 2, CL = 1): every 64-column chunk of the two query tiles travels
 // through the ring together with the bank tile's chunk; a tile's two accumulators are committed after the last chunk
 // (no ping-pong - the epilogue's ~700-cycle read of a buffer is small against the >= 3 x 4 MMAs x 2 of a tile).
-// NB = 4 (opt-in, VFR_SEL_NB=4; measured SLOWER): the 512 TMEM columns as FOUR accumulators of 128 columns, a job = one query
-// tile x one HALF of a bank tile (MMA N = 128).  The idea: a buffer's round trip - MMAs issued -> commit seen by the epilogue
-// (~550 cycles) -> its four warps have read it (~750 median, 1 200 p90) -> the issuer sees the release (~450) - is ~3 000
-// cycles, i.e. 1 500 per job with two buffers against 896 of MMA (tools/timeline_sel.py); four buffers would spread the same
-// latencies over four jobs in flight.  Measured on B200 (37 888 queries x 6 M clips, same box): the seven N = 128 MMAs of a
-// half job take ~855 cycles - as long as the seven N = 256 MMAs of a whole one (the A operand's 128 x 16 slice is re-read
-// per MMA; in isolation, with four repeating slices, N = 128 runs at its 64-cycle floor: tools/ubench_tc.cu) - so the scan
-// goes from 46 to 70 ms.  Kept as evidence that the N = 256 job is already the cheapest form of this loop.
+// Accumulator schemes (NB; 2 is the default, the others are opt-in through VFR_SEL_NB and return the same bits).  A buffer's
+// round trip - MMAs issued -> commit seen by the epilogue (~550 cycles) -> its four warps have read it (~750 median, 1 200
+// p90) -> the issuer sees the release (~450) - is ~3 000 cycles, i.e. 1 500 per job with two buffers against 896 of MMA
+// (tools/timeline_sel.py).  Smaller jobs on more buffers would spread the same latencies over more work in flight:
+//   NB = 4  four accumulators of 128 columns, a job = one query tile x one HALF of a bank tile (MMA N = 128);
+//   NB = 5  the same with ONE MMA ISSUER PER QUERY TILE (warps 1 and 2, 352 threads);
+//   NB = 3  the query tiles kept in TMEM (tcgen05.st once per CTA, MMA with the A operand from TMEM: no re-read of the
+//           128 x 16 A slice from shared memory per MMA, a sixth ring stage), three accumulators of 128 columns in rotation.
+// Measured on B200, 37 888 queries x 6 M clips, whole vfr_sel_topk, same box: NB = 2 49.7 ms, NB = 5 50.9, NB = 3 61.6,
+// NB = 4 62.7.  What round 2 found behind the first NB = 4 result (70 ms, "seven N = 128 MMAs take as long as seven N = 256
+// ones"): not the tensor pipe - in isolation N = 128 runs at its 64-cycle floor, dependent accumulation included
+// (tools/ubench_tc.cu dep) - but the ISSUING THREAD.  Issued one by one from `if (lane == 0)` code, every tcgen05.mma is
+// wrapped by the compiler in an ELECT / BRA.U.ANY loop with its operands moved by R2UR: ~120 cycles of issue per MMA
+// whatever N.  The issuer now runs as a converged warp and issues each chunk's MMAs from one asm block (sl_mma_block:
+// 7 MMAs in ~640 cycles, 1 100 before).  That moved NB = 4 from 77.8 to 62.7 ms and NB = 3 from 72 to 61.6, and left NB = 2
+// where it was: with N = 256 the chain (896 cycles of MMA + the two hand-offs + the read) binds, not the issue.  With half
+// jobs the issuer's fixed cost per job (~280 cycles of probes / commit / fence + the issue) is paid twice as often - one
+// issuer is bound by it (NB = 3 / 4), two issuers (NB = 5) reach the default's time but then wait for bank tiles (every
+// stage is released by both) - so N = 256 on two buffers stays the default.  Also measured and dropped: all eight
+// epilogue warps reading every buffer, 128 columns each (hold 740 -> 515 cycles, but every warp then pays the fixed costs
+// of every job and the lists double: 64.6 ms).
 template <int R, int CL, int MODE, bool BIG = false, int NB = 2>
-__global__ void __launch_bounds__(SL_THREADS, 1)
+__global__ void __launch_bounds__(NB == 5 ? SL_THREADS2 : SL_THREADS, 1)
 sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const SlParams p) {
   static_assert(!BIG || (R == 2 && CL == 1), "the K-streaming variant serves two query tiles per CTA, no cluster");
-  static_assert(NB == 2 || (NB == 4 && !BIG && CL == 1), "four accumulators: plain kernel only");
-  constexpr bool HALF = NB == 4;
+  static_assert(NB == 2 || ((NB == 4 || NB == 3 || NB == 5) && !BIG && CL == 1), "three / four accumulators: plain kernel only");
+  static_assert((NB != 3 && NB != 5) || R == 2, "query tiles in TMEM / two issuers: two query tiles per CTA");
+  constexpr bool ATM = NB == 3;                       // A operand (the query tiles) in TMEM, three accumulators of 128 columns
+  constexpr bool ISS2 = NB == 5;                      // four accumulators, ONE MMA ISSUER PER QUERY TILE (warps 1 and 2)
+  constexpr int NBUF = ISS2 ? 4 : NB;
+  constexpr int EW0 = ISS2 ? 3 : 2;                   // first epilogue warp
+  constexpr bool HALF = NB >= 3;
   constexpr int JOB_N = HALF ? SL_N / 2 : SL_N;       // accumulator columns of a job
-  constexpr int STAGES = BIG ? SL_BIG_STAGES : SlCfg<R>::STAGES;
+  constexpr int STAGES = BIG ? SL_BIG_STAGES : (ATM ? SL_ATM_STAGES : SlCfg<R>::STAGES);
   constexpr int STAGE_BYTES = BIG ? SL_BIG_STAGE : SL_B_CHUNK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                   // [R][2 chunks]   (BIG: unused, the chunks live in the stages)
-  uint8_t* smem_b = BIG ? smem : smem + R * 2 * SL_A_CHUNK; // [STAGES]
+  uint8_t* smem_b = (BIG || ATM) ? smem : smem + R * 2 * SL_A_CHUNK; // [STAGES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * STAGE_BYTES);
   uint64_t* full = bars;                        // [STAGES]
   uint64_t* empty = bars + STAGES;              // [STAGES]
@@ -709,9 +947,9 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int b_chunks = (p.ksteps > 4) ? 2 : 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-    mbar_init(a_full, 1);
-    for (int b = 0; b < NB; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], SL_SET_WARPS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ISS2 ? 2 : CL); }
+    mbar_init(a_full, ATM ? 2 * SL_SET_WARPS : 1);      // (ATM: every epilogue warp stores its 32 query rows into TMEM)
+    for (int b = 0; b < NBUF; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], SL_SET_WARPS); }
     fence_barrier_init();
   }
   const int crank = (CL == 2) ? sl_cluster_rank() : 0;
@@ -724,7 +962,10 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   sl_fence_before();
   __syncthreads();
   sl_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
+  // (through a shuffle: the compiler then knows the value is warp-uniform and keeps the accumulator addresses of the MMA
+  //  issuer in uniform registers - from a plain shared-memory load every tcgen05.mma is wrapped in an ELECT / R2UR /
+  //  BRA.U.ANY loop, ~120 cycles of issue per MMA, which bounds jobs of N = 128)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -745,10 +986,12 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     } else
     if (lane == 0 && n_my_tiles > 0) {
-      mbar_expect_tx(a_full, (uint32_t)(R * b_chunks) * SL_A_CHUNK);
-      for (int r = 0; r < R; ++r)
-        for (int c = 0; c < b_chunks; ++c)
-          sl_tma_load(smem_a + (r * 2 + c) * SL_A_CHUNK, &tm_a, c * 64, (qgroup * R + r) * SL_M, a_full);
+      if constexpr (!ATM) {
+        mbar_expect_tx(a_full, (uint32_t)(R * b_chunks) * SL_A_CHUNK);
+        for (int r = 0; r < R; ++r)
+          for (int c = 0; c < b_chunks; ++c)
+            sl_tma_load(smem_a + (r * 2 + c) * SL_A_CHUNK, &tm_a, c * 64, (qgroup * R + r) * SL_M, a_full);
+      }
       int it = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
         const int row = (tile_begin + t) * p.tile_stride * SL_N;
@@ -761,7 +1004,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (ISS2 && warp == 2)) {
     // ================= MMA issuer =================
     if (BIG) {
       if (lane == 0 && n_my_tiles > 0) {
@@ -789,7 +1032,8 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     } else
-    if (lane == 0 && n_my_tiles > 0) {
+    if (n_my_tiles > 0) {
+      // (the whole warp runs this loop converged; the tcgen05 instructions come from its elected lane - see sl_elect)
       // kind::f16, fp16 x fp16 -> fp32, K-major A and B, N = 256 (128 with four accumulators), M = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(JOB_N >> 3) << 17) | ((uint32_t)(SL_M >> 4) << 24);
       sl_wait(a_full, 0, p.wait_mode);
@@ -801,14 +1045,20 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int s0 = 0, s1 = 0, ph0 = 0, ph1 = 0;
       int pend_buf = -1, pend_s0 = 0, pend_s1 = 0;
       bool pend_release = false;
-      constexpr int JPT = (HALF ? 2 : 1) * R;     // jobs per bank tile
+      constexpr int JPT = ISS2 ? 2 : (HALF ? 2 : 1) * R;     // jobs per bank tile (of this issuer)
       const int n_jobs = n_my_tiles * JPT;
       for (int job = 0; job < n_jobs; ++job) {
         // two accumulators: buffer = query tile (R = 2) or tile parity (R = 1).  Four: a tile's jobs go (r0, h0), (r1, h0),
         // (r0, h1), (r1, h1) - the sets get their work evenly spaced - on buffer 2 r + h; R = 1: tile parity s, 2 s + h.
         int r, h, buf, use;
         bool first, last;
-        if (HALF) {
+        if (ISS2) {
+          // this issuer serves query tile r = warp - 1 alone: the two halves of every bank tile on its own two accumulators
+          r = warp - 1; h = job & 1; buf = 2 * r + h; use = job >> 1; first = h == 0; last = h == 1;
+        } else if (ATM) {
+          // three accumulators in rotation; jobs of a tile as below, so each epilogue set gets every other job
+          const int j4 = job & 3; r = j4 & 1; h = j4 >> 1; buf = job % 3; use = job / 3; first = j4 == 0; last = j4 == 3;
+        } else if (HALF) {
           if (R == 2) { const int j4 = job & 3; r = j4 & 1; h = j4 >> 1; buf = 2 * r + h; use = job >> 2; first = j4 == 0; last = j4 == 3; }
           else { const int tt = job >> 1; r = 0; h = job & 1; buf = 2 * (tt & 1) + h; use = tt >> 1; first = h == 0; last = h == 1; }
         } else {
@@ -826,10 +1076,13 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           ready = ready && sl_test(&full[s0], ph0);
           if (b_chunks == 2) ready = ready && sl_test(&full[s1], ph1);
         }
+        ready = __all_sync(0xffffffffu, ready);       // (one answer for the warp: the lanes probe at slightly different times)
         if (!ready || pend_buf < 0) {
           if (pend_buf >= 0) {
-            sl_commit(&tmem_full[pend_buf]);
-            if (pend_release) { sl_release<CL>(&empty[pend_s0]); if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]); }
+            if (sl_elect()) {
+              sl_commit(&tmem_full[pend_buf]);
+              if (pend_release) { sl_release<CL>(&empty[pend_s0]); if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]); }
+            }
             pend_buf = -1;
           }
           if (first) {
@@ -839,20 +1092,41 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           sl_wait(&tmem_empty[buf], pe, p.wait_mode);
         }
         sl_fence_after();
-        if (pend_buf >= 0) {
+        if (pend_buf >= 0 && sl_elect()) {
           sl_commit(&tmem_full[pend_buf]);
           if (pend_release) { sl_release<CL>(&empty[pend_s0]); if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]); }
         }
         const long long tm1 = p.dbg ? clock64() : 0;
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * JOB_N;
-        uint32_t accumulate = 0;
-        for (int c = 0; c < b_chunks; ++c) {
-          const int ks = (c == 0) ? min(p.ksteps, 4) : (p.ksteps - 4);
-          const uint64_t adesc = sl_desc(smem_a + (r * 2 + c) * SL_A_CHUNK);
-          const uint64_t bdesc = sl_desc(smem_b + (c ? s1 : s0) * SL_B_CHUNK + h * (SL_B_CHUNK / 2));
-          for (int k = 0; k < ks; ++k) {
-            sl_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
-            accumulate = 1;
+        // straight-line issue: compile-time k and accumulate flag, and every operand made KNOWN warp-uniform by a shuffle
+        // (the job's bookkeeping lives in vector registers; without it each UTCHMMA is preceded by ~7 R2UR and two VOTEU) -
+        // what sits between two UTCHMMAs is issue time of the one thread that feeds the tensor pipe
+        const uint32_t d_u = __shfl_sync(0xffffffffu, d_tmem, 0);
+        const uint32_t b0_lo = __shfl_sync(0xffffffffu, (uint32_t)sl_desc(smem_b + s0 * SL_B_CHUNK + h * (SL_B_CHUNK / 2)), 0);
+        const uint32_t b1_lo = __shfl_sync(0xffffffffu, (uint32_t)sl_desc(smem_b + s1 * SL_B_CHUNK + h * (SL_B_CHUNK / 2)), 0);
+        const uint32_t a_lo = ATM ? __shfl_sync(0xffffffffu, tmem_base + SL_ATM_ACOL + (uint32_t)(r * 64), 0)
+                                  : __shfl_sync(0xffffffffu, (uint32_t)sl_desc(smem_a + r * 2 * SL_A_CHUNK), 0);
+        constexpr uint64_t DESC_HI = (uint64_t)(sl_desc_hi()) << 32;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < b_chunks) {
+            const int ks = (c == 0) ? min(p.ksteps, 4) : (p.ksteps - 4);
+            const uint64_t bdesc = DESC_HI | (c ? b1_lo : b0_lo);
+            const uint32_t acc = c ? 1u : 0u;
+            if constexpr (ATM) {
+              // 16 fp16 of K = 8 TMEM columns; a 64-column chunk of the packed row = 32 TMEM columns
+              const uint32_t a_t = a_lo + (uint32_t)(c * 32);
+              if (ks >= 4) sl_mma_ts_block<4>(d_u, a_t, bdesc, idesc, acc);
+              else if (ks == 3) sl_mma_ts_block<3>(d_u, a_t, bdesc, idesc, acc);
+              else if (ks == 2) sl_mma_ts_block<2>(d_u, a_t, bdesc, idesc, acc);
+              else if (ks == 1) sl_mma_ts_block<1>(d_u, a_t, bdesc, idesc, acc);
+            } else {
+              const uint64_t adesc = DESC_HI | (a_lo + (uint32_t)(c * (SL_A_CHUNK >> 4)));
+              if (ks >= 4) sl_mma_block<4>(d_u, adesc, bdesc, idesc, acc);
+              else if (ks == 3) sl_mma_block<3>(d_u, adesc, bdesc, idesc, acc);
+              else if (ks == 2) sl_mma_block<2>(d_u, adesc, bdesc, idesc, acc);
+              else if (ks == 1) sl_mma_block<1>(d_u, adesc, bdesc, idesc, acc);
+            }
           }
         }
         pend_buf = buf;
@@ -860,19 +1134,20 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         pend_s1 = s1;
         pend_release = last;
         const int job0 = n_jobs - 256;
-        if (p.dbg && blockIdx.x == 0 && job >= job0) {
+        if (p.dbg && blockIdx.x == 0 && job >= job0 && lane == 0 && warp == 1) {
           long long* d = p.dbg + (0 * 256 + (job - job0)) * 4;
           d[0] = tm0; d[1] = tm1; d[2] = clock64(); d[3] = buf;
         }
       }
-      if (pend_buf >= 0) {
+      if (pend_buf >= 0 && sl_elect()) {
         sl_commit(&tmem_full[pend_buf]);
         if (pend_release) { sl_release<CL>(&empty[pend_s0]); if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]); }
       }
+      __syncwarp();
     }
   } else {
     // ================= epilogue: two sets of four warps, set s owns TMEM buffer s =================
-    const int ew = warp - 2;
+    const int ew = warp - EW0;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
     const int set = ew >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * SL_N);
@@ -881,6 +1156,25 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int part = (R == 2) ? split : (split * 2 + set);
     const int t_first = (R == 2) ? 0 : set;
     const int t_step = (R == 2) ? 1 : 2;
+    if constexpr (ATM) {
+      // this thread's packed query row (128 fp16 = 64 words) -> its TMEM lane, columns of query tile `set`
+      const uint32_t a_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + SL_ATM_ACOL + (uint32_t)(set * 64);
+      const uint4* src = reinterpret_cast<const uint4*>(p.qpack + ((int64_t)qtile * SL_M + quarter * 32 + lane) * (SL_ROW / 2));
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 x = __ldg(src + half * 8 + i);
+          w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+        }
+        sl_st32(a_addr + (uint32_t)(half * 32), w);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      sl_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+    }
     if constexpr (MODE == 1) {
       // ---- sample pass: no lists, only the sample_j-th smallest of the 64-column minima of a strided sample of
       //      the bank.  It becomes the query's STARTING threshold (stage 2 checks that the bank really holds k
@@ -894,9 +1188,14 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if constexpr (HALF) {
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
-            const int buf = 2 * set + h;
-            const uint32_t la = lane_addr + (uint32_t)h * JOB_N;
-            sl_wait(&tmem_full[buf], visit & 1, p.wait_mode);
+            int buf = 2 * set + h, par = visit & 1;
+            uint32_t la = lane_addr + (uint32_t)h * JOB_N;
+            if constexpr (ATM) {
+              const int j = 4 * visit + 2 * h + set;        // the issuer's job counter
+              buf = j % 3; par = (j / 3) & 1;
+              la = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * JOB_N);
+            }
+            sl_wait(&tmem_full[buf], par, p.wait_mode);
             sl_fence_after();
             float va[64], vb[64];
             sl_ld32(la, va, 0);
@@ -980,10 +1279,15 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if constexpr (HALF) {
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          const int buf = 2 * set + h;
-          const uint32_t la = lane_addr + (uint32_t)h * JOB_N;
+          int buf = 2 * set + h, par = visit & 1;
+          uint32_t la = lane_addr + (uint32_t)h * JOB_N;
+          if constexpr (ATM) {
+            const int j = 4 * visit + 2 * h + set;          // the issuer's job counter
+            buf = j % 3; par = (j / 3) & 1;
+            la = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * JOB_N);
+          }
           const long long te0 = p.dbg ? clock64() : 0;
-          sl_wait(&tmem_full[buf], visit & 1, p.wait_mode);
+          sl_wait(&tmem_full[buf], par, p.wait_mode);
           sl_fence_after();
           const long long te1 = p.dbg ? clock64() : 0;
           float va[64], vb[64];
@@ -1646,7 +1950,14 @@ struct SlPlan {
   int64_t n_tiles, qrows;
   int pitch;      // fp16 columns per packed row
   bool big;       // K-streaming kernel (pitch > 128)
+  int nb;         // accumulator scheme of the plain R = 2 kernel (sl_filter_kernel's NB): 2, or an opt-in variant (VFR_SEL_NB)
+  int lists;      // candidate lists per (query, bank split): 2 with R = 1 (one per tile parity)
 };
+// accumulator / epilogue scheme requested for the plain R = 2 kernel
+static int sl_nb_env() {
+  static const int nb = [] { const char* e = getenv("VFR_SEL_NB"); const int v = e ? atoi(e) : 2; return (v >= 3 && v <= 5) ? v : 2; }();
+  return nb;
+}
 
 static SlPlan sl_plan(int64_t n_queries, int64_t n_clips, int n_split, int dim = 100) {
   SlPlan pl;
@@ -1667,7 +1978,9 @@ static SlPlan sl_plan(int64_t n_queries, int64_t n_clips, int n_split, int dim =
   const int ns_req = sl_split(pl.n_qgroups, pl.n_tiles, n_split);
   pl.tiles_per_split = (int)((pl.n_tiles + ns_req - 1) / ns_req);
   pl.ns = (int)((pl.n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
-  pl.n_parts = pl.ns * (pl.R == 2 ? 1 : 2);
+  pl.nb = (pl.R == 2 && pl.CL == 1 && !pl.big) ? sl_nb_env() : 2;
+  pl.lists = pl.R == 1 ? 2 : 1;
+  pl.n_parts = pl.ns * pl.lists;
   return pl;
 }
 
@@ -1761,6 +2074,7 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
   __half* qp = reinterpret_cast<__half*>(query_packed);
   p = SlParams{};
   p.qmeta = reinterpret_cast<const float4*>(qp + pl.qrows * pl.pitch);
+  p.qpack = reinterpret_cast<const uint32_t*>(query_packed);
   p.flags = reinterpret_cast<int32_t*>(const_cast<float4*>(p.qmeta) + pl.qrows);
   p.n_clips = n_clips;
   p.n_queries = n_queries;
@@ -1802,7 +2116,7 @@ struct SlSample { int tiles, stride, j; };
 static SlSample sl_sample_plan(const SlPlan& pl, int64_t n_clips, int k, bool need_rank = true) {
   SlSample sp{0, 1, 0};
   { const char* e = getenv("VFR_SEL_SAMPLE"); if (e && e[0] == '0') return sp; }
-  const int lists = pl.ns * (pl.R == 2 ? 1 : 2);              // lists per query, each samples on its own
+  const int lists = pl.ns * pl.lists;                         // lists per query, each samples on its own
   const int64_t per_list = pl.n_tiles / lists;
   int tiles = 64;                                              // more sample for larger k: 8 k tiles, 64 ... 512
   while (tiles < 512 && tiles < 8 * k) tiles <<= 1;
@@ -1831,17 +2145,20 @@ static int sl_launch_filter(const SlPlan& pl, const SlParams& p, const CUtensorM
   const unsigned grid = (unsigned)(pl.n_qgroups * pl.ns);
   void (*kern)(CUtensorMap, CUtensorMap, SlParams) = nullptr;
   uint32_t smem_bytes = 0;
+  unsigned threads = SL_THREADS;
   // accumulators per CTA: two of 256 columns (default); VFR_SEL_NB=4: four of 128 (measured slower, see the kernel)
-  static const int nb = [] { const char* e = getenv("VFR_SEL_NB"); return (e && atoi(e) == 4) ? 4 : 2; }();
+  const int nb = pl.nb;
   if (pl.big) { kern = sl_filter_kernel<2, 1, MODE, true>; smem_bytes = SL_BIG_SMEM; }
   else if (pl.R == 2 && CL == 2) { kern = sl_filter_kernel<2, 2, 0>; smem_bytes = SlCfg<2>::SMEM; }
+  else if (pl.R == 2 && nb == 3) { kern = sl_filter_kernel<2, 1, MODE, false, 3>; smem_bytes = SL_ATM_SMEM; }
+  else if (pl.R == 2 && nb == 5) { kern = sl_filter_kernel<2, 1, MODE, false, 5>; smem_bytes = SlCfg<2>::SMEM; threads = SL_THREADS2; }
   else if (pl.R == 2) { kern = (nb == 4) ? sl_filter_kernel<2, 1, MODE, false, 4> : sl_filter_kernel<2, 1, MODE>; smem_bytes = SlCfg<2>::SMEM; }
   else if (CL == 2) { kern = sl_filter_kernel<1, 2, 0>; smem_bytes = SlCfg<1>::SMEM; }
   else { kern = (nb == 4) ? sl_filter_kernel<1, 1, MODE, false, 4> : sl_filter_kernel<1, 1, MODE>; smem_bytes = SlCfg<1>::SMEM; }
   VFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(SL_THREADS, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1861,7 +2178,7 @@ static int sl_launch_sample(const SlPlan& pl, const SlParams& p, const SlSample&
                             const CUtensorMap& mb, cudaStream_t st) {
   SlParams ps = p;
   ps.tile_lo = 0;
-  ps.tiles_per_split = sp.tiles * (pl.R == 2 ? 1 : 2);    // R = 1: the two sets of a CTA take alternate sample tiles
+  ps.tiles_per_split = sp.tiles * pl.lists;    // R = 1: the two sets of a CTA take alternate sample tiles
   ps.n_tiles = ps.tiles_per_split * pl.ns;
   ps.tile_stride = sp.stride;
   ps.sample_j = sp.j;
