@@ -20,7 +20,7 @@ d = dbg.cpu().numpy()[:9 * 256 * 4].reshape(9, 256, 4)
 t0 = d[0, 0, 0]
 print("MMA thread (job = tile*2 + r): wait_start wait_end issued(commit) | wait issue")
 for j in range(40, 48):
-    print("  job %3d buf %d  %8d %8d %8d | wait %5d issue %5d" % (j, d[0, j, 3], d[0, j, 0] - t0, d[0, j, 1] - t0, d[0, j, 2] - t0, d[0, j, 1] - d[0, j, 0], d[0, j, 2] - d[0, j, 1]))
+    print("  job %3d buf %d  %8d %8d %8d | wait %5d (probes + pending commit %5d, bank tile there after %5d) issue %5d" % (j, d[0, j, 3] & 255, d[0, j, 0] - t0, d[0, j, 1] - t0, d[0, j, 2] - t0, d[0, j, 1] - d[0, j, 0], (d[0, j, 3] >> 8) & 0xffffff, d[0, j, 3] >> 32, d[0, j, 2] - d[0, j, 1]))
 for s in (0, 1):
     print("epilogue set %d: per warp (ew) full_seen / released / done, visits 20..22" % s)
     for v in range(20, 23):
@@ -40,3 +40,12 @@ n_cta = 148
 print("compaction, all CTAs: %d warp events, %d lists, %.0f clk per list, %.0f clk per event; per CTA %.2f ms if serialised (1.9 GHz)" % (
     cnt[1], cnt[2], cnt[0] / max(cnt[2], 1), cnt[0] / max(cnt[1], 1), cnt[0] / n_cta / 1.9e6))
 print("  per list: load %.0f clk, select %.0f clk, write-back %.0f clk" % tuple(cnt[3 + i] / max(cnt[2], 1) for i in range(3)))
+if os.environ.get("VFR_SEL_PDBG"):
+    # producer of CTA 0: when it asked for the two chunks of each of the last 128 bank tiles (role 8 slots), against the
+    # issuer's first job of that tile (jobs 2 * tile of the last 256 jobs)
+    print("bank tile: requested chunk0 / chunk1 (producer) | issuer starts looking / has it  -> request-to-arrival of chunk1")
+    for tl in range(20, 28):
+        j = 2 * tl
+        looking = d[0, j, 0] + ((d[0, j, 3] >> 8) & 0xffffff)
+        has = d[0, j, 0] + (d[0, j, 3] >> 32)
+        print("  tile %3d: %8d %8d | %8d %8d -> %6d" % (tl, d[8, tl, 0] - t0, d[8, tl, 1] - t0, looking - t0, has - t0, has - d[8, tl, 1]))

@@ -59,6 +59,7 @@ constexpr int SL_THREADS = 64 + 2 * SL_SET_WARPS * 32;   // ... in two sets (one
 constexpr int SL_THREADS2 = SL_THREADS + 32;             // the two-issuer variant (NB = 5) has one more non-epilogue warp
 constexpr int SL_CAP = 1024;              // candidate slots per (query, part) list
 constexpr int SL_CAP_HI = SL_CAP - SL_N;  // a tile can append at most SL_N keys to a list
+constexpr int SL_PF_SHARE = 8;            // every SL_PF_SHARE-th CTA prefetches a given bank tile into L2
 constexpr int SL_QPAD = 512;              // packed query rows are padded to a multiple of this (R x 128 rows x CTA pair)
 
 struct SlBankMeta {          // written by the bank pack kernels, read by the query pack kernel
@@ -101,6 +102,9 @@ struct SlParams {
   long long* dbg;            // optional timeline of CTA 0 (development aid): [9 roles][256 events][4] + 8 counters
   int32_t* flags;            // [Qpad] != 0: a candidate list overflowed / scales out of range (see vfr.h)
   unsigned long long* stats; // [2] {warp-level compaction events, lists compacted} since the lists were started (vfr_sel_stats)
+  int prod_dbg;              // development aid: the producer's request times replace epilogue warp 7's slots of the timeline
+  int rot_step;              // tiles by which consecutive CTA groups are rotated against each other (0: off; VFR_SEL_ROT)
+  int prefetch;              // bank tiles the producer asks L2 for ahead of its loads (0: off; VFR_SEL_PF)
   const uint32_t* qpack;     // the packed query rows themselves ([Qpad][128] fp16 as 64 words): the NB = 3 kernel keeps them in TMEM
 };
 
@@ -298,6 +302,10 @@ __device__ __forceinline__ void sl_tma_load(void* dst, const CUtensorMap* map, i
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// ask L2 for a box of the tensor (no shared-memory destination, no completion): the later TMA load finds it there
+__device__ __forceinline__ void sl_tma_prefetch(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void sl_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void sl_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -912,16 +920,20 @@ __device__ __forceinline__ void sl_sample(const float (&v)[64], float (&a)[SL_J]
 // epilogue warps reading every buffer, 128 columns each (hold 740 -> 515 cycles, but every warp then pays the fixed costs
 // of every job and the lists double: 64.6 ms).
 template <int R, int CL, int MODE, bool BIG = false, int NB = 2>
-__global__ void __launch_bounds__(NB == 5 ? SL_THREADS2 : SL_THREADS, 1)
+__global__ void __launch_bounds__((NB == 5 || NB == 8) ? SL_THREADS2 : SL_THREADS, 1)
 sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const SlParams p) {
   static_assert(!BIG || (R == 2 && CL == 1), "the K-streaming variant serves two query tiles per CTA, no cluster");
-  static_assert(NB == 2 || ((NB == 4 || NB == 3 || NB == 5) && !BIG && CL == 1), "three / four accumulators: plain kernel only");
-  static_assert((NB != 3 && NB != 5) || R == 2, "query tiles in TMEM / two issuers: two query tiles per CTA");
+  static_assert(NB == 2 || ((NB == 4 || NB == 3 || NB == 5 || NB == 8) && !BIG && CL == 1), "three / four accumulators: plain kernel only");
+  static_assert((NB != 3 && NB != 5 && NB != 8) || R == 2, "query tiles in TMEM / two issuers: two query tiles per CTA");
   constexpr bool ATM = NB == 3;                       // A operand (the query tiles) in TMEM, three accumulators of 128 columns
-  constexpr bool ISS2 = NB == 5;                      // four accumulators, ONE MMA ISSUER PER QUERY TILE (warps 1 and 2)
-  constexpr int NBUF = ISS2 ? 4 : NB;
+  constexpr bool ISS2 = NB == 5 || NB == 8;           // ONE MMA ISSUER PER QUERY TILE (warps 1 and 2); NB = 5: four accumulators
+  // NB = 8: the two 256-column accumulators of NB = 2, each with its OWN issuer, which commits a job right after its MMAs:
+  // the stall of a barrier wait behind a commit (until the MMAs ahead have drained) costs an issuer nothing when its next
+  // job needs the same accumulator anyway, and the epilogue learns of a finished job without the delay of the deferred commit
+  constexpr bool OWN = NB == 8;
+  constexpr int NBUF = OWN ? 2 : (ISS2 ? 4 : NB);
   constexpr int EW0 = ISS2 ? 3 : 2;                   // first epilogue warp
-  constexpr bool HALF = NB >= 3;
+  constexpr bool HALF = NB >= 3 && !OWN;
   constexpr int JOB_N = HALF ? SL_N / 2 : SL_N;       // accumulator columns of a job
   constexpr int STAGES = BIG ? SL_BIG_STAGES : (ATM ? SL_ATM_STAGES : SlCfg<R>::STAGES);
   constexpr int STAGE_BYTES = BIG ? SL_BIG_STAGE : SL_B_CHUNK;
@@ -945,6 +957,11 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int tile_end = min(tile_begin + p.tiles_per_split, p.n_tiles);
   const int n_my_tiles = max(tile_end - tile_begin, 0);
   const int b_chunks = (p.ksteps > 4) ? 2 : 1;
+  // The CTAs of a bank split would walk the same bank tiles in step - every tile asked for by all of them at the same
+  // moment.  p.rot_step > 0 rotates the scan of CTA group (blockIdx.x % 8) by that many tiles (visit t reads tile
+  // tile_of(t)); the order in which a list sees the clips does not change what stage 2 returns.
+  const int rot = (BIG || MODE == 1 || p.rot_step <= 0 || n_my_tiles < 64) ? 0 : (int)(((blockIdx.x % 8) * (unsigned)p.rot_step) % (unsigned)n_my_tiles);
+  auto tile_of = [&](int t) { const int u = t + rot; return u < n_my_tiles ? u : u - n_my_tiles; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ISS2 ? 2 : CL); }
@@ -994,10 +1011,18 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       int it = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
-        const int row = (tile_begin + t) * p.tile_stride * SL_N;
+        const int row = (tile_begin + tile_of(t)) * p.tile_stride * SL_N;
+        // The CTAs of a bank split walk the same tiles nearly in step, so whoever comes first pays the DRAM latency of a tile
+        // and the ring (2.5 tiles) is not deep enough to hide it: the issuer waited ~900 cycles per tile for the bank tile
+        // (tools/timeline_sel.py).  One CTA in SL_PF_SHARE asks L2 for the tile p.prefetch tiles ahead.
+        if (p.prefetch > 0 && t + p.prefetch < n_my_tiles && ((tile_begin + t) % SL_PF_SHARE) == (int)(blockIdx.x % SL_PF_SHARE)) {
+          const int prow = (tile_begin + tile_of(t + p.prefetch)) * p.tile_stride * SL_N;
+          for (int c = 0; c < b_chunks; ++c) sl_tma_prefetch(&tm_b, c * 64, prow);
+        }
         for (int c = 0; c < b_chunks; ++c, ++it) {
           const int s = it % STAGES;
           sl_wait(&empty[s], ((it / STAGES) & 1) ^ 1, p.wait_mode);
+          if (p.dbg && p.prod_dbg && blockIdx.x == 0 && t >= n_my_tiles - 128) p.dbg[(8 * 256 + (t - (n_my_tiles - 128))) * 4 + c] = clock64();
           mbar_expect_tx(&full[s], SL_B_CHUNK);
           if (CL == 1) sl_tma_load(smem_b + s * SL_B_CHUNK, &tm_b, c * 64, row, &full[s]);
           else if ((it & 1) == crank) sl_tma_load_mc(smem_b + s * SL_B_CHUNK, &tm_b, c * 64, row, &full[s], (uint16_t)3);
@@ -1045,14 +1070,16 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int s0 = 0, s1 = 0, ph0 = 0, ph1 = 0;
       int pend_buf = -1, pend_s0 = 0, pend_s1 = 0;
       bool pend_release = false;
-      constexpr int JPT = ISS2 ? 2 : (HALF ? 2 : 1) * R;     // jobs per bank tile (of this issuer)
+      constexpr int JPT = OWN ? 1 : (ISS2 ? 2 : (HALF ? 2 : 1) * R);     // jobs per bank tile (of this issuer)
       const int n_jobs = n_my_tiles * JPT;
       for (int job = 0; job < n_jobs; ++job) {
         // two accumulators: buffer = query tile (R = 2) or tile parity (R = 1).  Four: a tile's jobs go (r0, h0), (r1, h0),
         // (r0, h1), (r1, h1) - the sets get their work evenly spaced - on buffer 2 r + h; R = 1: tile parity s, 2 s + h.
         int r, h, buf, use;
         bool first, last;
-        if (ISS2) {
+        if (OWN) {
+          r = warp - 1; h = 0; buf = r; use = job; first = true; last = true;
+        } else if (ISS2) {
           // this issuer serves query tile r = warp - 1 alone: the two halves of every bank tile on its own two accumulators
           r = warp - 1; h = job & 1; buf = 2 * r + h; use = job >> 1; first = h == 0; last = h == 1;
         } else if (ATM) {
@@ -1065,6 +1092,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           r = (R == 2) ? (job & 1) : 0; h = 0; buf = job & 1; use = job >> 1; first = r == 0; last = r == R - 1;
         }
         const long long tm0 = p.dbg ? clock64() : 0;
+        long long tm_full = tm0, tm_commit = tm0;   // (development aid) when the pending commit was out / the bank tile of this job was there
         if (first) {
           s0 = it % STAGES; ph0 = (it / STAGES) & 1;
           s1 = (it + 1) % STAGES; ph1 = ((it + 1) / STAGES) & 1;
@@ -1085,10 +1113,12 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             pend_buf = -1;
           }
+          if (p.dbg) tm_commit = clock64();
           if (first) {
             sl_wait(&full[s0], ph0, p.wait_mode);
             if (b_chunks == 2) sl_wait(&full[s1], ph1, p.wait_mode);
           }
+          if (p.dbg) tm_full = clock64();
           sl_wait(&tmem_empty[buf], pe, p.wait_mode);
         }
         sl_fence_after();
@@ -1133,10 +1163,18 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         pend_s0 = s0;
         pend_s1 = s1;
         pend_release = last;
+        if constexpr (OWN) {
+          if (sl_elect()) {
+            sl_commit(&tmem_full[pend_buf]);
+            sl_release<CL>(&empty[pend_s0]);
+            if (b_chunks == 2) sl_release<CL>(&empty[pend_s1]);
+          }
+          pend_buf = -1;
+        }
         const int job0 = n_jobs - 256;
         if (p.dbg && blockIdx.x == 0 && job >= job0 && lane == 0 && warp == 1) {
           long long* d = p.dbg + (0 * 256 + (job - job0)) * 4;
-          d[0] = tm0; d[1] = tm1; d[2] = clock64(); d[3] = buf;
+          d[0] = tm0; d[1] = tm1; d[2] = clock64(); d[3] = buf | ((tm_commit - tm0) << 8) | ((tm_full - tm0) << 32);
         }
       }
       if (pend_buf >= 0 && sl_elect()) {
@@ -1267,7 +1305,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
     int visit = 0;
     for (int t = t_first; t < n_my_tiles; t += t_step, ++visit) {
-      st.clip0 = (int64_t)(tile_begin + t) * SL_N;
+      st.clip0 = (int64_t)(tile_begin + tile_of(t)) * SL_N;
       if ((visit & 3) == 0 && (p.n_parts > 1 || visit == 0)) {
         // the other lists of this query (other bank splits / tile parities) may have tightened the threshold
         const float tg = tau_fetch(p.tau_g + st.q);
@@ -1339,7 +1377,7 @@ sl_filter_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       sl_process(va, 128, st, p);
       sl_process(vb, 192, st, p);
       const int visit0 = (n_my_tiles - t_first + t_step - 1) / t_step - 128;
-      if (p.dbg && blockIdx.x == 0 && visit >= visit0 && lane == 0) {
+      if (p.dbg && blockIdx.x == 0 && visit >= visit0 && lane == 0 && !(p.prod_dbg && ew == 7)) {
         long long* d = p.dbg + ((1 + ew) * 256 + (visit - visit0)) * 4;
         d[0] = te0; d[1] = te1; d[2] = te2; d[3] = clock64();
       }
@@ -1955,7 +1993,7 @@ struct SlPlan {
 };
 // accumulator / epilogue scheme requested for the plain R = 2 kernel
 static int sl_nb_env() {
-  static const int nb = [] { const char* e = getenv("VFR_SEL_NB"); const int v = e ? atoi(e) : 2; return (v >= 3 && v <= 5) ? v : 2; }();
+  static const int nb = [] { const char* e = getenv("VFR_SEL_NB"); const int v = e ? atoi(e) : 8; return ((v >= 2 && v <= 5) || v == 8) ? v : 8; }();
   return nb;
 }
 
@@ -2086,6 +2124,9 @@ static int sl_setup(SlPlan& pl, SlParams& p, void* query_packed, int64_t n_queri
   p.k = k;
   p.n_parts = pl.n_parts;
   { const char* wm = getenv("VFR_SEL_WAIT"); p.wait_mode = wm ? atoi(wm) : 0; }
+  { const char* pf = getenv("VFR_SEL_PF"); p.prefetch = pf ? std::max(0, atoi(pf)) : 0; }
+  { const char* pd = getenv("VFR_SEL_PDBG"); p.prod_dbg = pd ? atoi(pd) : 0; }
+  { const char* ro = getenv("VFR_SEL_ROT"); p.rot_step = ro ? std::max(0, atoi(ro)) : 0; }
   { const char* dg = getenv("VFR_SEL_DBG"); p.dbg = dg ? reinterpret_cast<long long*>(strtoull(dg, nullptr, 0)) : nullptr; }
   const size_t qpad = (size_t)pl.qrows;
   p.cand = reinterpret_cast<unsigned long long*>(workspace);
@@ -2151,6 +2192,7 @@ static int sl_launch_filter(const SlPlan& pl, const SlParams& p, const CUtensorM
   if (pl.big) { kern = sl_filter_kernel<2, 1, MODE, true>; smem_bytes = SL_BIG_SMEM; }
   else if (pl.R == 2 && CL == 2) { kern = sl_filter_kernel<2, 2, 0>; smem_bytes = SlCfg<2>::SMEM; }
   else if (pl.R == 2 && nb == 3) { kern = sl_filter_kernel<2, 1, MODE, false, 3>; smem_bytes = SL_ATM_SMEM; }
+  else if (pl.R == 2 && nb == 8) { kern = sl_filter_kernel<2, 1, MODE, false, 8>; smem_bytes = SlCfg<2>::SMEM; threads = SL_THREADS2; }
   else if (pl.R == 2 && nb == 5) { kern = sl_filter_kernel<2, 1, MODE, false, 5>; smem_bytes = SlCfg<2>::SMEM; threads = SL_THREADS2; }
   else if (pl.R == 2) { kern = (nb == 4) ? sl_filter_kernel<2, 1, MODE, false, 4> : sl_filter_kernel<2, 1, MODE>; smem_bytes = SlCfg<2>::SMEM; }
   else if (CL == 2) { kern = sl_filter_kernel<1, 2, 0>; smem_bytes = SlCfg<1>::SMEM; }
