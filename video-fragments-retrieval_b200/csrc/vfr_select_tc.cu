@@ -24,12 +24,13 @@
 // everything that survives with the arithmetic of vfr_score.cu (sequential fp32 FADD/FFMA over k,
 // IEEE sqrt and division), so scores, ids and tie order equal the exact engine's bit for bit.
 //
-// Stage 1 pipeline (one CTA per SM, 320 threads, warp-specialised):
+// Stage 1 pipeline (one CTA per SM, 352 threads, warp-specialised; the default scheme, NB = 8 below):
 //   warp 0       TMA producer: the CTA's query tiles (R x 128 rows, resident) once, then bank tiles of 256
 //                clip rows as two [256 x 64] fp16 boxes (SWIZZLE_128B) through an mbarrier ring
-//   warp 1       MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=256, K=16; 7 per (tile, query
-//                tile) at D=100; the 512 TMEM columns hold two accumulators (ping-pong)
-//   warps 2..9   epilogue, two sets of four warps (one warp per TMEM lane quarter); set s owns TMEM buffer
+//   warps 1, 2   MMA issuers, one per query tile and TMEM accumulator: tcgen05.mma cta_group::1 kind::f16, M=128,
+//                N=256, K=16; 7 per (tile, query tile) at D=100, committed right after they are issued; a ring
+//                stage is free when BOTH have released it (R = 1 and the other schemes: warp 1 alone, 320 threads)
+//   warps 3..10  epilogue, two sets of four warps (one warp per TMEM lane quarter); set s owns TMEM buffer
 //                s, so a thread sees ALL 256 columns of ONE query row and keeps ONE candidate list:
 //                tcgen05.ld 32x32b.x32 double-buffered in registers (the next 64 columns load while the
 //                current 64 go through an FMNMX3 tree and one compare against the query's threshold);
@@ -898,7 +899,13 @@ __device__ __forceinline__ void sl_sample(const float (&v)[64], float (&a)[SL_J]
 // BIG: the K-streaming variant for D + 3 > 128 (R = 2, CL = 1): every 64-column chunk of the two query tiles travels
 // through the ring together with the bank tile's chunk; a tile's two accumulators are committed after the last chunk
 // (no ping-pong - the epilogue's ~700-cycle read of a buffer is small against the >= 3 x 4 MMAs x 2 of a tile).
-// Accumulator schemes (NB; 2 is the default, the others are opt-in through VFR_SEL_NB and return the same bits).  A buffer's
+// Accumulator schemes (NB, VFR_SEL_NB; all return the same bits).  The default is NB = 8: the two 256-column accumulators
+// of NB = 2, each with its OWN issuer warp that commits a job right after its MMAs.  With one issuer the commit of job j is
+// deferred behind the probes of job j + 1 (a barrier wait right behind a tcgen05.commit stalls the thread until the MMAs
+// ahead have drained - and the one issuer has the other accumulator's job to issue meanwhile), so the epilogue learns of
+// a finished job 250 - 600 cycles late; an issuer of its own has nothing else to do until its accumulator comes back, the
+// stall costs it nothing.  Measured in the bench step (37 888 queries x 1 M videos, same box, back to back): scan 49.5 ->
+// 43.3 ms, step 76.1 -> 70.7 ms.  The history of the other schemes:  A buffer's
 // round trip - MMAs issued -> commit seen by the epilogue (~550 cycles) -> its four warps have read it (~750 median, 1 200
 // p90) -> the issuer sees the release (~450) - is ~3 000 cycles, i.e. 1 500 per job with two buffers against 896 of MMA
 // (tools/timeline_sel.py).  Smaller jobs on more buffers would spread the same latencies over more work in flight:
