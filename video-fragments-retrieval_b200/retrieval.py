@@ -365,9 +365,12 @@ class MomentRetriever:
             n_s = 0 if getattr(self, "sel_pool_samples", True) is False else \
                 lib.vfr_sel_sample_clips(Q, self.n_clips, self.k, self.plan.n_split, self.bank.dim)
             lists = lib.vfr_sel_sample_lists(Q, self.n_clips, self.plan.n_split, self.bank.dim)
-            t = torch.tensor([n_s, self.n_clips, 1 if n_s > 0 else 0, 1, lists], dtype=torch.int64, device=self.q_emb.device)
-            tot_s, tot_c, n_ok, n_ranks, tot_lists = comm.all_reduce_sum(t).tolist()
-            fits = tot_lists == lists * n_ranks and n_ranks * lists * 32 <= 1024     # same list count everywhere
+            t = torch.tensor([n_s, self.n_clips, 1 if n_s > 0 else 0, 1, lists, lists * lists], dtype=torch.int64,
+                             device=self.q_emb.device)
+            tot_s, tot_c, n_ok, n_ranks, tot_lists, tot_sq = comm.all_reduce_sum(t).tolist()
+            # the same list count on every shard (P sum(l^2) == (sum l)^2 holds only then), decided from reduced values
+            # alone: every rank must take the same branch of the protocol, whatever its own shard looks like
+            fits = n_ranks * tot_sq == tot_lists * tot_lists and tot_lists * 32 <= 1024
             cache[Q] = (lib.vfr_sel_sample_rank(self.k, tot_s, tot_c) if (n_ok == n_ranks and fits) else 0, int(n_ranks))
         return cache[Q]
 
